@@ -1,0 +1,242 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the REFERENCE's own code.
+
+Run in the authoring container only (it reads /root/reference, which does not exist on the GPU
+box):   python tests/golden/make_golden.py
+
+The reference package is loaded *in memory* (nothing is copied into the repo) with the two source
+fixes SURVEY.md section 0 documents:
+  1. pretraining/multimae/zorro_utils.py:255 contains U+FF1A instead of ':' (SyntaxError);
+  2. its Block_Fusion (:243-258) calls CrossAttention with the wrong kwargs; the working class is
+     downstream/instance_segmentation/modeling/multimae/zorro_utils.py:243-258.
+Weights come from ``oracle.init_state_dict`` + ``perturb_state_dict`` (reproducible anywhere) and
+are loaded into the reference model with ``strict=True`` -- which also pins the state_dict schema.
+Each fixture stores only inputs' seeds and the reference's outputs / loss / gradients.
+"""
+import importlib.util
+import io
+import os
+import re
+import sys
+import types
+import warnings
+from collections import OrderedDict
+from functools import partial
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+PKG = os.path.join(REF, "pretraining", "multimae")
+DOWN_ZORRO = os.path.join(REF, "downstream", "instance_segmentation", "modeling", "multimae", "zorro_utils.py")
+
+warnings.filterwarnings("ignore")
+
+
+def _read(path):
+    with io.open(path, "r", encoding="utf-8") as f:
+        return f.read().replace("\r\n", "\n")
+
+
+def _class_src(src, name):
+    m = re.search(r"^class %s\(.*?(?=^class |\Z)" % name, src, flags=re.S | re.M)
+    return m.group(0)
+
+
+def load_reference():
+    """Import the reference ``multimae`` package as ``refmm`` with the two fixes, from memory."""
+    if "refmm" in sys.modules:
+        return sys.modules["refmm"]
+    pkg = types.ModuleType("refmm")
+    pkg.__path__ = [PKG]
+    sys.modules["refmm"] = pkg
+
+    def load(mod, patch=None):
+        src = _read(os.path.join(PKG, mod + ".py"))
+        if patch:
+            src = patch(src)
+        m = types.ModuleType("refmm." + mod)
+        m.__package__ = "refmm"
+        m.__file__ = os.path.join(PKG, mod + ".py")
+        sys.modules["refmm." + mod] = m
+        exec(compile(src, m.__file__, "exec"), m.__dict__)
+        setattr(pkg, mod, m)
+        return m
+
+    def fix_zorro(src):
+        src = src.replace("：", ":")
+        good = _class_src(_read(DOWN_ZORRO), "Block_Fusion")
+        return src.replace(_class_src(src, "Block_Fusion"), good)
+
+    load("multimae_utils")
+    load("zorro_utils", fix_zorro)
+    load("output_adapter_utils")
+    load("input_adapters")
+    load("output_adapters")
+    load("output_adapters_simple")
+    load("criterion")
+    # the reference prints a tensor shape every step when sample_tasks_uniformly (multimae.py:177)
+    quiet = lambda s: s.replace("print(rand_per_sample_choice.shape)", "pass")
+    load("multimae", quiet)
+    load("multimae_crossattn", quiet)
+    return pkg
+
+
+def build_reference_model(cfg, sd):
+    ref = load_reference()
+    Adapter = ref.input_adapters.PatchedInputAdapter
+    FusAdapter = ref.input_adapters.FusionInputAdapter
+    Out = (ref.output_adapters_simple if cfg.decoder == "simple" else ref.output_adapters).SpatialOutputAdapter
+    ia = OrderedDict((t, Adapter(num_channels=C, stride_level=1, patch_size_full=cfg.patch, image_size=cfg.image_size))
+                     for t, C in cfg.channels.items())
+    ia["fusion"] = FusAdapter(num_channels=1, stride_level=1, patch_size_full=cfg.patch, image_size=cfg.image_size)
+    oa = OrderedDict((t, Out(num_channels=cfg.channels[t], stride_level=1, patch_size_full=cfg.patch,
+                             dim_tokens=cfg.dec_dim, depth=cfg.dec_depth, num_heads=cfg.dec_heads,
+                             use_task_queries=True, task=t, context_tasks=list(cfg.channels),
+                             image_size=cfg.image_size, use_xattn=True))
+                     for t in cfg.out_tasks)
+    mod = ref.multimae_crossattn if cfg.variant == "crossattn" else ref.multimae
+    T = ref.zorro_utils.TokenTypes
+    model = mod.MultiMAE(input_adapters=ia, output_adapters=oa, dim_tokens=cfg.dim, depth=cfg.depth,
+                         dim_head=cfg.dim_head, heads=cfg.heads, ff_mult=cfg.ff_mult,
+                         num_fusion_tokens=cfg.num_patches,
+                         return_token_types=tuple(T(v) for v in cfg.return_token_types),
+                         norm_layer=ref.zorro_utils.LayerNorm)
+    missing = model.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return model
+
+
+def make_inputs(cfg, batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    return OrderedDict((t, torch.randn(batch, C, cfg.image_size, cfg.image_size, generator=g))
+                       for t, C in cfg.channels.items())
+
+
+def reference_loss(ref, out, x, cfg):
+    """pretrain_mmae.py:476-500 with the reference's own criterion classes."""
+    mse = ref.criterion.MaskedMSELoss(patch_size=cfg.patch, stride=1)
+    l1 = ref.criterion.MaskedL1Loss(patch_size=cfg.patch, stride=1)
+    preds, masks = out[0], out[1]
+    total = 0
+    for t in preds:
+        total = total + (l1 if t == "dem" else mse)(preds[t].float(), x[t], mask=masks.get(t))
+    if len(out) == 8:
+        feats = [f.squeeze(1) for f in torch.chunk(out[2], 4, dim=1)]
+        toks = [o.squeeze(1) for o in out[5:8]]
+        contra = sum(ref.criterion.dino_loss_func(toks[i], feats[i]) for i in range(3))
+        total = total + 0.3 * contra
+    return total
+
+
+def model_case(name, cfg, batch, nenc, mask_seed, uniformly, task_masks=None):
+    from oracle import init_state_dict
+    from oracle.functional import perturb_state_dict
+    ref = load_reference()
+    sd = perturb_state_dict(init_state_dict(cfg, seed=0), seed=7)
+    model = build_reference_model(cfg, sd)
+    x = make_inputs(cfg, batch, seed=1234)
+    torch.manual_seed(mask_seed)
+    out = model(x, mask_inputs=True, task_masks=task_masks, num_encoded_tokens=nenc, alphas=1.0,
+                sample_tasks_uniformly=uniformly)
+    loss = reference_loss(ref, out, x, cfg)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    fx = {
+        "cfg": cfg.__dict__.copy(), "batch": batch, "nenc": nenc, "mask_seed": mask_seed,
+        "uniformly": uniformly, "input_seed": 1234, "sd_seed": 0, "perturb_seed": 7,
+        "task_masks_in": task_masks,
+        "preds": {t: v.detach() for t, v in out[0].items()},
+        "task_masks": {t: v for t, v in out[1].items()},
+        "return_tokens": out[2].detach(), "ori_tokens": out[3].detach(), "fusion_tokens": out[4].detach(),
+        "extra_return_tokens": [o.detach() for o in out[5:]],
+        "loss": loss.detach(),
+        "grad_norms": {k: v.norm() for k, v in grads.items()},
+        # a few full gradients (small tensors) + the big ones as norms only keeps the fixture small
+        "grads": {k: v for k, v in grads.items() if v.numel() <= 4096 or k.endswith("blocks.0.attn.to_q.weight")},
+        "state_dict_keys": [(k, tuple(v.shape)) for k, v in model.state_dict().items()],
+        "no_grad_params": [k for k, p in model.named_parameters() if p.requires_grad and p.grad is None],
+    }
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    print(name, "loss", float(loss), "n_grads", len(grads), "counts",
+          [int((m[0] == 0).sum()) for m in out[1].values()])
+
+
+def subset_case(cfg):
+    """The 7 non-empty modality subsets through explicit task_masks (infer_mmae.py:344-361)."""
+    from oracle import init_state_dict
+    from oracle.functional import perturb_state_dict
+    sd = perturb_state_dict(init_state_dict(cfg, seed=0), seed=7)
+    model = build_reference_model(cfg, sd).eval()
+    x = make_inputs(cfg, 2, seed=99)
+    Fn = cfg.num_patches
+    res = {}
+    for bits in range(1, 8):
+        present = [t for i, t in enumerate(("s1", "s2", "dem")) if bits >> i & 1]
+        tm = {t: (torch.zeros if t in present else torch.ones)(1, Fn, dtype=torch.long) for t in ("s1", "s2", "dem")}
+        with torch.no_grad():
+            out = model(x, mask_inputs=True, task_masks=tm, num_encoded_tokens=Fn * len(present))
+        res["+".join(present)] = {
+            "return_tokens": out[2], "ori_tokens": out[3], "fusion_tokens": out[4],
+            "preds": out[0], "extra_return_tokens": list(out[5:]),
+        }
+    torch.save({"cfg": cfg.__dict__.copy(), "input_seed": 99, "results": res}, os.path.join(HERE, "subsets.pt"))
+    print("subsets", list(res))
+
+
+def loss_case():
+    ref = load_reference()
+    g = torch.Generator().manual_seed(5)
+    pred = torch.randn(3, 2, 32, 32, generator=g)
+    tgt = torch.randn(3, 2, 32, 32, generator=g)
+    mask = (torch.rand(3, 16, generator=g) > 0.5).long()
+    mask[2] = 0                                     # a zero-mask sample -> nanmean path
+    a = torch.randn(6, 48, generator=g)
+    b = torch.randn(6, 48, generator=g)
+    torch.Tensor.cuda = lambda self, *a, **k: self   # HardNegtive_loss hard-codes .cuda() (criterion.py:242)
+    fx = {
+        "seed": 5,
+        "mse": ref.criterion.MaskedMSELoss(patch_size=8)(pred, tgt, mask),
+        "l1": ref.criterion.MaskedL1Loss(patch_size=8)(pred, tgt, mask),
+        "mse_nomask": ref.criterion.MaskedMSELoss(patch_size=8)(pred, tgt),
+        "mse_zeromask": ref.criterion.MaskedMSELoss(patch_size=8)(pred, tgt, torch.zeros_like(mask)),
+        "hardneg": ref.criterion.HardNegtive_loss()(a, b),
+        "dino": ref.criterion.dino_loss_func(a, b),
+    }
+    torch.save(fx, os.path.join(HERE, "losses.pt"))
+    print("losses", {k: float(v) for k, v in fx.items() if k != "seed"})
+
+
+def mask_case():
+    """Mask sampler on the CPU generator, several seeds, both sampling modes (int64, exact)."""
+    ref = load_reference()
+    from oracle import OracleConfig
+    cfg = OracleConfig(dim=64, depth=1, heads=1, image_size=64, patch=8)
+    from oracle import init_state_dict
+    model = build_reference_model(cfg, init_state_dict(cfg, 0))
+    n = OrderedDict((t, torch.zeros(3, cfg.num_patches, 1)) for t in ("s1", "s2", "dem"))
+    cases = []
+    for seed in range(12):
+        for uni in (False, True):
+            torch.manual_seed(seed)
+            tm, keep, restore = model.generate_random_masks(n, 96, alphas=1.0, sample_tasks_uniformly=uni)
+            cases.append({"seed": seed, "uniformly": uni, "task_masks": tm, "ids_keep": keep, "ids_restore": restore})
+    torch.save({"num_patches": cfg.num_patches, "nenc": 96, "batch": 3, "cases": cases}, os.path.join(HERE, "masks.pt"))
+    print("masks", len(cases))
+
+
+def main():
+    from oracle import OracleConfig
+    small = dict(dim=128, depth=2, heads=2, dim_head=64, image_size=32, patch=8, dec_dim=64, dec_depth=1, dec_heads=2)
+    model_case("crossattn_simple", OracleConfig(variant="crossattn", decoder="simple", **small), 2, 24, 1, False)
+    model_case("plain_xattn", OracleConfig(variant="plain", decoder="xattn", **small), 2, 24, 3, True)
+    model_case("crossattn_uniform", OracleConfig(variant="crossattn", decoder="simple", **small), 3, 20, 11, True)
+    subset_case(OracleConfig(variant="crossattn", decoder="simple", **small))
+    loss_case()
+    mask_case()
+
+
+if __name__ == "__main__":
+    main()
