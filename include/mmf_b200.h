@@ -1,0 +1,217 @@
+/*
+ * mmf_b200.h -- C ABI of the B200-native MultiMAE hot path (libmmf_b200.so).
+ *
+ * The reference (Yusin2Chen/incomplete_multimodal_fusion) has NO FFI/plugin boundary on this path:
+ * it is plain PyTorch eager.  Each entry point below therefore names the
+ * group of reference ATen call sites it replaces (file:line under /root/reference/pretraining/multimae).
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch types, no allocation, no exceptions, no global mutable state
+ *     (except a lazily resolved driver entry point for cuTensorMapEncodeTiled);
+ *   - all pointers are DEVICE pointers unless the name says `_host`; row-major; `ld*` in ELEMENTS;
+ *   - every call enqueues on `stream` and returns immediately;
+ *   - return value: 0 = ok, < 0 = argument error (-(line-ish code)), > 0 = cudaError_t / CUresult.
+ *   - bf16 = __nv_bfloat16 bit pattern (uint16_t), f32 = IEEE float.
+ */
+#ifndef MMF_B200_H_
+#define MMF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mmf_stream_t; /* == cudaStream_t */
+
+/* ------------------------------------------------------------------------------------------------
+ * Library info
+ * ---------------------------------------------------------------------------------------------- */
+/* ABI version of this header; bumps when a struct layout or signature changes. */
+int mmf_abi_version(void);
+/* Number of kernel launches issued through this library since load / last reset (for bench.py's
+ * `gpu_launches`). */
+int64_t mmf_launch_count(void);
+void mmf_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators), bf16 x bf16 -> fp32 accumulate.
+ *   out[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T )
+ * Replaces every nn.Linear / Conv2d(k=s=P) / einsum->bmm call on the path and their autograd
+ * backward: zorro_utils.py:125,127,166-168,179,194 (encoder), input_adapters.py:110 (patch
+ * projection as im2col GEMM), multimae_utils.py:143-153,164-181 (decoder), output_adapters_simple.py
+ * :168,180.  dgrad uses b_mn=1 (B = W read "transposed"), wgrad uses a_mn=b_mn=1 with split_k.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct MmfGemmArgs {
+  const void* a;           /* bf16. a_mn=0: [M,K] (lda>=K).  a_mn=1: stored [K,M] (lda>=M) */
+  const void* b;           /* bf16. b_mn=0: [N,K] (ldb>=K).  b_mn=1: stored [K,N] (ldb>=N) */
+  void* out;               /* bf16 or f32 [M,N] (ldo) -- see out_period for the row mapping */
+  const float* bias;       /* f32 [N] or NULL: added before the activation */
+  const float* residual;   /* f32 rows of length >= N (ldr) or NULL: added after the activation */
+  const float* residual2;  /* optional second residual source: rows >= res_split come from residual2[row - res_split] */
+  int64_t res_split;
+  const int32_t* res_row_map; /* int32 [res_period] or NULL */
+  int64_t M, N, K;
+  int64_t lda, ldb, ldo, ldr;
+  int32_t a_mn, b_mn;
+  int32_t out_f32;         /* 0: bf16 output, 1: f32 output */
+  int32_t act;             /* 0: none, 1: exact-erf GELU, 2: GEGLU (see below) */
+  int32_t split_k;         /* >=1.  >1: f32 atomic accumulation into a ZEROED `out`; requires out_f32=1,
+                              act=0, bias=residual=NULL */
+  int32_t res_period;      /* 0: residual row = r.  >0: residual row = map ? map[r % p] : r % p */
+  int32_t out_period;      /* 0: out row = r.  >0: out row = (r / p) * out_batch_rows + r % p */
+  int32_t out_batch_rows;
+  int32_t block_n;         /* 0: auto, or 128 / 256 */
+  float alpha;             /* scale applied to the accumulator first */
+  void* out2;              /* optional second output: bf16 copy of an f32 `out` (same mapping, ldo2) */
+  int64_t ldo2;
+  /* act=2 (GEGLU, zorro_utils.py:115-118): B is the [2*I_pad, K] weight; tile columns pair value
+   * row j with gate row I_pad + j; out[M, I_pad] = gelu(gate) * value; `out2` (optional, bf16,
+   * [M, 2*I_pad]) receives the pre-activation for the backward.  N must be passed as I_pad. */
+} MmfGemmArgs;
+int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm, single or fused double (fp32 math, warp per row).
+ *   y = LN2( LN1(x) )   LN1: gamma g1 (+ optional bias b1, eps1);  LN2 (optional, g2 != NULL): gamma g2, eps2
+ * Replaces zorro_utils.py:103-110 applied twice back to back (:238->:176, :239->:124), the final
+ * encoder norm multimae.py:431 and the decoder nn.LayerNorm(eps=1e-6) (multimae_utils.py:217-232).
+ * x rows may come from two buffers: rows [0, x_split) from x, rows >= x_split from x2 (row - x_split)
+ * (x2 == NULL: single source).  stats: f32 [rows, 4] = mean1, rstd1, mean2, rstd2 (nullable in fwd).
+ * The backward also adds the residual-branch gradient `dres` and can emit a bf16 copy of dx.
+ * dg1/db1/dg2 are ACCUMULATED with atomics: the caller zeroes them.
+ * ---------------------------------------------------------------------------------------------- */
+int mmf_layernorm_fwd(const float* x, const float* x2, int64_t x_split, int64_t rows, int32_t D, int64_t ldx,
+                      const float* g1, const float* b1, float eps1, const float* g2, float eps2, void* y, int64_t ldy,
+                      int32_t y_f32, float* stats, mmf_stream_t stream);
+int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, const float* x, const float* x2, int64_t x_split,
+                      int64_t rows, int32_t D, int64_t ldx, const float* g1, const float* b1, const float* g2,
+                      const float* stats, const float* dres, int64_t lddres, float* dx, int64_t lddx, void* dx_bf16,
+                      int64_t lddxb, float* dg1, float* db1, float* dg2, mmf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Zorro-masked flash attention (zorro_utils.py:181-193; decoder: multimae_utils.py:170-180).
+ * q/k/v/o are bf16 token-major matrices; head h occupies columns [h*dh, (h+1)*dh) of a row.
+ * Token (b, i) is row  i < n_head ? b*n_head + i : B*n_head + b*n_tail + (i - n_head).
+ * seg (device int32[nseg+1], or NULL): tokens [seg[s], seg[s+1]) form segment s; a segment attends
+ * to itself, the LAST segment (fusion tokens) attends to everything (multimae.py:410-426).  With seg,
+ * Nq == Nk.  The mask is realised by skipping key blocks, not by adding -inf.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct MmfAttnArgs {
+  const void* q; const void* k; const void* v;
+  void* o;                 /* bf16 [rows, H*dh] */
+  float* lse;              /* f32 [B, H, Nq] (fwd: optional output; bwd: input) */
+  int64_t ldq, ldk, ldv, ldo;
+  int32_t B, H, Nq, Nk, dh;          /* dh in {32, 64} */
+  int32_t n_head_q, n_tail_q, n_head_k, n_tail_k;
+  float scale;
+  const int32_t* seg;
+  int32_t nseg;
+  /* backward only */
+  const void* d_o; int64_t lddo;
+  float* delta;            /* f32 [B, H, Nq] scratch */
+  void* dq; void* dk; void* dv;
+  int64_t lddq, lddk, lddv;
+} MmfAttnArgs;
+int mmf_attn_fwd(const MmfAttnArgs* args, mmf_stream_t stream);
+int mmf_attn_bwd(const MmfAttnArgs* args, mmf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Slot ("modality") attention of Block_Fusion (downstream/.../zorro_utils.py:243-258, call site
+ * multimae_crossattn.py:450-470): per position p the fusion token's query attends to S slots:
+ * slot s < S-1 = modality s's visible token at p (row b*n_head + seg[s] + slotmap[s*F+p]) or, when
+ * slotmap is -1, the batch-invariant mask-embedding row p; slot S-1 = the fusion token itself.
+ * kv rows are [k | v] with H*dh columns each.  Only the fusion slot's output is produced.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct MmfSlotAttnArgs {
+  const void* q;          /* bf16 [B*F, H*dh] */
+  const void* kv_tok;     /* bf16 planar token rows [B*n_head + B*F, 2*H*dh] */
+  const void* kv_me;      /* bf16 [F, 2*H*dh] */
+  const int32_t* slotmap; /* int32 [S-1, F] */
+  const int32_t* seg;     /* int32 [>= S-1] segment starts inside the head plane */
+  void* out;              /* bf16 [B*F, H*dh] */
+  float* probs;           /* f32 [B*F, H, S] or NULL */
+  int64_t ldq, ldkv, ldme, ldo;
+  int32_t B, F, H, S, dh, n_head;   /* dh must be 64 */
+  float scale;
+  /* backward */
+  const void* dout; void* dq; void* dkv_tok; float* dkv_me; /* dkv_me f32 [F, 2*H*dh], caller zeroes */
+  int64_t lddout, lddq, lddkv, lddme;
+} MmfSlotAttnArgs;
+int mmf_slot_attn_fwd(const MmfSlotAttnArgs* args, mmf_stream_t stream);
+int mmf_slot_attn_bwd(const MmfSlotAttnArgs* args, mmf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pool attention: R learned queries over the N tokens of each sample with a dense boolean mask
+ * (multimae.py:434-455; per-modality pools multimae_crossattn.py:529-543).  masked_fill(-finfo.max)
+ * semantics: a row with no allowed key is UNIFORM over all N keys (mode[r] = 0) -- or, for an empty
+ * context (mode[r] = 1), zero.  stat: f32 [B,R,H,2] (max, sum) followed by [B,R,H] scratch.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct MmfPoolAttnArgs {
+  const void* q;          /* bf16 [Bq, R, H*dh]; q_bstride = 0 if batch-invariant */
+  const void* kv;         /* bf16 planar token rows [.., 2*H*dh] */
+  const uint8_t* mask;    /* [R, N] */
+  const int32_t* mode;    /* [R] */
+  void* out;              /* bf16 [B, R, H*dh] */
+  float* stat;            /* f32 [B*R*H*3] */
+  int64_t q_bstride, ldkv;
+  int32_t B, R, H, N, dh, n_head, n_tail;
+  float scale;
+  /* backward */
+  const void* dout;       /* bf16 [B, R, H*dh] */
+  float* dq;              /* f32 [Bq, R, H*dh], accumulated (caller zeroes) */
+  int64_t dq_bstride;
+  void* dkv;              /* bf16 planar token rows [.., 2*H*dh], every row written */
+  int64_t lddkv;
+} MmfPoolAttnArgs;
+int mmf_pool_attn_fwd(const MmfPoolAttnArgs* args, mmf_stream_t stream);
+int mmf_pool_attn_bwd(const MmfPoolAttnArgs* args, mmf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked reconstruction losses (criterion.py:85-115 MSE, :142-172 L1; norm_pix=False):
+ *   per pixel err averaged over channels, weighted by the nearest-upsampled patch mask, summed per
+ *   sample / (P*P*#masked patches), nanmean over the batch.  mask: int64 [B, F] (1 = masked) or NULL
+ *   (plain mean).  `work`: f32 [2*B + 2] scratch (zeroed by the call).  loss: f32 [1].
+ *   The backward writes dpred = dloss * d(loss)/d(pred) (bf16 or f32 like pred).
+ * ---------------------------------------------------------------------------------------------- */
+int mmf_masked_loss_fwd(const void* pred, int32_t pred_f32, const float* target, const int64_t* mask, int64_t mask_bstride,
+                        int64_t B, int32_t C, int32_t H, int32_t W, int32_t P, int32_t kind /*0 mse, 1 l1*/, float* work,
+                        float* loss, mmf_stream_t stream);
+int mmf_masked_loss_bwd(const void* pred, int32_t pred_f32, const float* target, const int64_t* mask, int64_t mask_bstride,
+                        int64_t B, int32_t C, int32_t H, int32_t W, int32_t P, int32_t kind, const float* work,
+                        const float* dloss, void* dpred, mmf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise / data movement (all HBM-bound)
+ * ---------------------------------------------------------------------------------------------- */
+/* f32 [rows, cols] -> bf16 [rows_pad, cols_pad] with zero padding and a scale: the per-step bf16
+ * weight images (what autocast's weight cast does in the reference, pretrain_mmae.py:466). */
+int mmf_cast_f32_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst, int64_t rows_pad,
+                      int64_t cols_pad, int64_t ld_dst, float scale, mmf_stream_t stream);
+/* GEGLU backward (zorro_utils.py:115-118): u bf16 [rows, 2*ipad] = [value | gate], dg bf16 [rows, ipad] */
+int mmf_geglu_bwd(const void* u, const void* dg, void* du, int64_t rows, int64_t ipad, mmf_stream_t stream);
+/* dpre = dy * gelu'(pre), bf16, n % 8 == 0 (decoder / pooling Mlp, multimae_utils.py:138-155) */
+int mmf_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, mmf_stream_t stream);
+/* out[c] += sum_r x[r, c]  (bias gradients); out f32, caller zeroes */
+int mmf_colsum(const void* x, int32_t x_f32, int64_t rows, int64_t cols, int64_t ld, float* out, mmf_stream_t stream);
+/* dst[b, r, :] = src[r, :] (fusion tokens + pos-emb broadcast, multimae.py:353-354) and its gradient */
+int mmf_bcast_rows(const float* src, float* dst, int64_t batch, int64_t rows, int64_t d, int64_t dst_batch_stride,
+                   mmf_stream_t stream);
+int mmf_reduce_batch(const float* src, float* dst, int64_t batch, int64_t rows, int64_t d, int64_t src_batch_stride,
+                     mmf_stream_t stream);
+/* im2col of the VISIBLE patches only (input_adapters.py:110 + multimae.py:378-383 fused):
+ * out[b*n_keep + i, (c ph pw)] = bf16(img[b, c, py*P+ph, px*P+pw]), patch idx[i] = py*(W/P)+px */
+int mmf_im2col_gather(const float* img, const int32_t* idx, void* out, int64_t batch, int32_t C, int32_t H, int32_t W,
+                      int32_t P, int32_t n_keep, int64_t ld_out, mmf_stream_t stream);
+/* 'b (nh nw) (c ph pw) -> b c (nh ph) (nw pw)' bf16 (output_adapters_simple.py:183-186); inverse=1 for the gradient */
+int mmf_unpatchify_bf16(void* tokens, void* image, int64_t batch, int32_t C, int32_t H, int32_t W, int32_t P,
+                        int32_t inverse, mmf_stream_t stream);
+/* dst[b*n + i, :] = cast(src[b*src_batch_rows + row_off + (idx ? idx[i] : i), :]) */
+int mmf_gather_rows(const void* src, int32_t src_f32, int64_t ld_src, int64_t src_batch_rows, int64_t row_off,
+                    const int32_t* idx, void* dst, int32_t dst_f32, int64_t ld_dst, int64_t batch, int32_t n, int32_t d,
+                    mmf_stream_t stream);
+int mmf_add_inplace_f32(float* y, const float* x, int64_t n, mmf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMF_B200_H_ */

@@ -1,0 +1,485 @@
+// tcgen05 GEMM for sm_100a:  out[M,N] = epilogue(alpha * A[M,K] . B[N,K]^T), bf16 in, fp32 accumulate.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1      : MMA issuer     (one elected lane issues tcgen05.mma 128 x BLOCK_N x 16, accumulators in TMEM)
+//   warps 2..5  : epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// Operands may be K-major ([rows, K]) or MN-major (stored [K, rows]); the latter serves dgrad / wgrad
+// without materialising transposes.  split_k > 1 accumulates with fp32 red.global.add.
+#include "common.cuh"
+#include "mmf_b200.h"
+
+#include <atomic>
+#include <mutex>
+
+namespace mmf {
+
+std::atomic<int64_t> g_launch_count{0};
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;  // 4 @256, 6 @128
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;             // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  void* out;
+  void* out2;
+  const float* bias;
+  const float* residual;
+  const float* residual2;
+  int64_t res_split;
+  const int32_t* res_row_map;
+  int64_t M, N, K;
+  int64_t ldo, ldo2, ldr;
+  int32_t out_f32, act, split_k, res_period, out_period, out_batch_rows;
+  int32_t m_tiles, n_tiles, num_kb, kb_per_split;
+  int64_t geglu_ipad;  // act==2: row offset of the gate half inside B
+  float alpha;
+};
+
+__device__ __forceinline__ void store_row32(const GemmParams& p, int64_t orow, int64_t col0, const float (&v)[32],
+                                            int ncols_valid) {
+  // 32 consecutive output columns of one row, starting at col0 (multiple of 32)
+  if (p.split_k > 1) {
+    float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols_valid) atomicAdd(o + j, v[j]);
+    return;
+  }
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
+    if (ncols_valid == 32 && (p.ldo & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols_valid) o[j] = v[j];
+    }
+    if (p.out2) {
+      __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0;
+      if (ncols_valid == 32 && (p.ldo2 & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          reinterpret_cast<uint4*>(o2)[j] =
+              make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols_valid) o2[j] = __float2bfloat16(v[j]);
+      }
+    }
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
+    if (ncols_valid == 32 && (p.ldo & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<uint4*>(o)[j] =
+            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols_valid) o[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;           // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool geglu = (p.act == 2);
+  // in GEGLU mode one 256-wide MMA tile yields 128 output columns (value | gate halves)
+  const int out_cols_per_tile = geglu ? BLOCK_N / 2 : BLOCK_N;
+  const int total_work = p.m_tiles * p.n_tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full[s], 1);
+        mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_base_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int tile = w % (p.m_tiles * p.n_tiles);
+        const int split = w / (p.m_tiles * p.n_tiles);
+        const int m0 = (tile / p.n_tiles) * BLOCK_M;
+        const int n0 = (tile % p.n_tiles) * out_cols_per_tile;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)  // box {64 m, 64 k}
+              tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + j * 64, k0);
+          }
+          if (!B_MN) {
+            if (!geglu) {
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);  // box {64 k, BLOCK_N rows}
+            } else {  // box {64 k, BLOCK_N/2 rows} twice: value rows then gate rows
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+              tma_load_2d(sb + Cfg::B_BYTES / 2, &tmap_b, &full_bar[stage], k0, (int)p.geglu_ipad + n0);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)  // box {64 n, 64 k}
+              tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w / (p.m_tiles * p.n_tiles);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * Cfg::A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: advance 16 elements = 32 B inside the swizzle atom; SBO = 1024 B (8 rows x 128 B).
+            // MN-major: advance 16 k-rows = 2048 B; LBO = 8192 B (next 64-wide MN atom), SBO = 1024 B.
+            const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, 8192, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb0) || (k > 0));
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int tile = w % (p.m_tiles * p.n_tiles);
+      const int m0 = (tile / p.n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.n_tiles) * out_cols_per_tile;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int64_t row = (int64_t)m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      int64_t orow = row;
+      if (p.out_period > 0) orow = (row / p.out_period) * p.out_batch_rows + (row % p.out_period);
+      const float* res_row = nullptr;
+      if (p.residual != nullptr && row_ok) {
+        int64_t rr = row;
+        if (p.res_period > 0) {
+          rr = row % p.res_period;
+          if (p.res_row_map) rr = p.res_row_map[rr];
+        }
+        res_row = (p.residual2 && rr >= p.res_split) ? p.residual2 + (rr - p.res_split) * p.ldr : p.residual + rr * p.ldr;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      uint32_t raw[32];
+      float v[32];
+      if (!geglu) {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          const int64_t col0 = (int64_t)n0 + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          tmem_ld_32x32(taddr + c * 32, raw);
+          tmem_wait_ld();
+          if (row_ok) {
+            const int nvalid = (int)min((int64_t)32, p.N - col0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(raw[j]) * p.alpha;
+              if (p.bias != nullptr && j < nvalid) x += __ldg(p.bias + col0 + j);
+              v[j] = x;
+            }
+            if (p.act == 1) {
+              if (p.out2 && !p.out_f32) {  // keep the pre-activation (bf16) for the backward
+                __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) o2[j] = __float2bfloat16(v[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            }
+            if (res_row != nullptr) {
+              if (nvalid == 32 && (p.ldr & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 r4 = __ldg(reinterpret_cast<const float4*>(res_row + col0) + j);
+                  v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) v[j] += __ldg(res_row + col0 + j);
+              }
+            }
+            store_row32(p, orow, col0, v, nvalid);
+          }
+        }
+      } else {
+        // GEGLU: accumulator columns [0, BLOCK_N/2) = value, [BLOCK_N/2, BLOCK_N) = gate of the same features
+        uint32_t rawg[32];
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 64; ++c) {
+          const int64_t col0 = (int64_t)n0 + c * 32;
+          if (col0 >= p.N) break;
+          tmem_ld_32x32(taddr + c * 32, raw);
+          tmem_ld_32x32(taddr + BLOCK_N / 2 + c * 32, rawg);
+          tmem_wait_ld();
+          if (row_ok) {
+            const int nvalid = (int)min((int64_t)32, p.N - col0);
+            if (p.out2) {  // pre-activation u = [value | gate], bf16 [M, 2*ipad]
+              __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (8 * j < nvalid) {
+                  reinterpret_cast<uint4*>(u + col0)[j] = make_uint4(
+                      pack_bf16(__uint_as_float(raw[8 * j]), __uint_as_float(raw[8 * j + 1])),
+                      pack_bf16(__uint_as_float(raw[8 * j + 2]), __uint_as_float(raw[8 * j + 3])),
+                      pack_bf16(__uint_as_float(raw[8 * j + 4]), __uint_as_float(raw[8 * j + 5])),
+                      pack_bf16(__uint_as_float(raw[8 * j + 6]), __uint_as_float(raw[8 * j + 7])));
+                  reinterpret_cast<uint4*>(u + p.geglu_ipad + col0)[j] = make_uint4(
+                      pack_bf16(__uint_as_float(rawg[8 * j]), __uint_as_float(rawg[8 * j + 1])),
+                      pack_bf16(__uint_as_float(rawg[8 * j + 2]), __uint_as_float(rawg[8 * j + 3])),
+                      pack_bf16(__uint_as_float(rawg[8 * j + 4]), __uint_as_float(rawg[8 * j + 5])),
+                      pack_bf16(__uint_as_float(rawg[8 * j + 6]), __uint_as_float(rawg[8 * j + 7])));
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__uint_as_float(rawg[j])) * __uint_as_float(raw[j]);
+            store_row32(p, orow, col0, v, nvalid);
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  // resolved through the runtime so the library has no link-time dependency on libcuda.so
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix (cols contiguous), 128B swizzle.
+static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                     int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return 1000;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2000 + (int)r;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch_gemm(const MmfGemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  const bool geglu = a.act == 2;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN) rc = make_tmap(&ta, a.a, a.M, a.K, a.lda, BLOCK_K, BLOCK_M);
+  else       rc = make_tmap(&ta, a.a, a.K, a.M, a.lda, 64, BLOCK_K);
+  if (rc) return rc;
+  const int64_t b_rows = geglu ? 2 * a.N : a.N;  // geglu: caller passes N = I_pad, B has 2*I_pad rows
+  if (!B_MN) rc = make_tmap(&tb, a.b, b_rows, a.K, a.ldb, BLOCK_K, geglu ? BLOCK_N / 2 : BLOCK_N);
+  else       rc = make_tmap(&tb, a.b, a.K, b_rows, a.ldb, 64, BLOCK_K);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.out = a.out; p.out2 = a.out2; p.bias = a.bias; p.residual = a.residual; p.residual2 = a.residual2; p.res_split = a.res_split; p.res_row_map = a.res_row_map;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.ldo = a.ldo; p.ldo2 = a.ldo2; p.ldr = a.ldr;
+  p.out_f32 = a.out_f32; p.act = a.act; p.split_k = a.split_k < 1 ? 1 : a.split_k;
+  p.res_period = a.res_period; p.out_period = a.out_period; p.out_batch_rows = a.out_batch_rows;
+  p.m_tiles = (int)ceil_div64(a.M, BLOCK_M);
+  p.n_tiles = (int)ceil_div64(a.N, geglu ? BLOCK_N / 2 : BLOCK_N);
+  p.num_kb = (int)ceil_div64(a.K, BLOCK_K);
+  if (p.split_k > p.num_kb) p.split_k = p.num_kb;
+  p.kb_per_split = ceil_div(p.num_kb, p.split_k);
+  p.split_k = ceil_div(p.num_kb, p.kb_per_split);  // no empty splits
+  p.geglu_ipad = a.N;
+  p.alpha = a.alpha;
+
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.split_k;
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mmf
+
+extern "C" int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream_) {
+  using namespace mmf;
+  if (!args) MMF_BAD_ARG(1);
+  const MmfGemmArgs& a = *args;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a.a || !a.b || !a.out) MMF_BAD_ARG(2);
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) MMF_BAD_ARG(3);
+  if (a.M > INT32_MAX || a.N > INT32_MAX || a.K > INT32_MAX) MMF_BAD_ARG(4);
+  // TMA: 16-byte aligned base and row pitch
+  if ((reinterpret_cast<uintptr_t>(a.a) & 15) || (reinterpret_cast<uintptr_t>(a.b) & 15)) MMF_BAD_ARG(5);
+  if ((a.lda & 7) || (a.ldb & 7)) MMF_BAD_ARG(6);
+  if (a.lda < (a.a_mn ? a.M : a.K) || a.ldb < (a.b_mn ? a.N : a.K) || a.ldo < a.N) MMF_BAD_ARG(7);
+  if (a.split_k > 1 && (!a.out_f32 || a.act != 0 || a.bias || a.residual || a.out2)) MMF_BAD_ARG(8);
+  if (a.act < 0 || a.act > 2) MMF_BAD_ARG(9);
+  if (a.act == 2 && (a.b_mn || a.out_f32 || a.bias || a.residual || (a.N & 7) || (a.out2 && (a.ldo2 & 7)) ||
+                     (a.ldo & 7) || a.split_k > 1))
+    MMF_BAD_ARG(10);
+  if (a.out2 && a.act == 0 && !a.out_f32) MMF_BAD_ARG(11);
+  if (a.residual && a.ldr < a.N) MMF_BAD_ARG(12);
+  if (a.out_period < 0 || a.res_period < 0) MMF_BAD_ARG(13);
+
+  int bn = a.block_n;
+  if (bn == 0) {
+    if (a.act == 2) bn = 256;
+    else {
+      const int64_t pad256 = ceil_div64(a.N, 256) * 256, pad128 = ceil_div64(a.N, 128) * 128;
+      bn = (pad256 == pad128) ? 256 : 128;
+    }
+  }
+  if (bn != 128 && bn != 256) MMF_BAD_ARG(14);
+  if (a.act == 2 && bn != 256) MMF_BAD_ARG(15);
+#define MMF_DISPATCH(BN)                                                         \
+  do {                                                                           \
+    if (!a.a_mn && !a.b_mn) return launch_gemm<BN, false, false>(a, stream);     \
+    if (!a.a_mn && a.b_mn) return launch_gemm<BN, false, true>(a, stream);       \
+    if (a.a_mn && !a.b_mn) return launch_gemm<BN, true, false>(a, stream);       \
+    return launch_gemm<BN, true, true>(a, stream);                               \
+  } while (0)
+  if (bn == 256) MMF_DISPATCH(256);
+  MMF_DISPATCH(128);
+#undef MMF_DISPATCH
+}
+
+extern "C" int mmf_abi_version(void) { return 1; }
+extern "C" int64_t mmf_launch_count(void) { return mmf::g_launch_count.load(); }
+extern "C" void mmf_reset_launch_count(void) { mmf::g_launch_count.store(0); }

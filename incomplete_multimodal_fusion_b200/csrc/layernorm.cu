@@ -1,0 +1,330 @@
+// LayerNorm kernels (HBM-bound, warp-per-row, 128-bit accesses, fp32 math).
+//
+// The reference's encoder applies LayerNorm twice back to back before every attention and every
+// FFN (Block.norm1 -> Attention.norm, Block.norm2 -> FeedForward[0]: zorro_utils.py:238->176,
+// 239->124), each a separate ATen launch reading and writing the fp32 [rows, D] stream.  Here the
+// pair is one pass: read fp32 x once, write the bf16 GEMM operand once.  The same kernel does the
+// single nn.LayerNorm(eps=1e-6, bias) of the decoders (multimae_utils.py:217-232) and the final
+// encoder norm (multimae.py:431).  The backward fuses both LN backwards, the residual-gradient add
+// and the bf16 copy the next dgrad GEMM needs.
+#include "common.cuh"
+#include "mmf_b200.h"
+#include <atomic>
+
+namespace mmf {
+extern std::atomic<int64_t> g_launch_count;
+
+constexpr int LN_MAX_D = 1024;  // up to 8 float4 chunks per lane
+constexpr int LN_WARPS = 8;
+
+struct LnParams {
+  const float* x;
+  const float* x2;   // optional second source for rows >= x_split
+  int64_t x_split;
+  int64_t rows, ldx;
+  int D;
+  const float* g1;
+  const float* b1;
+  const float* g2;
+  float eps1, eps2;
+  void* y;
+  int64_t ldy;
+  int y_f32;
+  float* stats;  // [rows, 4] mean1, rstd1, mean2, rstd2 (nullable)
+};
+
+// gamma1 / bias1 / gamma2 staged once per CTA in shared memory (index = float4 chunk)
+__device__ __forceinline__ void ln_stage_params(float4* sg1, float4* sb1, float4* sg2, const float* g1, const float* b1,
+                                                const float* g2, int nchunk) {
+  for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
+    sg1[c] = __ldg(reinterpret_cast<const float4*>(g1) + c);
+    sb1[c] = b1 ? __ldg(reinterpret_cast<const float4*>(b1) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sg2[c] = g2 ? __ldg(reinterpret_cast<const float4*>(g2) + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  __syncthreads();
+}
+
+template <int NC>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p) {
+  constexpr int LN_MAX_CHUNKS = NC;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nchunk = p.D >> 2;
+  const float invD = 1.0f / (float)p.D;
+  __shared__ float4 g1[NC * 32], b1[NC * 32], g2[NC * 32];
+  ln_stage_params(g1, b1, g2, p.g1, p.b1, p.g2, nchunk);
+  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < p.rows; row += (int64_t)gridDim.x * LN_WARPS) {
+    const float4* xr = reinterpret_cast<const float4*>(
+        (p.x2 && row >= p.x_split) ? p.x2 + (row - p.x_split) * p.ldx : p.x + row * p.ldx);
+    float4 v[LN_MAX_CHUNKS];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nchunk) v[i] = xr[c];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean1 = warp_sum(s) * invD;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunk) {
+        const float a = v[i].x - mean1, b = v[i].y - mean1, cc = v[i].z - mean1, d = v[i].w - mean1;
+        q += a * a + b * b + cc * cc + d * d;
+      }
+    }
+    const float rstd1 = rsqrtf(warp_sum(q) * invD + p.eps1);
+    float mean2 = 0.f, rstd2 = 1.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      v[i].x = (v[i].x - mean1) * rstd1 * g1[lane + 32 * i].x + b1[lane + 32 * i].x;
+      v[i].y = (v[i].y - mean1) * rstd1 * g1[lane + 32 * i].y + b1[lane + 32 * i].y;
+      v[i].z = (v[i].z - mean1) * rstd1 * g1[lane + 32 * i].z + b1[lane + 32 * i].z;
+      v[i].w = (v[i].w - mean1) * rstd1 * g1[lane + 32 * i].w + b1[lane + 32 * i].w;
+    }
+    if (p.g2) {
+      s = 0.f;
+#pragma unroll
+      for (int i = 0; i < LN_MAX_CHUNKS; ++i)
+        if (lane + 32 * i < nchunk) s += v[i].x + v[i].y + v[i].z + v[i].w;
+      mean2 = warp_sum(s) * invD;
+      q = 0.f;
+#pragma unroll
+      for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        if (lane + 32 * i < nchunk) {
+          const float a = v[i].x - mean2, b = v[i].y - mean2, cc = v[i].z - mean2, d = v[i].w - mean2;
+          q += a * a + b * b + cc * cc + d * d;
+        }
+      }
+      rstd2 = rsqrtf(warp_sum(q) * invD + p.eps2);
+#pragma unroll
+      for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        v[i].x = (v[i].x - mean2) * rstd2 * g2[lane + 32 * i].x;
+        v[i].y = (v[i].y - mean2) * rstd2 * g2[lane + 32 * i].y;
+        v[i].z = (v[i].z - mean2) * rstd2 * g2[lane + 32 * i].z;
+        v[i].w = (v[i].w - mean2) * rstd2 * g2[lane + 32 * i].w;
+      }
+    }
+    if (p.y_f32) {
+      float4* yr = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + row * p.ldy);
+#pragma unroll
+      for (int i = 0; i < LN_MAX_CHUNKS; ++i)
+        if (lane + 32 * i < nchunk) yr[lane + 32 * i] = v[i];
+    } else {
+      uint2* yr = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy);
+#pragma unroll
+      for (int i = 0; i < LN_MAX_CHUNKS; ++i)
+        if (lane + 32 * i < nchunk) yr[lane + 32 * i] = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+    }
+    if (p.stats && lane == 0) reinterpret_cast<float4*>(p.stats)[row] = make_float4(mean1, rstd1, mean2, rstd2);
+  }
+}
+
+struct LnBwdParams {
+  const void* dy;  // bf16 or f32 [rows, D]
+  int64_t lddy;
+  int dy_f32;
+  const float* x;
+  const float* x2;
+  int64_t x_split;
+  int64_t rows, ldx;
+  int D;
+  const float* g1;
+  const float* b1;
+  const float* g2;
+  const float* stats;
+  const float* dres;  // optional f32 [rows, D] added to dx (the residual branch's gradient)
+  int64_t lddres;
+  float* dx;          // f32 [rows, D]
+  int64_t lddx;
+  void* dx_bf16;      // optional bf16 copy of dx
+  int64_t lddxb;
+  float* dg1;         // f32 [D] accumulated with atomics (must be zeroed by the caller)
+  float* db1;         // optional
+  float* dg2;         // optional (double LN)
+};
+
+template <int NC>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams p) {
+  constexpr int LN_MAX_CHUNKS = NC;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nchunk = p.D >> 2;
+  const float invD = 1.0f / (float)p.D;
+  const bool dbl = p.g2 != nullptr;
+  __shared__ float4 g1[NC * 32], b1[NC * 32], g2[NC * 32];
+  ln_stage_params(g1, b1, g2, p.g1, p.b1, p.g2, nchunk);
+  float4 adg1[LN_MAX_CHUNKS], adg2[LN_MAX_CHUNKS], adb1[LN_MAX_CHUNKS];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) adg1[i] = adg2[i] = adb1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < p.rows; row += (int64_t)gridDim.x * LN_WARPS) {
+    const float4 st = __ldg(reinterpret_cast<const float4*>(p.stats) + row);
+    const float mean1 = st.x, rstd1 = st.y, mean2 = st.z, rstd2 = st.w;
+    const float4* xr = reinterpret_cast<const float4*>(
+        (p.x2 && row >= p.x_split) ? p.x2 + (row - p.x_split) * p.ldx : p.x + row * p.ldx);
+    float4 xh1[LN_MAX_CHUNKS], d[LN_MAX_CHUNKS];
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      const int c = lane + 32 * i;
+      xh1[i] = d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nchunk) {
+        const float4 xv = xr[c];
+        xh1[i] = make_float4((xv.x - mean1) * rstd1, (xv.y - mean1) * rstd1, (xv.z - mean1) * rstd1, (xv.w - mean1) * rstd1);
+        if (p.dy_f32) {
+          d[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + row * p.lddy)[c];
+        } else {
+          const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + row * p.lddy)[c];
+          const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
+          d[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+      }
+    }
+    if (dbl) {
+      // second LN: y = xh2 * g2, xh2 = (y1 - mean2) * rstd2, y1 = xh1 * g1 + b1
+      float s1 = 0.f, s2 = 0.f;
+      float4 xh2[LN_MAX_CHUNKS];
+#pragma unroll
+      for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        xh2[i].x = (xh1[i].x * g1[lane + 32 * i].x + b1[lane + 32 * i].x - mean2) * rstd2;
+        xh2[i].y = (xh1[i].y * g1[lane + 32 * i].y + b1[lane + 32 * i].y - mean2) * rstd2;
+        xh2[i].z = (xh1[i].z * g1[lane + 32 * i].z + b1[lane + 32 * i].z - mean2) * rstd2;
+        xh2[i].w = (xh1[i].w * g1[lane + 32 * i].w + b1[lane + 32 * i].w - mean2) * rstd2;
+        if (lane + 32 * i < nchunk) {
+          adg2[i].x += d[i].x * xh2[i].x; adg2[i].y += d[i].y * xh2[i].y;
+          adg2[i].z += d[i].z * xh2[i].z; adg2[i].w += d[i].w * xh2[i].w;
+          d[i].x *= g2[lane + 32 * i].x; d[i].y *= g2[lane + 32 * i].y; d[i].z *= g2[lane + 32 * i].z; d[i].w *= g2[lane + 32 * i].w;
+          s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+          s2 += d[i].x * xh2[i].x + d[i].y * xh2[i].y + d[i].z * xh2[i].z + d[i].w * xh2[i].w;
+        }
+      }
+      s1 = warp_sum(s1) * invD;
+      s2 = warp_sum(s2) * invD;
+#pragma unroll
+      for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        d[i].x = rstd2 * (d[i].x - s1 - xh2[i].x * s2);
+        d[i].y = rstd2 * (d[i].y - s1 - xh2[i].y * s2);
+        d[i].z = rstd2 * (d[i].z - s1 - xh2[i].z * s2);
+        d[i].w = rstd2 * (d[i].w - s1 - xh2[i].w * s2);
+      }
+    }
+    // first LN
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      if (lane + 32 * i < nchunk) {
+        adg1[i].x += d[i].x * xh1[i].x; adg1[i].y += d[i].y * xh1[i].y;
+        adg1[i].z += d[i].z * xh1[i].z; adg1[i].w += d[i].w * xh1[i].w;
+        adb1[i].x += d[i].x; adb1[i].y += d[i].y; adb1[i].z += d[i].z; adb1[i].w += d[i].w;
+        d[i].x *= g1[lane + 32 * i].x; d[i].y *= g1[lane + 32 * i].y; d[i].z *= g1[lane + 32 * i].z; d[i].w *= g1[lane + 32 * i].w;
+        s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+        s2 += d[i].x * xh1[i].x + d[i].y * xh1[i].y + d[i].z * xh1[i].z + d[i].w * xh1[i].w;
+      }
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunk) {
+        float4 o;
+        o.x = rstd1 * (d[i].x - s1 - xh1[i].x * s2);
+        o.y = rstd1 * (d[i].y - s1 - xh1[i].y * s2);
+        o.z = rstd1 * (d[i].z - s1 - xh1[i].z * s2);
+        o.w = rstd1 * (d[i].w - s1 - xh1[i].w * s2);
+        if (p.dres) {
+          const float4 r = reinterpret_cast<const float4*>(p.dres + row * p.lddres)[c];
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        reinterpret_cast<float4*>(p.dx + row * p.lddx)[c] = o;
+        if (p.dx_bf16)
+          reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.dx_bf16) + row * p.lddxb)[c] =
+              make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+  // parameter gradients: reduce the CTA's warps through shared memory, then one atomic per column
+  __shared__ float4 red[LN_WARPS][32];
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = pass == 0 ? p.dg1 : (pass == 1 ? p.dg2 : p.db1);
+    if (dst == nullptr) continue;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      if (32 * i >= nchunk) break;
+      __syncthreads();
+      red[warp][lane] = pass == 0 ? adg1[i] : (pass == 1 ? adg2[i] : adb1[i]);
+      __syncthreads();
+      if (warp == 0) {
+        float4 a = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < LN_WARPS; ++w) {
+          a.x += red[w][lane].x; a.y += red[w][lane].y; a.z += red[w][lane].z; a.w += red[w][lane].w;
+        }
+        const int c = lane + 32 * i;
+        if (c < nchunk) {
+          atomicAdd(dst + 4 * c, a.x); atomicAdd(dst + 4 * c + 1, a.y);
+          atomicAdd(dst + 4 * c + 2, a.z); atomicAdd(dst + 4 * c + 3, a.w);
+        }
+      }
+    }
+  }
+}
+
+static int ln_grid(int64_t rows) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t need = ceil_div64(rows, LN_WARPS);
+  const int64_t cap = (int64_t)sms * 8;  // 8 CTAs of 8 warps = 64 warps per SM
+  return (int)(need < cap ? need : cap);
+}
+
+}  // namespace mmf
+
+extern "C" int mmf_layernorm_fwd(const float* x, const float* x2, int64_t x_split, int64_t rows, int32_t D, int64_t ldx, const float* g1, const float* b1,
+                                 float eps1, const float* g2, float eps2, void* y, int64_t ldy, int32_t y_f32,
+                                 float* stats, mmf_stream_t stream) {
+  using namespace mmf;
+  if (!x || !g1 || !y) MMF_BAD_ARG(1);
+  if (rows <= 0) return 0;
+  if (D <= 0 || (D & 3) || D > LN_MAX_D) MMF_BAD_ARG(2);
+  if ((ldx & 3) || (ldy & 3) || ldx < D || ldy < D) MMF_BAD_ARG(3);
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) MMF_BAD_ARG(4);
+  LnParams p{x, x2, x_split, rows, ldx, D, g1, b1, g2, eps1, eps2, y, ldy, y_f32, stats};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nc = ceil_div(D, 128);
+  if (nc <= 2) ln_fwd_kernel<2><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(p);
+  else if (nc <= 4) ln_fwd_kernel<4><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(p);
+  else if (nc <= 6) ln_fwd_kernel<6><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(p);
+  else ln_fwd_kernel<8><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, const float* x, const float* x2,
+                                 int64_t x_split, int64_t rows, int32_t D, int64_t ldx, const float* g1, const float* b1, const float* g2, const float* stats,
+                                 const float* dres, int64_t lddres, float* dx, int64_t lddx, void* dx_bf16,
+                                 int64_t lddxb, float* dg1, float* db1, float* dg2, mmf_stream_t stream) {
+  using namespace mmf;
+  if (!dy || !x || !g1 || !stats || !dx || !dg1) MMF_BAD_ARG(1);
+  if (rows <= 0) return 0;
+  if (D <= 0 || (D & 3) || D > LN_MAX_D) MMF_BAD_ARG(2);
+  if ((ldx & 3) || (lddy & 3) || (lddx & 3) || (dres && (lddres & 3)) || (dx_bf16 && (lddxb & 3))) MMF_BAD_ARG(3);
+  if (g2 && !dg2) MMF_BAD_ARG(4);
+  LnBwdParams p{dy, lddy, dy_f32, x, x2, x_split, rows, ldx, D, g1, b1, g2, stats, dres, lddres, dx, lddx, dx_bf16, lddxb, dg1, db1,
+                g2 ? dg2 : nullptr};
+  // fewer CTAs than the forward: each CTA ends with D atomics per parameter vector
+  int grid = ln_grid(rows);
+  if (grid > 148 * 2) grid = 148 * 2;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nc = ceil_div(D, 128);
+  if (nc <= 2) ln_bwd_kernel<2><<<grid, LN_WARPS * 32, 0, st>>>(p);
+  else if (nc <= 4) ln_bwd_kernel<4><<<grid, LN_WARPS * 32, 0, st>>>(p);
+  else if (nc <= 6) ln_bwd_kernel<6><<<grid, LN_WARPS * 32, 0, st>>>(p);
+  else ln_bwd_kernel<8><<<grid, LN_WARPS * 32, 0, st>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,402 @@
+// Two small-attention kernels of the MultiMAE path (HBM/latency-bound, CUDA-core math):
+//
+//  * slot attention  -- the "modality attention" of Block_Fusion (reference: downstream/
+//    instance_segmentation/modeling/multimae/zorro_utils.py:243-258, call site
+//    pretraining/multimae/multimae_crossattn.py:450-470).  For every spatial position p the
+//    reference scatters the visible tokens of each modality into a clone of `mask_embedding`,
+//    stacks [s1(p), s2(p), dem(p), fusion(p)] and runs full self-attention over the S slots, then
+//    keeps only the fusion slot.  Here nothing is scattered: the fusion token's query attends to S
+//    key/value rows looked up through a slot map (visible token row, or the batch-invariant
+//    mask-embedding row), and only the fusion slot's output is computed.
+//
+//  * pool attention  -- the learned return-token queries (multimae.py:434-455,
+//    multimae_crossattn.py:529-543): a handful of queries over all N tokens with a dense boolean
+//    mask, reproducing masked_fill(-finfo.max) exactly: a row with no allowed key becomes the
+//    UNIFORM distribution over all keys (mode 0), or zero output for an empty context (mode 1).
+#include "common.cuh"
+#include "mmf_b200.h"
+
+#include <atomic>
+
+namespace mmf {
+extern std::atomic<int64_t> g_launch_count;
+
+constexpr int SLOT_MAX = 8;
+
+struct SlotParams {
+  const __nv_bfloat16* q;       // [B*F, H*64]
+  const __nv_bfloat16* kv_tok;  // planar token rows, [.., 2*H*64] = [k | v]
+  const __nv_bfloat16* kv_me;   // [F, 2*H*64] mask-embedding rows
+  const int32_t* slotmap;       // [S-1, F] rank in the modality's visible list or -1
+  const int32_t* seg;           // [S] start of each modality segment inside the head plane
+  __nv_bfloat16* out;           // [B*F, H*64]
+  float* probs;                 // [B*F, H, S]
+  int64_t ldq, ldkv, ldme, ldo;
+  int B, F, H, S, n_head;
+  float scale;
+  // backward
+  const __nv_bfloat16* dout;    // [B*F, H*64]
+  __nv_bfloat16* dq;            // [B*F, H*64]
+  __nv_bfloat16* dkv_tok;       // planar token rows (every row written exactly once)
+  float* dkv_me;                // [F, 2*H*64] f32, atomically accumulated (caller zeroes)
+  int64_t lddout, lddq, lddkv, lddme;
+};
+
+__device__ __forceinline__ int64_t slot_row(const SlotParams& p, int b, int pos, int s, bool& is_me) {
+  is_me = false;
+  if (s == p.S - 1) return (int64_t)p.B * p.n_head + (int64_t)b * p.F + pos;  // the fusion token itself
+  const int r = p.slotmap[s * p.F + pos];
+  if (r < 0) { is_me = true; return pos; }
+  return (int64_t)b * p.n_head + p.seg[s] + r;
+}
+
+// one warp per (b, pos, head); dh = 64 -> 2 elements per lane
+template <bool BWD>
+__global__ void slot_attn_kernel(const SlotParams p) {
+  const int lane = threadIdx.x & 31;
+  const int h = threadIdx.x >> 5;
+  const int64_t bp = blockIdx.x;  // b * F + pos
+  const int b = (int)(bp / p.F), pos = (int)(bp % p.F);
+  const int HD = p.H * 64;
+  const float2 q = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.q + bp * p.ldq + h * 64 + 2 * lane));
+  float2 k[SLOT_MAX], v[SLOT_MAX];
+  float s[SLOT_MAX];
+  int64_t rows[SLOT_MAX];
+  bool me[SLOT_MAX];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < SLOT_MAX; ++t) {
+    if (t < p.S) {
+      rows[t] = slot_row(p, b, pos, t, me[t]);
+      const __nv_bfloat16* base = me[t] ? p.kv_me + rows[t] * p.ldme : p.kv_tok + rows[t] * p.ldkv;
+      k[t] = unpack_bf16(*reinterpret_cast<const uint32_t*>(base + h * 64 + 2 * lane));
+      v[t] = unpack_bf16(*reinterpret_cast<const uint32_t*>(base + HD + h * 64 + 2 * lane));
+      s[t] = warp_sum(q.x * k[t].x + q.y * k[t].y) * p.scale;
+      mx = fmaxf(mx, s[t]);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < SLOT_MAX; ++t)
+    if (t < p.S) { s[t] = __expf(s[t] - mx); sum += s[t]; }
+  const float inv = 1.0f / sum;
+  if (!BWD) {
+    float2 o = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < SLOT_MAX; ++t)
+      if (t < p.S) { const float w = s[t] * inv; o.x += w * v[t].x; o.y += w * v[t].y; }
+    *reinterpret_cast<uint32_t*>(p.out + bp * p.ldo + h * 64 + 2 * lane) = pack_bf16(o.x, o.y);
+    if (p.probs && lane < p.S) {
+      float w = 0.f;
+#pragma unroll
+      for (int t = 0; t < SLOT_MAX; ++t) if (t == lane) w = s[t] * inv;
+      p.probs[(bp * p.H + h) * p.S + lane] = w;
+    }
+  } else {
+    const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.dout + bp * p.lddout + h * 64 + 2 * lane));
+    float dp[SLOT_MAX], dot = 0.f;
+#pragma unroll
+    for (int t = 0; t < SLOT_MAX; ++t)
+      if (t < p.S) { s[t] *= inv; dp[t] = warp_sum(d.x * v[t].x + d.y * v[t].y); dot += s[t] * dp[t]; }
+    float2 dq = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < SLOT_MAX; ++t) {
+      if (t < p.S) {
+        const float ds = s[t] * (dp[t] - dot) * p.scale;
+        dq.x += ds * k[t].x; dq.y += ds * k[t].y;
+        const float2 dk = make_float2(ds * q.x, ds * q.y);
+        const float2 dv = make_float2(s[t] * d.x, s[t] * d.y);
+        if (me[t]) {
+          float* base = p.dkv_me + rows[t] * p.lddme;
+          atomicAdd(base + h * 64 + 2 * lane, dk.x); atomicAdd(base + h * 64 + 2 * lane + 1, dk.y);
+          atomicAdd(base + HD + h * 64 + 2 * lane, dv.x); atomicAdd(base + HD + h * 64 + 2 * lane + 1, dv.y);
+        } else {
+          __nv_bfloat16* base = p.dkv_tok + rows[t] * p.lddkv;
+          *reinterpret_cast<uint32_t*>(base + h * 64 + 2 * lane) = pack_bf16(dk.x, dk.y);
+          *reinterpret_cast<uint32_t*>(base + HD + h * 64 + 2 * lane) = pack_bf16(dv.x, dv.y);
+        }
+      }
+    }
+    *reinterpret_cast<uint32_t*>(p.dq + bp * p.lddq + h * 64 + 2 * lane) = pack_bf16(dq.x, dq.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pool attention
+// ------------------------------------------------------------------------------------------------
+constexpr int POOL_MAX_N = 2048;
+
+struct PoolParams {
+  const __nv_bfloat16* q;    // [Bq, R, H*64] (q_bstride = 0 when batch-invariant)
+  const __nv_bfloat16* kv;   // planar token rows [.., 2*H*64]
+  const uint8_t* mask;       // [R, N] 1 = allowed
+  const int32_t* mode;       // [R] all-masked row: 0 -> uniform over N, 1 -> zero output
+  __nv_bfloat16* out;        // [B, R, H*64]
+  float* stat;               // [B, R, H, 2] = (max, sum) ; sum < 0 flags "all masked"
+  int64_t q_bstride, ldkv;
+  int B, R, H, N, n_head, n_tail;
+  float scale;
+  // backward
+  const __nv_bfloat16* dout; // [B, R, H*64]
+  float* dq;                 // [Bq, R, H*64] f32, atomically accumulated (caller zeroes)
+  int64_t dq_bstride;
+  __nv_bfloat16* dkv;        // planar token rows [.., 2*H*64]; every row written
+  int64_t lddkv;
+};
+
+__device__ __forceinline__ float dot64(const __nv_bfloat16* a_row, const float* q) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(a_row + c * 8);
+    const uint32_t* pu = &u.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(pu[k]);
+      acc += f.x * q[c * 8 + 2 * k] + f.y * q[c * 8 + 2 * k + 1];
+    }
+  }
+  return acc;
+}
+
+// one warp per (b, h, r)
+__global__ void pool_attn_fwd_kernel(const PoolParams p) {
+  extern __shared__ float sc_all[];
+  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+  float* sc = sc_all + (size_t)r * p.N;
+  __shared__ float qs[16][64];
+  const int HD = p.H * 64;
+  {
+    const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.q + b * p.q_bstride + (int64_t)r * HD + h * 64 + 2 * lane));
+    qs[r][2 * lane] = f.x; qs[r][2 * lane + 1] = f.y;
+  }
+  __syncwarp();
+  const int64_t head_rows = (int64_t)p.B * p.n_head;
+  float mx = -INFINITY;
+  bool any = false;
+  for (int j = lane; j < p.N; j += 32) {
+    const bool ok = p.mask[r * p.N + j] != 0;
+    float s = -INFINITY;
+    if (ok) {
+      const int64_t row = j < p.n_head ? (int64_t)b * p.n_head + j : head_rows + (int64_t)b * p.n_tail + (j - p.n_head);
+      s = dot64(p.kv + row * p.ldkv + h * 64, qs[r]) * p.scale;
+      any = true;
+    }
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  any = __any_sync(0xffffffffu, any);
+  const bool uniform = !any && p.mode[r] == 0;
+  float sum = 0.f;
+  for (int j = lane; j < p.N; j += 32) {
+    const float e = any ? __expf(sc[j] - mx) : (uniform ? 1.f : 0.f);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float2 o = make_float2(0.f, 0.f);
+  if (sum > 0.f) {
+    for (int j = 0; j < p.N; ++j) {
+      const float w = sc[j];
+      if (w != 0.f) {
+        const int64_t row = j < p.n_head ? (int64_t)b * p.n_head + j : head_rows + (int64_t)b * p.n_tail + (j - p.n_head);
+        const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.kv + row * p.ldkv + HD + h * 64 + 2 * lane));
+        o.x += w * v.x; o.y += w * v.y;
+      }
+    }
+    const float inv = 1.0f / sum;
+    o.x *= inv; o.y *= inv;
+  }
+  *reinterpret_cast<uint32_t*>(p.out + ((int64_t)b * p.R + r) * HD + h * 64 + 2 * lane) = pack_bf16(o.x, o.y);
+  if (lane == 0) {
+    float* st = p.stat + (((int64_t)b * p.R + r) * p.H + h) * 2;
+    st[0] = any ? mx : 0.f;
+    st[1] = any ? sum : (uniform ? -1.f : 0.f);  // -1: uniform row, 0: empty row
+  }
+}
+
+// backward: 4 lanes per key (16 of the 64 dims each), 64 keys per 256-thread block, looping over the
+// R queries.  delta[b,r,h] = dout.out sits right after the (max,sum) pairs in `stat`.
+__global__ void __launch_bounds__(256) pool_attn_bwd_kernel(const PoolParams p) {
+  __shared__ float qs[16][64], ds_[16][64], mxs[16], sums[16], dls[16];
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int HD = p.H * 64;
+  const int tid = threadIdx.x, sub = tid & 3;
+  for (int t = tid; t < p.R * 64; t += blockDim.x) {
+    const int r = t / 64, d = t % 64;
+    qs[r][d] = __bfloat162float(p.q[b * p.q_bstride + (int64_t)r * HD + h * 64 + d]);
+    ds_[r][d] = __bfloat162float(p.dout[((int64_t)b * p.R + r) * HD + h * 64 + d]);
+  }
+  if (tid < p.R) {
+    const int64_t brh = ((int64_t)b * p.R + tid) * p.H + h;
+    mxs[tid] = p.stat[brh * 2];
+    sums[tid] = p.stat[brh * 2 + 1];
+    dls[tid] = p.stat[(int64_t)p.B * p.R * p.H * 2 + brh];
+  }
+  __syncthreads();
+  const int j = blockIdx.x * 64 + (tid >> 2);
+  const bool valid = j < p.N;
+  const int64_t head_rows = (int64_t)p.B * p.n_head;
+  const int64_t row = !valid ? 0 : (j < p.n_head ? (int64_t)b * p.n_head + j : head_rows + (int64_t)b * p.n_tail + (j - p.n_head));
+  float kf[16], vf[16], dk[16], dv[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) kf[d] = vf[d] = dk[d] = dv[d] = 0.f;
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint4 uk = *reinterpret_cast<const uint4*>(p.kv + row * p.ldkv + h * 64 + sub * 16 + c * 8);
+      const uint4 uv = *reinterpret_cast<const uint4*>(p.kv + row * p.ldkv + HD + h * 64 + sub * 16 + c * 8);
+      const uint32_t* pk = &uk.x; const uint32_t* pv = &uv.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = unpack_bf16(pk[k]), c2 = unpack_bf16(pv[k]);
+        kf[c * 8 + 2 * k] = a.x; kf[c * 8 + 2 * k + 1] = a.y;
+        vf[c * 8 + 2 * k] = c2.x; vf[c * 8 + 2 * k + 1] = c2.y;
+      }
+    }
+  }
+  for (int r = 0; r < p.R; ++r) {
+    const float sum = sums[r];
+    float dp = 0.f, sdot = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) { dp += ds_[r][sub * 16 + d] * vf[d]; sdot += qs[r][sub * 16 + d] * kf[d]; }
+    dp += __shfl_xor_sync(0xffffffffu, dp, 1);   dp += __shfl_xor_sync(0xffffffffu, dp, 2);
+    sdot += __shfl_xor_sync(0xffffffffu, sdot, 1); sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+    float pj = 0.f, dsj = 0.f;
+    if (sum > 0.f) {
+      if (valid && p.mask[r * p.N + j] != 0) pj = __expf(sdot * p.scale - mxs[r]) / sum;
+      dsj = pj * (dp - dls[r]) * p.scale;
+    } else if (sum < 0.f) {
+      pj = valid ? 1.0f / (float)p.N : 0.f;  // uniform row: constant w.r.t. the scores, ds = 0
+    }
+#pragma unroll
+    for (int d = 0; d < 16; ++d) { dk[d] += dsj * qs[r][sub * 16 + d]; dv[d] += pj * ds_[r][sub * 16 + d]; }
+    if (sum > 0.f) {  // dq_r += sum_j ds_j k_j : reduce the 8 keys of the warp, then one atomic per dim
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        float c = dsj * kf[d];
+        c += __shfl_xor_sync(0xffffffffu, c, 4);
+        c += __shfl_xor_sync(0xffffffffu, c, 8);
+        c += __shfl_xor_sync(0xffffffffu, c, 16);
+        if ((tid & 31) < 4 && c != 0.f) atomicAdd(p.dq + b * p.dq_bstride + (int64_t)r * HD + h * 64 + sub * 16 + d, c);
+      }
+    }
+  }
+  if (valid) {
+    __nv_bfloat16* ok = p.dkv + row * p.lddkv + h * 64 + sub * 16;
+    __nv_bfloat16* ov = p.dkv + row * p.lddkv + HD + h * 64 + sub * 16;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      *reinterpret_cast<uint4*>(ok + c * 8) = make_uint4(pack_bf16(dk[c * 8], dk[c * 8 + 1]), pack_bf16(dk[c * 8 + 2], dk[c * 8 + 3]),
+                                                        pack_bf16(dk[c * 8 + 4], dk[c * 8 + 5]), pack_bf16(dk[c * 8 + 6], dk[c * 8 + 7]));
+      *reinterpret_cast<uint4*>(ov + c * 8) = make_uint4(pack_bf16(dv[c * 8], dv[c * 8 + 1]), pack_bf16(dv[c * 8 + 2], dv[c * 8 + 3]),
+                                                        pack_bf16(dv[c * 8 + 4], dv[c * 8 + 5]), pack_bf16(dv[c * 8 + 6], dv[c * 8 + 7]));
+    }
+  }
+}
+
+// delta[b, r, h] = dout[b, r, h, :] . out[b, r, h, :]   (one warp per (b, r, h))
+__global__ void pool_delta_kernel(const __nv_bfloat16* dout, const __nv_bfloat16* out, float* delta, int64_t n_brh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n_brh) return;
+  const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(dout + w * 64 + 2 * lane));
+  const float2 c = unpack_bf16(*reinterpret_cast<const uint32_t*>(out + w * 64 + 2 * lane));
+  const float s = warp_sum(a.x * c.x + a.y * c.y);
+  if (lane == 0) delta[w] = s;
+}
+
+}  // namespace mmf
+
+using namespace mmf;
+
+static int slot_check(const MmfSlotAttnArgs* a) {
+  if (!a || !a->q || !a->kv_tok || !a->kv_me || !a->slotmap || !a->seg) return 1;
+  if (a->S < 2 || a->S > SLOT_MAX || a->H < 1 || a->H > 32 || a->dh != 64) return 2;
+  if ((a->ldq & 1) || (a->ldkv & 1) || (a->ldme & 1)) return 3;
+  return 0;
+}
+static SlotParams slot_params(const MmfSlotAttnArgs& a) {
+  SlotParams p{};
+  p.q = (const __nv_bfloat16*)a.q; p.kv_tok = (const __nv_bfloat16*)a.kv_tok; p.kv_me = (const __nv_bfloat16*)a.kv_me;
+  p.slotmap = a.slotmap; p.seg = a.seg; p.out = (__nv_bfloat16*)a.out; p.probs = a.probs;
+  p.ldq = a.ldq; p.ldkv = a.ldkv; p.ldme = a.ldme; p.ldo = a.ldo;
+  p.B = a.B; p.F = a.F; p.H = a.H; p.S = a.S; p.n_head = a.n_head; p.scale = a.scale;
+  p.dout = (const __nv_bfloat16*)a.dout; p.dq = (__nv_bfloat16*)a.dq; p.dkv_tok = (__nv_bfloat16*)a.dkv_tok; p.dkv_me = a.dkv_me;
+  p.lddout = a.lddout; p.lddq = a.lddq; p.lddkv = a.lddkv; p.lddme = a.lddme;
+  return p;
+}
+
+extern "C" int mmf_slot_attn_fwd(const MmfSlotAttnArgs* a, mmf_stream_t stream) {
+  int rc = slot_check(a);
+  if (rc) MMF_BAD_ARG(rc);
+  if (!a->out || (a->ldo & 1)) MMF_BAD_ARG(10);
+  if ((int64_t)a->B * a->F == 0) return 0;
+  slot_attn_kernel<false><<<(unsigned)((int64_t)a->B * a->F), 32 * a->H, 0, reinterpret_cast<cudaStream_t>(stream)>>>(slot_params(*a));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmf_slot_attn_bwd(const MmfSlotAttnArgs* a, mmf_stream_t stream) {
+  int rc = slot_check(a);
+  if (rc) MMF_BAD_ARG(rc);
+  if (!a->dout || !a->dq || !a->dkv_tok || !a->dkv_me) MMF_BAD_ARG(11);
+  if ((a->lddout & 1) || (a->lddq & 1) || (a->lddkv & 1)) MMF_BAD_ARG(12);
+  if ((int64_t)a->B * a->F == 0) return 0;
+  slot_attn_kernel<true><<<(unsigned)((int64_t)a->B * a->F), 32 * a->H, 0, reinterpret_cast<cudaStream_t>(stream)>>>(slot_params(*a));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+static int pool_check(const MmfPoolAttnArgs* a) {
+  if (!a || !a->q || !a->kv || !a->mask || !a->mode || !a->stat) return 1;
+  if (a->R < 1 || a->R > 16 || a->H < 1 || a->dh != 64 || a->N < 1 || a->N > POOL_MAX_N) return 2;
+  if (a->n_head + a->n_tail != a->N || (a->ldkv & 7)) return 3;
+  return 0;
+}
+static PoolParams pool_params(const MmfPoolAttnArgs& a) {
+  PoolParams p{};
+  p.q = (const __nv_bfloat16*)a.q; p.kv = (const __nv_bfloat16*)a.kv; p.mask = a.mask; p.mode = a.mode;
+  p.out = (__nv_bfloat16*)a.out; p.stat = a.stat; p.q_bstride = a.q_bstride; p.ldkv = a.ldkv;
+  p.B = a.B; p.R = a.R; p.H = a.H; p.N = a.N; p.n_head = a.n_head; p.n_tail = a.n_tail; p.scale = a.scale;
+  p.dout = (const __nv_bfloat16*)a.dout; p.dq = a.dq; p.dq_bstride = a.dq_bstride; p.dkv = (__nv_bfloat16*)a.dkv; p.lddkv = a.lddkv;
+  return p;
+}
+
+extern "C" int mmf_pool_attn_fwd(const MmfPoolAttnArgs* a, mmf_stream_t stream) {
+  int rc = pool_check(a);
+  if (rc) MMF_BAD_ARG(rc);
+  if (!a->out) MMF_BAD_ARG(10);
+  const size_t smem = (size_t)a->R * a->N * sizeof(float);
+  if (smem > 200 * 1024) MMF_BAD_ARG(11);
+  static size_t configured = 0;
+  if (smem > 40 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(pool_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  pool_attn_fwd_kernel<<<dim3(a->H, a->B), 32 * a->R, smem, reinterpret_cast<cudaStream_t>(stream)>>>(pool_params(*a));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmf_pool_attn_bwd(const MmfPoolAttnArgs* a, mmf_stream_t stream) {
+  int rc = pool_check(a);
+  if (rc) MMF_BAD_ARG(rc);
+  if (!a->out || !a->dout || !a->dq || !a->dkv || (a->lddkv & 7) || a->dq_bstride < 0) MMF_BAD_ARG(12);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // stat layout: [B,R,H,2] (max,sum) followed by [B,R,H] delta scratch
+  const int64_t n_brh = (int64_t)a->B * a->R * a->H;
+  float* delta = a->stat + n_brh * 2;
+  pool_delta_kernel<<<(unsigned)((n_brh + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)a->dout, (const __nv_bfloat16*)a->out, delta, n_brh);
+  pool_attn_bwd_kernel<<<dim3((a->N + 63) / 64, a->H, a->B), 256, 0, st>>>(pool_params(*a));
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}

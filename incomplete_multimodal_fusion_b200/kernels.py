@@ -1,0 +1,272 @@
+"""Thin launch wrappers: torch tensors in, raw pointers + sizes across the C ABI (include/mmf_b200.h).
+
+torch is used here only for device memory and the current stream.  None of these functions is
+autograd-aware; `functions.py` composes them into `torch.autograd.Function`s.  Every wrapper raises
+if a tensor is not on a CUDA device: there is no CPU path.
+"""
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AttnArgs, GemmArgs, PoolAttnArgs, SlotAttnArgs, check
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("incomplete_multimodal_fusion_b200 ops need CUDA tensors (no CPU fallback); got device %s" % t.device)
+    return t.data_ptr()
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, "expected a row-major 2-D tensor, got shape %s strides %s" % (tuple(t.shape), t.stride())
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def launch_count() -> int:
+    return int(_L().mmf_launch_count())
+
+
+def reset_launch_count():
+    _L().mmf_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------
+def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, residual2=None, res_split=0,
+         res_row_map=None, res_period=0, out_period=0, out_batch_rows=0, split_k=1, alpha=1.0, out2=None, block_n=0,
+         M=None, N=None, K=None):
+    """out[M,N] = epilogue(alpha * A . B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn),
+    both bf16 row-major 2-D.  act=2 (GEGLU): b is [2*Ipad, K] and N = Ipad."""
+    assert a.dtype == bf16 and b.dtype == bf16
+    if M is None:
+        M = a.shape[1] if a_mn else a.shape[0]
+    if K is None:
+        K = a.shape[0] if a_mn else a.shape[1]
+    if N is None:
+        N = b.shape[1] if b_mn else b.shape[0]
+        if act == 2:
+            N //= 2
+    kb = b.shape[0] if b_mn else b.shape[1]
+    assert kb == K, "GEMM inner dimensions differ: %d vs %d" % (K, kb)
+    assert out.dtype in (bf16, f32)
+    args = GemmArgs()
+    args.a, args.b, args.out = _p(a), _p(b), _p(out)
+    args.bias, args.residual, args.residual2 = _p(bias), _p(residual), _p(residual2)
+    args.res_split = res_split
+    args.res_row_map = _p(res_row_map)
+    args.M, args.N, args.K = M, N, K
+    args.lda, args.ldb, args.ldo = _ld(a), _ld(b), _ld(out)
+    args.ldr = _ld(residual) if residual is not None else 0
+    if residual is not None:
+        assert residual.dtype == f32
+    if residual2 is not None:
+        assert residual2.dtype == f32 and _ld(residual2) == args.ldr
+    if bias is not None:
+        assert bias.dtype == f32 and bias.is_contiguous()
+    if res_row_map is not None:
+        assert res_row_map.dtype == torch.int32
+    args.a_mn, args.b_mn = int(a_mn), int(b_mn)
+    args.out_f32 = int(out.dtype == f32)
+    args.act, args.split_k = act, split_k
+    args.res_period, args.out_period, args.out_batch_rows = res_period, out_period, out_batch_rows
+    args.block_n = block_n
+    args.alpha = alpha
+    args.out2 = _p(out2)
+    args.ldo2 = _ld(out2) if out2 is not None else 0
+    if out2 is not None:
+        assert out2.dtype == bf16
+    check(_L().mmf_gemm_bf16(C.byref(args), _stream()), "mmf_gemm_bf16")
+    return out
+
+
+def layernorm_fwd(x, g1, y, *, b1=None, eps1=1e-5, g2=None, eps2=1e-5, stats=None, x2=None, x_split=0, rows=None):
+    assert x.dtype == f32 and y.dtype in (bf16, f32)
+    rows = rows if rows is not None else x.shape[0]
+    D = x.shape[1]
+    check(_L().mmf_layernorm_fwd(_p(x), _p(x2), x_split, rows, D, _ld(x), _p(g1), _p(b1), eps1, _p(g2), eps2, _p(y), _ld(y),
+                                 int(y.dtype == f32), _p(stats), _stream()), "mmf_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, g1, stats, dx, dg1, *, b1=None, g2=None, dres=None, dx_bf16=None, db1=None, dg2=None, x2=None,
+                  x_split=0, rows=None):
+    assert dy.dtype in (bf16, f32) and x.dtype == f32 and dx.dtype == f32
+    rows = rows if rows is not None else dy.shape[0]
+    D = dy.shape[1]
+    check(_L().mmf_layernorm_bwd(_p(dy), _ld(dy), int(dy.dtype == f32), _p(x), _p(x2), x_split, rows, D, _ld(x), _p(g1), _p(b1),
+                                 _p(g2), _p(stats), _p(dres), _ld(dres) if dres is not None else 0, _p(dx), _ld(dx),
+                                 _p(dx_bf16), _ld(dx_bf16) if dx_bf16 is not None else 0, _p(dg1), _p(db1), _p(dg2), _stream()),
+          "mmf_layernorm_bwd")
+    return dx
+
+
+def _attn_args(q, k, v, o, lse, B, H, Nq, Nk, dh, scale, n_head_q, n_head_k, seg, nseg):
+    a = AttnArgs()
+    a.q, a.k, a.v, a.o, a.lse = _p(q), _p(k), _p(v), _p(o), _p(lse)
+    a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
+    a.B, a.H, a.Nq, a.Nk, a.dh = B, H, Nq, Nk, dh
+    a.n_head_q = Nq if n_head_q is None else n_head_q
+    a.n_tail_q = Nq - a.n_head_q
+    a.n_head_k = Nk if n_head_k is None else n_head_k
+    a.n_tail_k = Nk - a.n_head_k
+    a.scale = scale
+    a.seg = _p(seg)
+    a.nseg = nseg
+    return a
+
+
+def attn_fwd(q, k, v, o, lse, *, B, H, Nq, Nk, dh, scale, n_head_q=None, n_head_k=None, seg=None, nseg=0):
+    """q/k/v/o: bf16 2-D token-major views (column slices of a fused qkv buffer are fine)."""
+    a = _attn_args(q, k, v, o, lse, B, H, Nq, Nk, dh, scale, n_head_q, n_head_k, seg, nseg)
+    check(_L().mmf_attn_fwd(C.byref(a), _stream()), "mmf_attn_fwd")
+    return o
+
+
+def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, delta, *, B, H, Nq, Nk, dh, scale, n_head_q=None, n_head_k=None, seg=None,
+             nseg=0):
+    a = _attn_args(q, k, v, o, lse, B, H, Nq, Nk, dh, scale, n_head_q, n_head_k, seg, nseg)
+    a.d_o, a.lddo, a.delta = _p(d_o), d_o.stride(0), _p(delta)
+    a.dq, a.dk, a.dv = _p(dq), _p(dk), _p(dv)
+    a.lddq, a.lddk, a.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+    check(_L().mmf_attn_bwd(C.byref(a), _stream()), "mmf_attn_bwd")
+
+
+def _slot_args(q, kv_tok, kv_me, slotmap, seg, B, F, H, S, n_head, scale):
+    a = SlotAttnArgs()
+    a.q, a.kv_tok, a.kv_me, a.slotmap, a.seg = _p(q), _p(kv_tok), _p(kv_me), _p(slotmap), _p(seg)
+    a.ldq, a.ldkv, a.ldme = q.stride(0), kv_tok.stride(0), kv_me.stride(0)
+    a.B, a.F, a.H, a.S, a.dh, a.n_head, a.scale = B, F, H, S, 64, n_head, scale
+    return a
+
+
+def slot_attn_fwd(q, kv_tok, kv_me, slotmap, seg, out, probs, *, B, F, H, S, n_head, scale):
+    a = _slot_args(q, kv_tok, kv_me, slotmap, seg, B, F, H, S, n_head, scale)
+    a.out, a.ldo, a.probs = _p(out), out.stride(0), _p(probs)
+    check(_L().mmf_slot_attn_fwd(C.byref(a), _stream()), "mmf_slot_attn_fwd")
+    return out
+
+
+def slot_attn_bwd(q, kv_tok, kv_me, slotmap, seg, dout, dq, dkv_tok, dkv_me, *, B, F, H, S, n_head, scale):
+    a = _slot_args(q, kv_tok, kv_me, slotmap, seg, B, F, H, S, n_head, scale)
+    a.dout, a.dq, a.dkv_tok, a.dkv_me = _p(dout), _p(dq), _p(dkv_tok), _p(dkv_me)
+    a.lddout, a.lddq, a.lddkv, a.lddme = dout.stride(0), dq.stride(0), dkv_tok.stride(0), dkv_me.stride(0)
+    check(_L().mmf_slot_attn_bwd(C.byref(a), _stream()), "mmf_slot_attn_bwd")
+
+
+def _pool_args(q, kv, mask, mode, out, stat, B, R, H, N, n_head, scale, q_batched):
+    a = PoolAttnArgs()
+    a.q, a.kv, a.mask, a.mode, a.out, a.stat = _p(q), _p(kv), _p(mask), _p(mode), _p(out), _p(stat)
+    a.q_bstride = R * H * 64 if q_batched else 0
+    a.ldkv = kv.stride(0)
+    a.B, a.R, a.H, a.N, a.dh, a.n_head, a.n_tail, a.scale = B, R, H, N, 64, n_head, N - n_head, scale
+    return a
+
+
+def pool_attn_fwd(q, kv, mask, mode, out, stat, *, B, R, H, N, n_head, scale, q_batched):
+    a = _pool_args(q, kv, mask, mode, out, stat, B, R, H, N, n_head, scale, q_batched)
+    check(_L().mmf_pool_attn_fwd(C.byref(a), _stream()), "mmf_pool_attn_fwd")
+    return out
+
+
+def pool_attn_bwd(q, kv, mask, mode, out, stat, dout, dq, dkv, *, B, R, H, N, n_head, scale, q_batched):
+    a = _pool_args(q, kv, mask, mode, out, stat, B, R, H, N, n_head, scale, q_batched)
+    a.dout, a.dq, a.dkv = _p(dout), _p(dq), _p(dkv)
+    a.dq_bstride = R * H * 64 if q_batched else 0
+    a.lddkv = dkv.stride(0)
+    check(_L().mmf_pool_attn_bwd(C.byref(a), _stream()), "mmf_pool_attn_bwd")
+
+
+def masked_loss_fwd(pred, target, mask, P, kind, work, loss):
+    B, Cc, H, W = pred.shape
+    assert pred.is_contiguous() and target.is_contiguous() and target.dtype == f32
+    mb = mask.stride(0) if mask is not None else 0
+    if mask is not None:
+        assert mask.dtype == torch.int64 and mask.stride(1) == 1
+    check(_L().mmf_masked_loss_fwd(_p(pred), int(pred.dtype == f32), _p(target), _p(mask), mb, B, Cc, H, W, P, kind, _p(work),
+                                   _p(loss), _stream()), "mmf_masked_loss_fwd")
+
+
+def masked_loss_bwd(pred, target, mask, P, kind, work, dloss, dpred):
+    B, Cc, H, W = pred.shape
+    mb = mask.stride(0) if mask is not None else 0
+    check(_L().mmf_masked_loss_bwd(_p(pred), int(pred.dtype == f32), _p(target), _p(mask), mb, B, Cc, H, W, P, kind, _p(work),
+                                   _p(dloss), _p(dpred), _stream()), "mmf_masked_loss_bwd")
+
+
+def cast_bf16(src, dst=None, *, rows_pad=None, cols_pad=None, scale=1.0):
+    """f32 [rows, cols] -> bf16 [rows_pad, cols_pad] (zero padded)."""
+    assert src.dtype == f32 and src.dim() == 2
+    rows, cols = src.shape
+    rows_pad = rows_pad or rows
+    cols_pad = cols_pad or cols
+    if dst is None:
+        dst = torch.empty(rows_pad, cols_pad, dtype=bf16, device=src.device)
+    check(_L().mmf_cast_f32_bf16(_p(src), rows, cols, _ld(src), _p(dst), rows_pad, cols_pad, _ld(dst), scale, _stream()),
+          "mmf_cast_f32_bf16")
+    return dst
+
+
+def geglu_bwd(u, dg, du):
+    rows, ipad = dg.shape
+    assert u.is_contiguous() and dg.is_contiguous() and du.is_contiguous() and u.shape[1] == 2 * ipad
+    check(_L().mmf_geglu_bwd(_p(u), _p(dg), _p(du), rows, ipad, _stream()), "mmf_geglu_bwd")
+    return du
+
+
+def gelu_bwd(pre, dy, dpre):
+    assert pre.is_contiguous() and dy.is_contiguous() and dpre.is_contiguous()
+    check(_L().mmf_gelu_bwd(_p(pre), _p(dy), _p(dpre), pre.numel(), _stream()), "mmf_gelu_bwd")
+    return dpre
+
+
+def colsum(x, out):
+    assert out.dtype == f32
+    check(_L().mmf_colsum(_p(x), int(x.dtype == f32), x.shape[0], x.shape[1], _ld(x), _p(out), _stream()), "mmf_colsum")
+    return out
+
+
+def bcast_rows(src, dst, batch, rows, d, dst_batch_stride):
+    check(_L().mmf_bcast_rows(_p(src), _p(dst), batch, rows, d, dst_batch_stride, _stream()), "mmf_bcast_rows")
+
+
+def reduce_batch(src, dst, batch, rows, d, src_batch_stride):
+    check(_L().mmf_reduce_batch(_p(src), _p(dst), batch, rows, d, src_batch_stride, _stream()), "mmf_reduce_batch")
+
+
+def im2col_gather(img, idx, out, P):
+    B, Cc, H, W = img.shape
+    assert img.is_contiguous() and img.dtype == f32 and idx.dtype == torch.int32 and out.dtype == bf16
+    check(_L().mmf_im2col_gather(_p(img), _p(idx), _p(out), B, Cc, H, W, P, idx.numel(), _ld(out), _stream()), "mmf_im2col_gather")
+    return out
+
+
+def unpatchify(tokens, image, Cc, H, W, P, inverse=False):
+    B = image.shape[0]
+    assert tokens.is_contiguous() and image.is_contiguous() and tokens.dtype == bf16 and image.dtype == bf16
+    check(_L().mmf_unpatchify_bf16(_p(tokens), _p(image), B, Cc, H, W, P, int(inverse), _stream()), "mmf_unpatchify_bf16")
+
+
+def gather_rows(src, dst, *, batch, n, d, src_batch_rows, row_off=0, idx=None):
+    check(_L().mmf_gather_rows(_p(src), int(src.dtype == f32), src.stride(0), src_batch_rows, row_off, _p(idx), _p(dst),
+                               int(dst.dtype == f32), dst.stride(0), batch, n, d, _stream()), "mmf_gather_rows")
+    return dst
+
+
+def add_inplace(y, x):
+    assert y.dtype == f32 and x.dtype == f32 and y.is_contiguous() and x.is_contiguous() and y.numel() == x.numel()
+    check(_L().mmf_add_inplace_f32(_p(y), _p(x), y.numel(), _stream()), "mmf_add_inplace_f32")
+    return y

@@ -1,0 +1,398 @@
+"""GPU: every C-ABI kernel against a plain PyTorch fp32 reference of the same op (through the C ABI)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def K():
+    from incomplete_multimodal_fusion_b200 import kernels
+    return kernels
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def rnd(*shape, dtype=f32, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K_", [(128, 128, 64), (256, 256, 128), (300, 200, 136), (1000, 768, 512), (77, 1536, 768),
+                                    (513, 96, 64)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_layouts(M, N, K_, a_mn, b_mn):
+    # MN-major operands need 16-byte row pitch on the contiguous (M or N) axis
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("pitch not 16B aligned for this layout")
+    A = rnd(M, K_, dtype=bf16, seed=1)
+    B = rnd(N, K_, dtype=bf16, seed=2)
+    ref = A.float() @ B.float().t()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    for out_dtype in (bf16, f32):
+        out = torch.empty(M, N, dtype=out_dtype, device="cuda")
+        K().gemm(a, b, out, a_mn=a_mn, b_mn=b_mn)
+        torch.cuda.synchronize()
+        assert rel(out, ref) < (6e-3 if out_dtype == bf16 else 1e-5), (out_dtype, rel(out, ref))
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_epilogues(block_n):
+    M, N, K_ = 700, 512, 256
+    A = rnd(M, K_, dtype=bf16, seed=3)
+    W = rnd(N, K_, dtype=bf16, seed=4, scale=0.1)
+    bias = rnd(N, seed=5)
+    res = rnd(M, N, seed=6)
+    acc = A.float() @ W.float().t()
+    # bias + gelu, bf16 out, pre-activation kept
+    out = torch.empty(M, N, dtype=bf16, device="cuda")
+    pre = torch.empty(M, N, dtype=bf16, device="cuda")
+    K().gemm(A, W, out, bias=bias, act=1, out2=pre, block_n=block_n)
+    assert rel(out, F.gelu(acc + bias)) < 6e-3
+    assert rel(pre, acc + bias) < 6e-3
+    # bias + residual, f32 out + bf16 copy, alpha
+    out = torch.empty(M, N, dtype=f32, device="cuda")
+    cp = torch.empty(M, N, dtype=bf16, device="cuda")
+    K().gemm(A, W, out, bias=bias, residual=res, alpha=0.5, out2=cp, block_n=block_n)
+    ref = 0.5 * acc + bias + res
+    assert rel(out, ref) < 1e-5
+    assert rel(cp, ref) < 6e-3
+    # two-source residual
+    r1, r2 = res[:300].contiguous(), res[300:].contiguous()
+    K().gemm(A, W, out, residual=r1, residual2=r2, res_split=300, block_n=block_n)
+    assert rel(out, acc + res) < 1e-5
+    # residual through a row map with a period (pos-emb gather) + batched output rows
+    period, nb = 70, 10
+    table = rnd(100, N, seed=7)
+    rmap = torch.randperm(100, device="cuda")[:period].int()
+    big = torch.zeros(nb * 90, N, dtype=f32, device="cuda")
+    K().gemm(A, W, big[5:], residual=table, res_row_map=rmap, res_period=period, out_period=period, out_batch_rows=90,
+             block_n=block_n)
+    ref = (acc.view(nb, period, N) + table[rmap.long()][None]).reshape(M, N)
+    got = big.view(nb, 90, N)[:, 5:5 + period].reshape(M, N)
+    assert rel(got, ref) < 1e-5
+    assert float(big.view(nb, 90, N)[:, :5].abs().max()) == 0.0
+
+
+def test_gemm_split_k_wgrad():
+    # dW[N_out, K_in] = dY^T X with both operands token-major (MN-major), huge K = tokens
+    T, NO, KI = 5000, 384, 256
+    dY = rnd(T, NO, dtype=bf16, seed=8)
+    X = rnd(T, KI, dtype=bf16, seed=9)
+    ref = dY.float().t() @ X.float()
+    for split in (1, 4, 7):
+        out = torch.zeros(NO, KI, dtype=f32, device="cuda")
+        K().gemm(dY, X, out, a_mn=True, b_mn=True, split_k=split)
+        assert rel(out, ref) < 1e-5, split
+
+
+@pytest.mark.parametrize("I", [512, 344, 2048])
+def test_gemm_geglu(I):
+    M, D = 333, 256
+    X = rnd(M, D, dtype=bf16, seed=10)
+    W = rnd(2 * I, D, dtype=bf16, seed=11, scale=0.1)
+    u = X.float() @ W.float().t()
+    ref = F.gelu(u[:, I:]) * u[:, :I]
+    out = torch.empty(M, I, dtype=bf16, device="cuda")
+    pre = torch.empty(M, 2 * I, dtype=bf16, device="cuda")
+    K().gemm(X, W, out, act=2, out2=pre)
+    assert rel(out, ref) < 6e-3
+    assert rel(pre, u) < 6e-3
+
+
+def test_gemm_large_persistent():
+    # more tiles than SMs: exercises the persistent loop, both accumulator stages and ring wrap-around
+    M, N, K_ = 4096 + 64, 2048, 1024
+    A = rnd(M, K_, dtype=bf16, seed=12)
+    B = rnd(N, K_, dtype=bf16, seed=13)
+    out = torch.empty(M, N, dtype=bf16, device="cuda")
+    K().gemm(A, B, out)
+    assert rel(out, A.float() @ B.float().t()) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D", [128, 192, 256, 768, 1024])
+@pytest.mark.parametrize("double", [False, True])
+def test_layernorm_fwd_bwd(D, double):
+    rows = 517
+    x = rnd(rows, D, seed=1, scale=2.0).requires_grad_(True)
+    g1 = (1 + 0.1 * rnd(D, seed=2)).requires_grad_(True)
+    b1 = None if double else (0.1 * rnd(D, seed=3)).requires_grad_(True)
+    g2 = (1 + 0.1 * rnd(D, seed=4)).requires_grad_(True) if double else None
+    eps1, eps2 = (1e-5, 1e-5) if double else (1e-6, 0.0)
+    y_ref = F.layer_norm(x, (D,), g1, b1, eps1)
+    if double:
+        y_ref = F.layer_norm(y_ref, (D,), g2, None, eps2)
+    dy = rnd(rows, D, seed=5)
+    dres = rnd(rows, D, seed=6)
+    y_ref.backward(dy)
+    for ydt in (f32, bf16):
+        y = torch.empty(rows, D, dtype=ydt, device="cuda")
+        stats = torch.empty(rows, 4, device="cuda")
+        K().layernorm_fwd(x.detach(), g1.detach(), y, b1=None if b1 is None else b1.detach(), eps1=eps1,
+                          g2=None if g2 is None else g2.detach(), eps2=eps2, stats=stats)
+        assert rel(y, y_ref) < (1e-5 if ydt == f32 else 5e-3)
+    dx = torch.empty(rows, D, device="cuda")
+    dxb = torch.empty(rows, D, dtype=bf16, device="cuda")
+    dg1 = torch.zeros(D, device="cuda"); db1 = torch.zeros(D, device="cuda"); dg2 = torch.zeros(D, device="cuda")
+    K().layernorm_bwd(dy, x.detach(), g1.detach(), stats, dx, dg1, b1=None if b1 is None else b1.detach(),
+                      g2=None if g2 is None else g2.detach(), dres=dres, dx_bf16=dxb, db1=None if b1 is None else db1,
+                      dg2=dg2 if double else None)
+    assert rel(dx, x.grad + dres) < 2e-5
+    assert rel(dxb, x.grad + dres) < 5e-3
+    assert rel(dg1, g1.grad) < 2e-5
+    if b1 is not None:
+        assert rel(db1, b1.grad) < 2e-5
+    if double:
+        assert rel(dg2, g2.grad) < 2e-5
+
+
+def test_layernorm_two_sources():
+    D = 256
+    xa, xb = rnd(100, D, seed=1), rnd(60, D, seed=2)
+    g = 1 + 0.1 * rnd(D, seed=3)
+    y = torch.empty(160, D, device="cuda")
+    K().layernorm_fwd(xa, g, y, x2=xb, x_split=100, rows=160)
+    ref = F.layer_norm(torch.cat([xa, xb]), (D,), g, None, 1e-5)
+    assert rel(y, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def _planar(x, B, n_head):
+    """[B, N, C] token-major -> planar rows (all head tokens of the batch, then all tail tokens)"""
+    return torch.cat([x[:, :n_head].reshape(-1, x.shape[-1]), x[:, n_head:].reshape(-1, x.shape[-1])], 0).contiguous()
+
+
+def _unplanar(x, B, N, n_head):
+    Cc = x.shape[-1]
+    return torch.cat([x[:B * n_head].view(B, n_head, Cc), x[B * n_head:].view(B, N - n_head, Cc)], 1)
+
+
+@pytest.mark.parametrize("dh,H", [(64, 2), (32, 4)])
+@pytest.mark.parametrize("counts,nf", [((40, 70, 18), 64), ((0, 100, 28), 64), ((64, 64, 0), 100), (None, 150)])
+def test_attention_fwd_bwd(dh, H, counts, nf):
+    B = 3
+    if counts is None:
+        N, n_head, seg, nseg, allowed = nf, nf, None, 0, None
+    else:
+        nenc = sum(counts)
+        N, n_head = nenc + nf, nenc
+        bounds = [0, counts[0], counts[0] + counts[1], nenc, N]
+        seg = torch.tensor(bounds, dtype=torch.int32, device="cuda")
+        nseg = 4
+        types = torch.cat([torch.full((c,), i) for i, c in enumerate(list(counts) + [nf])]).cuda()
+        allowed = (types[:, None] == types[None, :]) | (types[:, None] == 3)
+    scale = dh ** -0.5
+    qkv = rnd(B, N, 3 * H * dh, dtype=bf16, seed=1).requires_grad_(True)
+    q, k, v = [t.view(B, N, H, dh).transpose(1, 2).float() for t in qkv.chunk(3, -1)]
+    s = (q @ k.transpose(-1, -2)) * scale
+    if allowed is not None:
+        s = s.masked_fill(~allowed, float("-inf"))
+    o_ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, N, H * dh)
+    do = rnd(B, N, H * dh, dtype=bf16, seed=2)
+    o_ref.backward(do.float())
+
+    qkv_p = _planar(qkv.detach(), B, n_head)
+    HD = H * dh
+    o = torch.empty(B * N, HD, dtype=bf16, device="cuda")
+    lse = torch.empty(B, H, N, device="cuda")
+    kw = dict(B=B, H=H, Nq=N, Nk=N, dh=dh, scale=scale, n_head_q=n_head, n_head_k=n_head, seg=seg, nseg=nseg)
+    K().attn_fwd(qkv_p[:, :HD], qkv_p[:, HD:2 * HD], qkv_p[:, 2 * HD:], o, lse, **kw)
+    assert rel(_unplanar(o, B, N, n_head), o_ref) < 8e-3
+    dqkv = torch.full_like(qkv_p, float("nan"))
+    delta = torch.empty(B, H, N, device="cuda")
+    K().attn_bwd(qkv_p[:, :HD], qkv_p[:, HD:2 * HD], qkv_p[:, 2 * HD:], o, lse, _planar(do, B, n_head),
+                 dqkv[:, :HD], dqkv[:, HD:2 * HD], dqkv[:, 2 * HD:], delta, **kw)
+    got = _unplanar(dqkv, B, N, n_head)
+    assert torch.isfinite(got.float()).all()
+    assert rel(got, qkv.grad) < 1.5e-2
+
+
+def test_slot_attention_fwd_bwd():
+    B, Fn, H, S = 3, 16, 2, 4
+    counts = (9, 0, 5)
+    nenc = sum(counts)
+    HD = H * 64
+    g = torch.Generator().manual_seed(0)
+    idx = [torch.randperm(Fn, generator=g)[:c].sort().values for c in counts]
+    slotmap = torch.full((3, Fn), -1, dtype=torch.int32)
+    for m, ix in enumerate(idx):
+        slotmap[m, ix] = torch.arange(len(ix), dtype=torch.int32)
+    seg = torch.tensor([0, counts[0], counts[0] + counts[1], nenc], dtype=torch.int32)
+    q = rnd(B * Fn, HD, dtype=bf16, seed=1).requires_grad_(True)
+    kv_tok = rnd(B * nenc + B * Fn, 2 * HD, dtype=bf16, seed=2).requires_grad_(True)
+    kv_me = rnd(Fn, 2 * HD, dtype=bf16, seed=3).requires_grad_(True)
+    # reference: gather the S slot rows per (b, p)
+    rows = []
+    for s_ in range(3):
+        r = slotmap[s_].long()
+        tok = torch.stack([kv_tok.float()[b * nenc + seg[s_] + r.clamp_min(0).cuda()] for b in range(B)])   # [B, F, 2HD]
+        me = kv_me.float()[None].expand(B, -1, -1)
+        rows.append(torch.where((r >= 0).cuda()[None, :, None], tok, me))
+    rows.append(kv_tok.float()[B * nenc:].view(B, Fn, 2 * HD))
+    kvs = torch.stack(rows, 2)                                      # [B, F, S, 2HD]
+    kk = kvs[..., :HD].reshape(B, Fn, S, H, 64)
+    vv = kvs[..., HD:].reshape(B, Fn, S, H, 64)
+    qq = q.float().view(B, Fn, H, 64)
+    sc = torch.einsum("bfhd,bfshd->bfhs", qq, kk) * 0.125
+    pr = sc.softmax(-1)
+    ref = torch.einsum("bfhs,bfshd->bfhd", pr, vv).reshape(B * Fn, HD)
+    dout = rnd(B * Fn, HD, dtype=bf16, seed=4)
+    ref.backward(dout.float())
+
+    out = torch.empty(B * Fn, HD, dtype=bf16, device="cuda")
+    probs = torch.empty(B * Fn, H, S, device="cuda")
+    kw = dict(B=B, F=Fn, H=H, S=S, n_head=nenc, scale=0.125)
+    sm, sg = slotmap.cuda(), seg.cuda()
+    K().slot_attn_fwd(q.detach(), kv_tok.detach(), kv_me.detach(), sm, sg, out, probs, **kw)
+    assert rel(out, ref) < 6e-3
+    assert rel(probs.view(B, Fn, H, S), pr) < 1e-4
+    dq = torch.empty_like(out)
+    dkv = torch.full_like(kv_tok.detach(), float("nan"))
+    dme = torch.zeros(Fn, 2 * HD, device="cuda")
+    K().slot_attn_bwd(q.detach(), kv_tok.detach(), kv_me.detach(), sm, sg, dout, dq, dkv, dme, **kw)
+    assert torch.isfinite(dkv.float()).all()
+    assert rel(dq, q.grad) < 1e-2
+    assert rel(dkv, kv_tok.grad) < 1e-2
+    assert rel(dme, kv_me.grad) < 1e-2
+
+
+def test_pool_attention_fwd_bwd_uniform_rows():
+    B, H, R = 3, 2, 5
+    counts, nf = (30, 0, 21), 40
+    nenc = sum(counts); N = nenc + nf
+    HD = H * 64
+    types = torch.cat([torch.full((c,), i) for i, c in enumerate(list(counts) + [nf])]).cuda()
+    rtypes = torch.tensor([0, 1, 2, 3, 1]).cuda()
+    mask = (rtypes[:, None] == types[None, :]) | (rtypes[:, None] == 3)       # row 1 and 4: no allowed key
+    mode = torch.tensor([0, 0, 0, 0, 1], dtype=torch.int32, device="cuda")    # row 1 -> uniform, row 4 -> zero
+    q = rnd(R, HD, dtype=bf16, seed=1).requires_grad_(True)
+    kv = rnd(B, N, 2 * HD, dtype=bf16, seed=2).requires_grad_(True)
+    qq = q.float().view(R, H, 64).transpose(0, 1)[None]                        # [1, H, R, 64]
+    kk = kv.float()[..., :HD].view(B, N, H, 64).transpose(1, 2)
+    vv = kv.float()[..., HD:].view(B, N, H, 64).transpose(1, 2)
+    sim = (qq * 0.125) @ kk.transpose(-1, -2)
+    sim = sim.masked_fill(~mask, -torch.finfo(sim.dtype).max)
+    pr = sim.softmax(-1)
+    zero_rows = torch.tensor([False, False, False, False, True]).cuda()
+    pr = torch.where(zero_rows[None, None, :, None], torch.zeros_like(pr), pr)
+    ref = (pr @ vv).transpose(1, 2).reshape(B, R, HD)
+    dout = rnd(B, R, HD, dtype=bf16, seed=3)
+    ref.backward(dout.float())
+
+    kvp = _planar(kv.detach(), B, nenc)
+    out = torch.empty(B, R, HD, dtype=bf16, device="cuda")
+    stat = torch.empty(B * R * H * 3, device="cuda")
+    kw = dict(B=B, R=R, H=H, N=N, n_head=nenc, scale=0.125, q_batched=False)
+    m8 = mask.to(torch.uint8).contiguous()
+    K().pool_attn_fwd(q.detach(), kvp, m8, mode, out, stat, **kw)
+    assert rel(out, ref) < 6e-3
+    dq = torch.zeros(R, HD, device="cuda")
+    dkv = torch.full_like(kvp, float("nan"))
+    K().pool_attn_bwd(q.detach(), kvp, m8, mode, out, stat, dout, dq, dkv, **kw)
+    assert torch.isfinite(dkv.float()).all()
+    assert rel(dq, q.grad) < 1e-2
+    assert rel(_unplanar(dkv, B, N, nenc), kv.grad) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# losses and data movement
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("pdt", [bf16, f32])
+def test_masked_loss(kind, pdt):
+    import oracle
+    B, Cc, H, W, P = 5, 3, 32, 32, 8
+    pred = rnd(B, Cc, H, W, dtype=pdt, seed=1).requires_grad_(True)
+    tgt = rnd(B, Cc, H, W, seed=2)
+    mask = (torch.rand(B, 16, device="cuda") > 0.5).long()
+    mask[1] = 0                                      # nanmean path
+    fn = oracle.masked_mse_loss if kind == 0 else oracle.masked_l1_loss
+    for m in (mask, None, torch.zeros_like(mask)):
+        pred.grad = None
+        ref = fn(pred.float(), tgt, m, P)
+        work = torch.empty(2 * B + 2, device="cuda")
+        loss = torch.empty(1, device="cuda")
+        K().masked_loss_fwd(pred.detach(), tgt, m, P, kind, work, loss)
+        assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+        if ref.requires_grad:
+            (ref * 1.7).backward()
+            dpred = torch.empty_like(pred.detach())
+            K().masked_loss_bwd(pred.detach(), tgt, m, P, kind, work, torch.tensor([1.7], device="cuda"), dpred)
+            assert rel(dpred, pred.grad) < (1e-5 if pdt == f32 else 6e-3)
+
+
+def test_elementwise():
+    import oracle
+    k = K()
+    # cast with padding
+    w = rnd(341, 128, seed=1)
+    o = k.cast_bf16(w, rows_pad=384, cols_pad=128)
+    assert torch.equal(o[:341], w.to(bf16)) and float(o[341:].abs().max()) == 0
+    assert torch.equal(k.cast_bf16(w), w.to(bf16))
+    # geglu bwd
+    rows, I = 77, 64
+    u = rnd(rows, 2 * I, dtype=bf16, seed=2).float().requires_grad_(True)
+    dg = rnd(rows, I, dtype=bf16, seed=3)
+    (F.gelu(u[:, I:]) * u[:, :I]).backward(dg.float())
+    du = torch.empty(rows, 2 * I, dtype=bf16, device="cuda")
+    k.geglu_bwd(u.detach().to(bf16), dg, du)
+    assert rel(du, u.grad) < 6e-3
+    # gelu bwd
+    pre = rnd(50, 64, dtype=bf16, seed=4).float().requires_grad_(True)
+    dy = rnd(50, 64, dtype=bf16, seed=5)
+    F.gelu(pre).backward(dy.float())
+    dp = torch.empty(50, 64, dtype=bf16, device="cuda")
+    k.gelu_bwd(pre.detach().to(bf16), dy, dp)
+    assert rel(dp, pre.grad) < 6e-3
+    # colsum
+    x = rnd(999, 200, dtype=bf16, seed=6)
+    out = torch.zeros(200, device="cuda")
+    k.colsum(x, out)
+    assert rel(out, x.float().sum(0)) < 1e-5
+    # bcast / reduce
+    src = rnd(10, 64, seed=7)
+    dst = torch.zeros(4, 25, 64, device="cuda")
+    k.bcast_rows(src, dst[:, 15:], 4, 10, 64, 25 * 64)
+    assert torch.equal(dst[:, 15:], src[None].expand(4, -1, -1)) and float(dst[:, :15].abs().max()) == 0
+    red = torch.empty(10, 64, device="cuda")
+    k.reduce_batch(dst[:, 15:], red, 4, 10, 64, 25 * 64)
+    assert rel(red, 4 * src) < 1e-6
+    # im2col gather == conv patch projection operand
+    B, Cc, H, W, P = 2, 3, 32, 32, 8
+    img = rnd(B, Cc, H, W, seed=8)
+    idx = torch.tensor([0, 3, 7, 12, 15], dtype=torch.int32, device="cuda")
+    A = torch.empty(B * 5, Cc * P * P, dtype=bf16, device="cuda")
+    k.im2col_gather(img, idx, A, P)
+    ref = F.unfold(img, P, stride=P).transpose(1, 2)[:, idx.long()].reshape(B * 5, -1)
+    assert torch.equal(A, ref.to(bf16))
+    # unpatchify round trip vs oracle
+    cfg = oracle.OracleConfig(patch=P, image_size=H)
+    tok = rnd(B, 16, Cc * P * P, dtype=bf16, seed=9)
+    im = torch.empty(B, Cc, H, W, dtype=bf16, device="cuda")
+    k.unpatchify(tok, im, Cc, H, W, P)
+    assert torch.equal(im, oracle.functional._unpatchify(tok, cfg, Cc, H, W))
+    back = torch.empty_like(tok)
+    k.unpatchify(back, im, Cc, H, W, P, inverse=True)
+    assert torch.equal(back, tok)
+    # gather rows with cast
+    src = rnd(3 * 20, 64, seed=10)
+    gi = torch.tensor([1, 4, 9], dtype=torch.int32, device="cuda")
+    dst = torch.empty(9, 64, dtype=bf16, device="cuda")
+    k.gather_rows(src, dst, batch=3, n=3, d=64, src_batch_rows=20, row_off=2, idx=gi)
+    assert torch.equal(dst, src.view(3, 20, 64)[:, (gi.long() + 2)].reshape(9, 64).to(bf16))
