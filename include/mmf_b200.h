@@ -62,8 +62,10 @@ typedef struct MmfGemmArgs {
   int32_t out_batch_rows;
   int32_t block_n;         /* 0: auto, or 128 / 256 */
   float alpha;             /* scale applied to the accumulator first */
-  void* out2;              /* optional second output: bf16 copy of an f32 `out` (same mapping, ldo2) */
+  void* out2;              /* optional second output (bf16, same row mapping, ldo2): a bf16 copy of an f32
+                              `out`; or, with act=1 and a bf16 `out`, the PRE-activation (for the backward) */
   int64_t ldo2;
+  int32_t accumulate;      /* 1: out += result (f32: atomic adds; bf16: read-modify-write) */
   /* act=2 (GEGLU, zorro_utils.py:115-118): B is the [2*I_pad, K] weight; tile columns pair value
    * row j with gate row I_pad + j; out[M, I_pad] = gelu(gate) * value; `out2` (optional, bf16,
    * [M, 2*I_pad]) receives the pre-activation for the backward.  N must be passed as I_pad. */

@@ -22,7 +22,7 @@ class GemmArgs(C.Structure):
         ("lda", c_i64), ("ldb", c_i64), ("ldo", c_i64), ("ldr", c_i64),
         ("a_mn", c_i32), ("b_mn", c_i32), ("out_f32", c_i32), ("act", c_i32), ("split_k", c_i32),
         ("res_period", c_i32), ("out_period", c_i32), ("out_batch_rows", c_i32), ("block_n", c_i32),
-        ("alpha", c_f32), ("out2", c_vp), ("ldo2", c_i64),
+        ("alpha", c_f32), ("out2", c_vp), ("ldo2", c_i64), ("accumulate", c_i32),
     ]
 
 

@@ -43,7 +43,7 @@ struct GemmParams {
   const int32_t* res_row_map;
   int64_t M, N, K;
   int64_t ldo, ldo2, ldr;
-  int32_t out_f32, act, split_k, res_period, out_period, out_batch_rows;
+  int32_t out_f32, act, split_k, res_period, out_period, out_batch_rows, accumulate;
   int32_t m_tiles, n_tiles, num_kb, kb_per_split;
   int64_t geglu_ipad;  // act==2: row offset of the gate half inside B
   float alpha;
@@ -52,7 +52,7 @@ struct GemmParams {
 __device__ __forceinline__ void store_row32(const GemmParams& p, int64_t orow, int64_t col0, const float (&v)[32],
                                             int ncols_valid) {
   // 32 consecutive output columns of one row, starting at col0 (multiple of 32)
-  if (p.split_k > 1) {
+  if (p.split_k > 1 || (p.accumulate && p.out_f32)) {
     float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -86,6 +86,12 @@ __device__ __forceinline__ void store_row32(const GemmParams& p, int64_t orow, i
     }
   } else {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
+    if (p.accumulate) {  // out += result (each element owned by exactly one thread)
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols_valid) o[j] = __float2bfloat16(__bfloat162float(o[j]) + v[j]);
+      return;
+    }
     if (ncols_valid == 32 && (p.ldo & 7) == 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -411,6 +417,7 @@ static int launch_gemm(const MmfGemmArgs& a, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K = a.K; p.ldo = a.ldo; p.ldo2 = a.ldo2; p.ldr = a.ldr;
   p.out_f32 = a.out_f32; p.act = a.act; p.split_k = a.split_k < 1 ? 1 : a.split_k;
   p.res_period = a.res_period; p.out_period = a.out_period; p.out_batch_rows = a.out_batch_rows;
+  p.accumulate = a.accumulate;
   p.m_tiles = (int)ceil_div64(a.M, BLOCK_M);
   p.n_tiles = (int)ceil_div64(a.N, geglu ? BLOCK_N / 2 : BLOCK_N);
   p.num_kb = (int)ceil_div64(a.K, BLOCK_K);
@@ -457,6 +464,7 @@ extern "C" int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream_) {
   if (a.out2 && a.act == 0 && !a.out_f32) MMF_BAD_ARG(11);
   if (a.residual && a.ldr < a.N) MMF_BAD_ARG(12);
   if (a.out_period < 0 || a.res_period < 0) MMF_BAD_ARG(13);
+  if (a.accumulate && (a.act == 2 || a.out2)) MMF_BAD_ARG(16);
 
   int bn = a.block_n;
   if (bn == 0) {

@@ -1,0 +1,557 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels (host-side plumbing only).
+
+Numerics contract = the reference under CUDA autocast(bf16): the
+residual stream, LayerNorm, softmax statistics and losses are fp32; every contraction takes bf16
+operands with fp32 accumulation.  Weight gradients are produced in fp32 straight from the
+accumulators.
+
+The encoder stack (all zorro blocks, and for the crossattn variant all Block_Fusion blocks) is ONE
+autograd node, `EncoderStackFn`, with a hand-ordered backward: it keeps the token stream in the
+planar layout (all modality tokens of the batch, then all fusion tokens), never re-materialises the
+concatenated tensor between blocks, and accumulates the residual-stream gradient in place.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import kernels as K
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 weight images (what autocast's per-forward weight cast does in the reference), cached on the
+# parameter's version counter so they are rebuilt once per optimizer step, not once per use
+# ------------------------------------------------------------------------------------------------
+class _WeightCache:
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, params: Sequence[torch.Tensor], build):
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = build()
+        self._store[key] = (ver, val)
+        return val
+
+    def clear(self):
+        self._store.clear()
+
+
+WEIGHTS = _WeightCache()
+
+
+def w_bf16(w: torch.Tensor, rows_pad: Optional[int] = None, cols_pad: Optional[int] = None) -> torch.Tensor:
+    """bf16 image of a 2-D (or conv 4-D, flattened) fp32 weight, zero padded."""
+    w2 = w.detach().reshape(w.shape[0], -1)
+    return WEIGHTS.get(("w", id(w), rows_pad, cols_pad), [w], lambda: K.cast_bf16(w2, rows_pad=rows_pad, cols_pad=cols_pad))
+
+
+def w_cat_bf16(ws: Sequence[torch.Tensor]) -> torch.Tensor:
+    """row-concatenation of several [n_i, K] weights as one bf16 matrix (to_q || to_kv)."""
+    def build():
+        rows = sum(w.shape[0] for w in ws)
+        out = torch.empty(rows, ws[0].shape[1], dtype=bf16, device=ws[0].device)
+        r = 0
+        for w in ws:
+            K.cast_bf16(w.detach(), out[r:r + w.shape[0]])
+            r += w.shape[0]
+        return out
+    return WEIGHTS.get(("cat",) + tuple(id(w) for w in ws), list(ws), build)
+
+
+def w_geglu_bf16(w1: torch.Tensor, ipad: int) -> torch.Tensor:
+    """[2I, D] GEGLU weight -> bf16 [2*ipad, D]: value rows at [0, I), gate rows at [ipad, ipad+I), zero padding."""
+    def build():
+        I = w1.shape[0] // 2
+        if I == ipad:
+            return K.cast_bf16(w1.detach())
+        out = torch.zeros(2 * ipad, w1.shape[1], dtype=bf16, device=w1.device)
+        K.cast_bf16(w1.detach()[:I], out[:I])
+        K.cast_bf16(w1.detach()[I:], out[ipad:ipad + I])
+        return out
+    return WEIGHTS.get(("geglu", id(w1), ipad), [w1], build)
+
+
+def _wgrad_split(tokens: int, out_elems: int) -> int:
+    """split-K factor for a weight-gradient GEMM whose contraction runs over `tokens` rows."""
+    tiles = max(1, out_elems // (128 * 256))
+    want = max(1, (148 * 2) // tiles)
+    return max(1, min(want, tokens // 1024 if tokens >= 2048 else 1, 32))
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor, out_rows: Optional[int] = None, out_cols: Optional[int] = None,
+          out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """dW[n_out, k_in] = dy^T x with dy [T, n_out], x [T, k_in] both bf16 token-major (MN-major operands)."""
+    n_out = out_rows or dy.shape[1]
+    k_in = out_cols or x.shape[1]
+    if out is None:
+        out = torch.zeros(n_out, k_in, dtype=f32, device=dy.device)
+    K.gemm(dy, x, out, a_mn=True, b_mn=True, split_k=_wgrad_split(dy.shape[0], n_out * k_in), accumulate=accumulate,
+           M=n_out, N=k_in, K=dy.shape[0])
+    return out
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype == bf16:
+        return x
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    return K.cast_bf16(x2).view(x.shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# generic pieces used by the pooling head and the decoders
+# ------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) [+ residual].  x: [M, K] bf16 or f32 (cast once to bf16); y bf16, or f32 when a
+    residual (f32) is given or out_f32.  act: 0 none, 1 exact GELU."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, act, out_f32):
+        xb = to_bf16(x)
+        wb = w_bf16(weight)
+        M, N = xb.shape[0], weight.shape[0]
+        f32_out = out_f32 or residual is not None
+        out = torch.empty(M, N, dtype=f32 if f32_out else bf16, device=x.device)
+        pre = None
+        if act == 1:
+            if f32_out:
+                raise RuntimeError("GELU epilogue is only provided for bf16 outputs")
+            pre = torch.empty(M, N, dtype=bf16, device=x.device)
+        if M > 0:
+            K.gemm(xb, wb, out, bias=None if bias is None else bias.detach(), act=act,
+                   residual=None if residual is None else residual.detach(), out2=pre)
+        ctx.save_for_backward(xb, weight, pre)
+        ctx.x_dtype = x.dtype
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, weight, pre = ctx.saved_tensors
+        dy = dy.contiguous()
+        dyb = to_bf16(dy)
+        if pre is not None:
+            dyb = K.gelu_bwd(pre, dyb, torch.empty_like(dyb))
+        wb = w_bf16(weight)
+        M, Kd = xb.shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, Kd, dtype=ctx.x_dtype, device=dy.device)
+            if M > 0:
+                K.gemm(dyb, wb, dx, b_mn=True)
+        if ctx.needs_input_grad[1]:
+            dw = wgrad(dyb, xb) if M > 0 else torch.zeros_like(weight)
+            dw = dw.view(weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros(weight.shape[0], dtype=f32, device=dy.device)
+            if M > 0:
+                K.colsum(dyb, db)
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dres, None, None
+
+
+def linear(x, weight, bias=None, residual=None, act=0, out_f32=False):
+    return LinearFn.apply(x, weight, bias, residual, act, out_f32)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """single LayerNorm over the last dim of a 2-D fp32 tensor (gamma, optional bias), bf16 or f32 output"""
+
+    @staticmethod
+    def forward(ctx, x, gamma, bias, eps, out_bf16):
+        x = x.contiguous()
+        rows, D = x.shape
+        y = torch.empty(rows, D, dtype=bf16 if out_bf16 else f32, device=x.device)
+        stats = torch.empty(rows, 4, dtype=f32, device=x.device)
+        K.layernorm_fwd(x, gamma.detach(), y, b1=None if bias is None else bias.detach(), eps1=eps, stats=stats)
+        ctx.save_for_backward(x, gamma, bias, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, bias, stats = ctx.saved_tensors
+        dy = dy.contiguous()
+        D = x.shape[1]
+        dx = torch.empty_like(x)
+        dg = torch.zeros(D, dtype=f32, device=x.device)
+        db = torch.zeros(D, dtype=f32, device=x.device) if bias is not None else None
+        K.layernorm_bwd(dy, x, gamma.detach(), stats, dx, dg, b1=None if bias is None else bias.detach(), db1=db)
+        return dx, dg, db, None, None
+
+
+def layer_norm(x, gamma, bias=None, eps=1e-5, out_bf16=False):
+    return LayerNormFn.apply(x, gamma, bias, eps, out_bf16)
+
+
+class SelfAttentionFn(torch.autograd.Function):
+    """unmasked multi-head self-attention on a fused [B*N, 3*H*dh] bf16 qkv buffer (decoder blocks)"""
+
+    @staticmethod
+    def forward(ctx, qkv, B, N, H, dh, scale):
+        HD = H * dh
+        o = torch.empty(B * N, HD, dtype=bf16, device=qkv.device)
+        lse = torch.empty(B, H, N, dtype=f32, device=qkv.device)
+        K.attn_fwd(qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, B=B, H=H, Nq=N, Nk=N, dh=dh, scale=scale)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.dims = (B, N, H, dh, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        B, N, H, dh, scale = ctx.dims
+        HD = H * dh
+        do = to_bf16(do.contiguous())
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty(B, H, N, dtype=f32, device=qkv.device)
+        K.attn_bwd(qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do, dqkv[:, :HD], dqkv[:, HD:2 * HD],
+                   dqkv[:, 2 * HD:], delta, B=B, H=H, Nq=N, Nk=N, dh=dh, scale=scale)
+        return dqkv, None, None, None, None, None
+
+
+class PoolAttnFn(torch.autograd.Function):
+    """R queries (batch-invariant, [R, H*64] bf16) over planar kv rows with a dense mask; see kernels.pool_attn_fwd"""
+
+    @staticmethod
+    def forward(ctx, q, kv, mask_u8, mode, B, H, N, n_head, scale):
+        R = q.shape[0]
+        out = torch.empty(B, R, H * 64, dtype=bf16, device=q.device)
+        stat = torch.empty(B * R * H * 3, dtype=f32, device=q.device)
+        K.pool_attn_fwd(q, kv, mask_u8, mode, out, stat, B=B, R=R, H=H, N=N, n_head=n_head, scale=scale, q_batched=False)
+        ctx.save_for_backward(q, kv, mask_u8, mode, out, stat)
+        ctx.dims = (B, R, H, N, n_head, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv, mask_u8, mode, out, stat = ctx.saved_tensors
+        B, R, H, N, n_head, scale = ctx.dims
+        dout = to_bf16(dout.contiguous())
+        dq = torch.zeros(R, H * 64, dtype=f32, device=q.device)
+        dkv = torch.empty_like(kv)
+        K.pool_attn_bwd(q, kv, mask_u8, mode, out, stat, dout, dq, dkv, B=B, R=R, H=H, N=N, n_head=n_head, scale=scale,
+                        q_batched=False)
+        return dq.to(bf16), dkv, None, None, None, None, None, None, None
+
+
+class UnpatchifyFn(torch.autograd.Function):
+    """'b (nh nw) (c ph pw) -> b c (nh ph) (nw pw)' on bf16 (output_adapters_simple.py:183-186)"""
+
+    @staticmethod
+    def forward(ctx, tok, B, C, H, W, P):
+        img = torch.empty(B, C, H, W, dtype=bf16, device=tok.device)
+        K.unpatchify(tok.contiguous(), img, C, H, W, P)
+        ctx.dims = (B, C, H, W, P, tok.shape)
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        B, C, H, W, P, shape = ctx.dims
+        dtok = torch.empty(shape, dtype=bf16, device=dimg.device)
+        K.unpatchify(dtok, to_bf16(dimg.contiguous()), C, H, W, P, inverse=True)
+        return dtok, None, None, None, None, None
+
+
+class MaskedLossFn(torch.autograd.Function):
+    """criterion.py:85-115 / :142-172 (norm_pix=False) fused; kind 0 = MSE, 1 = L1"""
+
+    @staticmethod
+    def forward(ctx, pred, target, mask, P, kind):
+        pred = pred.contiguous()
+        target = target.contiguous()
+        B = pred.shape[0]
+        work = torch.empty(2 * B + 2, dtype=f32, device=pred.device)
+        loss = torch.empty(1, dtype=f32, device=pred.device)
+        K.masked_loss_fwd(pred, target, mask, P, kind, work, loss)
+        ctx.save_for_backward(pred, target, mask, work)
+        ctx.pk = (P, kind)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        pred, target, mask, work = ctx.saved_tensors
+        P, kind = ctx.pk
+        dpred = torch.empty_like(pred)
+        K.masked_loss_bwd(pred, target, mask, P, kind, work, dloss.reshape(1).to(f32).contiguous(), dpred)
+        return dpred, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# token embedding: visible-patch im2col + projection GEMM written straight into the planar stream
+# ------------------------------------------------------------------------------------------------
+class EmbedFn(torch.autograd.Function):
+    """Builds the planar token stream X [B*nenc + B*F, D] (f32):
+      head plane: for each modality m (in s1, s2, dem order) its n_m visible patches, projected with the
+                  conv weight viewed as [D, C*P*P] + bias + sin-cos pos-emb (input_adapters.py:97-119
+                  restricted to the visible patches, multimae.py:378-383)
+      tail plane: fusion_tokens + fusion pos-emb broadcast over the batch (multimae.py:353-354).
+    args: meta (dict), fusion_tokens [1,F,D], then per modality (image, proj_weight, proj_bias)."""
+
+    @staticmethod
+    def forward(ctx, meta, fusion_tokens, *mod_args):
+        B, D, P, Fn, nenc = meta["B"], meta["D"], meta["P"], meta["F"], meta["nenc"]
+        dev = fusion_tokens.device
+        Mh = B * nenc
+        X = torch.empty(Mh + B * Fn, D, dtype=f32, device=dev)
+        saved = []
+        off = 0
+        for m, idx in enumerate(meta["idx"]):
+            img, w, b = mod_args[3 * m: 3 * m + 3]
+            n = idx.numel()
+            A = None
+            if n > 0:
+                C = img.shape[1]
+                A = torch.empty(B * n, C * P * P, dtype=bf16, device=dev)
+                K.im2col_gather(img.contiguous(), idx, A, P)
+                K.gemm(A, w_bf16(w), X[off:], bias=b.detach(), residual=meta["pos"][m], res_row_map=idx, res_period=n,
+                       out_period=n, out_batch_rows=nenc)
+            saved.append(A)
+            off += n
+        fus = (fusion_tokens.detach()[0] + meta["pos_fusion"]).contiguous()
+        K.bcast_rows(fus, X[Mh:], B, Fn, D, Fn * D)
+        ctx.meta = meta
+        ctx.saved_A = saved
+        ctx.mod_shapes = [(mod_args[3 * m + 1].shape, ) for m in range(len(meta["idx"]))]
+        return X
+
+    @staticmethod
+    def backward(ctx, dX):
+        meta = ctx.meta
+        B, D, Fn, nenc = meta["B"], meta["D"], meta["F"], meta["nenc"]
+        Mh = B * nenc
+        dX = dX.contiguous()
+        grads: List[Optional[torch.Tensor]] = []
+        off = 0
+        for m, idx in enumerate(meta["idx"]):
+            n = idx.numel()
+            wshape = ctx.mod_shapes[m][0]
+            if n == 0:
+                grads += [None, torch.zeros(wshape, dtype=f32, device=dX.device), torch.zeros(D, dtype=f32, device=dX.device)]
+                continue
+            dY = torch.empty(B * n, D, dtype=bf16, device=dX.device)
+            K.gather_rows(dX, dY, batch=B, n=n, d=D, src_batch_rows=nenc, row_off=off)
+            dW = wgrad(dY, ctx.saved_A[m]).view(wshape)
+            db = K.colsum(dY, torch.zeros(D, dtype=f32, device=dX.device))
+            grads += [None, dW, db]
+            off += n
+        dfus = torch.empty(1, Fn, D, dtype=f32, device=dX.device)
+        K.reduce_batch(dX[Mh:], dfus, B, Fn, D, Fn * D)
+        return (None, dfus) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# the encoder stack
+# ------------------------------------------------------------------------------------------------
+ZB = 9  # tensors per (zorro or fusion) block: norm1.g, attn.norm.g, to_q.W, to_kv.W, to_out.W, norm2.g, mlp.0.g, mlp.1.W, mlp.3.W
+
+
+def _ln2(x, g1, g2, x2=None, split=0, rows=None):
+    rows = rows if rows is not None else x.shape[0]
+    y = torch.empty(rows, x.shape[1], dtype=bf16, device=x.device)
+    st = torch.empty(rows, 4, dtype=f32, device=x.device)
+    K.layernorm_fwd(x, g1, y, g2=g2, stats=st, x2=x2, x_split=split, rows=rows)
+    return y, st
+
+
+def _ffn_fwd(h, w1b, w2b, ipad, residual):
+    rows = h.shape[0]
+    g = torch.empty(rows, ipad, dtype=bf16, device=h.device)
+    u = torch.empty(rows, 2 * ipad, dtype=bf16, device=h.device)
+    K.gemm(h, w1b, g, act=2, out2=u)
+    out = torch.empty(rows, w2b.shape[0], dtype=f32, device=h.device)
+    K.gemm(g, w2b, out, residual=residual)
+    return out, g, u
+
+
+def _unpad_w1(dw1, I, ipad):
+    if I == ipad:
+        return dw1
+    return torch.cat([dw1[:I], dw1[ipad:ipad + I]], 0)
+
+
+class EncoderStackFn(torch.autograd.Function):
+    """All encoder layers as one node.  meta: dims + the per-step mask structures (device int32 `seg`
+    table, `slotmap`), fusion flag.  Flat params: [mask_embedding] (fusion variant) then per layer the
+    9 fusion-block tensors (fusion variant) followed by the 9 zorro-block tensors."""
+
+    @staticmethod
+    def forward(ctx, meta, X, *params):
+        B, D, H, Fn, nenc, fusion = meta["B"], meta["D"], meta["H"], meta["F"], meta["nenc"], meta["fusion"]
+        depth, I = meta["depth"], meta["I"]
+        ipad = _pad64(I)
+        HD = H * 64
+        Mh, Mf = B * nenc, B * Fn
+        Mt = Mh + Mf
+        N = nenc + Fn
+        seg, nseg, scale = meta["seg"], meta["nseg"], 0.125
+        per_layer = ZB * (2 if fusion else 1)
+        base = 1 if fusion else 0
+        me = params[0].detach()[0] if fusion else None
+        saved = []
+        X = X.contiguous()
+        for i in range(depth):
+            lp = [p.detach() for p in params[base + i * per_layer: base + (i + 1) * per_layer]]
+            rec = {"X": X}
+            Xf2 = None
+            if fusion:
+                fn1, fan, fwq, fwkv, fwo, fn2, fm0, fw1, fw2 = lp[:ZB]
+                hk, stA = _ln2(X, fn1, fan)
+                wkv = w_bf16(params[base + i * per_layer + 3])
+                kv = torch.empty(Mt, 2 * HD, dtype=bf16, device=X.device)
+                K.gemm(hk, wkv, kv)
+                q = torch.empty(Mf, HD, dtype=bf16, device=X.device)
+                K.gemm(hk[Mh:], w_bf16(params[base + i * per_layer + 2]), q)
+                hm, stM = _ln2(me.contiguous(), fn1, fan)
+                kvm = torch.empty(Fn, 2 * HD, dtype=bf16, device=X.device)
+                K.gemm(hm, wkv, kvm)
+                a = torch.empty(Mf, HD, dtype=bf16, device=X.device)
+                K.slot_attn_fwd(q, kv, kvm, meta["slotmap"], seg, a, None, B=B, F=Fn, H=H, S=nseg, n_head=nenc, scale=scale)
+                Xf1 = torch.empty(Mf, D, dtype=f32, device=X.device)
+                K.gemm(a, w_bf16(params[base + i * per_layer + 4]), Xf1, residual=X[Mh:])
+                h2, stB = _ln2(Xf1, fn2, fm0)
+                Xf2, g, u = _ffn_fwd(h2, w_geglu_bf16(params[base + i * per_layer + 7], ipad),
+                                     w_bf16(params[base + i * per_layer + 8], cols_pad=ipad), ipad, Xf1)
+                rec.update(hk=hk, stA=stA, kv=kv, q=q, hm=hm, stM=stM, kvm=kvm, a=a, Xf1=Xf1, h2=h2, stB=stB, g=g, u=u, Xf2=Xf2)
+            zo = base + i * per_layer + (ZB if fusion else 0)
+            n1, an, wq, wkv_, wo, n2, m0, w1, w2 = [p.detach() for p in params[zo: zo + ZB]]
+            h1, st1 = _ln2(X, n1, an, x2=Xf2, split=Mh if fusion else 0, rows=Mt)
+            qkv = torch.empty(Mt, 3 * HD, dtype=bf16, device=X.device)
+            K.gemm(h1, w_cat_bf16([params[zo + 2], params[zo + 3]]), qkv)
+            o = torch.empty(Mt, HD, dtype=bf16, device=X.device)
+            lse = torch.empty(B, H, N, dtype=f32, device=X.device)
+            K.attn_fwd(qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, B=B, H=H, Nq=N, Nk=N, dh=64, scale=scale,
+                       n_head_q=nenc, n_head_k=nenc, seg=seg, nseg=nseg)
+            X1 = torch.empty(Mt, D, dtype=f32, device=X.device)
+            K.gemm(o, w_bf16(params[zo + 4]), X1, residual=X, residual2=Xf2, res_split=Mh if fusion else 0)
+            h2z, st2 = _ln2(X1, n2, m0)
+            X2, gz, uz = _ffn_fwd(h2z, w_geglu_bf16(params[zo + 7], ipad), w_bf16(params[zo + 8], cols_pad=ipad), ipad, X1)
+            rec.update(h1=h1, st1=st1, qkv=qkv, o=o, lse=lse, X1=X1, h2z=h2z, st2=st2, gz=gz, uz=uz)
+            saved.append(rec)
+            X = X2
+        ctx.meta = meta
+        ctx.saved = saved
+        ctx.params = params
+        return X
+
+    @staticmethod
+    def backward(ctx, dX):
+        meta, saved, params = ctx.meta, ctx.saved, ctx.params
+        B, D, H, Fn, nenc, fusion = meta["B"], meta["D"], meta["H"], meta["F"], meta["nenc"], meta["fusion"]
+        depth, I = meta["depth"], meta["I"]
+        ipad = _pad64(I)
+        HD = H * 64
+        Mh, Mf = B * nenc, B * Fn
+        Mt = Mh + Mf
+        N = nenc + Fn
+        seg, nseg, scale = meta["seg"], meta["nseg"], 0.125
+        per_layer = ZB * (2 if fusion else 1)
+        base = 1 if fusion else 0
+        dev = dX.device
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        dme = torch.zeros(Fn, D, dtype=f32, device=dev) if fusion else None
+        dX = dX.contiguous()
+        zeros = lambda n: torch.zeros(n, dtype=f32, device=dev)
+
+        def ffn_bwd(dXo_b, g, u, h, w1_param, w2_param, rows):
+            """returns dh (bf16 [rows, D]), dW1, dW2"""
+            w2b = w_bf16(w2_param, cols_pad=ipad)
+            dg = torch.empty(rows, ipad, dtype=bf16, device=dev)
+            K.gemm(dXo_b, w2b, dg, b_mn=True)
+            dW2 = wgrad(dXo_b, g)[:, :I]
+            du = K.geglu_bwd(u, dg, torch.empty_like(u))
+            w1b = w_geglu_bf16(w1_param, ipad)
+            dh = torch.empty(rows, D, dtype=bf16, device=dev)
+            K.gemm(du, w1b, dh, b_mn=True)
+            dW1 = _unpad_w1(wgrad(du, h), I, ipad)
+            return dh, dW1, dW2.contiguous() if I != ipad else dW2
+
+        for i in reversed(range(depth)):
+            rec = saved[i]
+            saved[i] = None
+            X = rec["X"]
+            Xf2 = rec.get("Xf2")
+            zo = base + i * per_layer + (ZB if fusion else 0)
+            n1, an, n2, m0 = [params[zo + j].detach() for j in (0, 1, 5, 6)]
+            # ---------------- zorro block backward ----------------
+            dX2b = K.cast_bf16(dX)
+            dh2z, dW1, dW2 = ffn_bwd(dX2b, rec["gz"], rec["uz"], rec["h2z"], params[zo + 7], params[zo + 8], Mt)
+            grads[zo + 7], grads[zo + 8] = dW1, dW2
+            dX1 = torch.empty(Mt, D, dtype=f32, device=dev)
+            dX1b = torch.empty(Mt, D, dtype=bf16, device=dev)
+            dn2, dm0 = zeros(D), zeros(D)
+            K.layernorm_bwd(dh2z, rec["X1"], n2, rec["st2"], dX1, dn2, g2=m0, dres=dX, dx_bf16=dX1b, dg2=dm0)
+            grads[zo + 5], grads[zo + 6] = dn2, dm0
+            do = torch.empty(Mt, HD, dtype=bf16, device=dev)
+            K.gemm(dX1b, w_bf16(params[zo + 4]), do, b_mn=True)
+            grads[zo + 4] = wgrad(dX1b, rec["o"])
+            qkv = rec["qkv"]
+            dqkv = torch.empty_like(qkv)
+            delta = torch.empty(B, H, N, dtype=f32, device=dev)
+            K.attn_bwd(qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], rec["o"], rec["lse"], do, dqkv[:, :HD],
+                       dqkv[:, HD:2 * HD], dqkv[:, 2 * HD:], delta, B=B, H=H, Nq=N, Nk=N, dh=64, scale=scale,
+                       n_head_q=nenc, n_head_k=nenc, seg=seg, nseg=nseg)
+            dh1 = torch.empty(Mt, D, dtype=bf16, device=dev)
+            K.gemm(dqkv, w_cat_bf16([params[zo + 2], params[zo + 3]]), dh1, b_mn=True)
+            dWqkv = wgrad(dqkv, rec["h1"])
+            grads[zo + 2], grads[zo + 3] = dWqkv[:HD], dWqkv[HD:]
+            dZ = torch.empty(Mt, D, dtype=f32, device=dev)
+            dZb = torch.empty(Mt, D, dtype=bf16, device=dev) if fusion else None
+            dn1, dan = zeros(D), zeros(D)
+            K.layernorm_bwd(dh1, X, n1, rec["st1"], dZ, dn1, g2=an, dres=dX1, dx_bf16=dZb, dg2=dan, x2=Xf2,
+                            x_split=Mh if fusion else 0, rows=Mt)
+            grads[zo], grads[zo + 1] = dn1, dan
+            if not fusion:
+                dX = dZ
+                continue
+            # ---------------- fusion block backward (upstream: dZ[Mh:] = grad wrt Xf2) ----------------
+            fo = base + i * per_layer
+            fn1, fan, fn2, fm0 = [params[fo + j].detach() for j in (0, 1, 5, 6)]
+            dh2, dW1, dW2 = ffn_bwd(dZb[Mh:], rec["g"], rec["u"], rec["h2"], params[fo + 7], params[fo + 8], Mf)
+            grads[fo + 7], grads[fo + 8] = dW1, dW2
+            dXf1b = torch.empty(Mf, D, dtype=bf16, device=dev)
+            dfn2, dfm0 = zeros(D), zeros(D)
+            # in place: dZ[Mh:] (= dXf2) becomes dXf1, which is also the gradient of the fusion residual input
+            K.layernorm_bwd(dh2, rec["Xf1"], fn2, rec["stB"], dZ[Mh:], dfn2, g2=fm0, dres=dZ[Mh:], dx_bf16=dXf1b, dg2=dfm0)
+            grads[fo + 5], grads[fo + 6] = dfn2, dfm0
+            da = torch.empty(Mf, HD, dtype=bf16, device=dev)
+            K.gemm(dXf1b, w_bf16(params[fo + 4]), da, b_mn=True)
+            grads[fo + 4] = wgrad(dXf1b, rec["a"])
+            dq = torch.empty(Mf, HD, dtype=bf16, device=dev)
+            dkv = torch.empty(Mt, 2 * HD, dtype=bf16, device=dev)
+            dkvm = torch.zeros(Fn, 2 * HD, dtype=f32, device=dev)
+            K.slot_attn_bwd(rec["q"], rec["kv"], rec["kvm"], meta["slotmap"], seg, da, dq, dkv, dkvm, B=B, F=Fn, H=H, S=nseg,
+                            n_head=nenc, scale=scale)
+            wkvb, wqb = w_bf16(params[fo + 3]), w_bf16(params[fo + 2])
+            dhk = torch.empty(Mt, D, dtype=bf16, device=dev)
+            K.gemm(dkv, wkvb, dhk, b_mn=True)
+            K.gemm(dq, wqb, dhk[Mh:], b_mn=True, accumulate=True)
+            dWkv = wgrad(dkv, rec["hk"])
+            grads[fo + 2] = wgrad(dq, rec["hk"][Mh:])
+            # mask-embedding rows (batch-invariant keys/values)
+            dkvmb = K.cast_bf16(dkvm)
+            dhm = torch.empty(Fn, D, dtype=bf16, device=dev)
+            K.gemm(dkvmb, wkvb, dhm, b_mn=True)
+            wgrad(dkvmb, rec["hm"], out=dWkv, accumulate=True)
+            grads[fo + 3] = dWkv
+            dfn1, dfan = zeros(D), zeros(D)
+            dme_i = torch.empty(Fn, D, dtype=f32, device=dev)
+            K.layernorm_bwd(dhm, params[0].detach()[0].contiguous(), fn1, rec["stM"], dme_i, dfn1, g2=fan, dg2=dfan)
+            K.add_inplace(dme, dme_i)
+            dXin = torch.empty(Mt, D, dtype=f32, device=dev)
+            K.layernorm_bwd(dhk, X, fn1, rec["stA"], dXin, dfn1, g2=fan, dres=dZ, dg2=dfan)
+            grads[fo], grads[fo + 1] = dfn1, dfan
+            dX = dXin
+        if fusion:
+            grads[0] = dme.view(1, Fn, D)
+        ctx.saved = None
+        return (None, dX) + tuple(grads)

@@ -48,7 +48,7 @@ def reset_launch_count():
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, residual2=None, res_split=0,
          res_row_map=None, res_period=0, out_period=0, out_batch_rows=0, split_k=1, alpha=1.0, out2=None, block_n=0,
-         M=None, N=None, K=None):
+         accumulate=False, M=None, N=None, K=None):
     """out[M,N] = epilogue(alpha * A . B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn),
     both bf16 row-major 2-D.  act=2 (GEGLU): b is [2*Ipad, K] and N = Ipad."""
     assert a.dtype == bf16 and b.dtype == bf16
@@ -85,6 +85,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, 
     args.res_period, args.out_period, args.out_batch_rows = res_period, out_period, out_batch_rows
     args.block_n = block_n
     args.alpha = alpha
+    args.accumulate = int(accumulate)
     args.out2 = _p(out2)
     args.ldo2 = _ld(out2) if out2 is not None else 0
     if out2 is not None:

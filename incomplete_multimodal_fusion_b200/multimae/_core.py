@@ -1,0 +1,290 @@
+"""Shared implementation of the two MultiMAE variants the reference trains:
+`multimae.py` (plain zorro encoder) and `multimae_crossattn.py` (+ per-layer modality attention,
++ three per-modality return tokens).  Same constructor, `forward` signature, return tuples and
+state_dict as the reference; the compute is the fused sm_100a path:
+
+  masks (reference RNG call order kept verbatim) -> visible-patch embed GEMM -> EncoderStackFn
+  -> final norm -> pooling head (one pool-attention launch for all return tokens) -> decoders.
+
+Deliberate, documented differences from the reference:
+  * always runs with CUDA-autocast(bf16) numerics (fp32 residual stream / norms / softmax stats,
+    bf16 tensor-core operands), whatever the ambient autocast state; CPU tensors raise;
+  * requires sum of visible tokens == num_encoded_tokens (the reference silently mis-slices
+    otherwise, Appendix C) and raises instead;
+  * explicit `task_masks` use a stable argsort (the reference's CUDA argsort tie order is undefined).
+"""
+import itertools
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+from torch.distributions.dirichlet import Dirichlet
+
+from .. import functions as Fn
+from .multimae_utils import trunc_normal_
+from .zorro_utils import Attention, Block, Block_Fusion, LayerNorm, Mlp, TokenTypes, ZorroMask, block_params
+
+MODALITIES = ('s1', 's2', 'dem')   # hard-coded token order of the reference (multimae.py:378-407)
+
+
+class MultiMAEBase(nn.Module):
+    FUSION_BLOCKS = False
+
+    def __init__(self, input_adapters: Dict[str, nn.Module], output_adapters: Optional[Dict[str, nn.Module]],
+                 num_global_tokens: int = 1, dim_tokens: int = 768, depth: int = 12, dim_head: int = 64, heads: int = 8,
+                 ff_mult: int = 4, num_fusion_tokens: int = 16,
+                 return_token_types: Tuple[TokenTypes] = (TokenTypes.S1, TokenTypes.S2, TokenTypes.DEM, TokenTypes.FUSION),
+                 drop_path_rate: float = 0.0, norm_layer: nn.Module = LayerNorm):
+        super().__init__()
+        if drop_path_rate != 0.0:
+            raise NotImplementedError("stochastic depth is not built (rate 0 in every reference script)")
+        for adapter in input_adapters.values():
+            adapter.init(dim_tokens=dim_tokens)
+        self.input_adapters = nn.ModuleDict(input_adapters)
+        if output_adapters is not None:
+            for adapter in output_adapters.values():
+                adapter.init(dim_tokens_enc=dim_tokens)
+            self.output_adapters = nn.ModuleDict(output_adapters)
+        else:
+            self.output_adapters = None
+        assert num_fusion_tokens == input_adapters['s1'].num_patches
+
+        self.dim_tokens, self.depth, self.heads, self.dim_head, self.ff_mult = dim_tokens, depth, heads, dim_head, ff_mult
+        self.max_return_tokens = len(return_token_types)
+        self.return_token_types = return_token_types
+        self.register_buffer('return_token_types_tensor', torch.tensor([t.value for t in return_token_types]), persistent=False)
+
+        self.return_tokens = nn.Parameter(torch.randn(1, self.max_return_tokens, dim_tokens))
+        trunc_normal_(self.return_tokens, std=0.02)
+        self.attn_pool = Attention(dim=dim_tokens, dim_head=dim_head, heads=heads)
+        self.fusion_tokens = nn.Parameter(torch.randn(1, num_fusion_tokens, dim_tokens))
+        trunc_normal_(self.fusion_tokens, std=0.02)
+        if self.FUSION_BLOCKS:
+            self.return_token_s1 = nn.Parameter(torch.randn(1, 1, dim_tokens))
+            self.return_token_s2 = nn.Parameter(torch.randn(1, 1, dim_tokens))
+            self.return_token_dem = nn.Parameter(torch.randn(1, 1, dim_tokens))
+        self.mlp = Mlp(in_features=dim_tokens, hidden_features=int(dim_tokens * 4.0))
+        if self.FUSION_BLOCKS:
+            self.fus_blocks = nn.ModuleList([Block_Fusion(dim=dim_tokens, dim_head=dim_head, heads=heads, ff_mult=ff_mult,
+                                                          norm_layer=norm_layer) for _ in range(depth)])
+            self.mask_embedding = nn.Parameter(torch.zeros(1, num_fusion_tokens, dim_tokens))
+        self.blocks = nn.ModuleList([Block(dim=dim_tokens, dim_head=dim_head, heads=heads, ff_mult=ff_mult, drop_path=0.,
+                                           norm_layer=norm_layer) for _ in range(depth)])
+        self.norm = LayerNorm(dim_tokens)
+        self._init_parameters()
+
+    # ---- initialisation: multimae.py:116-142 ----
+    def _init_parameters(self):
+        for name, m in self.named_modules():
+            if isinstance(m, nn.Linear):
+                fan_out, fan_in = m.weight.shape
+                if 'qkv' in name:
+                    fan_out //= 3
+                elif 'kv' in name:
+                    fan_out //= 2
+                bound = math.sqrt(6. / float(fan_out + fan_in))
+                nn.init.uniform_(m.weight, -bound, bound)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+            elif isinstance(m, nn.Conv2d) and '.proj' in name:
+                w = m.weight.data
+                nn.init.xavier_uniform_(w.view([w.shape[0], -1]))
+
+    def get_num_layers(self):
+        return len(self.blocks)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        skip = {'global_tokens'}
+        for group, adapters in (('input_adapters', self.input_adapters), ('output_adapters', self.output_adapters or {})):
+            for task, adapter in adapters.items():
+                if hasattr(adapter, 'no_weight_decay'):
+                    skip |= {f'{group}.{task}.{name}' for name in adapter.no_weight_decay()}
+        return skip
+
+    # ---- mask sampling: same torch RNG calls, in the same order, as multimae.py:165-255 ----
+    def sample_alphas(self, B: int, n_tasks: int, alphas: float = 1.0, eps: float = 1e-5):
+        choices = torch.Tensor([list(c) for c in itertools.product([0, 1], repeat=n_tasks)][1:])
+        picked = torch.index_select(choices, 0, torch.randint(0, len(choices), (B,)))
+        return picked * torch.tensor(alphas) + eps
+
+    def generate_random_masks(self, input_tokens: Dict[str, torch.Tensor], num_encoded_tokens: int,
+                              alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False):
+        """One mask for the whole batch (the reference's edit of MultiMAE's per-sample masking).  Returns
+        (task_masks {task: [B, n] int64, 0 = keep}, ids_keep [B, nenc], ids_restore [B, sum n])."""
+        first = next(iter(input_tokens.values()))
+        B, device = first.shape[0], first.device
+        sizes = [t.shape[1] for t in input_tokens.values()]
+        alphas = [alphas] * len(sizes) if isinstance(alphas, float) else alphas
+        if sample_tasks_uniformly:
+            share = Dirichlet(self.sample_alphas(1, len(sizes), alphas=alphas)).sample().to(device)
+        else:
+            share = Dirichlet(torch.Tensor(alphas)).sample((1,)).to(device)
+        want = (share * num_encoded_tokens).round().long()
+        per_task = []
+        for i, n in enumerate(sizes):
+            order = torch.argsort(torch.rand(1, n, device=device), dim=1)
+            rank = torch.gather(torch.arange(n, device=device).unsqueeze(0), 1, order)
+            per_task.append(torch.where(rank < want[:, i].unsqueeze(1), 0, 1))
+        flat = torch.cat(per_task, dim=1)
+        ids_shuffle = torch.argsort(flat + torch.rand_like(flat.float()), dim=1)
+        ids_restore = torch.argsort(ids_shuffle, dim=1)
+        ids_keep = ids_shuffle[:, :num_encoded_tokens]
+        flat = torch.ones_like(flat)
+        flat[:, :num_encoded_tokens] = 0
+        flat = torch.gather(flat, 1, ids_restore)
+        masks = {t: m.repeat(B, 1) for t, m in zip(input_tokens.keys(), torch.split(flat, sizes, dim=1))}
+        return masks, ids_keep.repeat(B, 1), ids_restore.repeat(B, 1)
+
+    @staticmethod
+    def make_mask(N_H, N_W, xy_idxs, full_tasks=[], indicate_visible=True, flatten=True, device='cuda'):
+        """masks from lists of visible (x, y) patch coordinates (multimae.py:257-285)"""
+        masks = {}
+        for k, pts in xy_idxs.items():
+            m = torch.ones(N_H, N_W, device=device)
+            pts = torch.LongTensor(pts)
+            if len(pts) > 0:
+                m[pts[:, 1], pts[:, 0]] = 0
+            masks[k] = m
+        for task in full_tasks:
+            masks[task][:] = 0
+        if not indicate_visible:
+            masks = {k: 1 - v for k, v in masks.items()}
+        if flatten:
+            masks = {k: v.flatten().unsqueeze(0) for k, v in masks.items()}
+        return masks
+
+    def generate_input_info(self, input_task_tokens, image_size):
+        info = OrderedDict()
+        info['tasks'] = {}
+        start = 0
+        for domain, tensor in input_task_tokens.items():
+            n = tensor.shape[1]
+            info['tasks'][domain] = {'num_tokens': n, 'has_2d_posemb': True, 'start_idx': start, 'end_idx': start + n}
+            start += n
+        info['image_size'] = image_size
+        info['num_task_tokens'] = start
+        return info
+
+    # ---- forward ----
+    def forward(self, x: Union[Dict[str, torch.Tensor], torch.Tensor], mask_inputs: bool = True,
+                task_masks: Dict[str, torch.Tensor] = None, num_encoded_tokens: int = 128,
+                alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False,
+                fp32_output_adapters: List[str] = [], return_token_indices: Optional[Tuple[int]] = None):
+        x = {'s1': x} if isinstance(x, torch.Tensor) else x
+        B, _, H, W = x['s1'].shape
+        device = x['s1'].device
+        if device.type != 'cuda':
+            raise RuntimeError("incomplete_multimodal_fusion_b200.MultiMAE runs on CUDA only (no CPU fallback)")
+        for t in MODALITIES:
+            if t not in x or t not in self.input_adapters:
+                raise KeyError(f"input '{t}' is required (the reference hard-codes s1/s2/dem, multimae.py:378-383)")
+        D, Hh = self.dim_tokens, self.heads
+        tasks = [t for t in x if t in self.input_adapters]
+        grids = {t: self.input_adapters[t].grid(H, W) for t in tasks}
+        Fn_tok = self.fusion_tokens.shape[1]
+        # shape carriers: the mask sampler only looks at .shape[0], .shape[1] and .device
+        carriers = OrderedDict((t, torch.empty(B, grids[t][0] * grids[t][1], 0, device=device)) for t in tasks)
+        input_info = self.generate_input_info(carriers, image_size=(H, W))
+        nenc = num_encoded_tokens if mask_inputs else sum(c.shape[1] for c in carriers.values())
+
+        if task_masks is None:
+            task_masks, ids_keep, ids_restore = self.generate_random_masks(
+                carriers, nenc, alphas=alphas, sample_tasks_uniformly=sample_tasks_uniformly)
+        else:
+            flat = torch.cat([task_masks[t] for t in tasks], dim=1)
+            ids_shuffle = torch.argsort(flat, dim=1, stable=True)
+            ids_restore = torch.argsort(ids_shuffle, dim=1, stable=True)
+            ids_keep = ids_shuffle[:, :int((flat == 0).sum())]
+
+        idx = [(task_masks[t][0] == 0).nonzero(as_tuple=True)[0].to(torch.int32) for t in MODALITIES]
+        counts = [int(i.numel()) for i in idx]
+        if sum(counts) != nenc:
+            raise ValueError(f"num_encoded_tokens={nenc} but the masks keep {sum(counts)} tokens; pass the true count "
+                             "(the reference mis-slices silently in this case)")
+        zmask = ZorroMask(counts, Fn_tok, device)
+
+        # ---- tokens: visible-patch embedding + fusion tokens, planar layout ----
+        mod_args = []
+        for t in MODALITIES:
+            ad = self.input_adapters[t]
+            mod_args += [x[t].float(), ad.proj.weight, ad.proj.bias]
+        fus_ad = self.input_adapters['fusion']
+        meta_e = dict(B=B, D=D, P=self.input_adapters['s1'].P_H, F=Fn_tok, nenc=nenc, idx=idx,
+                      pos=[self.input_adapters[t].pos_table(*grids[t]) for t in MODALITIES],
+                      pos_fusion=fus_ad.pos_table(H // fus_ad.P_H, W // fus_ad.P_W))
+        X = Fn.EmbedFn.apply(meta_e, self.fusion_tokens, *mod_args)
+
+        # ---- encoder stack ----
+        slotmap = None
+        if self.FUSION_BLOCKS:
+            slotmap = torch.full((len(MODALITIES), Fn_tok), -1, dtype=torch.int32, device=device)
+            for m, ix in enumerate(idx):
+                slotmap[m, ix.long()] = torch.arange(ix.numel(), dtype=torch.int32, device=device)
+        meta = dict(B=B, D=D, H=Hh, F=Fn_tok, nenc=nenc, fusion=self.FUSION_BLOCKS, depth=self.depth,
+                    I=int(D * self.ff_mult * 2 / 3), seg=zmask.seg, nseg=zmask.nseg, slotmap=slotmap)
+        params = []
+        if self.FUSION_BLOCKS:
+            params.append(self.mask_embedding)
+            for fus, blk in zip(self.fus_blocks, self.blocks):
+                params += block_params(fus) + block_params(blk)
+        else:
+            for blk in self.blocks:
+                params += block_params(blk)
+        X = Fn.EncoderStackFn.apply(meta, X, *params)
+        Mh = B * nenc
+        T = Fn.layer_norm(X, self.norm.gamma, None, 1e-5, out_bf16=False)           # final norm, fp32 (multimae.py:431)
+        ori_tokens = T[:Mh].view(B, nenc, D)
+        enc_fusion = T[Mh:].view(B, Fn_tok, D)
+
+        # ---- pooling head: all return tokens in one pool-attention launch ----
+        rt = self.return_tokens
+        rtypes = self.return_token_types_tensor
+        if return_token_indices is not None:
+            assert len(set(return_token_indices)) == len(return_token_indices), 'all indices must be unique'
+            assert all(i < self.max_return_tokens for i in return_token_indices), \
+                'indices must range from 0 to max_num_return_tokens - 1'
+            sel = torch.tensor(return_token_indices, dtype=torch.long, device=device)
+            rt, rtypes = rt[:, sel], rtypes[sel]
+        R = rt.shape[1]
+        queries = [rt[0]]
+        if self.FUSION_BLOCKS:
+            queries += [self.return_token_s1[0], self.return_token_s2[0], self.return_token_dem[0]]
+        queries = torch.cat(queries, 0)
+        Rt = queries.shape[0]
+        N = nenc + Fn_tok
+        types = torch.repeat_interleave(torch.arange(4, device=device), torch.tensor(counts + [Fn_tok], device=device))
+        pmask = torch.zeros(Rt, N, dtype=torch.uint8, device=device)
+        pmask[:R] = ((rtypes[:, None] == types[None, :]) | (rtypes[:, None] == TokenTypes.FUSION.value)).to(torch.uint8)
+        mode = torch.zeros(Rt, dtype=torch.int32, device=device)
+        if self.FUSION_BLOCKS:
+            for j, ix in enumerate(idx):           # per-modality pools over the fusion tokens at that modality's
+                pmask[R + j, nenc + ix.long()] = 1  # visible positions (multimae_crossattn.py:529-543)
+            mode[R:] = 1                            # empty context -> zeros, not the uniform fallback
+        ap = self.attn_pool
+        qn = Fn.layer_norm(queries.float(), ap.norm.gamma, None, 1e-5, out_bf16=True)
+        q = Fn.linear(qn, ap.to_q.weight)
+        kv = Fn.linear(T, ap.to_kv.weight)
+        pooled = Fn.PoolAttnFn.apply(q, kv, pmask, mode, B, Hh, N, nenc, ap.scale)
+        r = Fn.linear(pooled.view(B * Rt, Hh * 64), ap.to_out.weight)
+        rn = Fn.layer_norm(r.float(), self.norm.gamma, None, 1e-5, out_bf16=True)
+        r = (r + self.mlp(rn)).view(B, Rt, D)
+        return_tokens = r[:, :R]
+
+        if self.output_adapters is None:
+            tokens = torch.cat([ori_tokens, enc_fusion], dim=1)
+            return tokens, return_tokens, task_masks
+
+        preds = {}
+        for domain, adapter in self.output_adapters.items():
+            p = adapter(encoder_tokens=enc_fusion, input_info=input_info, ids_keep=ids_keep, ids_restore=ids_restore)
+            preds[domain] = p.float() if domain in fp32_output_adapters else p
+        out = (preds, task_masks, return_tokens, ori_tokens, enc_fusion)
+        if self.FUSION_BLOCKS:
+            out = out + (r[:, R:R + 1], r[:, R + 1:R + 2], r[:, R + 2:R + 3])
+        return out
