@@ -10,6 +10,7 @@ autograd node, `EncoderStackFn`, with a hand-ordered backward: it keeps the toke
 planar layout (all modality tokens of the batch, then all fusion tokens), never re-materialises the
 concatenated tensor between blocks, and accumulates the residual-stream gradient in place.
 """
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -28,16 +29,23 @@ def _pad64(n: int) -> int:
 # parameter's version counter so they are rebuilt once per optimizer step, not once per use
 # ------------------------------------------------------------------------------------------------
 class _WeightCache:
+    """key -> (weak refs to the source parameters, their versions, bf16 image).  Entries are validated by
+    object identity through the weak refs: `id()` values are recycled once a model is garbage collected."""
+
     def __init__(self):
         self._store = {}
 
     def get(self, key, params: Sequence[torch.Tensor], build):
-        ver = tuple((p.data_ptr(), p._version) for p in params)
         hit = self._store.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
+        if hit is not None:
+            refs, vers, val = hit
+            if len(refs) == len(params) and all(r() is p for r, p in zip(refs, params)) and \
+                    vers == tuple((p.data_ptr(), p._version) for p in params):
+                return val
         val = build()
-        self._store[key] = (ver, val)
+        if len(self._store) > 4096:
+            self._store = {k: v for k, v in self._store.items() if all(r() is not None for r in v[0])}
+        self._store[key] = (tuple(weakref.ref(p) for p in params), tuple((p.data_ptr(), p._version) for p in params), val)
         return val
 
     def clear(self):

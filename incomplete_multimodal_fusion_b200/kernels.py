@@ -37,6 +37,17 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
+# Optional per-launch timing of the GEMM kernel (bench.py's roofline leg): a list of
+# (start_event, end_event, flops, kind) appended around every mmf_gemm_bf16 launch while enabled.
+GEMM_TIMING = None
+
+
+def enable_gemm_timing(flag: bool = True):
+    global GEMM_TIMING
+    GEMM_TIMING = [] if flag else None
+    return GEMM_TIMING
+
+
 def launch_count() -> int:
     return int(_L().mmf_launch_count())
 
@@ -90,7 +101,15 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, 
     args.ldo2 = _ld(out2) if out2 is not None else 0
     if out2 is not None:
         assert out2.dtype == bf16
+    if GEMM_TIMING is None:
+        check(_L().mmf_gemm_bf16(C.byref(args), _stream()), "mmf_gemm_bf16")
+        return out
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(_L().mmf_gemm_bf16(C.byref(args), _stream()), "mmf_gemm_bf16")
+    e1.record()
+    n_eff = 2 * N if act == 2 else N
+    GEMM_TIMING.append((e0, e1, 2.0 * M * n_eff * K, "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")))
     return out
 
 

@@ -334,7 +334,12 @@ def test_masked_loss(kind, pdt):
             (ref * 1.7).backward()
             dpred = torch.empty_like(pred.detach())
             K().masked_loss_bwd(pred.detach(), tgt, m, P, kind, work, torch.tensor([1.7], device="cuda"), dpred)
-            assert rel(dpred, pred.grad) < (1e-5 if pdt == f32 else 6e-3)
+            # a sample whose mask is all zero is 0/0 in the reference: nanmean drops it from the loss but
+            # autograd still sends NaN (0 * inf) to its pixels; the kernel sends 0.  Compare the other samples.
+            keep = torch.ones(B, dtype=torch.bool, device="cuda") if m is None else m.sum(1) > 0
+            if (~keep).any():
+                assert float(dpred[~keep].float().abs().max()) == 0.0
+            assert rel(dpred[keep], pred.grad[keep]) < (1e-5 if pdt == f32 else 6e-3)
 
 
 def test_elementwise():
