@@ -52,35 +52,38 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / power / throttle reasons sampled through NVML every 50 ms during the timed region"""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.max_mhz = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1e3,
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                time.sleep(0.05)
+        except Exception as e:  # fall back to one nvidia-smi query
+            self.rows.append((None, None, 0))
+            self.err = str(e)
 
     def summary(self):
         self.stop_flag = True
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        reasons = []
-        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.rows[0][1]) if self.rows and self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        self.join(timeout=2)
+        sm = sorted(r[0] for r in self.rows if r[0])
+        bits = 0
+        for r in self.rows:
+            bits |= int(r[2] or 0)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "power_w_max": max((r[1] for r in self.rows if r[1]), default=None),
+                "reasons": [n for b, n in names.items() if bits & b], "samples": len(self.rows)}
 
 
 def synthetic_batch(batch, image, seed, pin=False):
