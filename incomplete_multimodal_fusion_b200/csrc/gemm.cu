@@ -11,6 +11,7 @@
 #include "mmf_b200.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace mmf {
@@ -30,7 +31,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;  // 4 @256, 6 @128
   static constexpr int TMEM_COLS = 2 * BLOCK_N;             // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
 };
 
 struct GemmParams {
@@ -43,75 +44,165 @@ struct GemmParams {
   const int32_t* res_row_map;
   int64_t M, N, K;
   int64_t ldo, ldo2, ldr;
-  int32_t out_f32, act, split_k, res_period, out_period, out_batch_rows, accumulate;
+  int32_t out_f32, act, split_k, res_period, out_period, out_batch_rows, accumulate, a_mn, b_mn;
   int32_t m_tiles, n_tiles, num_kb, kb_per_split;
   int64_t geglu_ipad;  // act==2: row offset of the gate half inside B
   float alpha;
+  int32_t fast_ok;  // all pitches / pointers allow the vectorised epilogue
+  int32_t dbg;  // MMF_GEMM_DEBUG (profiling experiments only): 1 = no global I/O in the epilogue, 2 = also no staging, 3 = no tcgen05.ld
 };
 
-__device__ __forceinline__ void store_row32(const GemmParams& p, int64_t orow, int64_t col0, const float (&v)[32],
-                                            int ncols_valid) {
-  // 32 consecutive output columns of one row, starting at col0 (multiple of 32)
-  if (p.split_k > 1 || (p.accumulate && p.out_f32)) {
-    float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)(v & 0xffffffffu), src);
+  const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)((uint64_t)v >> 32), src);
+  return (int64_t)(((uint64_t)hi << 32) | lo);
+}
+
+// Epilogue kinds (compile-time: the four epilogue warps are instruction-issue bound, so each kind gets a lean
+// instruction stream instead of one generic, branchy one that overflows the instruction cache).
+enum : int {
+  EPI_BF16 = 0,     // out bf16 = alpha*acc (+bias)
+  EPI_GELU = 1,     // out bf16 = gelu(alpha*acc + bias), out2 (optional) = pre-activation bf16
+  EPI_F32 = 2,      // out f32 = alpha*acc (+bias) (+residual), out2 (optional) = bf16 copy
+  EPI_ATOMIC = 3,   // out f32 += alpha*acc   (split-K / accumulate)
+  EPI_GEGLU = 4,    // out bf16 = gelu(gate)*value, out2 (optional) = [value | gate] bf16
+  EPI_BF16_ACC = 5  // out bf16 += alpha*acc
+};
+
+constexpr int STG_LD = 36;  // row pitch (floats) of the per-warp 32x32 staging block: 16-byte aligned rows; the
+                            // row-per-lane 128-bit writes and the row-contiguous 128-bit reads are both conflict free
+
+__device__ __forceinline__ float4 gelu4(float4 x) { return make_float4(gelu_erf(x.x), gelu_erf(x.y), gelu_erf(x.z), gelu_erf(x.w)); }
+__device__ __forceinline__ uint2 pack4(float4 x) { return make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w)); }
+
+// The accumulator arrives "one row per lane" (tcgen05.ld 32x32b).  Global accesses in that shape touch 32 different
+// rows per instruction, so each warp transposes its 32x32 block through shared memory; afterwards lane l owns the 4
+// columns 4*(l%8).. of rows 4*i + l/8 (i = 0..7): 8 lanes x 16 B cover one 128-byte row segment.
+__device__ __forceinline__ void stage_raw(float* stg, const uint32_t (&raw)[32], int lane) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols_valid) atomicAdd(o + j, v[j]);
-    return;
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(stg + lane * STG_LD + 4 * j) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+  __syncwarp();
+}
+
+// one full, aligned 32-column chunk
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, const uint32_t (&raw)[32], int lane,
+                                          const int64_t (&orow_i)[8], const float* const (&res_i)[8], int64_t col0) {
+  const int c = (lane & 7) * 4;
+  float4 resv[8];
+  const bool has_res = (EPI == EPI_F32) && p.residual != nullptr;
+  if (has_res) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (orow_i[i] >= 0) resv[i] = __ldg(reinterpret_cast<const float4*>(res_i[i] + col0 + c));
   }
-  if (p.out_f32) {
-    float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
-    if (ncols_valid == 32 && (p.ldo & 3) == 0) {
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI != EPI_ATOMIC && EPI != EPI_BF16_ACC && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));
+  stage_raw(stg, raw, lane);
+  const float alpha = p.alpha;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols_valid) o[j] = v[j];
+  for (int i = 0; i < 8; ++i) {
+    const int64_t orow = orow_i[i];
+    if (orow < 0) continue;
+    float4 x = *reinterpret_cast<const float4*>(stg + (i * 4 + (lane >> 3)) * STG_LD + c);
+    x.x = fmaf(x.x, alpha, b4.x); x.y = fmaf(x.y, alpha, b4.y); x.z = fmaf(x.z, alpha, b4.z); x.w = fmaf(x.w, alpha, b4.w);
+    if (EPI == EPI_GELU) {
+      if (p.out2) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0 + c) = pack4(x);
+      x = gelu4(x);
     }
-    if (p.out2) {
-      __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0;
-      if (ncols_valid == 32 && (p.ldo2 & 7) == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          reinterpret_cast<uint4*>(o2)[j] =
-              make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols_valid) o2[j] = __float2bfloat16(v[j]);
+    if (EPI == EPI_F32) {
+      if (has_res) { x.x += resv[i].x; x.y += resv[i].y; x.z += resv[i].z; x.w += resv[i].w; }
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col0 + c) = x;
+      if (p.out2) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0 + c) = pack4(x);
+    } else if (EPI == EPI_ATOMIC) {
+      float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0 + c;
+      atomicAdd(o, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w);
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0 + c;
+      if (EPI == EPI_BF16_ACC) {
+        const uint2 old = *reinterpret_cast<const uint2*>(o);
+        const float2 a = unpack_bf16(old.x), b = unpack_bf16(old.y);
+        x.x += a.x; x.y += a.y; x.z += b.x; x.w += b.y;
       }
+      *reinterpret_cast<uint2*>(o) = pack4(x);
     }
-  } else {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
-    if (p.accumulate) {  // out += result (each element owned by exactly one thread)
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void epi_chunk_geglu(const GemmParams& p, float* stg, const uint32_t (&raw)[32],
+                                                const uint32_t (&rawg)[32], int lane, const int64_t (&orow_i)[8], int64_t col0) {
+  const int c = (lane & 7) * 4;
+  float4 val[8];
+  stage_raw(stg, raw, lane);
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols_valid) o[j] = __float2bfloat16(__bfloat162float(o[j]) + v[j]);
-      return;
+  for (int i = 0; i < 8; ++i) val[i] = *reinterpret_cast<const float4*>(stg + (i * 4 + (lane >> 3)) * STG_LD + c);
+  __syncwarp();
+  stage_raw(stg, rawg, lane);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t orow = orow_i[i];
+    if (orow < 0) continue;
+    const float4 g = *reinterpret_cast<const float4*>(stg + (i * 4 + (lane >> 3)) * STG_LD + c);
+    if (p.out2) {
+      __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0 + c;
+      *reinterpret_cast<uint2*>(u) = pack4(val[i]);
+      *reinterpret_cast<uint2*>(u + p.geglu_ipad) = pack4(g);
     }
-    if (ncols_valid == 32 && (p.ldo & 7) == 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        reinterpret_cast<uint4*>(o)[j] =
-            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    const float4 ge = gelu4(g);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0 + c) =
+        pack4(make_float4(ge.x * val[i].x, ge.y * val[i].y, ge.z * val[i].z, ge.w * val[i].w));
+  }
+  __syncwarp();
+}
+
+// ragged / unaligned chunk: row-per-lane scalar code, deliberately compact (runs only on the last column tile of
+// odd-sized problems); `g` is the gate accumulator in GEGLU mode
+template <int EPI>
+__device__ __noinline__ void epi_chunk_slow(const GemmParams& p, const uint32_t (&raw)[32], const uint32_t (&rawg)[32],
+                                            int64_t orow, const float* res_row, int64_t col0, int nvalid) {
+  if (orow < 0) return;
+#pragma unroll 1
+  for (int j = 0; j < nvalid; ++j) {
+    float x = __uint_as_float(raw[j]) * p.alpha;
+    const int64_t col = col0 + j;
+    if (EPI == EPI_GEGLU) {
+      const float g = __uint_as_float(rawg[j]);
+      if (p.out2) {
+        __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col;
+        u[0] = __float2bfloat16(x);
+        u[p.geglu_ipad] = __float2bfloat16(g);
+      }
+      reinterpret_cast<__nv_bfloat16*>(p.out)[orow * p.ldo + col] = __float2bfloat16(gelu_erf(g) * x);
+      continue;
+    }
+    if (EPI != EPI_ATOMIC && EPI != EPI_BF16_ACC && p.bias != nullptr) x += __ldg(p.bias + col);
+    if (EPI == EPI_GELU) {
+      if (p.out2) reinterpret_cast<__nv_bfloat16*>(p.out2)[orow * p.ldo2 + col] = __float2bfloat16(x);
+      x = gelu_erf(x);
+    }
+    if (EPI == EPI_F32) {
+      if (res_row != nullptr) x += __ldg(res_row + col);
+      reinterpret_cast<float*>(p.out)[orow * p.ldo + col] = x;
+      if (p.out2) reinterpret_cast<__nv_bfloat16*>(p.out2)[orow * p.ldo2 + col] = __float2bfloat16(x);
+    } else if (EPI == EPI_ATOMIC) {
+      atomicAdd(reinterpret_cast<float*>(p.out) + orow * p.ldo + col, x);
     } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols_valid) o[j] = __float2bfloat16(v[j]);
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col;
+      if (EPI == EPI_BF16_ACC) x += __bfloat162float(*o);
+      *o = __float2bfloat16(x);
     }
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr bool geglu = (EPI == EPI_GEGLU);
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -123,13 +214,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* stage_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool geglu = (p.act == 2);
   // in GEGLU mode one 256-wide MMA tile yields 128 output columns (value | gate halves)
-  const int out_cols_per_tile = geglu ? BLOCK_N / 2 : BLOCK_N;
-  const int total_work = p.m_tiles * p.n_tiles * p.split_k;
+  constexpr int out_cols_per_tile = geglu ? BLOCK_N / 2 : BLOCK_N;
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int total_work = tiles_mn * p.split_k;
+  const bool a_mn = p.a_mn != 0, b_mn = p.b_mn != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -162,8 +255,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int tile = w % (p.m_tiles * p.n_tiles);
-        const int split = w / (p.m_tiles * p.n_tiles);
+        const int tile = w % tiles_mn;
+        const int split = w / tiles_mn;
         const int m0 = (tile / p.n_tiles) * BLOCK_M;
         const int n0 = (tile % p.n_tiles) * out_cols_per_tile;
         const int kb0 = split * p.kb_per_split;
@@ -174,20 +267,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
           const int k0 = kb * BLOCK_K;
-          if (!A_MN) {
+          if (!a_mn) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j)  // box {64 m, 64 k}
               tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + j * 64, k0);
           }
-          if (!B_MN) {
-            if (!geglu) {
-              tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);  // box {64 k, BLOCK_N rows}
-            } else {  // box {64 k, BLOCK_N/2 rows} twice: value rows then gate rows
-              tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
-              tma_load_2d(sb + Cfg::B_BYTES / 2, &tmap_b, &full_bar[stage], k0, (int)p.geglu_ipad + n0);
-            }
+          if (geglu) {  // box {64 k, BLOCK_N/2 rows} twice: value rows then gate rows
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+            tma_load_2d(sb + Cfg::B_BYTES / 2, &tmap_b, &full_bar[stage], k0, (int)p.geglu_ipad + n0);
+          } else if (!b_mn) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);  // box {64 k, BLOCK_N rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 64; ++j)  // box {64 n, 64 k}
@@ -200,13 +291,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, a_mn, b_mn);
+      // K-major: advance 16 elements = 32 B inside the swizzle atom; SBO = 1024 B (8 rows x 128 B).
+      // MN-major: advance 16 k-rows = 2048 B; LBO = 8192 B (next 64-wide MN atom), SBO = 1024 B.
+      const uint32_t a_step = a_mn ? 2048 : 32, a_lbo = a_mn ? 8192 : 16;
+      const uint32_t b_step = b_mn ? 2048 : 32, b_lbo = b_mn ? 8192 : 16;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int split = w / (p.m_tiles * p.n_tiles);
+        const int split = w / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -219,10 +314,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // K-major: advance 16 elements = 32 B inside the swizzle atom; SBO = 1024 B (8 rows x 128 B).
-            // MN-major: advance 16 k-rows = 2048 B; LBO = 8192 B (next 64-wide MN atom), SBO = 1024 B.
-            const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, 8192, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
+            const uint64_t da = umma_smem_desc(sa + k * a_step, a_lbo, 1024);
+            const uint64_t db = umma_smem_desc(sb + k * b_step, b_lbo, 1024);
             umma_bf16(tmem_d, da, db, idesc, (kb > kb0) || (k > 0));
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
@@ -235,20 +328,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    float* stg = stage_all + (warp - 2) * 32 * STG_LD;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const int tile = w % (p.m_tiles * p.n_tiles);
+      const int tile = w % tiles_mn;
       const int m0 = (tile / p.n_tiles) * BLOCK_M;
       const int n0 = (tile % p.n_tiles) * out_cols_per_tile;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
+      // row bookkeeping (independent of the accumulator: done before waiting for the MMA)
       const int64_t row = (int64_t)m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      int64_t orow = row;
-      if (p.out_period > 0) orow = (row / p.out_period) * p.out_batch_rows + (row % p.out_period);
+      int64_t orow = -1;  // -1 marks a row beyond M
+      if (row < p.M) orow = p.out_period > 0 ? (row / p.out_period) * p.out_batch_rows + (row % p.out_period) : row;
       const float* res_row = nullptr;
-      if (p.residual != nullptr && row_ok) {
+      if (EPI == EPI_F32 && p.residual != nullptr && row < p.M) {
         int64_t rr = row;
         if (p.res_period > 0) {
           rr = row % p.res_period;
@@ -256,9 +348,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         res_row = (p.residual2 && rr >= p.res_split) ? p.residual2 + (rr - p.res_split) * p.ldr : p.residual + rr * p.ldr;
       }
+      int64_t orow_i[8];
+      const float* res_i[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        orow_i[i] = shfl_i64(orow, r);
+        res_i[i] = (EPI == EPI_F32) ? reinterpret_cast<const float*>(shfl_i64(reinterpret_cast<int64_t>(res_row), r)) : nullptr;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
       uint32_t raw[32];
-      float v[32];
       if (!geglu) {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -266,39 +367,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (col0 >= p.N) break;  // warp-uniform
           tmem_ld_32x32(taddr + c * 32, raw);
           tmem_wait_ld();
-          if (row_ok) {
-            const int nvalid = (int)min((int64_t)32, p.N - col0);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(raw[j]) * p.alpha;
-              if (p.bias != nullptr && j < nvalid) x += __ldg(p.bias + col0 + j);
-              v[j] = x;
-            }
-            if (p.act == 1) {
-              if (p.out2 && !p.out_f32) {  // keep the pre-activation (bf16) for the backward
-                __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) o2[j] = __float2bfloat16(v[j]);
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-            }
-            if (res_row != nullptr) {
-              if (nvalid == 32 && (p.ldr & 3) == 0) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 r4 = __ldg(reinterpret_cast<const float4*>(res_row + col0) + j);
-                  v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) v[j] += __ldg(res_row + col0 + j);
-              }
-            }
-            store_row32(p, orow, col0, v, nvalid);
-          }
+          if (p.dbg >= 2) continue;
+          if (col0 + 32 <= p.N && p.fast_ok) epi_chunk<EPI>(p, stg, raw, lane, orow_i, res_i, col0);
+          else epi_chunk_slow<EPI>(p, raw, raw, orow, res_row, col0, (int)min((int64_t)32, p.N - col0));
         }
       } else {
         // GEGLU: accumulator columns [0, BLOCK_N/2) = value, [BLOCK_N/2, BLOCK_N) = gate of the same features
@@ -310,30 +381,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_32x32(taddr + c * 32, raw);
           tmem_ld_32x32(taddr + BLOCK_N / 2 + c * 32, rawg);
           tmem_wait_ld();
-          if (row_ok) {
-            const int nvalid = (int)min((int64_t)32, p.N - col0);
-            if (p.out2) {  // pre-activation u = [value | gate], bf16 [M, 2*ipad]
-              __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (8 * j < nvalid) {
-                  reinterpret_cast<uint4*>(u + col0)[j] = make_uint4(
-                      pack_bf16(__uint_as_float(raw[8 * j]), __uint_as_float(raw[8 * j + 1])),
-                      pack_bf16(__uint_as_float(raw[8 * j + 2]), __uint_as_float(raw[8 * j + 3])),
-                      pack_bf16(__uint_as_float(raw[8 * j + 4]), __uint_as_float(raw[8 * j + 5])),
-                      pack_bf16(__uint_as_float(raw[8 * j + 6]), __uint_as_float(raw[8 * j + 7])));
-                  reinterpret_cast<uint4*>(u + p.geglu_ipad + col0)[j] = make_uint4(
-                      pack_bf16(__uint_as_float(rawg[8 * j]), __uint_as_float(rawg[8 * j + 1])),
-                      pack_bf16(__uint_as_float(rawg[8 * j + 2]), __uint_as_float(rawg[8 * j + 3])),
-                      pack_bf16(__uint_as_float(rawg[8 * j + 4]), __uint_as_float(rawg[8 * j + 5])),
-                      pack_bf16(__uint_as_float(rawg[8 * j + 6]), __uint_as_float(rawg[8 * j + 7])));
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__uint_as_float(rawg[j])) * __uint_as_float(raw[j]);
-            store_row32(p, orow, col0, v, nvalid);
-          }
+          if (col0 + 32 <= p.N && p.fast_ok) epi_chunk_geglu(p, stg, raw, rawg, lane, orow_i, col0);
+          else epi_chunk_slow<EPI_GEGLU>(p, raw, rawg, orow, nullptr, col0, (int)min((int64_t)32, p.N - col0));
         }
       }
       // release the accumulator stage back to the MMA warp
@@ -398,10 +447,11 @@ static int num_sms() {
   return n;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, int EPI>
 static int launch_gemm(const MmfGemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   const bool geglu = a.act == 2;
+  const bool A_MN = a.a_mn != 0, B_MN = a.b_mn != 0;
   CUtensorMap ta, tb;
   int rc;
   if (!A_MN) rc = make_tmap(&ta, a.a, a.M, a.K, a.lda, BLOCK_K, BLOCK_M);
@@ -418,6 +468,7 @@ static int launch_gemm(const MmfGemmArgs& a, cudaStream_t stream) {
   p.out_f32 = a.out_f32; p.act = a.act; p.split_k = a.split_k < 1 ? 1 : a.split_k;
   p.res_period = a.res_period; p.out_period = a.out_period; p.out_batch_rows = a.out_batch_rows;
   p.accumulate = a.accumulate;
+  p.a_mn = a.a_mn; p.b_mn = a.b_mn;
   p.m_tiles = (int)ceil_div64(a.M, BLOCK_M);
   p.n_tiles = (int)ceil_div64(a.N, geglu ? BLOCK_N / 2 : BLOCK_N);
   p.num_kb = (int)ceil_div64(a.K, BLOCK_K);
@@ -426,9 +477,15 @@ static int launch_gemm(const MmfGemmArgs& a, cudaStream_t stream) {
   p.split_k = ceil_div(p.num_kb, p.kb_per_split);  // no empty splits
   p.geglu_ipad = a.N;
   p.alpha = a.alpha;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.fast_ok = (a.ldo % 4 == 0) && al16(a.out) && (!a.residual || (a.ldr % 4 == 0 && al16(a.residual))) &&
+              (!a.residual2 || al16(a.residual2)) && (!a.bias || al16(a.bias)) && (!a.out2 || (a.ldo2 % 4 == 0 && al16(a.out2))) &&
+              (a.act != 2 || a.N % 4 == 0);
+  static const int dbg_env = getenv("MMF_GEMM_DEBUG") ? atoi(getenv("MMF_GEMM_DEBUG")) : 0;
+  p.dbg = dbg_env;
 
   static bool attr_set = false;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
@@ -461,7 +518,6 @@ extern "C" int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream_) {
   if (a.act == 2 && (a.b_mn || a.out_f32 || a.bias || a.residual || (a.N & 7) || (a.out2 && (a.ldo2 & 7)) ||
                      (a.ldo & 7) || a.split_k > 1))
     MMF_BAD_ARG(10);
-  if (a.out2 && a.act == 0 && !a.out_f32) MMF_BAD_ARG(11);
   if (a.residual && a.ldr < a.N) MMF_BAD_ARG(12);
   if (a.out_period < 0 || a.res_period < 0) MMF_BAD_ARG(13);
   if (a.accumulate && (a.act == 2 || a.out2)) MMF_BAD_ARG(16);
@@ -476,15 +532,32 @@ extern "C" int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream_) {
   }
   if (bn != 128 && bn != 256) MMF_BAD_ARG(14);
   if (a.act == 2 && bn != 256) MMF_BAD_ARG(15);
-#define MMF_DISPATCH(BN)                                                         \
-  do {                                                                           \
-    if (!a.a_mn && !a.b_mn) return launch_gemm<BN, false, false>(a, stream);     \
-    if (!a.a_mn && a.b_mn) return launch_gemm<BN, false, true>(a, stream);       \
-    if (a.a_mn && !a.b_mn) return launch_gemm<BN, true, false>(a, stream);       \
-    return launch_gemm<BN, true, true>(a, stream);                               \
-  } while (0)
-  if (bn == 256) MMF_DISPATCH(256);
-  MMF_DISPATCH(128);
+  int epi;
+  if (a.act == 2) epi = EPI_GEGLU;
+  else if (a.split_k > 1 || (a.accumulate && a.out_f32)) epi = EPI_ATOMIC;
+  else if (a.accumulate) epi = EPI_BF16_ACC;
+  else if (a.out_f32) epi = EPI_F32;
+  else if (a.act == 1) epi = EPI_GELU;
+  else epi = EPI_BF16;
+  if (epi == EPI_F32 && a.act == 1) MMF_BAD_ARG(17);            // GELU is provided for bf16 outputs only
+  if (epi != EPI_F32 && a.residual) MMF_BAD_ARG(18);            // the residual is an fp32 stream
+  if ((epi == EPI_ATOMIC || epi == EPI_BF16_ACC) && a.bias) MMF_BAD_ARG(19);
+  if (epi == EPI_BF16 && a.out2) MMF_BAD_ARG(11);
+#define MMF_DISPATCH(BN)                                                              \
+  switch (epi) {                                                                      \
+    case EPI_BF16: return launch_gemm<BN, EPI_BF16>(a, stream);                       \
+    case EPI_GELU: return launch_gemm<BN, EPI_GELU>(a, stream);                       \
+    case EPI_F32: return launch_gemm<BN, EPI_F32>(a, stream);                         \
+    case EPI_ATOMIC: return launch_gemm<BN, EPI_ATOMIC>(a, stream);                   \
+    case EPI_BF16_ACC: return launch_gemm<BN, EPI_BF16_ACC>(a, stream);               \
+    default: break;                                                                   \
+  }
+  if (bn == 256) {
+    if (epi == EPI_GEGLU) return launch_gemm<256, EPI_GEGLU>(a, stream);
+    MMF_DISPATCH(256)
+  }
+  MMF_DISPATCH(128)
+  MMF_BAD_ARG(20);
 #undef MMF_DISPATCH
 }
 

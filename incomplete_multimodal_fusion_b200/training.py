@@ -55,7 +55,7 @@ class GradAllReduce:
         self.bucket_bytes = bucket_mb << 20
         self.group = group
         self.buckets = None
-        self.stream = torch.cuda.Stream()
+        self.stream = None
 
     def _build(self):
         live = [p for p in self.params if p.grad is not None]
@@ -78,14 +78,25 @@ class GradAllReduce:
         if self.buckets is None:
             self._build()
         world = dist.get_world_size(self.group)
+        on_gpu = self.flat[0].is_cuda if self.flat else False
+
+        def run():
+            for bucket, flat in zip(self.buckets, self.flat):
+                sizes = [p.numel() for p in bucket]
+                torch._foreach_copy_(list(flat.split(sizes)), [p.grad.reshape(-1) for p in bucket])
+                flat.div_(world)
+                dist.all_reduce(flat, group=self.group)
+                torch._foreach_copy_([p.grad.reshape(-1) for p in bucket], list(flat.split(sizes)))
+
+        if not on_gpu:      # gloo / CPU (tests): same bucketing, no streams
+            run()
+            return
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
-            for bucket, flat in zip(self.buckets, self.flat):
-                torch._foreach_copy_(list(flat.split([p.numel() for p in bucket])), [p.grad.reshape(-1) for p in bucket])
-                flat.div_(world)
-                dist.all_reduce(flat, group=self.group)
-                torch._foreach_copy_([p.grad.reshape(-1) for p in bucket], list(flat.split([p.numel() for p in bucket])))
+            run()
         cur.wait_stream(self.stream)
 
 
