@@ -156,15 +156,31 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
   const bool dbl = p.g2 != nullptr;
   __shared__ float4 g1[NC * 32], b1[NC * 32], g2[NC * 32];
   ln_stage_params(g1, b1, g2, p.g1, p.b1, p.g2, nchunk);
-  float4 adg1[LN_MAX_CHUNKS], adg2[LN_MAX_CHUNKS], adb1[LN_MAX_CHUNKS];
+  // Parameter-gradient accumulators live in shared memory, one private slice per warp (lane-contiguous float4s:
+  // conflict free, no synchronisation).  Keeping them in registers cost ~70 registers and capped the kernel at 8
+  // resident warps per SM, far too few loads in flight for an HBM-bound kernel.
+  extern __shared__ float4 ln_acc[];
+  float4* adg1 = ln_acc + (size_t)warp * NC * 32;
+  float4* adg2 = adg1 + (size_t)LN_WARPS * NC * 32;
+  float4* adb1 = adg1 + (size_t)(dbl ? 2 : 1) * LN_WARPS * NC * 32;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_CHUNKS; ++i) adg1[i] = adg2[i] = adb1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    adg1[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dbl) adg2[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.db1) adb1[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < p.rows; row += (int64_t)gridDim.x * LN_WARPS) {
     const float4 st = __ldg(reinterpret_cast<const float4*>(p.stats) + row);
     const float mean1 = st.x, rstd1 = st.y, mean2 = st.z, rstd2 = st.w;
     const float4* xr = reinterpret_cast<const float4*>(
         (p.x2 && row >= p.x_split) ? p.x2 + (row - p.x_split) * p.ldx : p.x + row * p.ldx);
-    float4 xh1[LN_MAX_CHUNKS], d[LN_MAX_CHUNKS];
+    float4 xh1[LN_MAX_CHUNKS], d[LN_MAX_CHUNKS], rs[LN_MAX_CHUNKS];
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {  // all global loads of the row are issued before any arithmetic
+      const int c = lane + 32 * i;
+      rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.dres && c < nchunk) rs[i] = reinterpret_cast<const float4*>(p.dres + row * p.lddres)[c];
+    }
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
       const int c = lane + 32 * i;
@@ -192,8 +208,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
         xh2[i].z = (xh1[i].z * g1[lane + 32 * i].z + b1[lane + 32 * i].z - mean2) * rstd2;
         xh2[i].w = (xh1[i].w * g1[lane + 32 * i].w + b1[lane + 32 * i].w - mean2) * rstd2;
         if (lane + 32 * i < nchunk) {
-          adg2[i].x += d[i].x * xh2[i].x; adg2[i].y += d[i].y * xh2[i].y;
-          adg2[i].z += d[i].z * xh2[i].z; adg2[i].w += d[i].w * xh2[i].w;
+          float4 t = adg2[lane + 32 * i];
+          t.x += d[i].x * xh2[i].x; t.y += d[i].y * xh2[i].y; t.z += d[i].z * xh2[i].z; t.w += d[i].w * xh2[i].w;
+          adg2[lane + 32 * i] = t;
           d[i].x *= g2[lane + 32 * i].x; d[i].y *= g2[lane + 32 * i].y; d[i].z *= g2[lane + 32 * i].z; d[i].w *= g2[lane + 32 * i].w;
           s1 += d[i].x + d[i].y + d[i].z + d[i].w;
           s2 += d[i].x * xh2[i].x + d[i].y * xh2[i].y + d[i].z * xh2[i].z + d[i].w * xh2[i].w;
@@ -214,9 +231,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
       if (lane + 32 * i < nchunk) {
-        adg1[i].x += d[i].x * xh1[i].x; adg1[i].y += d[i].y * xh1[i].y;
-        adg1[i].z += d[i].z * xh1[i].z; adg1[i].w += d[i].w * xh1[i].w;
-        adb1[i].x += d[i].x; adb1[i].y += d[i].y; adb1[i].z += d[i].z; adb1[i].w += d[i].w;
+        float4 t = adg1[lane + 32 * i];
+        t.x += d[i].x * xh1[i].x; t.y += d[i].y * xh1[i].y; t.z += d[i].z * xh1[i].z; t.w += d[i].w * xh1[i].w;
+        adg1[lane + 32 * i] = t;
+        if (p.db1) {
+          float4 u = adb1[lane + 32 * i];
+          u.x += d[i].x; u.y += d[i].y; u.z += d[i].z; u.w += d[i].w;
+          adb1[lane + 32 * i] = u;
+        }
         d[i].x *= g1[lane + 32 * i].x; d[i].y *= g1[lane + 32 * i].y; d[i].z *= g1[lane + 32 * i].z; d[i].w *= g1[lane + 32 * i].w;
         s1 += d[i].x + d[i].y + d[i].z + d[i].w;
         s2 += d[i].x * xh1[i].x + d[i].y * xh1[i].y + d[i].z * xh1[i].z + d[i].w * xh1[i].w;
@@ -233,10 +255,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
         o.y = rstd1 * (d[i].y - s1 - xh1[i].y * s2);
         o.z = rstd1 * (d[i].z - s1 - xh1[i].z * s2);
         o.w = rstd1 * (d[i].w - s1 - xh1[i].w * s2);
-        if (p.dres) {
-          const float4 r = reinterpret_cast<const float4*>(p.dres + row * p.lddres)[c];
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
+        o.x += rs[i].x; o.y += rs[i].y; o.z += rs[i].z; o.w += rs[i].w;
         reinterpret_cast<float4*>(p.dx + row * p.lddx)[c] = o;
         if (p.dx_bf16)
           reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.dx_bf16) + row * p.lddxb)[c] =
@@ -244,29 +263,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
       }
     }
   }
-  // parameter gradients: reduce the CTA's warps through shared memory, then one atomic per column
-  __shared__ float4 red[LN_WARPS][32];
-  for (int pass = 0; pass < 3; ++pass) {
-    float* dst = pass == 0 ? p.dg1 : (pass == 1 ? p.dg2 : p.db1);
-    if (dst == nullptr) continue;
+  // parameter gradients: sum the warps' slices, then one atomic per column
+  __syncthreads();
+  const int narr = 1 + (dbl ? 1 : 0) + (p.db1 ? 1 : 0);
+  for (int a = 0; a < narr; ++a) {
+    float* dst = a == 0 ? p.dg1 : ((a == 1 && dbl) ? p.dg2 : p.db1);
+    const float4* base = ln_acc + (size_t)a * LN_WARPS * NC * 32;
+    for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
+      float4 t = base[c];
 #pragma unroll
-    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-      if (32 * i >= nchunk) break;
-      __syncthreads();
-      red[warp][lane] = pass == 0 ? adg1[i] : (pass == 1 ? adg2[i] : adb1[i]);
-      __syncthreads();
-      if (warp == 0) {
-        float4 a = red[0][lane];
-#pragma unroll
-        for (int w = 1; w < LN_WARPS; ++w) {
-          a.x += red[w][lane].x; a.y += red[w][lane].y; a.z += red[w][lane].z; a.w += red[w][lane].w;
-        }
-        const int c = lane + 32 * i;
-        if (c < nchunk) {
-          atomicAdd(dst + 4 * c, a.x); atomicAdd(dst + 4 * c + 1, a.y);
-          atomicAdd(dst + 4 * c + 2, a.z); atomicAdd(dst + 4 * c + 3, a.w);
-        }
+      for (int w = 1; w < LN_WARPS; ++w) {
+        const float4 u = base[(size_t)w * NC * 32 + c];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
       }
+      atomicAdd(dst + 4 * c, t.x); atomicAdd(dst + 4 * c + 1, t.y);
+      atomicAdd(dst + 4 * c + 2, t.z); atomicAdd(dst + 4 * c + 3, t.w);
     }
   }
 }
@@ -317,13 +328,24 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
                 g2 ? dg2 : nullptr};
   // fewer CTAs than the forward: each CTA ends with D atomics per parameter vector
   int grid = ln_grid(rows);
-  if (grid > 148 * 2) grid = 148 * 2;
+  if (grid > 148 * 3) grid = 148 * 3;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nc = ceil_div(D, 128);
-  if (nc <= 2) ln_bwd_kernel<2><<<grid, LN_WARPS * 32, 0, st>>>(p);
-  else if (nc <= 4) ln_bwd_kernel<4><<<grid, LN_WARPS * 32, 0, st>>>(p);
-  else if (nc <= 6) ln_bwd_kernel<6><<<grid, LN_WARPS * 32, 0, st>>>(p);
-  else ln_bwd_kernel<8><<<grid, LN_WARPS * 32, 0, st>>>(p);
+  const int ncp = nc <= 2 ? 2 : (nc <= 4 ? 4 : (nc <= 6 ? 6 : 8));
+  const int narr = 1 + (g2 ? 1 : 0) + (db1 ? 1 : 0);
+  const size_t smem = (size_t)narr * LN_WARPS * ncp * 32 * sizeof(float4);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(ln_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 2 * 32 * 16);
+    cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 4 * 32 * 16);
+    cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 6 * 32 * 16);
+    cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 8 * 32 * 16);
+    attr_done = true;
+  }
+  if (nc <= 2) ln_bwd_kernel<2><<<grid, LN_WARPS * 32, smem, st>>>(p);
+  else if (nc <= 4) ln_bwd_kernel<4><<<grid, LN_WARPS * 32, smem, st>>>(p);
+  else if (nc <= 6) ln_bwd_kernel<6><<<grid, LN_WARPS * 32, smem, st>>>(p);
+  else ln_bwd_kernel<8><<<grid, LN_WARPS * 32, smem, st>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
   return 0;

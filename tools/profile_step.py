@@ -24,6 +24,12 @@ step = PretrainStep(model, num_encoded_tokens=a.nenc, global_batch=a.batch)
 x = {k: v.cuda() for k, v in synthetic_batch(a.batch, a.image, 1234).items()}
 for i in range(a.steps):
     torch.manual_seed(1 + i)
+    if i == a.steps - 1:
+        torch.cuda.synchronize()
+        rid = torch.cuda.nvtx.range_start("laststep")
     loss = step(x)
+    if i == a.steps - 1:
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_end(rid)
 torch.cuda.synchronize()
 print("loss", float(loss))
