@@ -15,6 +15,7 @@
 #include "mmf_b200.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace mmf {
 extern std::atomic<int64_t> g_launch_count;
@@ -520,6 +521,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
   }
 }
 
+int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream);  // attention_tc.cu (tcgen05 path, dh = 64 self-attention)
+int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream);
+
 static int check_common(const MmfAttnArgs* a) {
   if (!a || !a->q || !a->k || !a->v) return 1;
   if (a->dh != 64 && a->dh != 32) return 2;
@@ -554,6 +558,14 @@ extern "C" int mmf_attn_fwd(const MmfAttnArgs* a, mmf_stream_t stream) {
   int rc = check_common(a);
   if (rc) MMF_BAD_ARG(rc);
   if (!a->o || (a->ldo & 1)) MMF_BAD_ARG(20);
+  {
+    // dh = 64 self-attention runs on the tcgen05 kernel; dh = 32 (decoders) and cross-attention use the kernel below
+    static const bool tc_on = !(getenv("MMF_ATTN_TC") && atoi(getenv("MMF_ATTN_TC")) == 0);
+    if (tc_on) {
+      const int rc_tc = attn_fwd_tc_launch(a, reinterpret_cast<cudaStream_t>(stream));
+      if (rc_tc != -1000) return rc_tc;
+    }
+  }
   AttnParams p = to_params(*a);
   const int tiles = (a->Nq + ATT_BM - 1) / ATT_BM + (a->seg ? a->nseg : 0);
   dim3 grid(tiles, a->H, a->B);
@@ -576,6 +588,15 @@ extern "C" int mmf_attn_bwd(const MmfAttnArgs* a, mmf_stream_t stream) {
   const int dgrid = (int)((rows + 7) / 8);
   const int qtiles = (a->Nq + 63) / 64 + (a->seg ? a->nseg : 0);
   const int ktiles = (a->Nk + 63) / 64 + (a->seg ? a->nseg : 0);
+  {
+    static const bool tc_on = !(getenv("MMF_ATTN_TC") && atoi(getenv("MMF_ATTN_TC")) == 0);
+    if (tc_on && a->dh == 64 && a->Nq == a->Nk && a->n_head_q == a->n_head_k && !(a->ldo & 7) && !(a->lddo & 7)) {
+      attn_delta_kernel<64><<<dgrid, 256, 0, st>>>(p);
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+      const int rc_tc = attn_bwd_tc_launch(a, st);
+      if (rc_tc != -1000) return rc_tc;
+    }
+  }
   const int smem_dq = 6 * 64 * a->dh * 2, smem_dkv = 6 * 64 * a->dh * 2 + 4 * 64 * 4;
   if (a->dh == 64) {
     static bool attr = false;

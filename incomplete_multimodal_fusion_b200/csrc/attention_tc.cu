@@ -1,0 +1,960 @@
+// Zorro-masked flash attention FORWARD on tcgen05 tensor cores (dh = 64).
+//
+//   per CTA: one 128-row query tile of one (batch, head).  Q, K, V tiles arrive by TMA (128B swizzle) straight
+//   from the fused [rows, 3*H*64] qkv matrix; S = Q.K^T accumulates in TMEM (128 lanes x 128 fp32 columns);
+//   four softmax warps (one thread per query row = one TMEM lane) read S with tcgen05.ld, keep the running
+//   max / sum in registers, and write P as packed bf16 back to TMEM with tcgen05.st; O += P.V is then a
+//   tcgen05.mma with the A operand in TMEM and V read MN-major from shared memory, accumulating in TMEM.
+//   The O rescale of online softmax is lazy (only when the row max grows by more than 2^8).
+//
+//   The zorro mask (multimae.py:410-426) is the segment table: query tiles are cut per segment; a modality
+//   tile visits only its own segment's key blocks, a fusion tile visits everything.  Masked key blocks are
+//   never loaded; only the ragged end of a key range is masked in registers, and the MMA N / K extents
+//   shrink to the valid keys (multiples of 16).
+//
+//   TMEM budget 256 columns (S 128 | P 64 | O 64) and ~81 KB smem so two CTAs share an SM: while one CTA's
+//   softmax warps work, the other CTA's MMAs run.
+#include "common.cuh"
+#include "mmf_b200.h"
+
+#include <atomic>
+#include <mutex>
+
+namespace mmf {
+extern std::atomic<int64_t> g_launch_count;
+
+constexpr int TC_BM = 128;   // query rows per CTA (UMMA M)
+constexpr int TC_BN = 128;   // keys per block (UMMA N of S, K extent of P.V)
+constexpr int TC_THREADS = 192;
+constexpr int TC_TILE_BYTES = 128 * 64 * 2;   // one 128 x 64 bf16 tile
+constexpr int TC_SMEM = 6 * TC_TILE_BYTES + 1024 + 128;   // 2xQ + 2x(K,V) + align + barriers
+constexpr uint32_t TMEM_S = 0, TMEM_P = 128, TMEM_O = 192, TMEM_COLS = 256;
+
+struct AttnTcParams {
+  __nv_bfloat16* o;
+  float* lse;
+  int64_t ldo;
+  int B, H, N;                // self-attention: Nq == Nk == N
+  int n_head, n_tail;
+  int64_t head_rows;
+  float scale_log2;           // scale * log2(e)
+  const int32_t* seg;
+  int nseg;
+};
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// key blocks of a query tile: the key range [k0, k1) is cut at the head/tail plane boundary, each part into
+// blocks of TC_BN keys.  Block j -> (global row of its first key, number of valid keys).
+struct KeyBlocks {
+  int a0, e0, a1, e1, nb0, nb;
+  int n_head, n_tail, b;
+  int64_t head_rows;
+  __device__ void init(int k0, int k1, int n_head_, int n_tail_, int64_t head_rows_, int b_) {
+    n_head = n_head_; n_tail = n_tail_; head_rows = head_rows_; b = b_;
+    a0 = k0; e0 = min(k1, n_head_);            // part in the head plane
+    a1 = max(k0, n_head_); e1 = k1;            // part in the tail plane
+    if (e0 < a0) e0 = a0;
+    if (e1 < a1) e1 = a1;
+    nb0 = (e0 - a0 + TC_BN - 1) / TC_BN;
+    nb = nb0 + (e1 - a1 + TC_BN - 1) / TC_BN;
+  }
+  __device__ void get(int j, int64_t& row, int& nvalid) const {
+    if (j < nb0) {
+      const int k = a0 + j * TC_BN;
+      row = (int64_t)b * n_head + k;
+      nvalid = min(TC_BN, e0 - k);
+    } else {
+      const int k = a1 + (j - nb0) * TC_BN;
+      row = head_rows + (int64_t)b * n_tail + (k - n_head);
+      nvalid = min(TC_BN, e1 - k);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // ---- which query tile? (tiles are cut per segment) ----
+  int r0 = 0, r1 = 0, k0 = 0, k1 = 0;
+  {
+    int tile = blockIdx.x;
+    bool found = false;
+    if (p.seg == nullptr) {
+      r0 = tile * TC_BM; r1 = min(r0 + TC_BM, p.N); k0 = 0; k1 = p.N; found = r0 < p.N;
+    } else {
+      for (int s = 0; s < p.nseg; ++s) {
+        const int a = p.seg[s], e = p.seg[s + 1];
+        const int nt = (e - a + TC_BM - 1) / TC_BM;
+        if (tile < nt) {
+          r0 = a + tile * TC_BM; r1 = min(r0 + TC_BM, e);
+          if (s == p.nseg - 1) { k0 = 0; k1 = p.N; } else { k0 = a; k1 = e; }
+          found = true;
+          break;
+        }
+        tile -= nt;
+      }
+    }
+    if (!found) return;
+  }
+  // One CTA serves this query tile for ALL heads of one sample: barriers / TMEM are set up once and the TMA
+  // producer runs ahead into the next head's Q/K/V while the current head is in softmax.
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                            // 2 buffers
+  uint8_t* sK = smem + 2 * TC_TILE_BYTES;        // 2 stages
+  uint8_t* sV = smem + 4 * TC_TILE_BYTES;        // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TC_TILE_BYTES);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* kv_full = bars + 4;    // [2]
+  uint64_t* kv_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;
+  uint64_t* p_full = bars + 9;
+  uint64_t* o_full = bars + 10;
+  uint64_t* o_empty = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  // all of a query tile's rows live in one plane (segments never straddle the head/tail boundary)
+  const int64_t q_row0 = r0 < p.n_head ? (int64_t)b * p.n_head + r0 : p.head_rows + (int64_t)b * p.n_tail + (r0 - p.n_head);
+  KeyBlocks kb;
+  kb.init(k0, k1, p.n_head, p.n_tail, p.head_rows, b);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
+        mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+      }
+      mbar_init(s_full, 1);
+      mbar_init(p_full, 4);
+      mbar_init(o_full, 1);
+      mbar_init(o_empty, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int g = 0;  // running key-block counter over all heads
+      for (int h = 0; h < p.H; ++h) {
+        const int qs = h & 1;
+        mbar_wait(&q_empty[qs], ((h >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qs], TC_TILE_BYTES);
+        tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], h * 64, (int)q_row0);
+        for (int j = 0; j < kb.nb; ++j, ++g) {
+          const int st = g & 1;
+          mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+          int64_t row; int nvalid;
+          kb.get(j, row, nvalid);
+          mbar_expect_tx(&kv_full[st], 2 * TC_TILE_BYTES);
+          tma_load_2d(sK + st * TC_TILE_BYTES, &tmap_k, &kv_full[st], h * 64, (int)row);
+          tma_load_2d(sV + st * TC_TILE_BYTES, &tmap_v, &kv_full[st], h * 64, (int)row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc_pv = umma_idesc_bf16(TC_BM, 64, false, true);   // A = P (TMEM, K-major), B = V (MN-major)
+      int g = 0;
+      auto issue_s = [&](int h, int j, int gg) {
+        const int st = gg & 1;
+        if (j == 0) {
+          mbar_wait(&q_full[h & 1], (h >> 1) & 1);
+        }
+        mbar_wait(&kv_full[st], (gg >> 1) & 1);
+        tc_fence_after();
+        int64_t row; int nvalid;
+        kb.get(j, row, nvalid);
+        const int n16 = (nvalid + 15) & ~15;
+        const uint32_t idesc = umma_idesc_bf16(TC_BM, n16, false, false);
+        const uint32_t q_addr = smem_u32(sQ + (h & 1) * TC_TILE_BYTES);
+        const uint32_t k_addr = smem_u32(sK + st * TC_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dh = 64 = 4 x 16
+          umma_bf16(tmem + TMEM_S, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024), idesc, k > 0);
+        umma_commit(s_full);
+      };
+      issue_s(0, 0, 0);
+      for (int h = 0; h < p.H; ++h) {
+        for (int j = 0; j < kb.nb; ++j, ++g) {
+          const int st = g & 1;
+          int64_t row; int nvalid;
+          kb.get(j, row, nvalid);
+          mbar_wait(p_full, g & 1);     // softmax wrote P and is done reading S
+          if (j == 0 && h > 0) mbar_wait(o_empty, (h - 1) & 1);   // previous head's O has been read out
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(sV + st * TC_TILE_BYTES);
+          const int ksteps = (nvalid + 15) >> 4;
+          for (int k = 0; k < ksteps; ++k)   // 16 keys per step: P advances 8 packed columns, V 16 rows of 128 B
+            umma_bf16_ts(tmem + TMEM_O, tmem + TMEM_P + k * 8, umma_smem_desc(v_addr + k * 2048, 8192, 1024), idesc_pv, (j > 0) || (k > 0));
+          umma_commit(&kv_empty[st]);          // K/V stage consumed
+          if (j + 1 < kb.nb) {
+            issue_s(h, j + 1, g + 1);          // in-order MMA pipe: S(next) completes after this P.V
+          } else {
+            umma_commit(o_full);
+            umma_commit(&q_empty[h & 1]);
+            if (h + 1 < p.H) issue_s(h + 1, 0, g + 1);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ softmax / output warps (2..5) ------------------------------
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int i = r0 + row_in_tile;
+    uint32_t raw[32];
+    int g = 0;
+    for (int h = 0; h < p.H; ++h) {
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < kb.nb; ++j, ++g) {
+        int64_t row; int nvalid;
+        kb.get(j, row, nvalid);
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+        const int nchunk = (nvalid + 31) >> 5;
+        // pass A: row max over the valid keys
+        float mx = -INFINITY;
+        for (int c = 0; c < nchunk; ++c) {
+          tmem_ld_32x32(lane_addr + TMEM_S + c * 32, raw);
+          tmem_wait_ld();
+          if (c * 32 + 32 <= nvalid) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(raw[t]));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              if (c * 32 + t < nvalid) mx = fmaxf(mx, __uint_as_float(raw[t]));
+          }
+        }
+        const float m_new = mx * p.scale_log2;
+        // lazy rescale: only when the max grew by more than 2^8 (warp-uniform decision: tcgen05.ld/st are warp-wide)
+        const bool grow = m_new > m_ref + 8.0f;
+        if (j == 0) {
+          m_ref = m_new;
+        } else if (__any_sync(0xffffffffu, grow)) {
+          const float new_ref = grow ? m_new : m_ref;
+          const float alpha = exp2f(m_ref - new_ref);
+          m_ref = new_ref;
+          l *= alpha;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {   // O row: 64 fp32 columns (the previous P.V has completed: S finished after it)
+            tmem_ld_32x32(lane_addr + TMEM_O + c * 32, raw);
+            tmem_wait_ld();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) raw[t] = __float_as_uint(__uint_as_float(raw[t]) * alpha);
+            tmem_st_32x32(lane_addr + TMEM_O + c * 32, raw);
+          }
+          tmem_wait_st();
+        }
+        // pass B: P = exp2(s*scale*log2e - m_ref) as packed bf16 -> TMEM
+        float rs = 0.f;
+        const int n16 = (nvalid + 15) & ~15;   // P.V reads ceil16(nvalid) keys
+        for (int c = 0; c * 32 < n16; ++c) {
+          tmem_ld_32x32(lane_addr + TMEM_S + c * 32, raw);
+          tmem_wait_ld();
+          uint32_t pk[16];
+          if (c * 32 + 32 <= nvalid) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const float p0 = exp2f(fmaf(__uint_as_float(raw[2 * t]), p.scale_log2, -m_ref));
+              const float p1 = exp2f(fmaf(__uint_as_float(raw[2 * t + 1]), p.scale_log2, -m_ref));
+              rs += p0 + p1;
+              pk[t] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const int c0 = c * 32 + 2 * t;
+              const float p0 = c0 < nvalid ? exp2f(fmaf(__uint_as_float(raw[2 * t]), p.scale_log2, -m_ref)) : 0.f;
+              const float p1 = c0 + 1 < nvalid ? exp2f(fmaf(__uint_as_float(raw[2 * t + 1]), p.scale_log2, -m_ref)) : 0.f;
+              rs += p0 + p1;
+              pk[t] = pack_bf16(p0, p1);
+            }
+          }
+          tmem_st_32x16(lane_addr + TMEM_P + c * 16, pk);
+        }
+        l += rs;
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // ---- head epilogue: O / l -> bf16 row, log-sum-exp ----
+      mbar_wait(o_full, h & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      __nv_bfloat16* orow = p.o + (q_row0 + row_in_tile) * p.ldo + h * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x32(lane_addr + TMEM_O + c * 32, raw);
+        tmem_wait_ld();
+        if (i < r1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = make_uint4(
+                pack_bf16(__uint_as_float(raw[8 * q]) * inv, __uint_as_float(raw[8 * q + 1]) * inv),
+                pack_bf16(__uint_as_float(raw[8 * q + 2]) * inv, __uint_as_float(raw[8 * q + 3]) * inv),
+                pack_bf16(__uint_as_float(raw[8 * q + 4]) * inv, __uint_as_float(raw[8 * q + 5]) * inv),
+                pack_bf16(__uint_as_float(raw[8 * q + 6]) * inv, __uint_as_float(raw[8 * q + 7]) * inv));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);   // the MMA warp may overwrite O for the next head
+      if (p.lse && i < r1) p.lse[((int64_t)b * p.H + h) * p.N + i] = (m_ref + log2f(l)) * 0.6931471805599453f;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tc_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+// [rows, cols] bf16 row-major (ld elements), box = 64 columns x 128 rows, 128B swizzle
+static int tc_make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = tc_encode_fn();
+  if (!enc) return 1000;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2000 + (int)r;
+}
+
+// returns -1000 if this problem is not eligible for the tcgen05 kernel (caller falls through to the generic kernel)
+int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
+  if (a->dh != 64 || a->Nq != a->Nk || a->n_head_q != a->n_head_k) return -1000;
+  if ((a->ldq & 7) || (a->ldk & 7) || (a->ldv & 7) || (a->ldo & 7)) return -1000;
+  const int64_t rows = (int64_t)a->B * a->Nq;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = tc_make_tmap(&tq, a->q, rows, (int64_t)a->H * 64, a->ldq))) return rc;
+  if ((rc = tc_make_tmap(&tk, a->k, rows, (int64_t)a->H * 64, a->ldk))) return rc;
+  if ((rc = tc_make_tmap(&tv, a->v, rows, (int64_t)a->H * 64, a->ldv))) return rc;
+  AttnTcParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.lse = a->lse; p.ldo = a->ldo;
+  p.B = a->B; p.H = a->H; p.N = a->Nq; p.n_head = a->n_head_q; p.n_tail = a->n_tail_q;
+  p.head_rows = (int64_t)a->B * a->n_head_q;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.seg = a->seg; p.nseg = a->nseg;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const int tiles = (a->Nq + TC_BM - 1) / TC_BM + (a->seg ? a->nseg : 0);
+  attn_fwd_tc_kernel<<<dim3(tiles, a->B), TC_THREADS, TC_SMEM, stream>>>(tq, tk, tv, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+
+// ================================================================================================
+// BACKWARD on tcgen05 (dh = 64).  Two kernels on the same skeleton as the forward (TMA producer warp, one MMA
+// issuing thread, four warps of one-thread-per-TMEM-lane elementwise work):
+//   dQ  kernel: CTA = 128 query rows, loops key blocks of 64:   S = Q.K^T, dP = dO.V^T  ->  dS = P*(dP - delta)
+//               (bf16, back into TMEM over S)  ->  dQ += dS.K   (A from TMEM, K read MN-major)
+//   dKV kernel: CTA = 128 keys, loops query blocks of 64 (own segment + fusion rows):  S^T = K.Q^T, dP^T = V.dO^T
+//               ->  P^T, dS^T (bf16 into TMEM)  ->  dV += P^T.dO,  dK += dS^T.Q   (dO / Q read MN-major)
+// P is recomputed from the saved log-sum-exp: P = exp2(s*scale*log2e - lse*log2e).
+// TMEM: 256 columns per CTA in both kernels, two CTAs per SM.
+// ================================================================================================
+constexpr int BW_BLK = 64;                        // rows of the inner (streamed) operand per block
+constexpr int BW_BLK_BYTES = BW_BLK * 64 * 2;     // 64 x 64 bf16 tile = 8 KB
+
+// blocks of BW_BLK token indices over up to two index ranges (each range lies inside one plane)
+struct RowBlocks {
+  int a[2], e[2], nbr[2], nb;
+  int n_head, n_tail, b;
+  int64_t head_rows;
+  __device__ void init(int a0, int e0, int a1, int e1, int n_head_, int n_tail_, int64_t head_rows_, int b_) {
+    n_head = n_head_; n_tail = n_tail_; head_rows = head_rows_; b = b_;
+    a[0] = a0; e[0] = max(e0, a0); a[1] = a1; e[1] = max(e1, a1);
+    nbr[0] = (e[0] - a[0] + BW_BLK - 1) / BW_BLK;
+    nbr[1] = (e[1] - a[1] + BW_BLK - 1) / BW_BLK;
+    nb = nbr[0] + nbr[1];
+  }
+  // block j -> first token index, global row of that token, number of valid rows
+  __device__ void get(int j, int& tok, int64_t& row, int& nvalid) const {
+    const int r = j < nbr[0] ? 0 : 1;
+    tok = a[r] + (j - (r ? nbr[0] : 0)) * BW_BLK;
+    nvalid = min(BW_BLK, e[r] - tok);
+    row = tok < n_head ? (int64_t)b * n_head + tok : head_rows + (int64_t)b * n_tail + (tok - n_head);
+  }
+};
+
+struct AttnBwdTcParams {
+  const float* lse;      // [B, H, N] natural log
+  const float* delta;    // [B, H, N]
+  __nv_bfloat16* dq; __nv_bfloat16* dk; __nv_bfloat16* dv;
+  int64_t lddq, lddk, lddv;
+  int B, H, N, n_head, n_tail;
+  int64_t head_rows;
+  float scale, scale_log2;
+  const int32_t* seg;
+  int nseg;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---------------------------------------- dQ ----------------------------------------
+constexpr uint32_t DQ_S = 0, DQ_DP = 64, DQ_ACC = 128, DQ_DS = 192;   // S | dP | dQ accumulator | dS (packed bf16)
+constexpr int DQ_SMEM = 4 * TC_TILE_BYTES + 4 * BW_BLK_BYTES + 1024 + 256;   // 2x(Q,dO) + 2x(K,V)
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                      const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                      const AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  int r0 = 0, r1 = 0, k0 = 0, k1 = 0;
+  {
+    int tile = blockIdx.x;
+    bool found = false;
+    if (p.seg == nullptr) {
+      r0 = tile * TC_BM; r1 = min(r0 + TC_BM, p.N); k0 = 0; k1 = p.N; found = r0 < p.N;
+    } else {
+      for (int s = 0; s < p.nseg; ++s) {
+        const int a = p.seg[s], e = p.seg[s + 1];
+        const int nt = (e - a + TC_BM - 1) / TC_BM;
+        if (tile < nt) {
+          r0 = a + tile * TC_BM; r1 = min(r0 + TC_BM, e);
+          if (s == p.nseg - 1) { k0 = 0; k1 = p.N; } else { k0 = a; k1 = e; }
+          found = true;
+          break;
+        }
+        tile -= nt;
+      }
+    }
+    if (!found) return;
+  }
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // 2 buffers of 128x64
+  uint8_t* sdO = smem + 2 * TC_TILE_BYTES;              // 2 buffers
+  uint8_t* sK = smem + 4 * TC_TILE_BYTES;               // 2 stages of 64x64
+  uint8_t* sV = sK + 2 * BW_BLK_BYTES;                  // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * BW_BLK_BYTES);
+  uint64_t* q_full = bars;         // [2] (Q and dO of a head)
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* kv_full = bars + 4;    // [2]
+  uint64_t* kv_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;     // S and dP ready
+  uint64_t* ds_full = bars + 9;    // dS written (and S / dP consumed)
+  uint64_t* acc_full = bars + 10;  // dQ of the head complete
+  uint64_t* acc_empty = bars + 11; // dQ read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int64_t q_row0 = r0 < p.n_head ? (int64_t)b * p.n_head + r0 : p.head_rows + (int64_t)b * p.n_tail + (r0 - p.n_head);
+  RowBlocks kb;   // key range split at the plane boundary
+  kb.init(k0, min(k1, p.n_head), max(k0, p.n_head), k1, p.n_head, p.n_tail, p.head_rows, b);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
+        mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+      }
+      mbar_init(s_full, 1); mbar_init(ds_full, 4); mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      for (int h = 0; h < p.H; ++h) {
+        const int qs = h & 1;
+        mbar_wait(&q_empty[qs], ((h >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qs], 2 * TC_TILE_BYTES);
+        tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], h * 64, (int)q_row0);
+        tma_load_2d(sdO + qs * TC_TILE_BYTES, &tmap_do, &q_full[qs], h * 64, (int)q_row0);
+        for (int j = 0; j < kb.nb; ++j, ++g) {
+          const int st = g & 1;
+          mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+          int tok, nvalid; int64_t row;
+          kb.get(j, tok, row, nvalid);
+          mbar_expect_tx(&kv_full[st], 2 * BW_BLK_BYTES);
+          tma_load_2d(sK + st * BW_BLK_BYTES, &tmap_k, &kv_full[st], h * 64, (int)row);
+          tma_load_2d(sV + st * BW_BLK_BYTES, &tmap_v, &kv_full[st], h * 64, (int)row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(TC_BM, BW_BLK, false, false);   // [128 x 64] = A[128 x 64dh] . B[64 keys x 64dh]^T
+      const uint32_t idesc_acc = umma_idesc_bf16(TC_BM, 64, false, true);      // dQ[128 x 64dh] += dS[128 x keys] . K (MN-major)
+      int g = 0;
+      auto issue_s = [&](int h, int j, int gg) {
+        const int st = gg & 1;
+        if (j == 0) mbar_wait(&q_full[h & 1], (h >> 1) & 1);
+        mbar_wait(&kv_full[st], (gg >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + (h & 1) * TC_TILE_BYTES), do_addr = smem_u32(sdO + (h & 1) * TC_TILE_BYTES);
+        const uint32_t k_addr = smem_u32(sK + st * BW_BLK_BYTES), v_addr = smem_u32(sV + st * BW_BLK_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + DQ_S, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + DQ_DP, umma_smem_desc(do_addr + k * 32, 16, 1024), umma_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(s_full);
+      };
+      issue_s(0, 0, 0);
+      for (int h = 0; h < p.H; ++h) {
+        for (int j = 0; j < kb.nb; ++j, ++g) {
+          const int st = g & 1;
+          int tok, nvalid; int64_t row;
+          kb.get(j, tok, row, nvalid);
+          mbar_wait(ds_full, g & 1);
+          if (j == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sK + st * BW_BLK_BYTES);
+          const int ksteps = (nvalid + 15) >> 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_ts(tmem + DQ_ACC, tmem + DQ_DS + k * 8, umma_smem_desc(k_addr + k * 2048, 8192, 1024), idesc_acc, (j > 0) || (k > 0));
+          umma_commit(&kv_empty[st]);
+          if (j + 1 < kb.nb) {
+            issue_s(h, j + 1, g + 1);
+          } else {
+            umma_commit(acc_full);
+            umma_commit(&q_empty[h & 1]);
+            if (h + 1 < p.H) issue_s(h + 1, 0, g + 1);
+          }
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int i = r0 + row_in_tile;
+    const bool row_ok = i < r1;
+    uint32_t rs[32], rd[32];
+    int g = 0;
+    for (int h = 0; h < p.H; ++h) {
+      const int64_t stat_idx = ((int64_t)b * p.H + h) * p.N + i;
+      const float lse2 = row_ok ? p.lse[stat_idx] * 1.4426950408889634f : INFINITY;   // invalid rows -> P = 0
+      const float dl = row_ok ? p.delta[stat_idx] : 0.f;
+      for (int j = 0; j < kb.nb; ++j, ++g) {
+        int tok, nvalid; int64_t row;
+        kb.get(j, tok, row, nvalid);
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_32x32(lane_addr + DQ_S + c * 32, rs);
+          tmem_ld_32x32(lane_addr + DQ_DP + c * 32, rd);
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            const int c0 = c * 32 + 2 * t;
+            const float p0 = c0 < nvalid ? ex2(fmaf(__uint_as_float(rs[2 * t]), p.scale_log2, -lse2)) : 0.f;
+            const float p1 = c0 + 1 < nvalid ? ex2(fmaf(__uint_as_float(rs[2 * t + 1]), p.scale_log2, -lse2)) : 0.f;
+            pk[t] = pack_bf16(p0 * (__uint_as_float(rd[2 * t]) - dl) * p.scale, p1 * (__uint_as_float(rd[2 * t + 1]) - dl) * p.scale);
+          }
+          tmem_st_32x16(lane_addr + DQ_DS + c * 16, pk);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ds_full);
+      }
+      mbar_wait(acc_full, h & 1);
+      tc_fence_after();
+      __nv_bfloat16* orow = p.dq + (q_row0 + row_in_tile) * p.lddq + h * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x32(lane_addr + DQ_ACC + c * 32, rs);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = make_uint4(
+                pack_bf16(__uint_as_float(rs[8 * q]), __uint_as_float(rs[8 * q + 1])),
+                pack_bf16(__uint_as_float(rs[8 * q + 2]), __uint_as_float(rs[8 * q + 3])),
+                pack_bf16(__uint_as_float(rs[8 * q + 4]), __uint_as_float(rs[8 * q + 5])),
+                pack_bf16(__uint_as_float(rs[8 * q + 6]), __uint_as_float(rs[8 * q + 7])));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ---------------------------------------- dK, dV ----------------------------------------
+constexpr uint32_t KV_ST = 0, KV_DPT = 64, KV_DV = 128, KV_DK = 192;   // P^T aliases S^T, dS^T aliases dP^T
+constexpr int DKV_SMEM = 4 * TC_TILE_BYTES + 4 * BW_BLK_BYTES + 2 * 2 * BW_BLK * 4 + 1024 + 256;
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                       const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                       const AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // key tile (cut per segment) and the query ranges that attend to it
+  int c0 = 0, c1 = 0, qa0 = 0, qe0 = 0, qa1 = 0, qe1 = 0;
+  {
+    int tile = blockIdx.x;
+    bool found = false;
+    if (p.seg == nullptr) {
+      c0 = tile * TC_BM; c1 = min(c0 + TC_BM, p.N); qa0 = 0; qe0 = p.N; found = c0 < p.N;
+    } else {
+      for (int s = 0; s < p.nseg; ++s) {
+        const int a = p.seg[s], e = p.seg[s + 1];
+        const int nt = (e - a + TC_BM - 1) / TC_BM;
+        if (tile < nt) {
+          c0 = a + tile * TC_BM; c1 = min(c0 + TC_BM, e);
+          qa0 = a; qe0 = e;                                       // its own segment ...
+          if (s != p.nseg - 1) { qa1 = p.seg[p.nseg - 1]; qe1 = p.seg[p.nseg]; }   // ... and the fusion rows
+          found = true;
+          break;
+        }
+        tile -= nt;
+      }
+    }
+    if (!found) return;
+  }
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                                   // 2 buffers of 128x64 (per head)
+  uint8_t* sV = smem + 2 * TC_TILE_BYTES;
+  uint8_t* sQ = smem + 4 * TC_TILE_BYTES;               // 2 stages of 64x64
+  uint8_t* sdO = sQ + 2 * BW_BLK_BYTES;
+  float* s_lse = reinterpret_cast<float*>(sdO + 2 * BW_BLK_BYTES);   // [2][64]
+  float* s_dl = s_lse + 2 * BW_BLK;                                  // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dl + 2 * BW_BLK);
+  uint64_t* kvt_full = bars;        // [2] K and V tile of a head
+  uint64_t* kvt_empty = bars + 2;   // [2]
+  uint64_t* qb_full = bars + 4;     // [2] Q / dO block
+  uint64_t* qb_empty = bars + 6;    // [2]
+  uint64_t* s_full = bars + 8;
+  uint64_t* ds_full = bars + 9;
+  uint64_t* acc_full = bars + 10;
+  uint64_t* acc_empty = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int64_t k_row0 = c0 < p.n_head ? (int64_t)b * p.n_head + c0 : p.head_rows + (int64_t)b * p.n_tail + (c0 - p.n_head);
+  RowBlocks qb;
+  qb.init(qa0, qe0, qa1, qe1, p.n_head, p.n_tail, p.head_rows, b);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&kvt_full[s], 1); mbar_init(&kvt_empty[s], 1);
+        mbar_init(&qb_full[s], 1); mbar_init(&qb_empty[s], 1);
+      }
+      mbar_init(s_full, 1); mbar_init(ds_full, 4); mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      for (int h = 0; h < p.H; ++h) {
+        const int ks = h & 1;
+        mbar_wait(&kvt_empty[ks], ((h >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kvt_full[ks], 2 * TC_TILE_BYTES);
+        tma_load_2d(sK + ks * TC_TILE_BYTES, &tmap_k, &kvt_full[ks], h * 64, (int)k_row0);
+        tma_load_2d(sV + ks * TC_TILE_BYTES, &tmap_v, &kvt_full[ks], h * 64, (int)k_row0);
+        for (int j = 0; j < qb.nb; ++j, ++g) {
+          const int st = g & 1;
+          mbar_wait(&qb_empty[st], ((g >> 1) & 1) ^ 1);
+          int tok, nvalid; int64_t row;
+          qb.get(j, tok, row, nvalid);
+          mbar_expect_tx(&qb_full[st], 2 * BW_BLK_BYTES);
+          tma_load_2d(sQ + st * BW_BLK_BYTES, &tmap_q, &qb_full[st], h * 64, (int)row);
+          tma_load_2d(sdO + st * BW_BLK_BYTES, &tmap_do, &qb_full[st], h * 64, (int)row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(TC_BM, BW_BLK, false, false);   // S^T[128 keys x 64 q] = K . Q^T
+      const uint32_t idesc_acc = umma_idesc_bf16(TC_BM, 64, false, true);      // dV/dK[128 x 64dh] += A(TMEM)[128 x q] . B (MN-major)
+      int g = 0;
+      auto issue_s = [&](int h, int j, int gg) {
+        const int st = gg & 1;
+        if (j == 0) mbar_wait(&kvt_full[h & 1], (h >> 1) & 1);
+        mbar_wait(&qb_full[st], (gg >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + (h & 1) * TC_TILE_BYTES), v_addr = smem_u32(sV + (h & 1) * TC_TILE_BYTES);
+        const uint32_t q_addr = smem_u32(sQ + st * BW_BLK_BYTES), do_addr = smem_u32(sdO + st * BW_BLK_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + KV_ST, umma_smem_desc(k_addr + k * 32, 16, 1024), umma_smem_desc(q_addr + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + KV_DPT, umma_smem_desc(v_addr + k * 32, 16, 1024), umma_smem_desc(do_addr + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(s_full);
+      };
+      if (qb.nb > 0) issue_s(0, 0, 0);
+      for (int h = 0; h < p.H; ++h) {
+        for (int j = 0; j < qb.nb; ++j, ++g) {
+          const int st = g & 1;
+          int tok, nvalid; int64_t row;
+          qb.get(j, tok, row, nvalid);
+          mbar_wait(ds_full, g & 1);
+          if (j == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);
+          tc_fence_after();
+          const uint32_t q_addr = smem_u32(sQ + st * BW_BLK_BYTES), do_addr = smem_u32(sdO + st * BW_BLK_BYTES);
+          const int ksteps = (nvalid + 15) >> 4;
+          for (int k = 0; k < ksteps; ++k)   // dV += P^T . dO
+            umma_bf16_ts(tmem + KV_DV, tmem + KV_ST + k * 8, umma_smem_desc(do_addr + k * 2048, 8192, 1024), idesc_acc, (j > 0) || (k > 0));
+          for (int k = 0; k < ksteps; ++k)   // dK += dS^T . Q
+            umma_bf16_ts(tmem + KV_DK, tmem + KV_DPT + k * 8, umma_smem_desc(q_addr + k * 2048, 8192, 1024), idesc_acc, (j > 0) || (k > 0));
+          umma_commit(&qb_empty[st]);
+          if (j + 1 < qb.nb) {
+            issue_s(h, j + 1, g + 1);
+          } else {
+            umma_commit(acc_full);
+            umma_commit(&kvt_empty[h & 1]);
+            if (h + 1 < p.H) issue_s(h + 1, 0, g + 1);
+          }
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;      // key row of this thread
+    const int tid128 = threadIdx.x - 64;              // 0..127 over the four elementwise warps
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const bool key_ok = c0 + row_in_tile < c1;
+    uint32_t rs[32], rd[32];
+    int g = 0;
+    for (int h = 0; h < p.H; ++h) {
+      const int64_t stat_base = ((int64_t)b * p.H + h) * p.N;
+      for (int j = 0; j < qb.nb; ++j, ++g) {
+        const int st = g & 1;
+        int tok, nvalid; int64_t row;
+        qb.get(j, tok, row, nvalid);
+        // stage lse*log2e and delta of the block's query rows (buffer st was last read two blocks ago, before the
+        // ds_full arrival that the s_full wait below transitively orders)
+        if (tid128 < BW_BLK) {
+          const bool ok = tid128 < nvalid;
+          s_lse[st * BW_BLK + tid128] = ok ? p.lse[stat_base + tok + tid128] * 1.4426950408889634f : INFINITY;
+          s_dl[st * BW_BLK + tid128] = ok ? p.delta[stat_base + tok + tid128] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four elementwise warps only
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+        const float* ls = s_lse + st * BW_BLK;
+        const float* dl = s_dl + st * BW_BLK;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_32x32(lane_addr + KV_ST + c * 32, rs);
+          tmem_ld_32x32(lane_addr + KV_DPT + c * 32, rd);
+          tmem_wait_ld();
+          uint32_t pk[16], dk_[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            const int q0 = c * 32 + 2 * t;
+            const float p0 = ex2(fmaf(__uint_as_float(rs[2 * t]), p.scale_log2, -ls[q0]));        // lse = +inf beyond nvalid -> 0
+            const float p1 = ex2(fmaf(__uint_as_float(rs[2 * t + 1]), p.scale_log2, -ls[q0 + 1]));
+            pk[t] = pack_bf16(p0, p1);
+            dk_[t] = pack_bf16(p0 * (__uint_as_float(rd[2 * t]) - dl[q0]), p1 * (__uint_as_float(rd[2 * t + 1]) - dl[q0 + 1]));
+          }
+          tmem_st_32x16(lane_addr + KV_ST + c * 16, pk);     // P^T over consumed S^T columns
+          tmem_st_32x16(lane_addr + KV_DPT + c * 16, dk_);   // dS^T over consumed dP^T columns
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ds_full);
+      }
+      if (qb.nb == 0) continue;
+      mbar_wait(acc_full, h & 1);
+      tc_fence_after();
+      const int64_t orow = k_row0 + row_in_tile;
+      __nv_bfloat16* vrow = p.dv + orow * p.lddv + h * 64;
+      __nv_bfloat16* krow = p.dk + orow * p.lddk + h * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x32(lane_addr + KV_DV + c * 32, rs);
+        tmem_ld_32x32(lane_addr + KV_DK + c * 32, rd);
+        tmem_wait_ld();
+        if (key_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<uint4*>(vrow + c * 32 + q * 8) = make_uint4(
+                pack_bf16(__uint_as_float(rs[8 * q]), __uint_as_float(rs[8 * q + 1])),
+                pack_bf16(__uint_as_float(rs[8 * q + 2]), __uint_as_float(rs[8 * q + 3])),
+                pack_bf16(__uint_as_float(rs[8 * q + 4]), __uint_as_float(rs[8 * q + 5])),
+                pack_bf16(__uint_as_float(rs[8 * q + 6]), __uint_as_float(rs[8 * q + 7])));
+            *reinterpret_cast<uint4*>(krow + c * 32 + q * 8) = make_uint4(
+                pack_bf16(__uint_as_float(rd[8 * q]) * p.scale, __uint_as_float(rd[8 * q + 1]) * p.scale),
+                pack_bf16(__uint_as_float(rd[8 * q + 2]) * p.scale, __uint_as_float(rd[8 * q + 3]) * p.scale),
+                pack_bf16(__uint_as_float(rd[8 * q + 4]) * p.scale, __uint_as_float(rd[8 * q + 5]) * p.scale),
+                pack_bf16(__uint_as_float(rd[8 * q + 6]) * p.scale, __uint_as_float(rd[8 * q + 7]) * p.scale));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+static int tc_make_tmap_box(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = tc_encode_fn();
+  if (!enc) return 1000;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2000 + (int)r;
+}
+
+// dq / dk / dv of the tcgen05 backward (delta must already be computed).  -1000: not eligible.
+int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
+  if (a->dh != 64 || a->Nq != a->Nk || a->n_head_q != a->n_head_k) return -1000;
+  if ((a->ldq & 7) || (a->ldk & 7) || (a->ldv & 7) || (a->lddo & 7) || (a->lddq & 7) || (a->lddk & 7) || (a->lddv & 7)) return -1000;
+  const int64_t rows = (int64_t)a->B * a->Nq;
+  const int64_t cols = (int64_t)a->H * 64;
+  CUtensorMap q128, do128, k64, v64, k128, v128, q64, do64;
+  int rc;
+  if ((rc = tc_make_tmap_box(&q128, a->q, rows, cols, a->ldq, 128))) return rc;
+  if ((rc = tc_make_tmap_box(&do128, a->d_o, rows, cols, a->lddo, 128))) return rc;
+  if ((rc = tc_make_tmap_box(&k64, a->k, rows, cols, a->ldk, 64))) return rc;
+  if ((rc = tc_make_tmap_box(&v64, a->v, rows, cols, a->ldv, 64))) return rc;
+  if ((rc = tc_make_tmap_box(&k128, a->k, rows, cols, a->ldk, 128))) return rc;
+  if ((rc = tc_make_tmap_box(&v128, a->v, rows, cols, a->ldv, 128))) return rc;
+  if ((rc = tc_make_tmap_box(&q64, a->q, rows, cols, a->ldq, 64))) return rc;
+  if ((rc = tc_make_tmap_box(&do64, a->d_o, rows, cols, a->lddo, 64))) return rc;
+  AttnBwdTcParams p;
+  p.lse = a->lse; p.delta = a->delta;
+  p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv);
+  p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+  p.B = a->B; p.H = a->H; p.N = a->Nq; p.n_head = a->n_head_q; p.n_tail = a->n_tail_q;
+  p.head_rows = (int64_t)a->B * a->n_head_q;
+  p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.seg = a->seg; p.nseg = a->nseg;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const int tiles = (a->Nq + TC_BM - 1) / TC_BM + (a->seg ? a->nseg : 0);
+  attn_bwd_dq_tc_kernel<<<dim3(tiles, a->B), TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
+  attn_bwd_dkv_tc_kernel<<<dim3(tiles, a->B), TC_THREADS, DKV_SMEM, stream>>>(k128, v128, q64, do64, p);
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace mmf
