@@ -79,12 +79,17 @@ int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream);
  * encoder norm multimae.py:431 and the decoder nn.LayerNorm(eps=1e-6) (multimae_utils.py:217-232).
  * x rows may come from two buffers: rows [0, x_split) from x, rows >= x_split from x2 (row - x_split)
  * (x2 == NULL: single source).  stats: f32 [rows, 4] = mean1, rstd1, mean2, rstd2 (nullable in fwd).
+ * Fused residual add (forward, delta != NULL): rows >= delta_row0 are normalised as x + delta[row - delta_row0] with
+ * delta the bf16 output of the previous sub-layer's last Linear (`x + attn(...)`, `x + ffn(...)`: zorro_utils.py:238-239;
+ * under autocast that Linear output is bf16 and the sum fp32, Appendix A #17), and the sum -- the new fp32 residual
+ * stream -- is written to xout[row - delta_row0].
  * The backward also adds the residual-branch gradient `dres` and can emit a bf16 copy of dx.
  * dg1/db1/dg2 are ACCUMULATED with atomics: the caller zeroes them.
  * ---------------------------------------------------------------------------------------------- */
 int mmf_layernorm_fwd(const float* x, const float* x2, int64_t x_split, int64_t rows, int32_t D, int64_t ldx,
                       const float* g1, const float* b1, float eps1, const float* g2, float eps2, void* y, int64_t ldy,
-                      int32_t y_f32, float* stats, mmf_stream_t stream);
+                      int32_t y_f32, float* stats, const void* delta, int64_t delta_row0, int64_t lddelta, float* xout,
+                      int64_t ldxout, mmf_stream_t stream);
 int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, const float* x, const float* x2, int64_t x_split,
                       int64_t rows, int32_t D, int64_t ldx, const float* g1, const float* b1, const float* g2,
                       const float* stats, const float* dres, int64_t lddres, float* dx, int64_t lddx, void* dx_bf16,
@@ -212,6 +217,8 @@ int mmf_gather_rows(const void* src, int32_t src_f32, int64_t ld_src, int64_t sr
                     const int32_t* idx, void* dst, int32_t dst_f32, int64_t ld_dst, int64_t batch, int32_t n, int32_t d,
                     mmf_stream_t stream);
 int mmf_add_inplace_f32(float* y, const float* x, int64_t n, mmf_stream_t stream);
+/* out (f32) = x (f32) + d (bf16): the residual stream after the last sub-layer (zorro_utils.py:239) */
+int mmf_add_bf16_f32(float* out, const float* x, const void* d, int64_t n, mmf_stream_t stream);
 
 #ifdef __cplusplus
 }

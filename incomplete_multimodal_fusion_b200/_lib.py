@@ -66,7 +66,8 @@ SIGNATURES = {
     "mmf_launch_count": [],
     "mmf_reset_launch_count": [],
     "mmf_gemm_bf16": [C.POINTER(GemmArgs), c_vp],
-    "mmf_layernorm_fwd": [c_vp, c_vp, c_i64, c_i64, c_i32, c_i64, c_vp, c_vp, c_f32, c_vp, c_f32, c_vp, c_i64, c_i32, c_vp, c_vp],
+    "mmf_layernorm_fwd": [c_vp, c_vp, c_i64, c_i64, c_i32, c_i64, c_vp, c_vp, c_f32, c_vp, c_f32, c_vp, c_i64, c_i32, c_vp,
+                          c_vp, c_i64, c_i64, c_vp, c_i64, c_vp],
     "mmf_layernorm_bwd": [c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
                           c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
     "mmf_attn_fwd": [C.POINTER(AttnArgs), c_vp],
@@ -87,6 +88,7 @@ SIGNATURES = {
     "mmf_unpatchify_bf16": [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "mmf_gather_rows": [c_vp, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_i32, c_i64, c_i64, c_i32, c_i32, c_vp],
     "mmf_add_inplace_f32": [c_vp, c_vp, c_i64, c_vp],
+    "mmf_add_bf16_f32": [c_vp, c_vp, c_vp, c_i64, c_vp],
 }
 _RESTYPES = {"mmf_launch_count": c_i64, "mmf_reset_launch_count": None}
 

@@ -209,6 +209,17 @@ __global__ void add_inplace_kernel(float4* __restrict__ y, const float4* __restr
   }
 }
 
+// out (f32) = x (f32) + d (bf16), n % 4 == 0: materialises the residual stream after the last sub-layer
+__global__ void add_bf16_kernel(float4* __restrict__ out, const float4* __restrict__ x, const uint2* __restrict__ d, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = x[i];
+    const uint2 u = d[i];
+    const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
+    a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
+    out[i] = a;
+  }
+}
+
 }  // namespace mmf
 
 using namespace mmf;
@@ -351,6 +362,17 @@ extern "C" int mmf_add_inplace_f32(float* y, const float* x, int64_t n, mmf_stre
   if (n == 0) return 0;
   add_inplace_kernel<<<ew_grid(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), n / 4);
+  MMF_COUNT_LAUNCH();
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmf_add_bf16_f32(float* out, const float* x, const void* d, int64_t n, mmf_stream_t stream) {
+  if (!out || !x || !d) MMF_BAD_ARG(1);
+  if (n & 3) MMF_BAD_ARG(2);
+  if (n == 0) return 0;
+  add_bf16_kernel<<<ew_grid(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(out), reinterpret_cast<const float4*>(x), reinterpret_cast<const uint2*>(d), n / 4);
   MMF_COUNT_LAUNCH();
   MMF_LAUNCH_CHECK();
   return 0;

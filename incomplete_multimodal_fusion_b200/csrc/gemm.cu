@@ -23,6 +23,7 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int STG_FLOATS = 32 * 32;  // per-warp 32x32 fp32 epilogue staging block
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -31,7 +32,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;  // 4 @256, 6 @128
   static constexpr int TMEM_COLS = 2 * BLOCK_N;             // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * STG_FLOATS * 4 /*epilogue staging*/;
 };
 
 struct GemmParams {
@@ -69,8 +70,8 @@ enum : int {
   EPI_BF16_ACC = 5  // out bf16 += alpha*acc
 };
 
-constexpr int STG_LD = 36;  // row pitch (floats) of the per-warp 32x32 staging block: 16-byte aligned rows; the
-                            // row-per-lane 128-bit writes and the row-contiguous 128-bit reads are both conflict free
+// Per-warp 32x32 fp32 staging block, 128-byte rows, 16-byte groups XOR-swizzled with (row & 7): the row-per-lane
+// 128-bit writes and the row-contiguous 128-bit reads both run at one 128-byte wavefront per 8 lanes.
 
 __device__ __forceinline__ float4 gelu4(float4 x) { return make_float4(gelu_erf(x.x), gelu_erf(x.y), gelu_erf(x.z), gelu_erf(x.w)); }
 __device__ __forceinline__ uint2 pack4(float4 x) { return make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w)); }
@@ -81,22 +82,28 @@ __device__ __forceinline__ uint2 pack4(float4 x) { return make_uint2(pack_bf16(x
 __device__ __forceinline__ void stage_raw(float* stg, const uint32_t (&raw)[32], int lane) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<uint4*>(stg + lane * STG_LD + 4 * j) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+    *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
   __syncwarp();
 }
+__device__ __forceinline__ float4 stage_read(const float* stg, int i, int lane) {
+  const int row = i * 4 + (lane >> 3);
+  return *reinterpret_cast<const float4*>(stg + row * 32 + (((lane & 7) ^ (row & 7)) << 2));
+}
 
-// one full, aligned 32-column chunk
+// residual values of one 32-column chunk in the post-transpose ownership (8 rows x 4 columns per lane)
+__device__ __forceinline__ void load_res8(float4 (&resv)[8], const int64_t (&orow_i)[8], const float* const (&res_i)[8],
+                                          int64_t col) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (orow_i[i] >= 0) resv[i] = __ldg(reinterpret_cast<const float4*>(res_i[i] + col));
+}
+
+// one full, aligned 32-column chunk; `resv` = the chunk's residual values (EPI_F32 with a residual only)
 template <int EPI>
 __device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, const uint32_t (&raw)[32], int lane,
-                                          const int64_t (&orow_i)[8], const float* const (&res_i)[8], int64_t col0) {
+                                          const int64_t (&orow_i)[8], const float4 (&resv)[8], int64_t col0) {
   const int c = (lane & 7) * 4;
-  float4 resv[8];
   const bool has_res = (EPI == EPI_F32) && p.residual != nullptr;
-  if (has_res) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (orow_i[i] >= 0) resv[i] = __ldg(reinterpret_cast<const float4*>(res_i[i] + col0 + c));
-  }
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (EPI != EPI_ATOMIC && EPI != EPI_BF16_ACC && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));
   stage_raw(stg, raw, lane);
@@ -105,7 +112,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, const
   for (int i = 0; i < 8; ++i) {
     const int64_t orow = orow_i[i];
     if (orow < 0) continue;
-    float4 x = *reinterpret_cast<const float4*>(stg + (i * 4 + (lane >> 3)) * STG_LD + c);
+    float4 x = stage_read(stg, i, lane);
     x.x = fmaf(x.x, alpha, b4.x); x.y = fmaf(x.y, alpha, b4.y); x.z = fmaf(x.z, alpha, b4.z); x.w = fmaf(x.w, alpha, b4.w);
     if (EPI == EPI_GELU) {
       if (p.out2) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0 + c) = pack4(x);
@@ -125,7 +132,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, const
         const float2 a = unpack_bf16(old.x), b = unpack_bf16(old.y);
         x.x += a.x; x.y += a.y; x.z += b.x; x.w += b.y;
       }
-      *reinterpret_cast<uint2*>(o) = pack4(x);
+      if (p.dbg != 1) *reinterpret_cast<uint2*>(o) = pack4(x);
     }
   }
   __syncwarp();
@@ -137,14 +144,14 @@ __device__ __forceinline__ void epi_chunk_geglu(const GemmParams& p, float* stg,
   float4 val[8];
   stage_raw(stg, raw, lane);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) val[i] = *reinterpret_cast<const float4*>(stg + (i * 4 + (lane >> 3)) * STG_LD + c);
+  for (int i = 0; i < 8; ++i) val[i] = stage_read(stg, i, lane);
   __syncwarp();
   stage_raw(stg, rawg, lane);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int64_t orow = orow_i[i];
     if (orow < 0) continue;
-    const float4 g = *reinterpret_cast<const float4*>(stg + (i * 4 + (lane >> 3)) * STG_LD + c);
+    const float4 g = stage_read(stg, i, lane);
     if (p.out2) {
       __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0 + c;
       *reinterpret_cast<uint2*>(u) = pack4(val[i]);
@@ -328,7 +335,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = stage_all + (warp - 2) * 32 * STG_LD;
+    float* stg = stage_all + (warp - 2) * STG_FLOATS;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -368,8 +375,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_32x32(taddr + c * 32, raw);
           tmem_wait_ld();
           if (p.dbg >= 2) continue;
-          if (col0 + 32 <= p.N && p.fast_ok) epi_chunk<EPI>(p, stg, raw, lane, orow_i, res_i, col0);
-          else epi_chunk_slow<EPI>(p, raw, raw, orow, res_row, col0, (int)min((int64_t)32, p.N - col0));
+          if (col0 + 32 <= p.N && p.fast_ok) {
+            float4 resv[8];
+            if (EPI == EPI_F32 && p.residual != nullptr) load_res8(resv, orow_i, res_i, col0 + (lane & 7) * 4);
+            epi_chunk<EPI>(p, stg, raw, lane, orow_i, resv, col0);
+          } else {
+            epi_chunk_slow<EPI>(p, raw, raw, orow, res_row, col0, (int)min((int64_t)32, p.N - col0));
+          }
         }
       } else {
         // GEGLU: accumulator columns [0, BLOCK_N/2) = value, [BLOCK_N/2, BLOCK_N) = gate of the same features
@@ -398,6 +410,357 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ================================================================================================
+// CTA-pair variant (cta_group::2): a 2-CTA cluster owns one 256 x 256 output tile.  Each CTA loads its own 128 rows
+// of A and 128 of the 256 B rows per k-block (32 KB per stage per CTA instead of 48 KB for the same 128 x 256 MMA
+// work), which is what lifts the kernel off the L2 -> SM bandwidth ceiling the single-CTA tile sits on.  The leader
+// (cluster rank 0) issues tcgen05.mma.cta_group::2; both CTAs run 8 epilogue warps over their own 128 accumulator rows.
+//   barriers:  full[s]   leader only   1 arrival (leader's expect_tx) + the bytes of BOTH CTAs' TMA loads
+//              empty[s]  each CTA      multicast tcgen05.commit from the leader
+//              tmem_full[a]  each CTA  multicast tcgen05.commit from the leader
+//              tmem_empty[a] leader    16 arrivals: 8 epilogue warps x 2 CTAs (remote arrive from the peer)
+// ================================================================================================
+constexpr int GEMM2_THREADS = 320;     // warp 0 TMA, warp 1 MMA / TMEM owner, warps 2..9 epilogue
+constexpr int G2_BN = 256;
+constexpr int G2_A_BYTES = 128 * BLOCK_K * 2;
+constexpr int G2_B_BYTES = 128 * BLOCK_K * 2;
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+// TS = "TMA-store epilogue" (bf16 / GEGLU outputs with a plain row mapping): every epilogue warp pulls its whole share
+// of the accumulator out of TMEM in one go (a tcgen05.ld issued while MMAs are queued completes late, so serial
+// load -> use -> load round trips made the epilogue the pacing stage), releases the accumulator, packs bf16 into a
+// 128B-swizzled 32-row box in shared memory and hands it to the TMA store engine.
+template <bool TS>
+struct G2Cfg {
+  static constexpr int STAGES = TS ? 5 : 6;
+  static constexpr int STG_BYTES = TS ? 8 * 8192 : 8 * STG_FLOATS * 4;   // per epilogue warp: two 4 KB boxes / one 32x32 fp32 block
+  static constexpr int SMEM_BYTES = STAGES * G2_STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// 64 fp32 accumulator columns of this lane's row -> bf16 -> one 32-row x 128-byte box, 16-byte groups XOR-swizzled
+// with (row & 7) (= CU_TENSOR_MAP_SWIZZLE_128B for a 1024-byte aligned box)
+__device__ __forceinline__ void pack_box(uint8_t* box, const uint32_t (&v)[64], int lane, const float* bias, float alpha) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      x[t] = __uint_as_float(v[8 * j + t]) * alpha;
+      if (bias != nullptr) x[t] += __ldg(bias + 8 * j + t);
+    }
+    *reinterpret_cast<uint4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+  }
+}
+
+template <int EPI, bool TS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
+                     const GemmParams p) {
+  constexpr bool geglu = (EPI == EPI_GEGLU);
+  constexpr int STAGES = G2Cfg<TS>::STAGES;
+  static_assert(!TS || EPI == EPI_BF16 || EPI == EPI_GEGLU, "TMA-store epilogue: bf16 / GEGLU outputs only");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * G2_A_BYTES;
+  uint8_t* stage_bytes = smem + STAGES * G2_STAGE_BYTES;   // 1024-byte aligned (TMA-store boxes need it)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_bytes + G2Cfg<TS>::STG_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;           // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* stage_all = reinterpret_cast<float*>(stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  constexpr int out_cols_per_tile = geglu ? G2_BN / 2 : G2_BN;
+  const int tiles_mn = p.m_tiles * p.n_tiles;     // m_tiles counts 256-row pair tiles here
+  const int total_work = tiles_mn * p.split_k;
+  const bool a_mn = p.a_mn != 0, b_mn = p.b_mn != 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if (TS) {
+      tma_prefetch_desc(&tmap_o);
+      if (geglu) tma_prefetch_desc(&tmap_o2);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full[s], 1);
+        mbar_init(&tmem_empty[s], 16);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc_cg2(tmem_base_slot, 512);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / multicast commit lands
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs, each its own halves) ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        const int tile = w % tiles_mn;
+        const int split = w / tiles_mn;
+        const int m0 = (tile / p.n_tiles) * 256 + (int)rank * 128;
+        const int n0 = (tile % p.n_tiles) * out_cols_per_tile;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * G2_A_BYTES;
+          uint8_t* sb = smem_b + stage * G2_B_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if (!a_mn) {
+            tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], k0, m0);               // box {64 k, 128 rows}
+          } else {
+            tma_load_2d_cg2(sa, &tmap_a, &full_bar[stage], m0, k0);               // box {64 m, 64 k} x 2
+            tma_load_2d_cg2(sa + 8192, &tmap_a, &full_bar[stage], m0 + 64, k0);
+          }
+          if (geglu) {   // leader: 128 value rows, peer: the 128 gate rows of the same features
+            tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], k0, (leader ? 0 : (int)p.geglu_ipad) + n0);
+          } else if (!b_mn) {
+            tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], k0, n0 + (int)rank * 128);   // box {64 k, 128 rows}
+          } else {
+            tma_load_2d_cg2(sb, &tmap_b, &full_bar[stage], n0 + (int)rank * 128, k0);   // box {64 n, 64 k} x 2
+            tma_load_2d_cg2(sb + 8192, &tmap_b, &full_bar[stage], n0 + (int)rank * 128 + 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (leader && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, G2_BN, a_mn, b_mn);
+      const uint32_t a_step = a_mn ? 2048 : 32, a_lbo = a_mn ? 8192 : 16;
+      const uint32_t b_step = b_mn ? 2048 : 32, b_lbo = b_mn ? 8192 : 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        const int split = w / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * G2_BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * G2_A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * G2_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * a_step, a_lbo, 1024);
+            const uint64_t db = umma_smem_desc(sb + k * b_step, b_lbo, 1024);
+            umma_bf16_cg2(tmem_d, da, db, idesc, (kb > kb0) || (k > 0));
+          }
+          umma_commit_cg2(&empty_bar[stage]);   // frees this smem slot in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_cg2(&tmem_full[acc]);       // accumulator ready, both CTAs' epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..9, both CTAs) ------------------------------
+    const int ew = warp - 2;
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
+    const int half = ew >> 2;       // which half of the tile's columns
+    float* stg = stage_all + ew * STG_FLOATS;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if constexpr (TS) {
+      uint8_t* sbox = stage_bytes + ew * 8192;   // two 4 KB boxes
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        const int tile = w % tiles_mn;
+        const int m0 = (tile / p.n_tiles) * 256 + (int)rank * 128;
+        const int n0 = (tile % p.n_tiles) * out_cols_per_tile;
+        const int row0 = m0 + quarter * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G2_BN;
+        uint32_t v0[64], v1[64];
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if constexpr (!geglu) {
+          const int col_base = n0 + half * 128;
+          const bool live0 = col_base < p.N && row0 < p.M, live1 = col_base + 64 < p.N && row0 < p.M;   // warp-uniform
+          if (live0) tmem_ld_32x64(taddr + half * 128, v0);
+          if (live1) tmem_ld_32x64(taddr + half * 128 + 64, v1);
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);   // accumulator released before any store work
+          if (live0) {
+            if (lane == 0) tma_store_wait_read<0>();   // the previous tile's stores have drained this warp's boxes
+            __syncwarp();
+            pack_box(sbox, v0, lane, p.bias ? p.bias + col_base : nullptr, p.alpha);
+            if (live1) pack_box(sbox + 4096, v1, lane, p.bias ? p.bias + col_base + 64 : nullptr, p.alpha);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_o, sbox, col_base, row0);
+              if (live1) tma_store_2d(&tmap_o, sbox + 4096, col_base + 64, row0);
+              tma_store_commit();
+            }
+          }
+        } else {
+          // value columns [half*64, +64) and the gate columns of the same 64 features
+          const int col_base = n0 + half * 64;
+          const bool live = col_base < p.N && row0 < p.M;
+          if (live) {
+            tmem_ld_32x64(taddr + half * 64, v0);
+            tmem_ld_32x64(taddr + G2_BN / 2 + half * 64, v1);
+          }
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          if (live) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            if (p.out2) {   // pre-activations [value | gate] for the backward pass
+              pack_box(sbox, v0, lane, nullptr, 1.0f);
+              pack_box(sbox + 4096, v1, lane, nullptr, 1.0f);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmap_o2, sbox, col_base, row0);
+                tma_store_2d(&tmap_o2, sbox + 4096, (int)p.geglu_ipad + col_base, row0);
+                tma_store_commit();
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < 64; ++t) v0[t] = __float_as_uint(gelu_erf(__uint_as_float(v1[t])) * __uint_as_float(v0[t]));
+            if (lane == 0) tma_store_wait_read<0>();   // box 0 is read out (the GELU math above covered the wait)
+            __syncwarp();
+            pack_box(sbox, v0, lane, nullptr, 1.0f);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_o, sbox, col_base, row0);
+              tma_store_commit();
+            }
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) tma_store_wait_all<0>();   // stores complete before this CTA's shared memory goes away
+    } else
+    for (int w = cluster_id; w < total_work; w += num_clusters) {
+      const int tile = w % tiles_mn;
+      const int m0 = (tile / p.n_tiles) * 256 + (int)rank * 128;
+      const int n0 = (tile % p.n_tiles) * out_cols_per_tile;
+      const int64_t row = (int64_t)m0 + quarter * 32 + lane;
+      int64_t orow = -1;
+      if (row < p.M) orow = p.out_period > 0 ? (row / p.out_period) * p.out_batch_rows + (row % p.out_period) : row;
+      const float* res_row = nullptr;
+      if (EPI == EPI_F32 && p.residual != nullptr && row < p.M) {
+        int64_t rr = row;
+        if (p.res_period > 0) {
+          rr = row % p.res_period;
+          if (p.res_row_map) rr = p.res_row_map[rr];
+        }
+        res_row = (p.residual2 && rr >= p.res_split) ? p.residual2 + (rr - p.res_split) * p.ldr : p.residual + rr * p.ldr;
+      }
+      int64_t orow_i[8];
+      const float* res_i[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        orow_i[i] = shfl_i64(orow, r);
+        res_i[i] = (EPI == EPI_F32) ? reinterpret_cast<const float*>(shfl_i64(reinterpret_cast<int64_t>(res_row), r)) : nullptr;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G2_BN;
+      uint32_t raw[32];
+      if (!geglu) {
+        const bool has_res = (EPI == EPI_F32) && p.residual != nullptr;
+        const int cl = (lane & 7) * 4;
+        float4 res_next[8];
+        // the first chunk's residual is fetched while the MMA of this tile is still running
+        if (has_res && p.fast_ok && (int64_t)n0 + half * 128 + 32 <= p.N) load_res8(res_next, orow_i, res_i, (int64_t)n0 + half * 128 + cl);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if (p.dbg == 4) {   // experiment: all four TMEM loads in flight at once, data discarded
+          uint32_t r2[32], r3[32], r4[32];
+          tmem_ld_32x32(taddr + (half * 4 + 0) * 32, raw);
+          tmem_ld_32x32(taddr + (half * 4 + 1) * 32, r2);
+          tmem_ld_32x32(taddr + (half * 4 + 2) * 32, r3);
+          tmem_ld_32x32(taddr + (half * 4 + 3) * 32, r4);
+          tmem_wait_ld();
+          if (raw[0] + r2[1] + r3[2] + r4[3] == 0x7fc12345u) reinterpret_cast<uint32_t*>(p.out)[0] = 1;
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < 4 && p.dbg != 4; ++cc) {
+          const int c = half * 4 + cc;
+          const int64_t col0 = (int64_t)n0 + c * 32;
+          if (col0 < p.N && p.dbg < 3) {   // warp-uniform
+            tmem_ld_32x32(taddr + c * 32, raw);
+            float4 resv[8];
+            if (has_res) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) resv[i] = res_next[i];
+              if (cc + 1 < 4 && p.fast_ok && col0 + 64 <= p.N) load_res8(res_next, orow_i, res_i, col0 + 32 + cl);
+            }
+            tmem_wait_ld();
+            if (p.dbg == 2) continue;
+            if (col0 + 32 <= p.N && p.fast_ok) epi_chunk<EPI>(p, stg, raw, lane, orow_i, resv, col0);
+            else epi_chunk_slow<EPI>(p, raw, raw, orow, res_row, col0, (int)min((int64_t)32, p.N - col0));
+          }
+        }
+      } else {
+        uint32_t rawg[32];
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 2 + cc;
+          const int64_t col0 = (int64_t)n0 + c * 32;
+          if (col0 >= p.N) break;
+          tmem_ld_32x32(taddr + c * 32, raw);
+          tmem_ld_32x32(taddr + G2_BN / 2 + c * 32, rawg);
+          tmem_wait_ld();
+          if (col0 + 32 <= p.N && p.fast_ok) epi_chunk_geglu(p, stg, raw, rawg, lane, orow_i, col0);
+          else epi_chunk_slow<EPI_GEGLU>(p, raw, rawg, orow, nullptr, col0, (int)min((int64_t)32, p.N - col0));
+        }
+      }
+      // release the accumulator stage: the MMA warp of the LEADER waits for both CTAs' epilogue warps
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // no CTA of the pair may free TMEM / exit while the peer still signals or reads
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, 512);
   }
 }
 
@@ -499,6 +862,64 @@ static int launch_gemm(const MmfGemmArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+template <int EPI, bool TS>
+static int launch_gemm2(const MmfGemmArgs& a, cudaStream_t stream) {
+  const bool geglu = a.act == 2;
+  const bool A_MN = a.a_mn != 0, B_MN = a.b_mn != 0;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN) rc = make_tmap(&ta, a.a, a.M, a.K, a.lda, BLOCK_K, 128);
+  else       rc = make_tmap(&ta, a.a, a.K, a.M, a.lda, 64, BLOCK_K);
+  if (rc) return rc;
+  const int64_t b_rows = geglu ? 2 * a.N : a.N;
+  if (!B_MN) rc = make_tmap(&tb, a.b, b_rows, a.K, a.ldb, BLOCK_K, 128);
+  else       rc = make_tmap(&tb, a.b, a.K, b_rows, a.ldb, 64, BLOCK_K);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.out = a.out; p.out2 = a.out2; p.bias = a.bias; p.residual = a.residual; p.residual2 = a.residual2; p.res_split = a.res_split; p.res_row_map = a.res_row_map;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.ldo = a.ldo; p.ldo2 = a.ldo2; p.ldr = a.ldr;
+  p.out_f32 = a.out_f32; p.act = a.act; p.split_k = a.split_k < 1 ? 1 : a.split_k;
+  p.res_period = a.res_period; p.out_period = a.out_period; p.out_batch_rows = a.out_batch_rows;
+  p.accumulate = a.accumulate;
+  p.a_mn = a.a_mn; p.b_mn = a.b_mn;
+  p.m_tiles = (int)ceil_div64(a.M, 256);
+  p.n_tiles = (int)ceil_div64(a.N, geglu ? G2_BN / 2 : G2_BN);
+  p.num_kb = (int)ceil_div64(a.K, BLOCK_K);
+  if (p.split_k > p.num_kb) p.split_k = p.num_kb;
+  p.kb_per_split = ceil_div(p.num_kb, p.split_k);
+  p.split_k = ceil_div(p.num_kb, p.kb_per_split);
+  p.geglu_ipad = a.N;
+  p.alpha = a.alpha;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.fast_ok = (a.ldo % 4 == 0) && al16(a.out) && (!a.residual || (a.ldr % 4 == 0 && al16(a.residual))) &&
+              (!a.residual2 || al16(a.residual2)) && (!a.bias || al16(a.bias)) && (!a.out2 || (a.ldo2 % 4 == 0 && al16(a.out2))) &&
+              (a.act != 2 || a.N % 4 == 0);
+  static const int dbg_env = getenv("MMF_GEMM_DEBUG") ? atoi(getenv("MMF_GEMM_DEBUG")) : 0;
+  p.dbg = dbg_env;
+  CUtensorMap to = ta, to2 = ta;   // placeholders unless TS
+  if (TS) {   // bf16 outputs as 32-row x 64-column boxes
+    if ((rc = make_tmap(&to, a.out, a.M, a.N, a.ldo, 64, 32))) return rc;
+    if (a.out2 && (rc = make_tmap(&to2, a.out2, a.M, geglu ? 2 * a.N : a.N, a.ldo2, 64, 32))) return rc;
+  }
+
+  static bool attr_set = false;
+  auto kern = gemm2_tcgen05_kernel<EPI, TS>;
+  constexpr int SMEM = G2Cfg<TS>::SMEM_BYTES;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.split_k;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = (int)(total < max_clusters ? total : max_clusters);
+  kern<<<2 * clusters, GEMM2_THREADS, SMEM, stream>>>(ta, tb, to, to2, p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace mmf
 
 extern "C" int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream_) {
@@ -551,6 +972,21 @@ extern "C" int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream_) {
     case EPI_ATOMIC: return launch_gemm<BN, EPI_ATOMIC>(a, stream);                   \
     case EPI_BF16_ACC: return launch_gemm<BN, EPI_BF16_ACC>(a, stream);               \
     default: break;                                                                   \
+  }
+  static const bool pair_on = !(getenv("MMF_GEMM_2CTA") && atoi(getenv("MMF_GEMM_2CTA")) == 0);
+  if (bn == 256 && pair_on) {   // CTA-pair kernel (cta_group::2, 256 x 256 tile per cluster)
+    static const bool ts_on = !(getenv("MMF_GEMM_TMA_STORE") && atoi(getenv("MMF_GEMM_TMA_STORE")) == 0);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool ts = ts_on && a.out_period == 0 && (a.ldo & 7) == 0 && al16(a.out) && (!a.out2 || ((a.ldo2 & 7) == 0 && al16(a.out2)));
+    switch (epi) {
+      case EPI_BF16: return ts ? launch_gemm2<EPI_BF16, true>(a, stream) : launch_gemm2<EPI_BF16, false>(a, stream);
+      case EPI_GELU: return launch_gemm2<EPI_GELU, false>(a, stream);
+      case EPI_F32: return launch_gemm2<EPI_F32, false>(a, stream);
+      case EPI_ATOMIC: return launch_gemm2<EPI_ATOMIC, false>(a, stream);
+      case EPI_BF16_ACC: return launch_gemm2<EPI_BF16_ACC, false>(a, stream);
+      case EPI_GEGLU: return ts ? launch_gemm2<EPI_GEGLU, true>(a, stream) : launch_gemm2<EPI_GEGLU, false>(a, stream);
+      default: break;
+    }
   }
   if (bn == 256) {
     if (epi == EPI_GEGLU) return launch_gemm<256, EPI_GEGLU>(a, stream);

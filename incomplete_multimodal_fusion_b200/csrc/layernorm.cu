@@ -31,6 +31,12 @@ struct LnParams {
   int64_t ldy;
   int y_f32;
   float* stats;  // [rows, 4] mean1, rstd1, mean2, rstd2 (nullable)
+  // fused residual add: rows >= delta_row0 are normalised as x + delta[row - delta_row0] (delta bf16: the output of the
+  // sub-layer's last GEMM) and that sum, the new fp32 residual stream, is written to xout[row - delta_row0]
+  const __nv_bfloat16* delta;
+  int64_t delta_row0, lddelta;
+  float* xout;
+  int64_t ldxout;
 };
 
 // gamma1 / bias1 / gamma2 staged once per CTA in shared memory (index = float4 chunk)
@@ -63,8 +69,25 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p)
       const int c = lane + 32 * i;
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < nchunk) v[i] = xr[c];
-      s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
+    if (p.delta && row >= p.delta_row0) {
+      const uint2* dr = reinterpret_cast<const uint2*>(p.delta + (row - p.delta_row0) * p.lddelta);
+      float4* xo = reinterpret_cast<float4*>(p.xout + (row - p.delta_row0) * p.ldxout);
+      uint2 u[LN_MAX_CHUNKS];
+#pragma unroll
+      for (int i = 0; i < LN_MAX_CHUNKS; ++i)
+        if (lane + 32 * i < nchunk) u[i] = dr[lane + 32 * i];
+#pragma unroll
+      for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        if (lane + 32 * i < nchunk) {
+          const float2 lo = unpack_bf16(u[i].x), hi = unpack_bf16(u[i].y);
+          v[i].x += lo.x; v[i].y += lo.y; v[i].z += hi.x; v[i].w += hi.y;
+          xo[lane + 32 * i] = v[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
     const float mean1 = warp_sum(s) * invD;
     float q = 0.f;
 #pragma unroll
@@ -295,14 +318,19 @@ static int ln_grid(int64_t rows) {
 
 extern "C" int mmf_layernorm_fwd(const float* x, const float* x2, int64_t x_split, int64_t rows, int32_t D, int64_t ldx, const float* g1, const float* b1,
                                  float eps1, const float* g2, float eps2, void* y, int64_t ldy, int32_t y_f32,
-                                 float* stats, mmf_stream_t stream) {
+                                 float* stats, const void* delta, int64_t delta_row0, int64_t lddelta, float* xout,
+                                 int64_t ldxout, mmf_stream_t stream) {
   using namespace mmf;
   if (!x || !g1 || !y) MMF_BAD_ARG(1);
   if (rows <= 0) return 0;
   if (D <= 0 || (D & 3) || D > LN_MAX_D) MMF_BAD_ARG(2);
   if ((ldx & 3) || (ldy & 3) || ldx < D || ldy < D) MMF_BAD_ARG(3);
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) MMF_BAD_ARG(4);
-  LnParams p{x, x2, x_split, rows, ldx, D, g1, b1, g2, eps1, eps2, y, ldy, y_f32, stats};
+  if (delta && (!xout || delta_row0 < 0 || (lddelta & 3) || (ldxout & 3) || lddelta < D || ldxout < D ||
+                (reinterpret_cast<uintptr_t>(delta) & 7) || (reinterpret_cast<uintptr_t>(xout) & 15)))
+    MMF_BAD_ARG(5);
+  LnParams p{x, x2, x_split, rows, ldx, D, g1, b1, g2, eps1, eps2, y, ldy, y_f32, stats,
+             reinterpret_cast<const __nv_bfloat16*>(delta), delta_row0, lddelta, xout, ldxout};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nc = ceil_div(D, 128);
   if (nc <= 2) ln_fwd_kernel<2><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(p);

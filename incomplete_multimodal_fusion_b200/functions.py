@@ -363,22 +363,25 @@ class EmbedFn(torch.autograd.Function):
 ZB = 9  # tensors per (zorro or fusion) block: norm1.g, attn.norm.g, to_q.W, to_kv.W, to_out.W, norm2.g, mlp.0.g, mlp.1.W, mlp.3.W
 
 
-def _ln2(x, g1, g2, x2=None, split=0, rows=None):
+def _ln2(x, g1, g2, x2=None, split=0, rows=None, delta=None, delta_row0=0, xout=None):
+    """fused double LayerNorm of (x [+ delta]) -> bf16; see kernels.layernorm_fwd for the residual-add arguments"""
     rows = rows if rows is not None else x.shape[0]
     y = torch.empty(rows, x.shape[1], dtype=bf16, device=x.device)
     st = torch.empty(rows, 4, dtype=f32, device=x.device)
-    K.layernorm_fwd(x, g1, y, g2=g2, stats=st, x2=x2, x_split=split, rows=rows)
+    K.layernorm_fwd(x, g1, y, g2=g2, stats=st, x2=x2, x_split=split, rows=rows, delta=delta, delta_row0=delta_row0, xout=xout)
     return y, st
 
 
-def _ffn_fwd(h, w1b, w2b, ipad, residual):
+def _ffn_fwd(h, w1b, w2b, ipad):
+    """GEGLU feed-forward without the residual add: returns (delta bf16 [rows, D], g, u).  The caller's next
+    LayerNorm launch adds delta to the fp32 residual stream (reference: Linear output bf16, sum fp32)."""
     rows = h.shape[0]
     g = torch.empty(rows, ipad, dtype=bf16, device=h.device)
     u = torch.empty(rows, 2 * ipad, dtype=bf16, device=h.device)
     K.gemm(h, w1b, g, act=2, out2=u)
-    out = torch.empty(rows, w2b.shape[0], dtype=f32, device=h.device)
-    K.gemm(g, w2b, out, residual=residual)
-    return out, g, u
+    delta = torch.empty(rows, w2b.shape[0], dtype=bf16, device=h.device)
+    K.gemm(g, w2b, delta)
+    return delta, g, u
 
 
 def _unpad_w1(dw1, I, ipad):
@@ -406,46 +409,59 @@ class EncoderStackFn(torch.autograd.Function):
         base = 1 if fusion else 0
         me = params[0].detach()[0] if fusion else None
         saved = []
-        X = X.contiguous()
+        # The fp32 residual stream is S (+ pend): `pend` is the bf16 output of the last sub-layer GEMM that has not
+        # been added yet; the next LayerNorm launch adds it and writes the materialised stream (one pass, no fp32
+        # read-modify-write in a GEMM epilogue).
+        S = X.contiguous()
+        pend = None
         for i in range(depth):
             lp = [p.detach() for p in params[base + i * per_layer: base + (i + 1) * per_layer]]
-            rec = {"X": X}
+            rec = {}
             Xf2 = None
+            Xin = S if pend is None else torch.empty(Mt, D, dtype=f32, device=S.device)
             if fusion:
                 fn1, fan, fwq, fwkv, fwo, fn2, fm0, fw1, fw2 = lp[:ZB]
-                hk, stA = _ln2(X, fn1, fan)
+                hk, stA = _ln2(S, fn1, fan, delta=pend, xout=Xin if pend is not None else None)
                 wkv = w_bf16(params[base + i * per_layer + 3])
-                kv = torch.empty(Mt, 2 * HD, dtype=bf16, device=X.device)
+                kv = torch.empty(Mt, 2 * HD, dtype=bf16, device=S.device)
                 K.gemm(hk, wkv, kv)
-                q = torch.empty(Mf, HD, dtype=bf16, device=X.device)
+                q = torch.empty(Mf, HD, dtype=bf16, device=S.device)
                 K.gemm(hk[Mh:], w_bf16(params[base + i * per_layer + 2]), q)
                 hm, stM = _ln2(me.contiguous(), fn1, fan)
-                kvm = torch.empty(Fn, 2 * HD, dtype=bf16, device=X.device)
+                kvm = torch.empty(Fn, 2 * HD, dtype=bf16, device=S.device)
                 K.gemm(hm, wkv, kvm)
-                a = torch.empty(Mf, HD, dtype=bf16, device=X.device)
+                a = torch.empty(Mf, HD, dtype=bf16, device=S.device)
                 K.slot_attn_fwd(q, kv, kvm, meta["slotmap"], seg, a, None, B=B, F=Fn, H=H, S=nseg, n_head=nenc, scale=scale)
-                Xf1 = torch.empty(Mf, D, dtype=f32, device=X.device)
-                K.gemm(a, w_bf16(params[base + i * per_layer + 4]), Xf1, residual=X[Mh:])
-                h2, stB = _ln2(Xf1, fn2, fm0)
-                Xf2, g, u = _ffn_fwd(h2, w_geglu_bf16(params[base + i * per_layer + 7], ipad),
-                                     w_bf16(params[base + i * per_layer + 8], cols_pad=ipad), ipad, Xf1)
+                dA = torch.empty(Mf, D, dtype=bf16, device=S.device)
+                K.gemm(a, w_bf16(params[base + i * per_layer + 4]), dA)
+                Xf1 = torch.empty(Mf, D, dtype=f32, device=S.device)
+                h2, stB = _ln2(Xin[Mh:], fn2, fm0, delta=dA, xout=Xf1)            # Xf1 = fusion tokens + attention
+                dF, g, u = _ffn_fwd(h2, w_geglu_bf16(params[base + i * per_layer + 7], ipad),
+                                    w_bf16(params[base + i * per_layer + 8], cols_pad=ipad), ipad)
+                Xf2 = torch.empty(Mf, D, dtype=f32, device=S.device)
                 rec.update(hk=hk, stA=stA, kv=kv, q=q, hm=hm, stM=stM, kvm=kvm, a=a, Xf1=Xf1, h2=h2, stB=stB, g=g, u=u, Xf2=Xf2)
             zo = base + i * per_layer + (ZB if fusion else 0)
             n1, an, wq, wkv_, wo, n2, m0, w1, w2 = [p.detach() for p in params[zo: zo + ZB]]
-            h1, st1 = _ln2(X, n1, an, x2=Xf2, split=Mh if fusion else 0, rows=Mt)
-            qkv = torch.empty(Mt, 3 * HD, dtype=bf16, device=X.device)
+            if fusion:   # rows >= Mh: Xf2 = Xf1 + ffn (written by this launch), rows < Mh: the block input
+                h1, st1 = _ln2(Xin, n1, an, x2=Xf1, split=Mh, rows=Mt, delta=dF, delta_row0=Mh, xout=Xf2)
+            else:
+                h1, st1 = _ln2(S, n1, an, delta=pend, xout=Xin if pend is not None else None)
+            rec["X"] = Xin
+            qkv = torch.empty(Mt, 3 * HD, dtype=bf16, device=S.device)
             K.gemm(h1, w_cat_bf16([params[zo + 2], params[zo + 3]]), qkv)
-            o = torch.empty(Mt, HD, dtype=bf16, device=X.device)
-            lse = torch.empty(B, H, N, dtype=f32, device=X.device)
+            o = torch.empty(Mt, HD, dtype=bf16, device=S.device)
+            lse = torch.empty(B, H, N, dtype=f32, device=S.device)
             K.attn_fwd(qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, B=B, H=H, Nq=N, Nk=N, dh=64, scale=scale,
                        n_head_q=nenc, n_head_k=nenc, seg=seg, nseg=nseg)
-            X1 = torch.empty(Mt, D, dtype=f32, device=X.device)
-            K.gemm(o, w_bf16(params[zo + 4]), X1, residual=X, residual2=Xf2, res_split=Mh if fusion else 0)
-            h2z, st2 = _ln2(X1, n2, m0)
-            X2, gz, uz = _ffn_fwd(h2z, w_geglu_bf16(params[zo + 7], ipad), w_bf16(params[zo + 8], cols_pad=ipad), ipad, X1)
+            dO = torch.empty(Mt, D, dtype=bf16, device=S.device)
+            K.gemm(o, w_bf16(params[zo + 4]), dO)
+            X1 = torch.empty(Mt, D, dtype=f32, device=S.device)
+            h2z, st2 = _ln2(Xin, n2, m0, x2=Xf2, split=Mh if fusion else 0, rows=Mt, delta=dO, xout=X1)   # X1 = x + attn
+            dZ, gz, uz = _ffn_fwd(h2z, w_geglu_bf16(params[zo + 7], ipad), w_bf16(params[zo + 8], cols_pad=ipad), ipad)
             rec.update(h1=h1, st1=st1, qkv=qkv, o=o, lse=lse, X1=X1, h2z=h2z, st2=st2, gz=gz, uz=uz)
             saved.append(rec)
-            X = X2
+            S, pend = X1, dZ
+        X = K.add_bf16(S, pend) if pend is not None else S
         ctx.meta = meta
         ctx.saved = saved
         ctx.params = params

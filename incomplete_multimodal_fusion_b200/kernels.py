@@ -113,12 +113,18 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, 
     return out
 
 
-def layernorm_fwd(x, g1, y, *, b1=None, eps1=1e-5, g2=None, eps2=1e-5, stats=None, x2=None, x_split=0, rows=None):
+def layernorm_fwd(x, g1, y, *, b1=None, eps1=1e-5, g2=None, eps2=1e-5, stats=None, x2=None, x_split=0, rows=None,
+                  delta=None, delta_row0=0, xout=None):
+    """y = LN2(LN1(x')) with x' = x (+ delta for rows >= delta_row0, in which case x' of those rows is written to xout)"""
     assert x.dtype == f32 and y.dtype in (bf16, f32)
     rows = rows if rows is not None else x.shape[0]
     D = x.shape[1]
+    if delta is not None:
+        assert delta.dtype == bf16 and xout is not None and xout.dtype == f32
+        assert delta.shape[0] >= rows - delta_row0 and xout.shape[0] >= rows - delta_row0
     check(_L().mmf_layernorm_fwd(_p(x), _p(x2), x_split, rows, D, _ld(x), _p(g1), _p(b1), eps1, _p(g2), eps2, _p(y), _ld(y),
-                                 int(y.dtype == f32), _p(stats), _stream()), "mmf_layernorm_fwd")
+                                 int(y.dtype == f32), _p(stats), _p(delta), delta_row0, _ld(delta) if delta is not None else 0,
+                                 _p(xout), _ld(xout) if xout is not None else 0, _stream()), "mmf_layernorm_fwd")
     return y
 
 
@@ -290,3 +296,12 @@ def add_inplace(y, x):
     assert y.dtype == f32 and x.dtype == f32 and y.is_contiguous() and x.is_contiguous() and y.numel() == x.numel()
     check(_L().mmf_add_inplace_f32(_p(y), _p(x), y.numel(), _stream()), "mmf_add_inplace_f32")
     return y
+
+
+def add_bf16(x, d, out=None):
+    """out (f32) = x (f32) + d (bf16)"""
+    assert x.dtype == f32 and d.dtype == bf16 and x.is_contiguous() and d.is_contiguous() and x.numel() == d.numel()
+    if out is None:
+        out = torch.empty_like(x)
+    check(_L().mmf_add_bf16_f32(_p(out), _p(x), _p(d), x.numel(), _stream()), "mmf_add_bf16_f32")
+    return out
