@@ -643,7 +643,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           if (live) {
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
-            if (p.out2) {   // pre-activations [value | gate] for the backward pass
+            if (p.out2 && p.dbg != 5 && p.dbg != 7) {   // pre-activations [value | gate] for the backward pass
               pack_box(sbox, v0, lane, nullptr, 1.0f);
               pack_box(sbox + 4096, v1, lane, nullptr, 1.0f);
               fence_proxy_async_smem();
@@ -654,14 +654,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 tma_store_commit();
               }
             }
+            if (p.dbg != 6) {
 #pragma unroll
-            for (int t = 0; t < 64; ++t) v0[t] = __float_as_uint(gelu_erf(__uint_as_float(v1[t])) * __uint_as_float(v0[t]));
+              for (int t = 0; t < 64; ++t) v0[t] = __float_as_uint(gelu_fast(__uint_as_float(v1[t])) * __uint_as_float(v0[t]));
+            }
             if (lane == 0) tma_store_wait_read<0>();   // box 0 is read out (the GELU math above covered the wait)
             __syncwarp();
             pack_box(sbox, v0, lane, nullptr, 1.0f);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && p.dbg != 7) {
               tma_store_2d(&tmap_o, sbox, col_base, row0);
               tma_store_commit();
             }

@@ -305,12 +305,16 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
   }
 }
 
-static int ln_grid(int64_t rows) {
-  int dev = 0, sms = 148;
+// Persistent grid = exactly the CTAs that are co-resident (occupancy x SMs): the row loop is grid-strided, so a grid
+// that is not a whole number of resident waves leaves SMs idle during the last wave.
+template <typename Kern>
+static int ln_grid(Kern kern, size_t dyn_smem, int64_t rows, int waves = 1) {
+  int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LN_WARPS * 32, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int64_t need = ceil_div64(rows, LN_WARPS);
-  const int64_t cap = (int64_t)sms * 8;  // 8 CTAs of 8 warps = 64 warps per SM
+  const int64_t cap = (int64_t)sms * per_sm * waves;
   return (int)(need < cap ? need : cap);
 }
 
@@ -333,10 +337,10 @@ extern "C" int mmf_layernorm_fwd(const float* x, const float* x2, int64_t x_spli
              reinterpret_cast<const __nv_bfloat16*>(delta), delta_row0, lddelta, xout, ldxout};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nc = ceil_div(D, 128);
-  if (nc <= 2) ln_fwd_kernel<2><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(p);
-  else if (nc <= 4) ln_fwd_kernel<4><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(p);
-  else if (nc <= 6) ln_fwd_kernel<6><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(p);
-  else ln_fwd_kernel<8><<<ln_grid(rows), LN_WARPS * 32, 0, st>>>(p);
+  if (nc <= 2) ln_fwd_kernel<2><<<ln_grid(ln_fwd_kernel<2>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p);
+  else if (nc <= 4) ln_fwd_kernel<4><<<ln_grid(ln_fwd_kernel<4>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p);
+  else if (nc <= 6) ln_fwd_kernel<6><<<ln_grid(ln_fwd_kernel<6>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p);
+  else ln_fwd_kernel<8><<<ln_grid(ln_fwd_kernel<8>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
   return 0;
@@ -354,9 +358,6 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
   if (g2 && !dg2) MMF_BAD_ARG(4);
   LnBwdParams p{dy, lddy, dy_f32, x, x2, x_split, rows, ldx, D, g1, b1, g2, stats, dres, lddres, dx, lddx, dx_bf16, lddxb, dg1, db1,
                 g2 ? dg2 : nullptr};
-  // fewer CTAs than the forward: each CTA ends with D atomics per parameter vector
-  int grid = ln_grid(rows);
-  if (grid > 148 * 3) grid = 148 * 3;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nc = ceil_div(D, 128);
   const int ncp = nc <= 2 ? 2 : (nc <= 4 ? 4 : (nc <= 6 ? 6 : 8));
@@ -370,10 +371,10 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
     cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 8 * 32 * 16);
     attr_done = true;
   }
-  if (nc <= 2) ln_bwd_kernel<2><<<grid, LN_WARPS * 32, smem, st>>>(p);
-  else if (nc <= 4) ln_bwd_kernel<4><<<grid, LN_WARPS * 32, smem, st>>>(p);
-  else if (nc <= 6) ln_bwd_kernel<6><<<grid, LN_WARPS * 32, smem, st>>>(p);
-  else ln_bwd_kernel<8><<<grid, LN_WARPS * 32, smem, st>>>(p);
+  if (nc <= 2) ln_bwd_kernel<2><<<ln_grid(ln_bwd_kernel<2>, smem, rows), LN_WARPS * 32, smem, st>>>(p);
+  else if (nc <= 4) ln_bwd_kernel<4><<<ln_grid(ln_bwd_kernel<4>, smem, rows), LN_WARPS * 32, smem, st>>>(p);
+  else if (nc <= 6) ln_bwd_kernel<6><<<ln_grid(ln_bwd_kernel<6>, smem, rows), LN_WARPS * 32, smem, st>>>(p);
+  else ln_bwd_kernel<8><<<ln_grid(ln_bwd_kernel<8>, smem, rows), LN_WARPS * 32, smem, st>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
   return 0;

@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""FFN-1 GEGLU GEMM timed alone next to a plain bf16 GEMM of the same MMA work and cuBLAS (profiling experiments)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from incomplete_multimodal_fusion_b200 import kernels as K
+M, D, I = 125440, 768, 2048
+a = (torch.randn(M, D, device="cuda") * .1).bfloat16(); w = (torch.randn(2 * I, D, device="cuda") * .1).bfloat16()
+g = torch.empty(M, I, dtype=torch.bfloat16, device="cuda"); u = torch.empty(M, 2 * I, dtype=torch.bfloat16, device="cuda")
+def t(fn):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 20
+fl = 2 * M * 2 * I * D / 1e9
+mode = sys.argv[1] if len(sys.argv) > 1 else "geglu"
+if mode == "geglu":
+    ms = t(lambda: K.gemm(a, w, g, act=2, out2=u))
+elif mode == "geglu_noU":
+    ms = t(lambda: K.gemm(a, w, g, act=2))
+elif mode == "plain":
+    ms = t(lambda: K.gemm(a, w, u))
+else:
+    ms = t(lambda: torch.matmul(a, w.t(), out=u))
+print(f"{mode:10s} dbg={os.environ.get('MMF_GEMM_DEBUG','0')}: {ms:.3f} ms {fl/ms:.0f} TFLOP/s")

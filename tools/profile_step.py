@@ -26,10 +26,10 @@ for i in range(a.steps):
     torch.manual_seed(1 + i)
     if i == a.steps - 1:
         torch.cuda.synchronize()
-        rid = torch.cuda.nvtx.range_start("laststep")
+        torch.cuda.nvtx.range_push("laststep")
     loss = step(x)
     if i == a.steps - 1:
         torch.cuda.synchronize()
-        torch.cuda.nvtx.range_end(rid)
+        torch.cuda.nvtx.range_pop()
 torch.cuda.synchronize()
 print("loss", float(loss))
