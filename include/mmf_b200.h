@@ -220,6 +220,21 @@ int mmf_add_inplace_f32(float* y, const float* x, int64_t n, mmf_stream_t stream
 /* out (f32) = x (f32) + d (bf16): the residual stream after the last sub-layer (zorro_utils.py:239) */
 int mmf_add_bf16_f32(float* out, const float* x, const void* d, int64_t n, mmf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Mask sampling downstream of the random draws, one single-CTA launch (multimae.py:182-255 generate_random_masks and
+ * the per-modality token selection / zorro-mask bookkeeping of forward, :378-426; masks are one row for the batch).
+ *   noise1 [sum sizes]: the per-task torch.rand(1, n_t) draws concatenated in task order; noise2 [sum sizes]: the
+ *   rand_like draw of :241; share [T]: the Dirichlet sample; want_t = round_half_even(share_t * nenc) (:210).
+ * Outputs (device): mask [sum sizes] int64 (0 = visible), ids_restore [sum sizes] / ids_keep [nenc] int64,
+ *   idx: task t's ascending visible positions (int32) at offset sum(sizes[:t]), counts [T], seg [T+2] =
+ *   [0, c0, c0+c1, .., nenc, nenc + n_fusion], slotmap [T, n_fusion] (rank of a position in idx_t or -1; nullable).
+ * argsort is stable (rank counting); the reference's CUDA argsort leaves the order of equal keys unspecified.
+ * sizes is a HOST array.  sum sizes <= 4096, T <= 8.
+ * ---------------------------------------------------------------------------------------------- */
+int mmf_mask_build(const float* noise1, const float* noise2, const float* share, int32_t T, const int32_t* sizes,
+                   int32_t nenc, int32_t n_fusion, int64_t* mask, int64_t* ids_restore, int64_t* ids_keep, int32_t* idx,
+                   int32_t* counts, int32_t* seg, int32_t* slotmap, mmf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -227,6 +227,34 @@ class SelfAttentionFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None
 
 
+class CrossAttentionFn(torch.autograd.Function):
+    """unmasked multi-head cross-attention: q [B*Nq, H*dh], kv [B*Nk, 2*H*dh] (k | v), both bf16 token-major
+    (decoder CrossAttention, multimae_utils.py:185-214)"""
+
+    @staticmethod
+    def forward(ctx, q, kv, B, Nq, Nk, H, dh, scale):
+        HD = H * dh
+        o = torch.empty(B * Nq, HD, dtype=bf16, device=q.device)
+        lse = torch.empty(B, H, Nq, dtype=f32, device=q.device)
+        K.attn_fwd(q, kv[:, :HD], kv[:, HD:], o, lse, B=B, H=H, Nq=Nq, Nk=Nk, dh=dh, scale=scale)
+        ctx.save_for_backward(q, kv, o, lse)
+        ctx.dims = (B, Nq, Nk, H, dh, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, kv, o, lse = ctx.saved_tensors
+        B, Nq, Nk, H, dh, scale = ctx.dims
+        HD = H * dh
+        do = to_bf16(do.contiguous())
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        delta = torch.empty(B, H, Nq, dtype=f32, device=q.device)
+        K.attn_bwd(q, kv[:, :HD], kv[:, HD:], o, lse, do, dq, dkv[:, :HD], dkv[:, HD:], delta, B=B, H=H, Nq=Nq, Nk=Nk,
+                   dh=dh, scale=scale)
+        return dq, dkv, None, None, None, None, None, None
+
+
 class PoolAttnFn(torch.autograd.Function):
     """R queries (batch-invariant, [R, H*64] bf16) over planar kv rows with a dense mask; see kernels.pool_attn_fwd"""
 

@@ -305,3 +305,24 @@ def add_bf16(x, d, out=None):
         out = torch.empty_like(x)
     check(_L().mmf_add_bf16_f32(_p(out), _p(x), _p(d), x.numel(), _stream()), "mmf_add_bf16_f32")
     return out
+
+
+def mask_build(noise1, noise2, share, sizes, nenc, n_fusion, want_slotmap):
+    """Everything of generate_random_masks / token selection after the random draws (see include/mmf_b200.h).
+    Returns (mask [n] int64, ids_restore [n] int64, ids_keep [nenc] int64, idx [n] int32, counts [T] int32,
+    seg [T+2] int32, slotmap [T, n_fusion] int32 or None), all on the device, no host sync."""
+    dev = noise1.device
+    T, n = len(sizes), int(sum(sizes))
+    assert noise1.dtype == f32 and noise2.dtype == f32 and share.dtype == f32
+    assert noise1.numel() == n and noise2.numel() == n and share.numel() == T
+    mask = torch.empty(n, dtype=torch.int64, device=dev)
+    ids_restore = torch.empty(n, dtype=torch.int64, device=dev)
+    ids_keep = torch.empty(nenc, dtype=torch.int64, device=dev)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    counts = torch.empty(T, dtype=torch.int32, device=dev)
+    seg = torch.empty(T + 2, dtype=torch.int32, device=dev)
+    slotmap = torch.empty(T, n_fusion, dtype=torch.int32, device=dev) if want_slotmap else None
+    csizes = (C.c_int32 * T)(*[int(v) for v in sizes])
+    check(_L().mmf_mask_build(_p(noise1), _p(noise2), _p(share), T, csizes, nenc, n_fusion, _p(mask), _p(ids_restore),
+                              _p(ids_keep), _p(idx), _p(counts), _p(seg), _p(slotmap), _stream()), "mmf_mask_build")
+    return mask, ids_restore, ids_keep, idx, counts, seg, slotmap

@@ -5,4 +5,4 @@ port by changing the package prefix."""
 from .criterion import MaskedL1Loss, MaskedMSELoss  # noqa: F401
 from .input_adapters import FusionInputAdapter, PatchedInputAdapter  # noqa: F401
 from .multimae import MultiMAE  # noqa: F401
-from .output_adapters_simple import SpatialOutputAdapter  # noqa: F401
+from .output_adapters import SpatialOutputAdapter  # noqa: F401  (the cross-attention decoder, as in the reference's __init__)

@@ -23,6 +23,7 @@ import torch.nn as nn
 from torch.distributions.dirichlet import Dirichlet
 
 from .. import functions as Fn
+from .. import kernels as K
 from .multimae_utils import trunc_normal_
 from .zorro_utils import Attention, Block, Block_Fusion, LayerNorm, Mlp, TokenTypes, ZorroMask, block_params
 
@@ -113,33 +114,42 @@ class MultiMAEBase(nn.Module):
         picked = torch.index_select(choices, 0, torch.randint(0, len(choices), (B,)))
         return picked * torch.tensor(alphas) + eps
 
-    def generate_random_masks(self, input_tokens: Dict[str, torch.Tensor], num_encoded_tokens: int,
-                              alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False):
-        """One mask for the whole batch (the reference's edit of MultiMAE's per-sample masking).  Returns
-        (task_masks {task: [B, n] int64, 0 = keep}, ids_keep [B, nenc], ids_restore [B, sum n])."""
+    def _sample_masks(self, input_tokens: Dict[str, torch.Tensor], num_encoded_tokens: int,
+                      alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False):
+        """The reference's torch RNG calls verbatim (same generator, shapes and order: CPU Dirichlet :208, one
+        torch.rand(1, n) per task on the device :217, rand_like over all tokens :241), then ONE mask-builder launch
+        (kernels.mask_build) for the argsorts / gathers / where / nonzero bookkeeping of :210-255 and :378-426."""
         first = next(iter(input_tokens.values()))
         B, device = first.shape[0], first.device
+        if device.type != 'cuda':
+            raise RuntimeError("mask sampling runs on CUDA only (no CPU fallback)")
         sizes = [t.shape[1] for t in input_tokens.values()]
         alphas = [alphas] * len(sizes) if isinstance(alphas, float) else alphas
         if sample_tasks_uniformly:
             share = Dirichlet(self.sample_alphas(1, len(sizes), alphas=alphas)).sample().to(device)
         else:
             share = Dirichlet(torch.Tensor(alphas)).sample((1,)).to(device)
-        want = (share * num_encoded_tokens).round().long()
-        per_task = []
-        for i, n in enumerate(sizes):
-            order = torch.argsort(torch.rand(1, n, device=device), dim=1)
-            rank = torch.gather(torch.arange(n, device=device).unsqueeze(0), 1, order)
-            per_task.append(torch.where(rank < want[:, i].unsqueeze(1), 0, 1))
-        flat = torch.cat(per_task, dim=1)
-        ids_shuffle = torch.argsort(flat + torch.rand_like(flat.float()), dim=1)
-        ids_restore = torch.argsort(ids_shuffle, dim=1)
-        ids_keep = ids_shuffle[:, :num_encoded_tokens]
-        flat = torch.ones_like(flat)
-        flat[:, :num_encoded_tokens] = 0
-        flat = torch.gather(flat, 1, ids_restore)
-        masks = {t: m.repeat(B, 1) for t, m in zip(input_tokens.keys(), torch.split(flat, sizes, dim=1))}
-        return masks, ids_keep.repeat(B, 1), ids_restore.repeat(B, 1)
+        noise1 = torch.cat([torch.rand(1, n, device=device) for n in sizes], dim=1)
+        noise2 = torch.rand_like(noise1)
+        Fn_tok = self.fusion_tokens.shape[1]
+        want_slot = self.FUSION_BLOCKS and all(n == Fn_tok for n in sizes)
+        mask, ids_restore, ids_keep, idx, counts, seg, slotmap = K.mask_build(
+            noise1.view(-1), noise2.view(-1), share.float().view(-1).contiguous(), sizes, num_encoded_tokens, Fn_tok, want_slot)
+        return dict(tasks=list(input_tokens.keys()), sizes=sizes, B=B, mask=mask, ids_restore=ids_restore, ids_keep=ids_keep,
+                    idx=idx, counts=counts, seg=seg, slotmap=slotmap)
+
+    def generate_random_masks(self, input_tokens: Dict[str, torch.Tensor], num_encoded_tokens: int,
+                              alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False):
+        """One mask for the whole batch (the reference's edit of MultiMAE's per-sample masking).  Returns
+        (task_masks {task: [B, n] int64, 0 = keep}, ids_keep [B, nenc], ids_restore [B, sum n])."""
+        r = self._sample_masks(input_tokens, num_encoded_tokens, alphas, sample_tasks_uniformly)
+        return self._public_masks(r)
+
+    @staticmethod
+    def _public_masks(r):
+        B = r["B"]
+        masks = {t: m.unsqueeze(0).repeat(B, 1) for t, m in zip(r["tasks"], torch.split(r["mask"], r["sizes"]))}
+        return masks, r["ids_keep"].unsqueeze(0).repeat(B, 1), r["ids_restore"].unsqueeze(0).repeat(B, 1)
 
     @staticmethod
     def make_mask(N_H, N_W, xy_idxs, full_tasks=[], indicate_visible=True, flatten=True, device='cuda'):
@@ -193,17 +203,27 @@ class MultiMAEBase(nn.Module):
         input_info = self.generate_input_info(carriers, image_size=(H, W))
         nenc = num_encoded_tokens if mask_inputs else sum(c.shape[1] for c in carriers.values())
 
+        slotmap = None
         if task_masks is None:
-            task_masks, ids_keep, ids_restore = self.generate_random_masks(
-                carriers, nenc, alphas=alphas, sample_tasks_uniformly=sample_tasks_uniformly)
+            r = self._sample_masks(carriers, nenc, alphas=alphas, sample_tasks_uniformly=sample_tasks_uniformly)
+            task_masks, ids_keep, ids_restore = self._public_masks(r)
+            cnt = r["counts"].tolist()                                  # the one host sync of the step: token counts
+            off = [0]
+            for n in r["sizes"]:
+                off.append(off[-1] + n)
+            where = {t: i for i, t in enumerate(r["tasks"])}
+            idx = [r["idx"][off[where[t]]: off[where[t]] + cnt[where[t]]] for t in MODALITIES]
+            counts = [cnt[where[t]] for t in MODALITIES]
+            if r["slotmap"] is not None:
+                slotmap = r["slotmap"] if r["tasks"][:3] == list(MODALITIES) else \
+                    torch.stack([r["slotmap"][where[t]] for t in MODALITIES]).contiguous()
         else:
             flat = torch.cat([task_masks[t] for t in tasks], dim=1)
             ids_shuffle = torch.argsort(flat, dim=1, stable=True)
             ids_restore = torch.argsort(ids_shuffle, dim=1, stable=True)
             ids_keep = ids_shuffle[:, :int((flat == 0).sum())]
-
-        idx = [(task_masks[t][0] == 0).nonzero(as_tuple=True)[0].to(torch.int32) for t in MODALITIES]
-        counts = [int(i.numel()) for i in idx]
+            idx = [(task_masks[t][0] == 0).nonzero(as_tuple=True)[0].to(torch.int32) for t in MODALITIES]
+            counts = [int(i.numel()) for i in idx]
         if sum(counts) != nenc:
             raise ValueError(f"num_encoded_tokens={nenc} but the masks keep {sum(counts)} tokens; pass the true count "
                              "(the reference mis-slices silently in this case)")
@@ -221,8 +241,7 @@ class MultiMAEBase(nn.Module):
         X = Fn.EmbedFn.apply(meta_e, self.fusion_tokens, *mod_args)
 
         # ---- encoder stack ----
-        slotmap = None
-        if self.FUSION_BLOCKS:
+        if self.FUSION_BLOCKS and slotmap is None:
             slotmap = torch.full((len(MODALITIES), Fn_tok), -1, dtype=torch.int32, device=device)
             for m, ix in enumerate(idx):
                 slotmap[m, ix.long()] = torch.arange(ix.numel(), dtype=torch.int32, device=device)

@@ -86,6 +86,34 @@ class Attention(nn.Module):
         return y.view(B, N, C)
 
 
+class CrossAttention(nn.Module):
+    """queries attend to a context sequence (multimae_utils.py:185-214): q / kv / proj Linears, scale on the scores"""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        if attn_drop != 0. or proj_drop != 0.:
+            raise NotImplementedError("dropout is never active in the reference path")
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        if self.head_dim not in (32, 64):
+            raise NotImplementedError("attention kernels are built for head_dim 32 and 64")
+        self.scale = self.head_dim ** -0.5
+        self.q = nn.Linear(dim, dim, bias=qkv_bias)
+        self.kv = nn.Linear(dim, dim * 2, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+    def forward(self, x, context):
+        """x [B, N, C], context [B, M, C] (already normalised, bf16 or f32) -> proj(attention) bf16 [B, N, C]"""
+        B, N, C = x.shape
+        M = context.shape[1]
+        q = Fn.linear(_flat(x), self.q.weight, self.q.bias)
+        kv = Fn.linear(_flat(context), self.kv.weight, self.kv.bias)
+        o = Fn.CrossAttentionFn.apply(q, kv, B, N, M, self.num_heads, self.head_dim, self.scale)
+        return Fn.linear(o, self.proj.weight, self.proj.bias).view(B, N, C)
+
+
 class Block(nn.Module):
     """pre-LN ViT block of the decoders (multimae_utils.py:217-232); residual stream in fp32"""
 

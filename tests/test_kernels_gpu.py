@@ -401,3 +401,49 @@ def test_elementwise():
     dst = torch.empty(9, 64, dtype=bf16, device="cuda")
     k.gather_rows(src, dst, batch=3, n=3, d=64, src_batch_rows=20, row_off=2, idx=gi)
     assert torch.equal(dst, src.view(3, 20, 64)[:, (gi.long() + 2)].reshape(9, 64).to(bf16))
+
+
+@pytest.mark.parametrize("sizes,nenc", [((196, 196, 196), 294), ((64, 64), 64), ((256, 256, 256, 256), 1000), ((16, 16, 16), 1),
+                                        ((49, 49, 49), 147)])
+def test_mask_build_matches_torch_ops(sizes, nenc):
+    """the single-CTA mask builder against the reference's op sequence (multimae.py:210-255, 378-382) on the same noise:
+    int64 masks / ids bit-exact, index lists = nonzero(), counts, segment table, slot map"""
+    T, n = len(sizes), sum(sizes)
+    for seed in range(4):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        noise1 = torch.rand(n, device="cuda", generator=g)
+        noise2 = torch.rand(n, device="cuda", generator=g)
+        share = torch.distributions.Dirichlet(torch.ones(T)).sample().cuda() if seed else torch.tensor([1.0] + [0.0] * (T - 1)).cuda()
+        same = len(set(sizes)) == 1
+        mask, ids_restore, ids_keep, idx, counts, seg, slotmap = K().mask_build(noise1, noise2, share, sizes, nenc, sizes[0], same)
+        # reference op sequence
+        want = (share * nenc).round().long()
+        pre = []
+        off = 0
+        for t, nt in enumerate(sizes):
+            order = torch.argsort(noise1[off:off + nt].unsqueeze(0), dim=1, stable=True)
+            rank = torch.gather(torch.arange(nt, device="cuda").unsqueeze(0), 1, order)
+            pre.append(torch.where(rank < want[t], 0, 1))
+            off += nt
+        flat = torch.cat(pre, dim=1)
+        ids_shuffle = torch.argsort(flat + noise2.unsqueeze(0), dim=1, stable=True)
+        r_restore = torch.argsort(ids_shuffle, dim=1)
+        r_keep = ids_shuffle[:, :nenc]
+        m = torch.ones_like(flat)
+        m[:, :nenc] = 0
+        m = torch.gather(m, 1, r_restore)
+        assert torch.equal(mask, m[0]) and torch.equal(ids_restore, r_restore[0]) and torch.equal(ids_keep, r_keep[0])
+        off, acc = 0, 0
+        assert int(seg[0]) == 0
+        for t, nt in enumerate(sizes):
+            ix = (m[0, off:off + nt] == 0).nonzero(as_tuple=True)[0]
+            assert int(counts[t]) == ix.numel()
+            assert torch.equal(idx[off:off + ix.numel()].long(), ix)
+            acc += ix.numel()
+            assert int(seg[t + 1]) == acc
+            if same:
+                sm = torch.full((nt,), -1, dtype=torch.int32, device="cuda")
+                sm[ix] = torch.arange(ix.numel(), dtype=torch.int32, device="cuda")
+                assert torch.equal(slotmap[t], sm)
+            off += nt
+        assert acc == nenc and int(seg[T + 1]) == nenc + sizes[0]

@@ -95,14 +95,16 @@ def test_mask_sampler_bit_exact_on_device(uniformly):
         assert torch.equal(ref[1], got[1]) and torch.equal(ref[2], got[2])
 
 
-@pytest.mark.parametrize("variant,dim,heads,img,patch,batch,nenc", [
-    ("crossattn", 192, 3, 96, 16, 4, 50),
-    ("plain", 128, 2, 64, 8, 3, 70),
-    ("crossattn", 256, 4, 64, 16, 5, 24),
+@pytest.mark.parametrize("variant,dim,heads,img,patch,batch,nenc,decoder", [
+    ("crossattn", 192, 3, 96, 16, 4, 50, "simple"),
+    ("plain", 128, 2, 64, 8, 3, 70, "simple"),
+    ("crossattn", 256, 4, 64, 16, 5, 24, "simple"),
+    ("plain", 128, 2, 64, 8, 3, 70, "xattn"),          # the cross-attention decoder of output_adapters.py
+    ("crossattn", 192, 3, 96, 16, 4, 50, "xattn"),
 ])
-def test_fwd_bwd_matches_oracle(variant, dim, heads, img, patch, batch, nenc):
+def test_fwd_bwd_matches_oracle(variant, dim, heads, img, patch, batch, nenc, decoder):
     cfg = OracleConfig(variant=variant, dim=dim, depth=3, heads=heads, image_size=img, patch=patch, dec_dim=64,
-                       dec_depth=2, dec_heads=2)
+                       dec_depth=2, dec_heads=2, decoder=decoder)
     sd = default_sd(cfg)
     model = build_model(cfg, sd)
     x = make_inputs(cfg, batch, 11, "cuda")
