@@ -418,6 +418,18 @@ def _unpad_w1(dw1, I, ipad):
     return torch.cat([dw1[:I], dw1[ipad:ipad + I]], 0)
 
 
+def _layer_hook(meta, grads, slots):
+    """hand one encoder layer's parameter gradients to the data-parallel reducer while the backward continues
+    (training.GradAllReduce.reduce_now); the hook returns the tensors autograd should install instead"""
+    hook = meta.get("grad_hook")
+    if hook is None:
+        return
+    slots = [j for j in slots if grads[j] is not None]
+    out = hook([grads[j].contiguous() for j in slots])
+    for j, g in zip(slots, out):
+        grads[j] = g
+
+
 class EncoderStackFn(torch.autograd.Function):
     """All encoder layers as one node.  meta: dims + the per-step mask structures (device int32 `seg`
     table, `slotmap`), fusion flag.  Flat params: [mask_embedding] (fusion variant) then per layer the
@@ -564,6 +576,7 @@ class EncoderStackFn(torch.autograd.Function):
             grads[zo], grads[zo + 1] = dn1, dan
             if not fusion:
                 dX = dZ
+                _layer_hook(meta, grads, range(zo, zo + ZB))
                 continue
             # ---------------- fusion block backward (upstream: dZ[Mh:] = grad wrt Xf2) ----------------
             fo = base + i * per_layer
@@ -603,6 +616,7 @@ class EncoderStackFn(torch.autograd.Function):
             K.layernorm_bwd(dhk, X, fn1, rec["stA"], dXin, dfn1, g2=fan, dres=dZ, dg2=dfan)
             grads[fo], grads[fo + 1] = dfn1, dfan
             dX = dXin
+            _layer_hook(meta, grads, range(fo, fo + 2 * ZB))
         if fusion:
             grads[0] = dme.view(1, Fn, D)
         ctx.saved = None

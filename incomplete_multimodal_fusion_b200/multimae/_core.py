@@ -246,7 +246,8 @@ class MultiMAEBase(nn.Module):
             for m, ix in enumerate(idx):
                 slotmap[m, ix.long()] = torch.arange(ix.numel(), dtype=torch.int32, device=device)
         meta = dict(B=B, D=D, H=Hh, F=Fn_tok, nenc=nenc, fusion=self.FUSION_BLOCKS, depth=self.depth,
-                    I=int(D * self.ff_mult * 2 / 3), seg=zmask.seg, nseg=zmask.nseg, slotmap=slotmap)
+                    I=int(D * self.ff_mult * 2 / 3), seg=zmask.seg, nseg=zmask.nseg, slotmap=slotmap,
+                    grad_hook=getattr(self, 'grad_hook', None))
         params = []
         if self.FUSION_BLOCKS:
             params.append(self.mask_embedding)

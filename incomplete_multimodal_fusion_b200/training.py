@@ -46,58 +46,79 @@ def build_pretrain_model(size: str = "base", variant: str = "crossattn", image_s
 
 
 class GradAllReduce:
-    """Bucketed gradient all-reduce (mean) for identical replicas.  Parameters that never receive a gradient
-    (the off-task `task_embeddings`, `return_tokens` under the DINO-style loss -- SURVEY.md 2.2) are excluded
-    statically after the first step instead of DDP's per-step unused-parameter search."""
+    """Gradient all-reduce (sum) for identical replicas, overlapped with the backward pass (reference: DDP's bucketed
+    reducer, pretrain_mmae.py:342-345).
 
-    def __init__(self, params: List[torch.nn.Parameter], bucket_mb: int = 64, group=None):
+    * `reduce_now(tensors)` is the in-backward hook: EncoderStackFn.backward calls it once per encoder layer with that
+      layer's freshly produced weight gradients (~55 MB fp32 for ViT-B).  They are packed into a persistent flat bucket
+      and all-reduced on a side stream while the next layer's backward kernels run; the hook returns views of the
+      bucket, which autograd then installs as `.grad`, so there is no unpack copy.
+    * `finish()` reduces whatever did not go through the hook (embeddings, pooling head, decoders: a few M parameters)
+      in one more bucket and makes the current stream wait for all outstanding reductions.
+    The mean over ranks comes from scaling the loss by 1/world before backward (PretrainStep), not from an extra pass
+    over the gradients.  Parameters that never receive a gradient (the off-task `task_embeddings`, `return_tokens`
+    under the DINO-style loss -- SURVEY.md 2.2) simply never show up: no DDP-style unused-parameter search."""
+
+    def __init__(self, params: List[torch.nn.Parameter], group=None):
         self.params = [p for p in params if p.requires_grad]
-        self.bucket_bytes = bucket_mb << 20
         self.group = group
-        self.buckets = None
         self.stream = None
+        self._pool = []          # persistent flat buffers, one per reduce call of a step (call order is static)
+        self._call = 0
+        self._reduced = set()    # data_ptr of gradients already reduced this step
+        self._keep = []          # source tensors kept alive until the side stream has consumed them
 
-    def _build(self):
-        live = [p for p in self.params if p.grad is not None]
-        self.buckets = []
-        cur, size = [], 0
-        for p in reversed(live):                      # reverse registration order ~ order gradients become ready
-            cur.append(p)
-            size += p.numel() * 4
-            if size >= self.bucket_bytes:
-                self.buckets.append(cur)
-                cur, size = [], 0
-        if cur:
-            self.buckets.append(cur)
-        self.flat = [torch.empty(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device) for b in self.buckets]
+    def enabled(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
-    def reduce(self):
-        """call after backward(); returns when the averaged gradients are visible to the current stream"""
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
-            return
-        if self.buckets is None:
-            self._build()
-        world = dist.get_world_size(self.group)
-        on_gpu = self.flat[0].is_cuda if self.flat else False
+    def _flat(self, numel, device):
+        if self._call == len(self._pool):
+            self._pool.append(torch.empty(numel, dtype=torch.float32, device=device))
+        flat = self._pool[self._call]
+        if flat.numel() != numel or flat.device != device:
+            flat = self._pool[self._call] = torch.empty(numel, dtype=torch.float32, device=device)
+        self._call += 1
+        return flat
 
-        def run():
-            for bucket, flat in zip(self.buckets, self.flat):
-                sizes = [p.numel() for p in bucket]
-                torch._foreach_copy_(list(flat.split(sizes)), [p.grad.reshape(-1) for p in bucket])
-                flat.div_(world)
+    def reduce_now(self, tensors: List[torch.Tensor]) -> List[torch.Tensor]:
+        """pack -> all-reduce (async w.r.t. the current stream) -> views of the bucket, in the order given"""
+        if not self.enabled() or not tensors:
+            return tensors
+        dev = tensors[0].device
+        sizes = [t.numel() for t in tensors]
+        flat = self._flat(sum(sizes), dev)
+        views = [v.view(t.shape) for v, t in zip(flat.split(sizes), tensors)]
+        if dev.type != "cuda":                      # gloo / CPU (tests): same bucketing, no streams
+            torch._foreach_copy_(views, [t.reshape(v.shape) for t, v in zip(tensors, views)])
+            dist.all_reduce(flat, group=self.group)
+        else:
+            if self.stream is None:
+                self.stream = torch.cuda.Stream()
+            ready = torch.cuda.Event()
+            ready.record()
+            self._keep.extend(tensors)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ready)
+                torch._foreach_copy_(views, list(tensors))
                 dist.all_reduce(flat, group=self.group)
-                torch._foreach_copy_([p.grad.reshape(-1) for p in bucket], list(flat.split(sizes)))
+        self._reduced.update(v.data_ptr() for v in views)
+        return views
 
-        if not on_gpu:      # gloo / CPU (tests): same bucketing, no streams
-            run()
-            return
-        if self.stream is None:
-            self.stream = torch.cuda.Stream()
-        cur = torch.cuda.current_stream()
-        self.stream.wait_stream(cur)
-        with torch.cuda.stream(self.stream):
-            run()
-        cur.wait_stream(self.stream)
+    def finish(self):
+        """call after backward(): reduces the remaining gradients; returns with every reduction visible to the current stream"""
+        if self.enabled():
+            rest = [p for p in self.params if p.grad is not None and p.grad.data_ptr() not in self._reduced]
+            if rest:
+                views = self.reduce_now([p.grad for p in rest])
+                for p, v in zip(rest, views):
+                    p.grad = v
+            if self.stream is not None:
+                torch.cuda.current_stream().wait_stream(self.stream)
+        self._call = 0
+        self._reduced.clear()
+        self._keep.clear()
+
+    reduce = finish   # earlier name
 
 
 class PretrainStep:
@@ -116,6 +137,9 @@ class PretrainStep:
         self.opt = torch.optim.AdamW(model.parameters(), lr=blr * global_batch / 256, betas=(0.9, 0.95),
                                      weight_decay=weight_decay, fused=True)
         self.reducer = GradAllReduce(list(model.parameters()))
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if self.world > 1:
+            model.grad_hook = self.reducer.reduce_now   # per-layer reduction from inside the encoder backward
 
     def loss(self, out, targets):
         preds, masks = out[0], out[1]
@@ -131,7 +155,7 @@ class PretrainStep:
         self.opt.zero_grad(set_to_none=True)
         out = self.model(inputs, num_encoded_tokens=self.nenc, alphas=self.alphas, sample_tasks_uniformly=self.uniformly)
         loss = self.loss(out, inputs)
-        loss.backward()
-        self.reducer.reduce()
+        (loss / self.world if self.world > 1 else loss).backward()   # 1/world here -> the all-reduce is a plain sum
+        self.reducer.finish()
         self.opt.step()
         return loss.detach()

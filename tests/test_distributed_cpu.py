@@ -1,6 +1,7 @@
-"""CPU, world_size 2, gloo: the bucketed gradient all-reduce of the data-parallel path (the one collective of the
-hot path; reference: DDP at pretrain_mmae.py:342-345) averages gradients across ranks, keeps replicas identical and
-skips parameters that never receive a gradient."""
+"""CPU, world_size 2, gloo: the gradient all-reduce of the data-parallel path (the one collective of the hot path;
+reference: DDP at pretrain_mmae.py:342-345).  `reduce_now` is the in-backward per-layer hook, `finish` reduces the
+rest; gradients are summed (the 1/world factor is applied to the loss), replicas stay identical, parameters that never
+receive a gradient are skipped, and the flat buckets are reused from step to step."""
 import os
 import socket
 
@@ -23,16 +24,33 @@ def _worker(rank, world, port, out):
     torch.manual_seed(0)
     params = [torch.nn.Parameter(torch.randn(n)) for n in (1000, 7, 300000, 12)]
     unused = torch.nn.Parameter(torch.randn(5))
-    red = GradAllReduce(params + [unused], bucket_mb=1)
-    for step in range(2):
-        for i, p in enumerate(params):
-            p.grad = torch.full_like(p, float(rank + 1 + i + step))
-        red.reduce()
-        for i, p in enumerate(params):
-            expect = sum(r + 1 + i + step for r in range(world)) / world
-            assert torch.allclose(p.grad, torch.full_like(p, expect)), (rank, i)
+    red = GradAllReduce(params + [unused])
+    assert red.enabled()
+    pool_ptrs = None
+    for step in range(3):
+        # "layer" gradients go through the hook while backward would still be running ...
+        layer = [torch.full((3, 4), float(rank + step)), torch.full((5,), float(10 * rank + step))]
+        got = red.reduce_now(layer)
+        assert torch.allclose(got[0], torch.full((3, 4), float(sum(r + step for r in range(world)))))
+        assert torch.allclose(got[1], torch.full((5,), float(sum(10 * r + step for r in range(world)))))
+        params[1].grad = got[1][:7] if got[1].numel() >= 7 else torch.full_like(params[1], 1.0 + rank)
+        # ... the remaining parameters at the end
+        for i in (0, 2, 3):
+            params[i].grad = torch.full_like(params[i], float(rank + 1 + i + step))
+        before1 = params[1].grad.clone()
+        red.finish()
+        for i in (0, 2, 3):
+            expect = float(sum(r + 1 + i + step for r in range(world)))
+            assert torch.allclose(params[i].grad, torch.full_like(params[i], expect)), (rank, i)
+        if got[1].numel() < 7:
+            assert torch.allclose(params[1].grad, torch.full_like(params[1], float(sum(1.0 + r for r in range(world)))))
+        else:
+            assert torch.equal(params[1].grad, before1)          # reduced by the hook already: not reduced twice
         assert unused.grad is None
-    assert len(red.buckets) >= 2          # 1 MB buckets over ~1.2 MB of gradients
+        ptrs = [b.data_ptr() for b in red._pool]
+        assert pool_ptrs is None or ptrs == pool_ptrs             # persistent buckets
+        pool_ptrs = ptrs
+    assert len(red._pool) == 2
     out.put((rank, float(params[2].grad[0])))
     dist.destroy_process_group()
 
