@@ -235,6 +235,14 @@ int mmf_mask_build(const float* noise1, const float* noise2, const float* share,
                    int32_t nenc, int32_t n_fusion, int64_t* mask, int64_t* ids_restore, int64_t* ids_keep, int32_t* idx,
                    int32_t* counts, int32_t* seg, int32_t* slotmap, mmf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * DINO-style distillation loss, forward and student gradient in one launch (criterion.py:328-335 dino_loss_func;
+ * call sites pretrain_mmae.py:489-493).  student / teacher: [B, D] rows (bf16 or f32, is_f32), the teacher is
+ * detached.  row_loss [B] f32 = per-sample loss (the caller averages); dstudent [B, D] f32 = d(mean loss)/d student.
+ * ---------------------------------------------------------------------------------------------- */
+int mmf_dino_loss(const void* student, int64_t lds, const void* teacher, int64_t ldt, int32_t is_f32, int32_t B, int32_t D,
+                  float student_temp, float teacher_temp, float* row_loss, float* dstudent, mmf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,7 @@ SIGNATURES = {
     "mmf_gather_rows": [c_vp, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_i32, c_i64, c_i64, c_i32, c_i32, c_vp],
     "mmf_add_inplace_f32": [c_vp, c_vp, c_i64, c_vp],
     "mmf_add_bf16_f32": [c_vp, c_vp, c_vp, c_i64, c_vp],
+    "mmf_dino_loss": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp],
     "mmf_mask_build": [c_vp, c_vp, c_vp, c_i32, C.POINTER(c_i32), c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
 }
 _RESTYPES = {"mmf_launch_count": c_i64, "mmf_reset_launch_count": None}

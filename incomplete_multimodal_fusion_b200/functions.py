@@ -322,6 +322,59 @@ class MaskedLossFn(torch.autograd.Function):
         return dpred, None, None, None, None
 
 
+class DinoLossFn(torch.autograd.Function):
+    """criterion.py:328-335 fused (forward + student gradient in one launch); the teacher gets no gradient"""
+
+    @staticmethod
+    def forward(ctx, student, teacher, student_temp, teacher_temp):
+        s = student if student.stride(-1) == 1 else student.contiguous()
+        t = teacher.detach()
+        t = t if t.stride(-1) == 1 else t.contiguous()
+        if t.dtype != s.dtype:
+            s, t = s.float(), t.float()
+        row_loss, ds = K.dino_loss(s, t, student_temp, teacher_temp)
+        ctx.save_for_backward(ds)
+        ctx.in_dtype = student.dtype
+        return row_loss.mean()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (ds,) = ctx.saved_tensors
+        return (ds * dloss).to(ctx.in_dtype), None, None, None
+
+
+class MatmulNTFn(torch.autograd.Function):
+    """C = A . B^T with bf16 tensor-core operands and an fp32 result (what torch.mm does under the reference's
+    autocast, e.g. the [2B, D] x [D, 2B] similarity of HardNegtive_loss, criterion.py:240).  A [M, K], B [N, K]."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        M, Kd = a.shape
+        N = b.shape[0]
+        pad8 = lambda n: (n + 7) // 8 * 8        # TMA operands need 16-byte row pitches in every layout used below
+        ab = K.cast_bf16(a.detach().float().contiguous(), rows_pad=pad8(M), cols_pad=pad8(Kd))
+        bb = K.cast_bf16(b.detach().float().contiguous(), rows_pad=pad8(N), cols_pad=pad8(Kd))
+        out = torch.empty(pad8(M), pad8(N), dtype=f32, device=a.device)
+        K.gemm(ab, bb, out)
+        ctx.save_for_backward(ab, bb)
+        ctx.meta = (M, N, Kd, a.dtype, b.dtype)
+        return out[:M, :N]
+
+    @staticmethod
+    def backward(ctx, dc):
+        ab, bb = ctx.saved_tensors
+        M, N, Kd, adt, bdt = ctx.meta
+        dcb = K.cast_bf16(dc.float().contiguous(), rows_pad=ab.shape[0], cols_pad=bb.shape[0])
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty(ab.shape, dtype=f32, device=dc.device)
+            K.gemm(dcb, bb, da, b_mn=True)                      # dA = dC . B
+            da = da[:M, :Kd].to(adt)
+        if ctx.needs_input_grad[1]:
+            db = wgrad(dcb, ab)[:N, :Kd].to(bdt)                # dB = dC^T . A
+        return da, db
+
+
 # ------------------------------------------------------------------------------------------------
 # token embedding: visible-patch im2col + projection GEMM written straight into the planar stream
 # ------------------------------------------------------------------------------------------------

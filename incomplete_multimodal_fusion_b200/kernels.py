@@ -326,3 +326,15 @@ def mask_build(noise1, noise2, share, sizes, nenc, n_fusion, want_slotmap):
     check(_L().mmf_mask_build(_p(noise1), _p(noise2), _p(share), T, csizes, nenc, n_fusion, _p(mask), _p(ids_restore),
                               _p(ids_keep), _p(idx), _p(counts), _p(seg), _p(slotmap), _stream()), "mmf_mask_build")
     return mask, ids_restore, ids_keep, idx, counts, seg, slotmap
+
+
+def dino_loss(student, teacher, student_temp, teacher_temp):
+    """-> (row_loss [B] f32, dstudent [B, D] f32 for an upstream gradient of 1)"""
+    assert student.dim() == 2 and student.shape == teacher.shape and student.dtype == teacher.dtype
+    assert student.dtype in (bf16, f32) and student.stride(1) == 1 and teacher.stride(1) == 1
+    B, D = student.shape
+    row_loss = torch.empty(B, dtype=f32, device=student.device)
+    dstudent = torch.empty(B, D, dtype=f32, device=student.device)
+    check(_L().mmf_dino_loss(_p(student), student.stride(0), _p(teacher), teacher.stride(0), int(student.dtype == f32), B, D,
+                             student_temp, teacher_temp, _p(row_loss), _p(dstudent), _stream()), "mmf_dino_loss")
+    return row_loss, dstudent

@@ -41,22 +41,28 @@ class MaskedL1Loss(_MaskedReconLoss):
 
 
 class HardNegtive_loss(nn.Module):
-    """Debiased hard-negative contrastive loss (criterion.py:214-268).  Tiny [2B, 2B] problem: expressed with
-    torch ops on the device (no Python loop over the batch, no hard-coded .cuda())."""
+    """Debiased hard-negative contrastive loss (criterion.py:214-268).  The [2B, D] x [D, 2B] similarity runs on the
+    tcgen05 GEMM with bf16 operands (torch.mm under the reference's autocast, Appendix A #19); normalisation, exp / log
+    and the row reductions are fp32 device ops (no Python loop over the batch, no hard-coded .cuda())."""
 
     def __init__(self, tau_plus=0.1, beta=1.0, temperature=0.5, alpha=256, estimator='hard'):
         super().__init__()
         self.tau_plus, self.beta, self.temperature, self.alpha, self.estimator = tau_plus, beta, temperature, alpha, estimator
 
+    def get_negative_mask(self, batch_size, device=None):
+        """[2B, 2B] bool, False on the diagonal and on the positive pair (criterion.py:224-231 without the loop)"""
+        eye = torch.eye(batch_size, dtype=torch.bool, device=device)
+        return ~torch.cat([torch.cat([eye, eye], 1), torch.cat([eye, eye], 1)], 0)
+
     def forward(self, out_1, out_2):
         B = out_1.shape[0]
+        if not out_1.is_cuda:
+            raise RuntimeError("HardNegtive_loss runs on CUDA only (no CPU fallback)")
         o1 = F.normalize(out_1.float(), dim=1)
         o2 = F.normalize(out_2.float(), dim=1)
         out = torch.cat([o1, o2], dim=0)
-        neg = torch.exp(out @ out.t() / self.temperature)
-        eye = torch.eye(B, dtype=torch.bool, device=out.device)
-        keep = ~torch.cat([torch.cat([eye, eye], 1), torch.cat([eye, eye], 1)], 0)
-        neg = neg.masked_select(keep).view(2 * B, -1)
+        neg = torch.exp(Fn.MatmulNTFn.apply(out, out) / self.temperature)
+        neg = neg.masked_select(self.get_negative_mask(B, out.device)).view(2 * B, -1)
         pos = torch.exp((o1 * o2).sum(-1) / self.temperature)
         pos = torch.cat([pos, pos], 0)
         if self.estimator == 'hard':
@@ -73,7 +79,7 @@ class HardNegtive_loss(nn.Module):
 
 
 def dino_loss_func(student_output, teacher_output, teacher_temp=0.04, student_temp=0.1):
-    """criterion.py:328-335 -- [B, D] problem, fp32"""
-    s = F.log_softmax(F.normalize(student_output.float(), dim=1) / student_temp, dim=-1)
-    t = F.softmax(F.normalize(teacher_output.float(), dim=1) / teacher_temp, dim=-1).detach()
-    return (-t * s).sum(-1).mean()
+    """criterion.py:328-335 -- one fused launch (forward + student gradient), fp32; the teacher is detached"""
+    if not student_output.is_cuda:
+        raise RuntimeError("dino_loss_func runs on CUDA only (no CPU fallback)")
+    return Fn.DinoLossFn.apply(student_output, teacher_output, student_temp, teacher_temp)

@@ -447,3 +447,44 @@ def test_mask_build_matches_torch_ops(sizes, nenc):
                 assert torch.equal(slotmap[t], sm)
             off += nt
         assert acc == nenc and int(seg[T + 1]) == nenc + sizes[0]
+
+
+@pytest.mark.parametrize("dtype", [f32, bf16])
+@pytest.mark.parametrize("B,D", [(4, 192), (37, 768), (256, 1024)])
+def test_dino_loss_fused(B, D, dtype):
+    """fused forward + student gradient against the reference op sequence (criterion.py:328-335) in fp32: <= 1e-5"""
+    from incomplete_multimodal_fusion_b200.multimae.criterion import dino_loss_func
+    s = rnd(B, 3, D, seed=1)[:, 1].to(dtype).requires_grad_(True)      # strided rows, like the pooled return tokens
+    t = rnd(B, D, seed=2).to(dtype)
+    loss = dino_loss_func(s, t)
+    (loss * 1.7).backward()
+    s32 = s.detach().float().requires_grad_(True)
+    so = F.log_softmax(F.normalize(s32, dim=1) / 0.1, dim=-1)
+    to = F.softmax(F.normalize(t.float(), dim=1) / 0.04, dim=-1)
+    ref = (-to * so).sum(-1).mean()
+    (ref * 1.7).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    tol = 1e-5 if dtype == f32 else 1e-2
+    assert rel(s.grad, s32.grad) < tol
+
+
+def test_hard_negative_loss_matches_golden_and_oracle(golden_dir):
+    """HardNegtive_loss (criterion.py:233-268) with the similarity on the tcgen05 GEMM: golden value from the reference's
+    arithmetic (fp32) within the bf16 operand tolerance, gradients against the oracle"""
+    import os
+    import oracle
+    from incomplete_multimodal_fusion_b200.multimae.criterion import HardNegtive_loss
+    fx = torch.load(os.path.join(golden_dir, "losses.pt"), weights_only=False)
+    g = torch.Generator().manual_seed(fx["seed"])      # same draw order as tests/golden/make_golden.py
+    torch.randn(3, 2, 32, 32, generator=g); torch.randn(3, 2, 32, 32, generator=g); torch.rand(3, 16, generator=g)
+    fa, fb = torch.randn(6, 48, generator=g), torch.randn(6, 48, generator=g)
+    a, b = fa.cuda().requires_grad_(True), fb.cuda().requires_grad_(True)
+    loss = HardNegtive_loss()(a, b)
+    assert abs(float(loss) - float(fx["hardneg"])) < 1e-2 * abs(float(fx["hardneg"]))
+    loss.backward()
+    a2, b2 = fa.cuda().requires_grad_(True), fb.cuda().requires_grad_(True)
+    oracle.hard_negative_loss(a2, b2).backward()
+    assert rel(a.grad, a2.grad) < 3e-2 and rel(b.grad, b2.grad) < 3e-2
+    from incomplete_multimodal_fusion_b200.multimae.criterion import dino_loss_func
+    d = dino_loss_func(fa.cuda(), fb.cuda())
+    assert abs(float(d) - float(fx["dino"])) < 1e-5 * abs(float(fx["dino"]))
