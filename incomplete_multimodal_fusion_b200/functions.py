@@ -406,8 +406,9 @@ class EmbedFn(torch.autograd.Function):
                        out_period=n, out_batch_rows=nenc)
             saved.append(A)
             off += n
-        fus = (fusion_tokens.detach()[0] + meta["pos_fusion"]).contiguous()
-        K.bcast_rows(fus, X[Mh:], B, Fn, D, Fn * D)
+        if Fn > 0:
+            fus = (fusion_tokens.detach()[0] + meta["pos_fusion"]).contiguous()
+            K.bcast_rows(fus, X[Mh:], B, Fn, D, Fn * D)
         ctx.meta = meta
         ctx.saved_A = saved
         ctx.mod_shapes = [(mod_args[3 * m + 1].shape, ) for m in range(len(meta["idx"]))]
@@ -433,8 +434,10 @@ class EmbedFn(torch.autograd.Function):
             db = K.colsum(dY, torch.zeros(D, dtype=f32, device=dX.device))
             grads += [None, dW, db]
             off += n
-        dfus = torch.empty(1, Fn, D, dtype=f32, device=dX.device)
-        K.reduce_batch(dX[Mh:], dfus, B, Fn, D, Fn * D)
+        dfus = None
+        if Fn > 0:
+            dfus = torch.empty(1, Fn, D, dtype=f32, device=dX.device)
+            K.reduce_batch(dX[Mh:], dfus, B, Fn, D, Fn * D)
         return (None, dfus) + tuple(grads)
 
 

@@ -25,13 +25,16 @@ from torch.distributions.dirichlet import Dirichlet
 from .. import functions as Fn
 from .. import kernels as K
 from .multimae_utils import trunc_normal_
-from .zorro_utils import Attention, Block, Block_Fusion, LayerNorm, Mlp, TokenTypes, ZorroMask, block_params
+from .zorro_utils import Attention, AttentionBiLSTM, Block, Block_Fusion, LayerNorm, Mlp, TokenTypes, ZorroMask, block_params
 
 MODALITIES = ('s1', 's2', 'dem')   # hard-coded token order of the reference (multimae.py:378-407)
 
 
 class MultiMAEBase(nn.Module):
-    FUSION_BLOCKS = False
+    FUSION_BLOCKS = False              # per-layer modality attention (multimae_crossattn.py)
+    LSTM_FUSION = False                # one BiLSTM-initialised fusion token per visible token (multimae_lstm_s2dsm.py)
+    MODALITIES = MODALITIES            # token order of the variant's forward
+    TYPE_IDS = {'s1': TokenTypes.S1.value, 's2': TokenTypes.S2.value, 'dem': TokenTypes.DEM.value}
 
     def __init__(self, input_adapters: Dict[str, nn.Module], output_adapters: Optional[Dict[str, nn.Module]],
                  num_global_tokens: int = 1, dim_tokens: int = 768, depth: int = 12, dim_head: int = 64, heads: int = 8,
@@ -50,7 +53,7 @@ class MultiMAEBase(nn.Module):
             self.output_adapters = nn.ModuleDict(output_adapters)
         else:
             self.output_adapters = None
-        assert num_fusion_tokens == input_adapters['s1'].num_patches
+        assert num_fusion_tokens == input_adapters[self.MODALITIES[0]].num_patches
 
         self.dim_tokens, self.depth, self.heads, self.dim_head, self.ff_mult = dim_tokens, depth, heads, dim_head, ff_mult
         self.max_return_tokens = len(return_token_types)
@@ -67,6 +70,8 @@ class MultiMAEBase(nn.Module):
             self.return_token_s2 = nn.Parameter(torch.randn(1, 1, dim_tokens))
             self.return_token_dem = nn.Parameter(torch.randn(1, 1, dim_tokens))
         self.mlp = Mlp(in_features=dim_tokens, hidden_features=int(dim_tokens * 4.0))
+        if self.LSTM_FUSION:
+            self.attn_lstm = AttentionBiLSTM(dim_tokens)
         if self.FUSION_BLOCKS:
             self.fus_blocks = nn.ModuleList([Block_Fusion(dim=dim_tokens, dim_head=dim_head, heads=heads, ff_mult=ff_mult,
                                                           norm_layer=norm_layer) for _ in range(depth)])
@@ -186,14 +191,16 @@ class MultiMAEBase(nn.Module):
                 task_masks: Dict[str, torch.Tensor] = None, num_encoded_tokens: int = 128,
                 alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False,
                 fp32_output_adapters: List[str] = [], return_token_indices: Optional[Tuple[int]] = None):
-        x = {'s1': x} if isinstance(x, torch.Tensor) else x
-        B, _, H, W = x['s1'].shape
-        device = x['s1'].device
+        MODALITIES = self.MODALITIES
+        first = MODALITIES[0]
+        x = {first: x} if isinstance(x, torch.Tensor) else x
+        B, _, H, W = x[first].shape
+        device = x[first].device
         if device.type != 'cuda':
             raise RuntimeError("incomplete_multimodal_fusion_b200.MultiMAE runs on CUDA only (no CPU fallback)")
         for t in MODALITIES:
             if t not in x or t not in self.input_adapters:
-                raise KeyError(f"input '{t}' is required (the reference hard-codes s1/s2/dem, multimae.py:378-383)")
+                raise KeyError(f"input '{t}' is required (the reference hard-codes its modalities, multimae.py:378-383)")
         D, Hh = self.dim_tokens, self.heads
         tasks = [t for t in x if t in self.input_adapters]
         grids = {t: self.input_adapters[t].grid(H, W) for t in tasks}
@@ -215,7 +222,7 @@ class MultiMAEBase(nn.Module):
             idx = [r["idx"][off[where[t]]: off[where[t]] + cnt[where[t]]] for t in MODALITIES]
             counts = [cnt[where[t]] for t in MODALITIES]
             if r["slotmap"] is not None:
-                slotmap = r["slotmap"] if r["tasks"][:3] == list(MODALITIES) else \
+                slotmap = r["slotmap"] if r["tasks"][:len(MODALITIES)] == list(MODALITIES) else \
                     torch.stack([r["slotmap"][where[t]] for t in MODALITIES]).contiguous()
         else:
             flat = torch.cat([task_masks[t] for t in tasks], dim=1)
@@ -227,7 +234,8 @@ class MultiMAEBase(nn.Module):
         if sum(counts) != nenc:
             raise ValueError(f"num_encoded_tokens={nenc} but the masks keep {sum(counts)} tokens; pass the true count "
                              "(the reference mis-slices silently in this case)")
-        zmask = ZorroMask(counts, Fn_tok, device)
+        n_tail = nenc if self.LSTM_FUSION else Fn_tok          # fusion tokens in the encoder sequence
+        zmask = ZorroMask(counts, n_tail, device)
 
         # ---- tokens: visible-patch embedding + fusion tokens, planar layout ----
         mod_args = []
@@ -235,17 +243,27 @@ class MultiMAEBase(nn.Module):
             ad = self.input_adapters[t]
             mod_args += [x[t].float(), ad.proj.weight, ad.proj.bias]
         fus_ad = self.input_adapters['fusion']
-        meta_e = dict(B=B, D=D, P=self.input_adapters['s1'].P_H, F=Fn_tok, nenc=nenc, idx=idx,
-                      pos=[self.input_adapters[t].pos_table(*grids[t]) for t in MODALITIES],
-                      pos_fusion=fus_ad.pos_table(H // fus_ad.P_H, W // fus_ad.P_W))
+        pos_fusion = fus_ad.pos_table(H // fus_ad.P_H, W // fus_ad.P_W)
+        meta_e = dict(B=B, D=D, P=self.input_adapters[first].P_H, F=0 if self.LSTM_FUSION else Fn_tok, nenc=nenc, idx=idx,
+                      pos=[self.input_adapters[t].pos_table(*grids[t]) for t in MODALITIES], pos_fusion=pos_fusion)
         X = Fn.EmbedFn.apply(meta_e, self.fusion_tokens, *mod_args)
+        complete_fusion = None
+        if self.LSTM_FUSION:
+            # multimae_lstm_s2dsm.py:384-434: the fusion token of every visible position, merged with that position's
+            # modality token by the BiLSTM (cuDNN under bf16 autocast, like the reference's AMP step)
+            complete_fusion = self.fusion_tokens[0] + pos_fusion                      # [F, D]
+            sel = torch.cat([i.long() for i in idx])
+            pairs = torch.stack([X.view(B, nenc, D), complete_fusion[sel].unsqueeze(0).expand(B, -1, -1)], dim=2)
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                fus0 = self.attn_lstm(pairs.reshape(B * nenc, 2, D))
+            X = torch.cat([X, fus0.float()], dim=0)                                   # planar: modality rows, then fusion rows
 
         # ---- encoder stack ----
         if self.FUSION_BLOCKS and slotmap is None:
             slotmap = torch.full((len(MODALITIES), Fn_tok), -1, dtype=torch.int32, device=device)
             for m, ix in enumerate(idx):
                 slotmap[m, ix.long()] = torch.arange(ix.numel(), dtype=torch.int32, device=device)
-        meta = dict(B=B, D=D, H=Hh, F=Fn_tok, nenc=nenc, fusion=self.FUSION_BLOCKS, depth=self.depth,
+        meta = dict(B=B, D=D, H=Hh, F=n_tail, nenc=nenc, fusion=self.FUSION_BLOCKS, depth=self.depth,
                     I=int(D * self.ff_mult * 2 / 3), seg=zmask.seg, nseg=zmask.nseg, slotmap=slotmap,
                     grad_hook=getattr(self, 'grad_hook', None))
         params = []
@@ -260,7 +278,7 @@ class MultiMAEBase(nn.Module):
         Mh = B * nenc
         T = Fn.layer_norm(X, self.norm.gamma, None, 1e-5, out_bf16=False)           # final norm, fp32 (multimae.py:431)
         ori_tokens = T[:Mh].view(B, nenc, D)
-        enc_fusion = T[Mh:].view(B, Fn_tok, D)
+        enc_fusion = T[Mh:].view(B, n_tail, D)
 
         # ---- pooling head: all return tokens in one pool-attention launch ----
         rt = self.return_tokens
@@ -277,8 +295,9 @@ class MultiMAEBase(nn.Module):
             queries += [self.return_token_s1[0], self.return_token_s2[0], self.return_token_dem[0]]
         queries = torch.cat(queries, 0)
         Rt = queries.shape[0]
-        N = nenc + Fn_tok
-        types = torch.repeat_interleave(torch.arange(4, device=device), torch.tensor(counts + [Fn_tok], device=device))
+        N = nenc + n_tail
+        types = torch.repeat_interleave(torch.tensor([self.TYPE_IDS[t] for t in MODALITIES] + [TokenTypes.FUSION.value],
+                                                     device=device), torch.tensor(counts + [n_tail], device=device))
         pmask = torch.zeros(Rt, N, dtype=torch.uint8, device=device)
         pmask[:R] = ((rtypes[:, None] == types[None, :]) | (rtypes[:, None] == TokenTypes.FUSION.value)).to(torch.uint8)
         mode = torch.zeros(Rt, dtype=torch.int32, device=device)
@@ -300,9 +319,19 @@ class MultiMAEBase(nn.Module):
             tokens = torch.cat([ori_tokens, enc_fusion], dim=1)
             return tokens, return_tokens, task_masks
 
+        dec_in = enc_fusion
+        if self.LSTM_FUSION:
+            # decoders read the whole fusion grid with the encoded tokens scattered back (multimae_lstm_s2dsm.py:470-477;
+            # the reference writes position by position in order, so a position visible in both modalities keeps the
+            # later, dem, copy: one index_copy per modality in order reproduces that deterministically)
+            dec_in = complete_fusion.unsqueeze(0).expand(B, -1, -1).clone()
+            o = 0
+            for ix in idx:
+                dec_in = dec_in.index_copy(1, ix.long(), enc_fusion[:, o:o + ix.numel()])
+                o += ix.numel()
         preds = {}
         for domain, adapter in self.output_adapters.items():
-            p = adapter(encoder_tokens=enc_fusion, input_info=input_info, ids_keep=ids_keep, ids_restore=ids_restore)
+            p = adapter(encoder_tokens=dec_in, input_info=input_info, ids_keep=ids_keep, ids_restore=ids_restore)
             preds[domain] = p.float() if domain in fp32_output_adapters else p
         out = (preds, task_masks, return_tokens, ori_tokens, enc_fusion)
         if self.FUSION_BLOCKS:

@@ -109,6 +109,39 @@ class Attention(nn.Module):
         raise RuntimeError("zorro Attention runs inside Block (self-attention) or the MultiMAE pooling head")
 
 
+class Attention_LSTM(nn.Module):
+    """softmax over time of Linear(tanh(H)) (zorro_utils.py:261-273)"""
+
+    def __init__(self, hidden_size):
+        super().__init__()
+        self.attention = nn.Linear(hidden_size, 1)
+
+    def forward(self, H, mask=None):
+        M = self.attention(torch.tanh(H)).squeeze(2)
+        if mask is not None:
+            M = M.masked_fill(mask == 0, -1e+4)
+        return torch.softmax(M, dim=1).unsqueeze(1)
+
+
+class AttentionBiLSTM(nn.Module):
+    """Bidirectional LSTM over a short sequence, directions summed, attention-pooled over time
+    (zorro_utils.py:276-299).  Used by the BiLSTM-fusion variant on length-2 (token, fusion token) sequences; the
+    recurrence stays the library LSTM (cuDNN) -- SURVEY.md 8a row a21 keeps it out of the custom-kernel scope."""
+
+    def __init__(self, embedding_dim, num_layers=1, dropout=0.0, emb_layer_dropout=0.0):
+        super().__init__()
+        self.embedding_dim = embedding_dim
+        self.lstm = nn.LSTM(embedding_dim, embedding_dim, num_layers, dropout=(0 if num_layers == 1 else dropout),
+                            bidirectional=True, batch_first=True)
+        self.attention = Attention_LSTM(embedding_dim)
+
+    def forward(self, embedded, mask=None):
+        y, _ = self.lstm(embedded)
+        y = y[:, :, :self.embedding_dim] + y[:, :, self.embedding_dim:]
+        alpha = self.attention(y, mask)
+        return alpha.bmm(y).squeeze(1)
+
+
 def block_params(blk):
     """the 9 tensors EncoderStackFn expects for one Block / Block_Fusion, in its order"""
     return [blk.norm1.gamma, blk.attn.norm.gamma, blk.attn.to_q.weight, blk.attn.to_kv.weight, blk.attn.to_out.weight,

@@ -13,7 +13,8 @@ import torch.distributed as dist
 
 from .multimae import multimae as _plain
 from .multimae import multimae_crossattn as _cross
-from .multimae.criterion import MaskedL1Loss, MaskedMSELoss, dino_loss_func
+from .multimae import multimae_lstm_s2dsm as _lstm
+from .multimae.criterion import HardNegtive_loss, MaskedL1Loss, MaskedMSELoss, dino_loss_func
 from .multimae.input_adapters import FusionInputAdapter, PatchedInputAdapter
 from .multimae.output_adapters_simple import SpatialOutputAdapter
 
@@ -32,6 +33,8 @@ def build_pretrain_model(size: str = "base", variant: str = "crossattn", image_s
     """MultiMAE with the three PatchedInputAdapters, the fusion adapter and the simple decoders, wired the way
     pretrain_mmae.py:get_model does (but honouring `size`; the reference hard-codes the tiny factory)."""
     dim, dflt_depth, heads = SIZES[size]
+    if variant == "lstm_s2dsm" and channels is None:          # pretrain_mmae_s2dsm.py DOMAIN_CONF (:45-65); BASELINE
+        channels = OrderedDict([("s2", 4), ("dem", 1)])       # config 1 uses the 4-band S2 optical input
     ch = channels or {k: v["channels"] for k, v in DOMAIN_CONF.items()}
     ia = OrderedDict((d, PatchedInputAdapter(num_channels=c, stride_level=1, patch_size_full=patch_size, image_size=image_size))
                      for d, c in ch.items())
@@ -40,9 +43,13 @@ def build_pretrain_model(size: str = "base", variant: str = "crossattn", image_s
                                               depth=decoder_depth, num_heads=decoder_heads, use_task_queries=True, task=d,
                                               context_tasks=list(ch), image_size=image_size, use_xattn=True))
                      for d, c in ch.items())
-    cls = _cross.MultiMAE if variant == "crossattn" else _plain.MultiMAE
+    cls = {"crossattn": _cross.MultiMAE, "lstm_s2dsm": _lstm.MultiMAE}.get(variant, _plain.MultiMAE)
+    kw = {}
+    if variant == "lstm_s2dsm":
+        from .multimae.zorro_utils import TokenTypes
+        kw["return_token_types"] = (TokenTypes.S2, TokenTypes.DEM, TokenTypes.FUSION)   # pretrain_mmae_s2dsm.py:232-236
     return cls(input_adapters=ia, output_adapters=oa, dim_tokens=dim, depth=depth or dflt_depth, dim_head=64, heads=heads,
-               ff_mult=4, num_fusion_tokens=(image_size // patch_size) ** 2)
+               ff_mult=4, num_fusion_tokens=(image_size // patch_size) ** 2, **kw)
 
 
 class GradAllReduce:
@@ -134,6 +141,7 @@ class PretrainStep:
         self.alphas = alphas
         self.cw = contrastive_weight
         self.losses = {d: DOMAIN_CONF[d]["loss"](patch_size=patch_size, stride=1) for d in DOMAIN_CONF}
+        self.hard_negative = HardNegtive_loss()
         self.opt = torch.optim.AdamW(model.parameters(), lr=blr * global_batch / 256, betas=(0.9, 0.95),
                                      weight_decay=weight_decay, fused=True)
         self.reducer = GradAllReduce(list(model.parameters()))
@@ -149,6 +157,9 @@ class PretrainStep:
         if len(out) == 8:   # crossattn variant: DINO-style terms, fusion pool = teacher (pretrain_mmae.py:489-493)
             pooled = torch.chunk(out[2], 4, dim=1)
             total = total + self.cw * sum(dino_loss_func(out[5 + i].squeeze(1), pooled[i].squeeze(1)) for i in range(3))
+        elif getattr(self.model, "LSTM_FUSION", False):   # s2dsm script: hard-negative pairs, weight 1 (pretrain_mmae_s2dsm.py:482-492)
+            a, b, c = [t.squeeze(1) for t in torch.chunk(out[2], 3, dim=1)]
+            total = total + self.hard_negative(a, b) + self.hard_negative(a, c) + self.hard_negative(b, c)
         return total
 
     def __call__(self, inputs: Dict[str, torch.Tensor]) -> torch.Tensor:

@@ -27,16 +27,32 @@ def build_model(cfg, sd=None, device="cuda"):
                                               dim_tokens=cfg.dec_dim, depth=cfg.dec_depth, num_heads=cfg.dec_heads, task=t,
                                               context_tasks=list(cfg.channels), image_size=cfg.image_size))
                      for t in cfg.out_tasks)
-    mod = m_cross if cfg.variant == "crossattn" else m_plain
+    from incomplete_multimodal_fusion_b200.multimae import multimae_lstm_s2dsm as m_lstm
+    from incomplete_multimodal_fusion_b200.multimae.zorro_utils import TokenTypes
+    mod = {"crossattn": m_cross, "lstm_s2dsm": m_lstm}.get(cfg.variant, m_plain)
     model = mod.MultiMAE(ia, oa, dim_tokens=cfg.dim, depth=cfg.depth, dim_head=cfg.dim_head, heads=cfg.heads,
-                         ff_mult=cfg.ff_mult, num_fusion_tokens=cfg.num_patches)
+                         ff_mult=cfg.ff_mult, num_fusion_tokens=cfg.num_patches,
+                         return_token_types=tuple(TokenTypes(v) for v in cfg.return_token_types))
     if sd is not None:
         model.load_state_dict(sd, strict=True)
     return model.to(device)
 
 
 def default_sd(cfg):
+    if cfg.variant == "lstm_s2dsm":
+        from oracle.lstm_variant import init_state_dict as lstm_init
+        return oracle.perturb_state_dict(lstm_init(cfg, seed=0), seed=7)
     return oracle.perturb_state_dict(oracle.init_state_dict(cfg, seed=0), seed=7)
+
+
+def pretrain_loss_s2dsm_ours(out, targets, patch):
+    """pretrain_mmae_s2dsm.py:470-492 with the drop-in criterion classes"""
+    from incomplete_multimodal_fusion_b200.multimae.criterion import HardNegtive_loss, MaskedL1Loss, MaskedMSELoss
+    total = MaskedMSELoss(patch_size=patch)(out[0]["s2"], targets["s2"], mask=out[1]["s2"]) + \
+        MaskedL1Loss(patch_size=patch)(out[0]["dem"], targets["dem"], mask=out[1]["dem"])
+    a, b, c = [t.squeeze(1) for t in torch.chunk(out[2], 3, dim=1)]
+    hn = HardNegtive_loss()
+    return total + hn(a, b) + hn(a, c) + hn(b, c)
 
 
 def rel(a, b):

@@ -81,6 +81,7 @@ def load_reference():
     quiet = lambda s: s.replace("print(rand_per_sample_choice.shape)", "pass")
     load("multimae", quiet)
     load("multimae_crossattn", quiet)
+    load("multimae_lstm_s2dsm", quiet)
     return pkg
 
 
@@ -97,7 +98,7 @@ def build_reference_model(cfg, sd):
                              use_task_queries=True, task=t, context_tasks=list(cfg.channels),
                              image_size=cfg.image_size, use_xattn=True))
                      for t in cfg.out_tasks)
-    mod = ref.multimae_crossattn if cfg.variant == "crossattn" else ref.multimae
+    mod = {"crossattn": ref.multimae_crossattn, "lstm_s2dsm": ref.multimae_lstm_s2dsm}.get(cfg.variant, ref.multimae)
     T = ref.zorro_utils.TokenTypes
     model = mod.MultiMAE(input_adapters=ia, output_adapters=oa, dim_tokens=cfg.dim, depth=cfg.depth,
                          dim_head=cfg.dim_head, heads=cfg.heads, ff_mult=cfg.ff_mult,
@@ -162,6 +163,39 @@ def model_case(name, cfg, batch, nenc, mask_seed, uniformly, task_masks=None):
     torch.save(fx, os.path.join(HERE, name + ".pt"))
     print(name, "loss", float(loss), "n_grads", len(grads), "counts",
           [int((m[0] == 0).sum()) for m in out[1].values()])
+
+
+def lstm_case(name, cfg, batch, nenc, mask_seed):
+    """BASELINE config 1 path: multimae_lstm_s2dsm.MultiMAE + the loss assembly of pretrain_mmae_s2dsm.py:470-492"""
+    from oracle.functional import perturb_state_dict
+    from oracle.lstm_variant import init_state_dict as lstm_init
+    ref = load_reference()
+    sd = perturb_state_dict(lstm_init(cfg, seed=0), seed=7)
+    model = build_reference_model(cfg, sd)
+    x = make_inputs(cfg, batch, seed=1234)
+    torch.manual_seed(mask_seed)
+    out = model(x, mask_inputs=True, num_encoded_tokens=nenc, alphas=1.0, sample_tasks_uniformly=False)
+    mse = ref.criterion.MaskedMSELoss(patch_size=cfg.patch, stride=1)
+    l1 = ref.criterion.MaskedL1Loss(patch_size=cfg.patch, stride=1)
+    torch.Tensor.cuda = lambda self, *a, **k: self   # HardNegtive_loss hard-codes .cuda() (criterion.py:242)
+    hn = ref.criterion.HardNegtive_loss()
+    loss = mse(out[0]["s2"].float(), x["s2"], mask=out[1]["s2"]) + l1(out[0]["dem"].float(), x["dem"], mask=out[1]["dem"])
+    a, b, c = [t.squeeze() for t in torch.chunk(out[2], 3, dim=1)]
+    loss = loss + hn(a, b) + hn(a, c) + hn(b, c)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    fx = {
+        "cfg": cfg.__dict__.copy(), "batch": batch, "nenc": nenc, "mask_seed": mask_seed, "input_seed": 1234,
+        "preds": {t: v.detach() for t, v in out[0].items()}, "task_masks": dict(out[1]),
+        "return_tokens": out[2].detach(), "ori_tokens": out[3].detach(), "fusion_tokens": out[4].detach(),
+        "loss": loss.detach(), "grad_norms": {k: v.norm() for k, v in grads.items()},
+        "grads": {k: v for k, v in grads.items() if v.numel() <= 4096 or k.endswith("blocks.0.attn.to_q.weight")
+                  or k == "attn_lstm.lstm.weight_hh_l0"},
+        "state_dict_keys": [(k, tuple(v.shape)) for k, v in model.state_dict().items()],
+        "no_grad_params": [k for k, p in model.named_parameters() if p.requires_grad and p.grad is None],
+    }
+    torch.save(fx, os.path.join(HERE, name + ".pt"))
+    print(name, "loss", float(loss), "n_grads", len(grads), "counts", [int((m[0] == 0).sum()) for m in out[1].values()])
 
 
 def subset_case(cfg):
@@ -229,10 +263,17 @@ def mask_case():
 
 def main():
     from oracle import OracleConfig
+    only = sys.argv[1:]     # e.g. `make_golden.py lstm_s2dsm` regenerates just that fixture
     small = dict(dim=128, depth=2, heads=2, dim_head=64, image_size=32, patch=8, dec_dim=64, dec_depth=1, dec_heads=2)
-    model_case("crossattn_simple", OracleConfig(variant="crossattn", decoder="simple", **small), 2, 24, 1, False)
-    model_case("plain_xattn", OracleConfig(variant="plain", decoder="xattn", **small), 2, 24, 3, True)
-    model_case("crossattn_uniform", OracleConfig(variant="crossattn", decoder="simple", **small), 3, 20, 11, True)
+    if not only:
+        model_case("crossattn_simple", OracleConfig(variant="crossattn", decoder="simple", **small), 2, 24, 1, False)
+        model_case("plain_xattn", OracleConfig(variant="plain", decoder="xattn", **small), 2, 24, 3, True)
+        model_case("crossattn_uniform", OracleConfig(variant="crossattn", decoder="simple", **small), 3, 20, 11, True)
+    from oracle.lstm_variant import lstm_config
+    if not only or "lstm_s2dsm" in only:
+        lstm_case("lstm_s2dsm", lstm_config(decoder="simple", **small), 3, 12, 2)
+    if only:
+        return
     subset_case(OracleConfig(variant="crossattn", decoder="simple", **small))
     loss_case()
     mask_case()

@@ -167,3 +167,52 @@ def test_reference_autocast_noise_floor():
           f"preds: ours {a_ours:.4f}, emulation {a_ac:.4f}")
     assert e_ours < max(GRAD_TOL, 2 * e_ac)
     assert a_ours < max(ACT_TOL, 2 * a_ac)
+
+
+def test_lstm_s2dsm_variant_matches_reference_golden_and_oracle(golden_dir):
+    """BASELINE config 1 path (multimae_lstm_s2dsm + the pretrain_mmae_s2dsm.py loss assembly) on the GPU: the
+    reference's golden outputs with its masks passed in explicitly, then a sampled-mask step against the oracle"""
+    from oracle import lstm_variant as L
+    from _util import pretrain_loss_s2dsm_ours
+    fx = _golden(golden_dir, "lstm_s2dsm")
+    cfg = OracleConfig(**fx["cfg"])
+    sd = default_sd(cfg)
+    model = build_model(cfg, sd)
+    x = make_inputs(cfg, fx["batch"], fx["input_seed"], "cuda")
+    tm = {t: m.cuda() for t, m in fx["task_masks"].items()}
+    out = model(x, task_masks=tm, num_encoded_tokens=fx["nenc"])
+    assert len(out) == 5
+    for t in fx["preds"]:
+        assert rel(out[0][t], fx["preds"][t].cuda()) < ACT_TOL, t
+    assert rel(out[2], fx["return_tokens"].cuda()) < ACT_TOL
+    assert rel(out[3], fx["ori_tokens"].cuda()) < ACT_TOL
+    assert rel(out[4], fx["fusion_tokens"].cuda()) < ACT_TOL
+    loss = pretrain_loss_s2dsm_ours(out, x, cfg.patch)
+    assert abs(float(loss) - float(fx["loss"])) < ACT_TOL * abs(float(fx["loss"]))
+
+    # sampled masks (device RNG), forward + backward against the oracle
+    cfg2 = L.lstm_config(dim=192, depth=2, heads=3, image_size=64, patch=8, dec_dim=64, dec_depth=1, dec_heads=2)
+    sd2 = default_sd(cfg2)
+    model2 = build_model(cfg2, sd2)
+    x2 = make_inputs(cfg2, 4, 21, "cuda")
+    torch.manual_seed(9)
+    out2 = model2(x2, num_encoded_tokens=40)
+    loss2 = pretrain_loss_s2dsm_ours(out2, x2, cfg2.patch)
+    loss2.backward()
+    sd_o = OrderedDict((k, v.cuda().requires_grad_(not (k.endswith(".beta") or k.endswith("pos_emb")))) for k, v in sd2.items())
+    torch.manual_seed(9)
+    ref = L.multimae_lstm_forward(sd_o, cfg2, x2, num_encoded_tokens=40)
+    ref_loss = L.pretrain_loss_s2dsm(ref, x2, cfg2)
+    ref_loss.backward()
+    for t in ref[1]:
+        assert torch.equal(out2[1][t], ref[1][t])
+    for t in ref[0]:
+        assert rel(out2[0][t], ref[0][t]) < ACT_TOL, t
+    for i in (2, 3, 4):
+        assert rel(out2[i], ref[i]) < ACT_TOL, i
+    assert abs(float(loss2) - float(ref_loss)) < ACT_TOL * abs(float(ref_loss))
+    for k, p in model2.named_parameters():
+        g_ref = sd_o[k].grad
+        if g_ref is None or float(g_ref.norm()) < 1e-7:
+            continue
+        assert rel(p.grad, g_ref) < GOLDEN_GRAD_TOL, (k, rel(p.grad, g_ref))

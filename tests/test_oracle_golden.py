@@ -127,3 +127,35 @@ def test_all_masked_row_is_uniform():
     v = torch.nn.functional.linear(ctx, sd["attn_pool.to_kv.weight"])[..., 64:]
     uni = torch.nn.functional.linear(v.mean(dim=1), sd["attn_pool.to_out.weight"])
     torch.testing.assert_close(out[:, 1], uni, rtol=1e-5, atol=1e-6)
+
+
+def test_lstm_s2dsm_variant_matches_reference(golden_dir):
+    """BASELINE config 1 path (multimae_lstm_s2dsm.MultiMAE + the pretrain_mmae_s2dsm.py loss assembly): oracle vs the
+    reference's own run -- schema, int64 masks, every output, the loss and all parameter gradients"""
+    from oracle import lstm_variant as L
+    fx = _load(golden_dir, "lstm_s2dsm")
+    cfg = _cfg(fx["cfg"])
+    sd = oracle.perturb_state_dict(L.init_state_dict(cfg, seed=0), seed=7)
+    for k, v in sd.items():
+        if not (k.endswith(".beta") or k.endswith("pos_emb")):
+            v.requires_grad_(True)
+    assert {k: tuple(v.shape) for k, v in sd.items()} == dict(fx["state_dict_keys"])
+    x = _inputs(cfg, fx["batch"], fx["input_seed"])
+    torch.manual_seed(fx["mask_seed"])
+    out = L.multimae_lstm_forward(sd, cfg, x, num_encoded_tokens=fx["nenc"], alphas=1.0)
+    for t in fx["task_masks"]:
+        assert torch.equal(out[1][t], fx["task_masks"][t])
+    for t in fx["preds"]:
+        torch.testing.assert_close(out[0][t], fx["preds"][t], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out[2], fx["return_tokens"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out[3], fx["ori_tokens"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out[4], fx["fusion_tokens"], rtol=1e-5, atol=1e-5)
+    loss = L.pretrain_loss_s2dsm(out, x, cfg)
+    torch.testing.assert_close(loss, fx["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    got = {k for k, v in sd.items() if v.requires_grad and v.grad is not None}
+    assert got == set(fx["grad_norms"])
+    for k, n in fx["grad_norms"].items():
+        torch.testing.assert_close(sd[k].grad.norm(), n, rtol=2e-4, atol=1e-6)
+    for k, g in fx["grads"].items():
+        torch.testing.assert_close(sd[k].grad, g, rtol=1e-4, atol=2e-6)
