@@ -197,12 +197,15 @@ def run_ours(args):
     launches = kernels.launch_count()
     kernels.enable_gemm_timing(False)
     clocks = sampler.summary()
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in timing)
-    gemm_flops = sum(f for _, _, f, _ in timing)
-    by_kind = {}
-    for a, b, f, kind in timing:
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _, _ in timing)
+    gemm_flops = sum(f for _, _, f, _, _ in timing)
+    by_kind, by_shape = {}, {}
+    for a, b, f, kind, shape in timing:
+        dt = a.elapsed_time(b)
         t, fl, n = by_kind.get(kind, (0.0, 0.0, 0))
-        by_kind[kind] = (t + a.elapsed_time(b), fl + f, n + 1)
+        by_kind[kind] = (t + dt, fl + f, n + 1)
+        t, fl, n = by_shape.get(shape, (0.0, 0.0, 0))
+        by_shape[shape] = (t + dt, fl + f, n + 1)
     t_max = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
@@ -252,7 +255,10 @@ def run_ours(args):
                      "peak_source": pk["source"] + ", sustained cuBLAS bf16",
                      "gemm_share_of_step": gemm_ms / ms if ms else None,
                      "by_kind": {k: {"tflops": fl / (t / 1e3) / 1e12, "ms_per_step": t / args.steps, "launches_per_step": n / args.steps}
-                                 for k, (t, fl, n) in by_kind.items()}},
+                                 for k, (t, fl, n) in by_kind.items()},
+                     "top_shapes": [{"gemm": "%s M=%d N=%d K=%d" % k, "tflops": round(fl / (t / 1e3) / 1e12, 1),
+                                     "ms_per_step": round(t / args.steps, 3), "launches_per_step": n / args.steps}
+                                    for k, (t, fl, n) in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("MMF_BENCH_TOP_SHAPES", "14"))]]},
         "loss": float(loss),
     }
     if e2e:

@@ -97,6 +97,13 @@ struct KeyBlocks {
   }
 };
 
+#ifdef MMF_ATTN_CLOCKS
+__device__ unsigned long long g_attn_clk[16];
+#define CLK(i, expr) do { if (dbg_on) { const long long t__ = clock64(); g_attn_clk[i] += (unsigned long long)(t__ - t_last); t_last = t__; } } while (0)
+#else
+#define CLK(i, expr) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
@@ -249,13 +256,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int i = r0 + row_in_tile;
     uint32_t raw[32];
     int g = 0;
+#ifdef MMF_ATTN_CLOCKS
+    const bool dbg_on = (blockIdx.y == 3) && (kb.nb == 5) && (r0 == p.n_head) && warp == 2 && lane == 0;
+    long long t_last = clock64();
+#endif
     for (int h = 0; h < p.H; ++h) {
       float m_ref = -INFINITY, l = 0.f;
       for (int j = 0; j < kb.nb; ++j, ++g) {
         int64_t row; int nvalid;
         kb.get(j, row, nvalid);
+        CLK(4, 0);
         mbar_wait(s_full, g & 1);
         tc_fence_after();
+        CLK(0, 0);
         const int nchunk = (nvalid + 31) >> 5;
         // pass A: row max over the valid keys
         float mx = -INFINITY;
@@ -271,6 +284,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               if (c * 32 + t < nvalid) mx = fmaxf(mx, __uint_as_float(raw[t]));
           }
         }
+        CLK(1, 0);
         const float m_new = mx * p.scale_log2;
         // lazy rescale: only when the max grew by more than 2^8 (warp-uniform decision: tcgen05.ld/st are warp-wide)
         const bool grow = m_new > m_ref + 8.0f;
@@ -319,14 +333,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           tmem_st_32x16(lane_addr + TMEM_P + c * 16, pk);
         }
         l += rs;
+        CLK(2, 0);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+        CLK(3, 0);
       }
       // ---- head epilogue: O / l -> bf16 row, log-sum-exp ----
       mbar_wait(o_full, h & 1);
       tc_fence_after();
+      CLK(5, 0);
       const float inv = 1.0f / l;
       __nv_bfloat16* orow = p.o + (q_row0 + row_in_tile) * p.ldo + h * 64;
 #pragma unroll
@@ -347,6 +364,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);   // the MMA warp may overwrite O for the next head
       if (p.lse && i < r1) p.lse[((int64_t)b * p.H + h) * p.N + i] = (m_ref + log2f(l)) * 0.6931471805599453f;
+      CLK(6, 0);
     }
   }
 
@@ -958,3 +976,13 @@ int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
 }
 
 }  // namespace mmf
+
+#ifdef MMF_ATTN_CLOCKS
+extern "C" int mmf_debug_attn_clocks(unsigned long long* out16, int reset) {
+  if (reset) {
+    unsigned long long z[16] = {0};
+    return (int)cudaMemcpyToSymbol(mmf::g_attn_clk, z, sizeof(z));
+  }
+  return (int)cudaMemcpyFromSymbol(out16, mmf::g_attn_clk, 16 * sizeof(unsigned long long));
+}
+#endif

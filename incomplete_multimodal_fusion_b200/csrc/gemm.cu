@@ -124,7 +124,8 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, const
       if (p.out2) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + orow * p.ldo2 + col0 + c) = pack4(x);
     } else if (EPI == EPI_ATOMIC) {
       float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0 + c;
-      atomicAdd(o, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w);
+      // one 16-byte vector reduction instead of four scalar ones: split-K wgrads are paced by L2 atomic throughput
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
     } else {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0 + c;
       if (EPI == EPI_BF16_ACC) {
@@ -432,6 +433,16 @@ constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 // of the accumulator out of TMEM in one go (a tcgen05.ld issued while MMAs are queued completes late, so serial
 // load -> use -> load round trips made the epilogue the pacing stage), releases the accumulator, packs bf16 into a
 // 128B-swizzled 32-row box in shared memory and hands it to the TMA store engine.
+// x = alpha * acc + bias on 64 accumulator columns held in registers (bias nullable; uniform loads)
+__device__ __forceinline__ void bias_scale64(uint32_t (&v)[64], const float* bias, float alpha) {
+#pragma unroll
+  for (int t = 0; t < 64; ++t) {
+    float x = __uint_as_float(v[t]) * alpha;
+    if (bias != nullptr) x += __ldg(bias + t);
+    v[t] = __float_as_uint(x);
+  }
+}
+
 template <bool TS>
 struct G2Cfg {
   static constexpr int STAGES = TS ? 5 : 6;
@@ -462,7 +473,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                      const GemmParams p) {
   constexpr bool geglu = (EPI == EPI_GEGLU);
   constexpr int STAGES = G2Cfg<TS>::STAGES;
-  static_assert(!TS || EPI == EPI_BF16 || EPI == EPI_GEGLU, "TMA-store epilogue: bf16 / GEGLU outputs only");
+  static_assert(!TS || EPI == EPI_BF16 || EPI == EPI_GEGLU || EPI == EPI_GELU, "TMA-store epilogue: bf16 outputs only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -492,7 +503,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     tma_prefetch_desc(&tmap_b);
     if (TS) {
       tma_prefetch_desc(&tmap_o);
-      if (geglu) tma_prefetch_desc(&tmap_o2);
+      if (geglu || EPI == EPI_GELU) tma_prefetch_desc(&tmap_o2);
     }
   }
   if (warp == 1) {
@@ -618,8 +629,37 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           if (live0) {
             if (lane == 0) tma_store_wait_read<0>();   // the previous tile's stores have drained this warp's boxes
             __syncwarp();
-            pack_box(sbox, v0, lane, p.bias ? p.bias + col_base : nullptr, p.alpha);
-            if (live1) pack_box(sbox + 4096, v1, lane, p.bias ? p.bias + col_base + 64 : nullptr, p.alpha);
+            if constexpr (EPI == EPI_GELU) {
+              // x = alpha * acc + bias; out2 (optional) = x, out = gelu(x): both leave through the same two boxes
+              bias_scale64(v0, p.bias ? p.bias + col_base : nullptr, p.alpha);
+              if (live1) bias_scale64(v1, p.bias ? p.bias + col_base + 64 : nullptr, p.alpha);
+              if (p.out2) {
+                pack_box(sbox, v0, lane, nullptr, 1.0f);
+                if (live1) pack_box(sbox + 4096, v1, lane, nullptr, 1.0f);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&tmap_o2, sbox, col_base, row0);
+                  if (live1) tma_store_2d(&tmap_o2, sbox + 4096, col_base + 64, row0);
+                  tma_store_commit();
+                }
+              }
+#pragma unroll
+              for (int t = 0; t < 64; ++t) v0[t] = __float_as_uint(gelu_fast(__uint_as_float(v0[t])));
+              if (live1) {
+#pragma unroll
+                for (int t = 0; t < 64; ++t) v1[t] = __float_as_uint(gelu_fast(__uint_as_float(v1[t])));
+              }
+              if (p.out2) {
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+              }
+              pack_box(sbox, v0, lane, nullptr, 1.0f);
+              if (live1) pack_box(sbox + 4096, v1, lane, nullptr, 1.0f);
+            } else {
+              pack_box(sbox, v0, lane, p.bias ? p.bias + col_base : nullptr, p.alpha);
+              if (live1) pack_box(sbox + 4096, v1, lane, p.bias ? p.bias + col_base + 64 : nullptr, p.alpha);
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -982,7 +1022,7 @@ extern "C" int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream_) {
     const bool ts = ts_on && a.out_period == 0 && (a.ldo & 7) == 0 && al16(a.out) && (!a.out2 || ((a.ldo2 & 7) == 0 && al16(a.out2)));
     switch (epi) {
       case EPI_BF16: return ts ? launch_gemm2<EPI_BF16, true>(a, stream) : launch_gemm2<EPI_BF16, false>(a, stream);
-      case EPI_GELU: return launch_gemm2<EPI_GELU, false>(a, stream);
+      case EPI_GELU: return ts ? launch_gemm2<EPI_GELU, true>(a, stream) : launch_gemm2<EPI_GELU, false>(a, stream);
       case EPI_F32: return launch_gemm2<EPI_F32, false>(a, stream);
       case EPI_ATOMIC: return launch_gemm2<EPI_ATOMIC, false>(a, stream);
       case EPI_BF16_ACC: return launch_gemm2<EPI_BF16_ACC, false>(a, stream);

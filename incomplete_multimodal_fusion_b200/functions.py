@@ -201,6 +201,57 @@ def layer_norm(x, gamma, bias=None, eps=1e-5, out_bf16=False):
     return LayerNormFn.apply(x, gamma, bias, eps, out_bf16)
 
 
+class AddLayerNormFn(torch.autograd.Function):
+    """(x_new, y) = (x + delta, LN(x + delta)): the residual add of a sub-layer fused into the next LayerNorm
+    (x fp32 stream, delta = bf16 output of the sub-layer's last Linear, y bf16)"""
+
+    @staticmethod
+    def forward(ctx, x, delta, gamma, bias, eps):
+        x = x.contiguous()
+        delta = delta.contiguous()
+        rows, D = x.shape
+        xout = torch.empty(rows, D, dtype=f32, device=x.device)
+        y = torch.empty(rows, D, dtype=bf16, device=x.device)
+        stats = torch.empty(rows, 4, dtype=f32, device=x.device)
+        K.layernorm_fwd(x, gamma.detach(), y, b1=None if bias is None else bias.detach(), eps1=eps, stats=stats,
+                        delta=delta, xout=xout)
+        ctx.save_for_backward(xout, gamma, bias, stats)
+        ctx.set_materialize_grads(False)
+        return xout, y
+
+    @staticmethod
+    def backward(ctx, dxout, dy):
+        xout, gamma, bias, stats = ctx.saved_tensors
+        D = xout.shape[1]
+        dg = torch.zeros(D, dtype=f32, device=xout.device)
+        db = torch.zeros(D, dtype=f32, device=xout.device) if bias is not None else None
+        if dy is None:      # only the residual stream was used downstream
+            dx = dxout.contiguous()
+            return dx, to_bf16(dx), dg, db, None
+        dx = torch.empty_like(xout)
+        dxb = torch.empty(xout.shape, dtype=bf16, device=xout.device)
+        K.layernorm_bwd(dy.contiguous(), xout, gamma.detach(), stats, dx, dg, b1=None if bias is None else bias.detach(),
+                        db1=db, dres=None if dxout is None else dxout.contiguous(), dx_bf16=dxb)
+        return dx, dxb, dg, db, None
+
+
+def add_layer_norm(x, delta, gamma, bias=None, eps=1e-5):
+    return AddLayerNormFn.apply(x, delta, gamma, bias, eps)
+
+
+class AddDeltaFn(torch.autograd.Function):
+    """x (f32) + delta (bf16) -> f32: materialises a residual stream whose last delta is still pending"""
+
+    @staticmethod
+    def forward(ctx, x, delta):
+        return K.add_bf16(x.contiguous(), delta.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        return dy, to_bf16(dy)
+
+
 class SelfAttentionFn(torch.autograd.Function):
     """unmasked multi-head self-attention on a fused [B*N, 3*H*dh] bf16 qkv buffer (decoder blocks)"""
 
@@ -647,15 +698,18 @@ class EncoderStackFn(torch.autograd.Function):
             da = torch.empty(Mf, HD, dtype=bf16, device=dev)
             K.gemm(dXf1b, w_bf16(params[fo + 4]), da, b_mn=True)
             grads[fo + 4] = wgrad(dXf1b, rec["a"])
-            dq = torch.empty(Mf, HD, dtype=bf16, device=dev)
-            dkv = torch.empty(Mt, 2 * HD, dtype=bf16, device=dev)
+            # dkv [Mt, 2HD] and dq [Mf, HD] share one buffer, [dk | dv | dq] per row (the dq columns of the modality rows
+            # stay unused): the fusion rows' dgrad is then ONE GEMM over K = 3HD against [Wkv; Wq] instead of a second,
+            # read-modify-write GEMM into the same rows
+            dkvq = torch.empty(Mt, 3 * HD, dtype=bf16, device=dev)
+            dkv, dq = dkvq[:, :2 * HD], dkvq[Mh:, 2 * HD:]
             dkvm = torch.zeros(Fn, 2 * HD, dtype=f32, device=dev)
             K.slot_attn_bwd(rec["q"], rec["kv"], rec["kvm"], meta["slotmap"], seg, da, dq, dkv, dkvm, B=B, F=Fn, H=H, S=nseg,
                             n_head=nenc, scale=scale)
-            wkvb, wqb = w_bf16(params[fo + 3]), w_bf16(params[fo + 2])
+            wkvb = w_bf16(params[fo + 3])
             dhk = torch.empty(Mt, D, dtype=bf16, device=dev)
-            K.gemm(dkv, wkvb, dhk, b_mn=True)
-            K.gemm(dq, wqb, dhk[Mh:], b_mn=True, accumulate=True)
+            K.gemm(dkv[:Mh], wkvb, dhk[:Mh], b_mn=True)
+            K.gemm(dkvq[Mh:], w_cat_bf16([params[fo + 3], params[fo + 2]]), dhk[Mh:], b_mn=True)
             dWkv = wgrad(dkv, rec["hk"])
             grads[fo + 2] = wgrad(dq, rec["hk"][Mh:])
             # mask-embedding rows (batch-invariant keys/values)

@@ -109,7 +109,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, 
     check(_L().mmf_gemm_bf16(C.byref(args), _stream()), "mmf_gemm_bf16")
     e1.record()
     n_eff = 2 * N if act == 2 else N
-    GEMM_TIMING.append((e0, e1, 2.0 * M * n_eff * K, "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")))
+    kind = "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")
+    GEMM_TIMING.append((e0, e1, 2.0 * M * n_eff * K, kind, (kind + ("_geglu" if act == 2 else ""), M, n_eff, K)))
     return out
 
 

@@ -114,6 +114,24 @@ class CrossAttention(nn.Module):
         return Fn.linear(o, self.proj.weight, self.proj.bias).view(B, N, C)
 
 
+class ResidualStream:
+    """fp32 residual stream [rows, C] plus the bf16 output of the last sub-layer that has not been added yet: the next
+    LayerNorm launch adds it (functions.add_layer_norm), so no GEMM epilogue does an fp32 read-modify-write.
+    `Block` accepts and returns this carrier when chained; given a plain tensor it returns a plain tensor."""
+
+    def __init__(self, x, pend, shape):
+        self.x, self.pend, self.shape = x, pend, tuple(shape)
+
+    @staticmethod
+    def wrap(t):
+        return ResidualStream(_flat(t if t.dtype == torch.float32 else t.float()), None, t.shape)
+
+    def tensor(self):
+        """fp32 [..., C] with the pending delta added"""
+        x = self.x if self.pend is None else Fn.AddDeltaFn.apply(self.x, self.pend)
+        return x.view(self.shape)
+
+
 class Block(nn.Module):
     """pre-LN ViT block of the decoders (multimae_utils.py:217-232); residual stream in fp32"""
 
@@ -129,9 +147,15 @@ class Block(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x):
-        B, N, C = x.shape
-        x = x.float() if x.dtype != torch.float32 else x
-        h = Fn.layer_norm(_flat(x), self.norm1.weight, self.norm1.bias, self.norm1.eps, out_bf16=True).view(B, N, C)
-        x = self.attn(h, residual=x)
-        h = Fn.layer_norm(_flat(x), self.norm2.weight, self.norm2.bias, self.norm2.eps, out_bf16=True).view(B, N, C)
-        return self.mlp(h, residual=x)
+        chained = isinstance(x, ResidualStream)
+        st = x if chained else ResidualStream.wrap(x)
+        B, N, C = st.shape
+        if st.pend is None:
+            x32 = st.x
+            h = Fn.layer_norm(x32, self.norm1.weight, self.norm1.bias, self.norm1.eps, out_bf16=True)
+        else:   # x + (previous sub-layer) and norm1 in one pass
+            x32, h = Fn.add_layer_norm(st.x, st.pend, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        d_attn = self.attn(h.view(B, N, C))                                   # bf16, no residual in the GEMM
+        x32, h = Fn.add_layer_norm(x32, _flat(d_attn), self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        out = ResidualStream(x32, _flat(self.mlp(h.view(B, N, C))), st.shape)
+        return out if chained else out.tensor()

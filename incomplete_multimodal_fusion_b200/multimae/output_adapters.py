@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import functions as Fn
-from .multimae_utils import Block, CrossAttention, Mlp, build_2d_sincos_posemb, pair, trunc_normal_
+from .multimae_utils import Block, CrossAttention, Mlp, ResidualStream, build_2d_sincos_posemb, pair, trunc_normal_
 
 
 class SpatialOutputAdapter(nn.Module):
@@ -153,9 +153,9 @@ class SpatialOutputAdapter(nn.Module):
             x = self.decoder(qn, cn).float()                        # no residual around the cross-attention (:265)
             h = Fn.layer_norm(x.reshape(B * Nq, d), self.out_norm.weight, self.out_norm.bias, self.out_norm.eps,
                               out_bf16=True).view(B, Nq, d)
-            x = self.mlp(h, residual=x)
+            st = ResidualStream(x.reshape(B * Nq, d), self.mlp(h).reshape(B * Nq, d), (B, Nq, d))   # x + Mlp(out_norm(x)) (:266)
         else:
-            x = queries
-        x = self.decoder_transformer(x)
+            st = ResidualStream.wrap(queries)
+        x = self.decoder_transformer(st).tensor()
         x = Fn.linear(x.reshape(B * Nq, d), self.out_proj.weight, self.out_proj.bias)
         return Fn.UnpatchifyFn.apply(x, B, self.num_channels, H, W, self.P_H)

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import functions as Fn
-from .multimae_utils import Block, build_2d_sincos_posemb, pair, trunc_normal_
+from .multimae_utils import Block, ResidualStream, build_2d_sincos_posemb, pair, trunc_normal_
 
 
 class SpatialOutputAdapter(nn.Module):
@@ -79,6 +79,6 @@ class SpatialOutputAdapter(nn.Module):
         if self.task_embeddings is not None and self.task in self.task_embeddings:
             bias = bias + self.task_embeddings[self.task].reshape(d)   # broadcast add folded into the GEMM bias
         x = Fn.linear(encoder_tokens.reshape(B * N, -1), self.proj_context.weight, bias, out_f32=True).view(B, N, d)
-        x = self.decoder_transformer(x)
+        x = self.decoder_transformer(ResidualStream.wrap(x)).tensor()
         x = Fn.linear(x.reshape(B * N, d), self.out_proj.weight, self.out_proj.bias)
         return Fn.UnpatchifyFn.apply(x, B, self.num_channels, H, W, self.P_H)

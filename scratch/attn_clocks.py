@@ -1,0 +1,26 @@
+"""debug: per-phase clock totals of one fusion-tile CTA of the attention forward (needs scratch/dbg_libmmf.so)"""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from incomplete_multimodal_fusion_b200 import _lib
+_lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dbg_libmmf.so")
+from incomplete_multimodal_fusion_b200 import kernels as K
+lib = _lib.load()
+raw = C.CDLL(_lib.LIB_PATH)
+B, nenc, Fn, H = 256, 294, 196, 8
+N = nenc + Fn; Mt = B * N; HD = 512
+seg = torch.tensor([0, 98, 196, 294, 490], dtype=torch.int32, device="cuda")
+qkv = torch.randn(Mt, 3 * HD, device="cuda").bfloat16(); o = torch.empty(Mt, HD, dtype=torch.bfloat16, device="cuda"); lse = torch.empty(B, H, N, device="cuda")
+kw = dict(B=B, H=H, Nq=N, Nk=N, dh=64, scale=0.125, n_head_q=nenc, n_head_k=nenc, seg=seg, nseg=4)
+f = lambda: K.attn_fwd(qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, **kw)
+for _ in range(3): f()
+torch.cuda.synchronize()
+buf = (C.c_ulonglong * 16)()
+raw.mmf_debug_attn_clocks(buf, 1)
+f(); torch.cuda.synchronize()
+raw.mmf_debug_attn_clocks(buf, 0)
+names = ["wait s_full", "ld + row max (pass A)", "exp + pack + st (pass B)", "wait_st+arrive", "loop top", "wait o_full", "head epilogue"]
+tot = sum(buf[i] for i in range(7))
+print("one fusion-tile CTA, 8 heads x 5 key blocks = 40 iterations; total cycles", tot)
+for i, n in enumerate(names):
+    print(f"  {n:28s} {buf[i]:10d} cycles  {100*buf[i]/tot:5.1f}%   per iteration {buf[i]/40:8.0f}")
