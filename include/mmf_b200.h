@@ -143,6 +143,8 @@ typedef struct MmfSlotAttnArgs {
   /* backward */
   const void* dout; void* dq; void* dkv_tok; float* dkv_me; /* dkv_me f32 [F, 2*H*dh], caller zeroes */
   int64_t lddout, lddq, lddkv, lddme;
+  float* me_scratch;      /* optional f32 [B*F, H, S-1, 2]: enables the atomic-free backward (masks are shared by the
+                             batch, so the mask-embedding gradients are a plain reduction over the samples) */
 } MmfSlotAttnArgs;
 int mmf_slot_attn_fwd(const MmfSlotAttnArgs* args, mmf_stream_t stream);
 int mmf_slot_attn_bwd(const MmfSlotAttnArgs* args, mmf_stream_t stream);

@@ -47,6 +47,7 @@ class SlotAttnArgs(C.Structure):
         ("scale", c_f32),
         ("dout", c_vp), ("dq", c_vp), ("dkv_tok", c_vp), ("dkv_me", c_vp),
         ("lddout", c_i64), ("lddq", c_i64), ("lddkv", c_i64), ("lddme", c_i64),
+        ("me_scratch", c_vp),
     ]
 
 

@@ -40,6 +40,7 @@ struct SlotParams {
   __nv_bfloat16* dkv_tok;       // planar token rows (every row written exactly once)
   float* dkv_me;                // [F, 2*H*64] f32, atomically accumulated (caller zeroes)
   int64_t lddout, lddq, lddkv, lddme;
+  float* me_scratch;            // [B*F, H, S-1, 2] f32: (ds, w) of every modality slot (wide backward path)
 };
 
 __device__ __forceinline__ int64_t slot_row(const SlotParams& p, int b, int pos, int s, bool& is_me) {
@@ -118,6 +119,182 @@ __global__ void slot_attn_kernel(const SlotParams p) {
       }
     }
     *reinterpret_cast<uint32_t*>(p.dq + bp * p.lddq + h * 64 + 2 * lane) = pack_bf16(dq.x, dq.y);
+  }
+}
+
+// ---- wide variant (H <= 8, 16-byte aligned rows): ONE warp per (b, pos) covers all heads: lane = (head, quarter of the
+// head's 64 dims), 32-byte loads per lane and 4-lane dot-product reductions, instead of one warp per head with 4-byte
+// loads.  Backward: whether slot s of position p is a mask-embedding row does not depend on the sample (masks are
+// shared by the batch), so the mask-embedding gradients are a reduction over the batch: this kernel stores the two
+// scalars (ds, w) per (b, p, head, slot) and slot_me_reduce_kernel sums ds*q / w*dout over b -- no atomics.
+__device__ __forceinline__ void ld16(const __nv_bfloat16* p, float (&f)[16]) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 8);
+  const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float2 t = unpack_bf16(u[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void st16(__nv_bfloat16* p, const float (&f)[16]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  *reinterpret_cast<uint4*>(p + 8) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+constexpr int SLOTW_WARPS = 4;
+
+struct Pk16 { uint4 a, b; };   // 16 bf16 values, kept packed in registers until used
+__device__ __forceinline__ Pk16 ldpk(const __nv_bfloat16* p) {
+  Pk16 r;
+  r.a = *reinterpret_cast<const uint4*>(p);
+  r.b = *reinterpret_cast<const uint4*>(p + 8);
+  return r;
+}
+__device__ __forceinline__ void unpk(const Pk16& r, float (&f)[16]) {
+  const uint32_t u[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float2 t = unpack_bf16(u[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ float dot16(const Pk16& r, const float (&x)[16]) {
+  float f[16];
+  unpk(r, f);
+  float d = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) d += f[i] * x[i];
+  return d;
+}
+__device__ __forceinline__ void axpy16(float a, const Pk16& r, float (&y)[16]) {
+  float f[16];
+  unpk(r, f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) y[i] += a * f[i];
+}
+
+template <bool BWD, int S>
+__global__ void __launch_bounds__(SLOTW_WARPS * 32) slot_attn_wide_kernel(const SlotParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t bp = (int64_t)blockIdx.x * SLOTW_WARPS + (threadIdx.x >> 5);   // b * F + pos
+  if (bp >= (int64_t)p.B * p.F) return;
+  const int b = (int)(bp / p.F), pos = (int)(bp % p.F);
+  const int h = lane >> 2, sub = lane & 3;
+  const bool act = h < p.H;
+  const int HD = p.H * 64;
+  const int col = (act ? h : 0) * 64 + sub * 16;
+  float q[16];
+  ld16(p.q + bp * p.ldq + col, q);
+  Pk16 k[S], v[S];
+  float sc[S];
+  int64_t rows[S];
+  bool me[S];
+#pragma unroll
+  for (int t = 0; t < S; ++t) {   // all row loads are issued before any arithmetic
+    rows[t] = slot_row(p, b, pos, t, me[t]);
+    const __nv_bfloat16* base = me[t] ? p.kv_me + rows[t] * p.ldme : p.kv_tok + rows[t] * p.ldkv;
+    k[t] = ldpk(base + col);
+    v[t] = ldpk(base + HD + col);
+  }
+  float d[16];
+  if (BWD) ld16(p.dout + bp * p.lddout + col, d);
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < S; ++t) {
+    sc[t] = quad_sum(dot16(k[t], q)) * p.scale;
+    mx = fmaxf(mx, sc[t]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < S; ++t) { sc[t] = __expf(sc[t] - mx); sum += sc[t]; }
+  const float inv = 1.0f / sum;
+  if (!BWD) {
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < S; ++t) axpy16(sc[t] * inv, v[t], o);
+    if (act) st16(p.out + bp * p.ldo + col, o);
+  } else {
+    float dp[S], dot = 0.f;
+#pragma unroll
+    for (int t = 0; t < S; ++t) {
+      sc[t] *= inv;
+      dp[t] = quad_sum(dot16(v[t], d));
+      dot += sc[t] * dp[t];
+    }
+    float dq[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dq[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < S; ++t) {
+      const float ds = sc[t] * (dp[t] - dot) * p.scale;
+      axpy16(ds, k[t], dq);
+      if (t < S - 1 && act && sub == 0)
+        *reinterpret_cast<float2*>(p.me_scratch + ((bp * p.H + h) * (S - 1) + t) * 2) = make_float2(ds, sc[t]);
+      if (!me[t] && act) {
+        float dk[16], dv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { dk[i] = ds * q[i]; dv[i] = sc[t] * d[i]; }
+        __nv_bfloat16* base = p.dkv_tok + rows[t] * p.lddkv;
+        st16(base + col, dk);
+        st16(base + HD + col, dv);
+      }
+    }
+    if (act) st16(p.dq + bp * p.lddq + col, dq);
+  }
+}
+
+template <bool BWD>
+static void launch_slot_wide(const SlotParams& p, cudaStream_t st) {
+  const int64_t n = (int64_t)p.B * p.F;
+  const unsigned grid = (unsigned)((n + SLOTW_WARPS - 1) / SLOTW_WARPS);
+  switch (p.S) {
+    case 2: slot_attn_wide_kernel<BWD, 2><<<grid, SLOTW_WARPS * 32, 0, st>>>(p); break;
+    case 3: slot_attn_wide_kernel<BWD, 3><<<grid, SLOTW_WARPS * 32, 0, st>>>(p); break;
+    case 4: slot_attn_wide_kernel<BWD, 4><<<grid, SLOTW_WARPS * 32, 0, st>>>(p); break;
+    default: slot_attn_wide_kernel<BWD, 5><<<grid, SLOTW_WARPS * 32, 0, st>>>(p); break;
+  }
+}
+
+// dkv_me[pos, :] = sum over the batch of the mask-embedding slots' (ds * q | w * dout); one CTA of 8 warps per
+// (pos, head): warp w takes the samples b = w, w + 8, ..; lane = 2 of the head's 64 dims; the warps' partial sums meet in
+// shared memory.  Positions / slots that are real tokens contribute nothing (written as 0).
+constexpr int MERED_WARPS = 8;
+__global__ void __launch_bounds__(MERED_WARPS * 32) slot_me_reduce_kernel(const SlotParams p) {
+  __shared__ float4 part[MERED_WARPS][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int pos = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int HD = p.H * 64;
+  const int nm = p.S - 1;
+  bool is_me[SLOT_MAX];
+  bool any = false;
+#pragma unroll
+  for (int t = 0; t < SLOT_MAX; ++t) { is_me[t] = t < nm && p.slotmap[t * p.F + pos] < 0; any |= is_me[t]; }
+  float2 dk = make_float2(0.f, 0.f), dv = make_float2(0.f, 0.f);
+  if (any) {
+#pragma unroll 4
+    for (int b = w; b < p.B; b += MERED_WARPS) {
+      const int64_t bp = (int64_t)b * p.F + pos;
+      const float2 q = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.q + bp * p.ldq + h * 64 + 2 * lane));
+      const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.dout + bp * p.lddout + h * 64 + 2 * lane));
+      const float* sw = p.me_scratch + (bp * p.H + h) * nm * 2;
+      float ds = 0.f, wt = 0.f;
+#pragma unroll
+      for (int t = 0; t < SLOT_MAX; ++t)
+        if (is_me[t]) { ds += __ldg(sw + 2 * t); wt += __ldg(sw + 2 * t + 1); }
+      dk.x += ds * q.x; dk.y += ds * q.y;
+      dv.x += wt * d.x; dv.y += wt * d.y;
+    }
+  }
+  part[w][lane] = make_float4(dk.x, dk.y, dv.x, dv.y);
+  __syncthreads();
+  if (w == 0) {
+    float4 t = part[0][lane];
+#pragma unroll
+    for (int i = 1; i < MERED_WARPS; ++i) { const float4 u = part[i][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    float* base = p.dkv_me + (int64_t)pos * p.lddme;
+    *reinterpret_cast<float2*>(base + h * 64 + 2 * lane) = make_float2(t.x, t.y);
+    *reinterpret_cast<float2*>(base + HD + h * 64 + 2 * lane) = make_float2(t.z, t.w);
   }
 }
 
@@ -327,7 +504,16 @@ static SlotParams slot_params(const MmfSlotAttnArgs& a) {
   p.B = a.B; p.F = a.F; p.H = a.H; p.S = a.S; p.n_head = a.n_head; p.scale = a.scale;
   p.dout = (const __nv_bfloat16*)a.dout; p.dq = (__nv_bfloat16*)a.dq; p.dkv_tok = (__nv_bfloat16*)a.dkv_tok; p.dkv_me = a.dkv_me;
   p.lddout = a.lddout; p.lddq = a.lddq; p.lddkv = a.lddkv; p.lddme = a.lddme;
+  p.me_scratch = a.me_scratch;
   return p;
+}
+// the wide kernels need every row slice 16-byte aligned and all heads inside one warp
+static bool slot_wide_ok(const MmfSlotAttnArgs& a, bool bwd) {
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  bool ok = a.H <= 8 && a.S >= 2 && a.S <= 5 && !(a.ldq & 7) && !(a.ldkv & 7) && !(a.ldme & 7) && al(a.q) && al(a.kv_tok) && al(a.kv_me) && !a.probs;
+  if (!bwd) return ok && !(a.ldo & 7) && al(a.out);
+  return ok && a.me_scratch && !(a.lddout & 7) && !(a.lddq & 7) && !(a.lddkv & 7) && !(a.lddme & 1) && al(a.dout) && al(a.dq) &&
+         al(a.dkv_tok) && (reinterpret_cast<uintptr_t>(a.dkv_me) & 7) == 0;
 }
 
 extern "C" int mmf_slot_attn_fwd(const MmfSlotAttnArgs* a, mmf_stream_t stream) {
@@ -335,6 +521,9 @@ extern "C" int mmf_slot_attn_fwd(const MmfSlotAttnArgs* a, mmf_stream_t stream) 
   if (rc) MMF_BAD_ARG(rc);
   if (!a->out || (a->ldo & 1)) MMF_BAD_ARG(10);
   if ((int64_t)a->B * a->F == 0) return 0;
+  if (slot_wide_ok(*a, false)) {
+    launch_slot_wide<false>(slot_params(*a), reinterpret_cast<cudaStream_t>(stream));
+  } else
   slot_attn_kernel<false><<<(unsigned)((int64_t)a->B * a->F), 32 * a->H, 0, reinterpret_cast<cudaStream_t>(stream)>>>(slot_params(*a));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
@@ -347,6 +536,12 @@ extern "C" int mmf_slot_attn_bwd(const MmfSlotAttnArgs* a, mmf_stream_t stream) 
   if (!a->dout || !a->dq || !a->dkv_tok || !a->dkv_me) MMF_BAD_ARG(11);
   if ((a->lddout & 1) || (a->lddq & 1) || (a->lddkv & 1)) MMF_BAD_ARG(12);
   if ((int64_t)a->B * a->F == 0) return 0;
+  if (slot_wide_ok(*a, true)) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    launch_slot_wide<true>(slot_params(*a), st);
+    slot_me_reduce_kernel<<<(unsigned)(a->F * a->H), MERED_WARPS * 32, 0, st>>>(slot_params(*a));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  } else
   slot_attn_kernel<true><<<(unsigned)((int64_t)a->B * a->F), 32 * a->H, 0, reinterpret_cast<cudaStream_t>(stream)>>>(slot_params(*a));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();

@@ -190,6 +190,8 @@ def slot_attn_fwd(q, kv_tok, kv_me, slotmap, seg, out, probs, *, B, F, H, S, n_h
 def slot_attn_bwd(q, kv_tok, kv_me, slotmap, seg, dout, dq, dkv_tok, dkv_me, *, B, F, H, S, n_head, scale):
     a = _slot_args(q, kv_tok, kv_me, slotmap, seg, B, F, H, S, n_head, scale)
     a.dout, a.dq, a.dkv_tok, a.dkv_me = _p(dout), _p(dq), _p(dkv_tok), _p(dkv_me)
+    scratch = torch.empty(B * F * H * (S - 1) * 2, dtype=f32, device=q.device)   # (ds, w) per sample / position / head / slot
+    a.me_scratch = _p(scratch)
     a.lddout, a.lddq, a.lddkv, a.lddme = dout.stride(0), dq.stride(0), dkv_tok.stride(0), dkv_me.stride(0)
     check(_L().mmf_slot_attn_bwd(C.byref(a), _stream()), "mmf_slot_attn_bwd")
 

@@ -262,9 +262,12 @@ def test_slot_attention_fwd_bwd():
     K().slot_attn_fwd(q.detach(), kv_tok.detach(), kv_me.detach(), sm, sg, out, probs, **kw)
     assert rel(out, ref) < 6e-3
     assert rel(probs.view(B, Fn, H, S), pr) < 1e-4
+    out2 = torch.empty_like(out)                              # without probs: the warp-per-position kernel
+    K().slot_attn_fwd(q.detach(), kv_tok.detach(), kv_me.detach(), sm, sg, out2, None, **kw)
+    assert rel(out2, ref) < 6e-3
     dq = torch.empty_like(out)
     dkv = torch.full_like(kv_tok.detach(), float("nan"))
-    dme = torch.zeros(Fn, 2 * HD, device="cuda")
+    dme = torch.full((Fn, 2 * HD), float("nan"), device="cuda")   # the batch-reduction kernel writes every element
     K().slot_attn_bwd(q.detach(), kv_tok.detach(), kv_me.detach(), sm, sg, dout, dq, dkv, dme, **kw)
     assert torch.isfinite(dkv.float()).all()
     assert rel(dq, q.grad) < 1e-2
