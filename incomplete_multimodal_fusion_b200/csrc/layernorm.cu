@@ -51,7 +51,7 @@ __device__ __forceinline__ void ln_stage_params(float4* sg1, float4* sb1, float4
 }
 
 template <int NC>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p) {
+__global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_fwd_kernel(const LnParams p) {
   constexpr int LN_MAX_CHUNKS = NC;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -170,7 +170,7 @@ struct LnBwdParams {
 };
 
 template <int NC>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams p) {
+__global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_bwd_kernel(const LnBwdParams p) {
   constexpr int LN_MAX_CHUNKS = NC;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -180,8 +180,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
   __shared__ float4 g1[NC * 32], b1[NC * 32], g2[NC * 32];
   ln_stage_params(g1, b1, g2, p.g1, p.b1, p.g2, nchunk);
   // Parameter-gradient accumulators live in shared memory, one private slice per warp (lane-contiguous float4s:
-  // conflict free, no synchronisation).  Keeping them in registers cost ~70 registers and capped the kernel at 8
-  // resident warps per SM, far too few loads in flight for an HBM-bound kernel.
+  // conflict free, no synchronisation).  The kernel is latency bound (ncu: long-scoreboard stalls, 48 % of DRAM
+  // peak at 16 resident warps), so registers are what is budgeted: only the normalised input and the running
+  // gradient stay live per row (2 x NC float4); the second LayerNorm's xhat is recomputed from them and the
+  // residual-branch gradient is read where it is added.  That fits 3 CTAs (24 warps) per SM for D <= 768.
   extern __shared__ float4 ln_acc[];
   float4* adg1 = ln_acc + (size_t)warp * NC * 32;
   float4* adg2 = adg1 + (size_t)LN_WARPS * NC * 32;
@@ -197,20 +199,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
     const float mean1 = st.x, rstd1 = st.y, mean2 = st.z, rstd2 = st.w;
     const float4* xr = reinterpret_cast<const float4*>(
         (p.x2 && row >= p.x_split) ? p.x2 + (row - p.x_split) * p.ldx : p.x + row * p.ldx);
-    float4 xh1[LN_MAX_CHUNKS], d[LN_MAX_CHUNKS], rs[LN_MAX_CHUNKS];
+    float4 xh1[LN_MAX_CHUNKS], d[LN_MAX_CHUNKS];
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {  // all global loads of the row are issued before any arithmetic
       const int c = lane + 32 * i;
-      rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.dres && c < nchunk) rs[i] = reinterpret_cast<const float4*>(p.dres + row * p.lddres)[c];
-    }
-#pragma unroll
-    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-      const int c = lane + 32 * i;
       xh1[i] = d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < nchunk) {
-        const float4 xv = xr[c];
-        xh1[i] = make_float4((xv.x - mean1) * rstd1, (xv.y - mean1) * rstd1, (xv.z - mean1) * rstd1, (xv.w - mean1) * rstd1);
+        xh1[i] = xr[c];
         if (p.dy_f32) {
           d[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + row * p.lddy)[c];
         } else {
@@ -220,33 +215,41 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
         }
       }
     }
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      const bool in = lane + 32 * i < nchunk;
+      xh1[i].x = in ? (xh1[i].x - mean1) * rstd1 : 0.f; xh1[i].y = in ? (xh1[i].y - mean1) * rstd1 : 0.f;
+      xh1[i].z = in ? (xh1[i].z - mean1) * rstd1 : 0.f; xh1[i].w = in ? (xh1[i].w - mean1) * rstd1 : 0.f;
+    }
     if (dbl) {
       // second LN: y = xh2 * g2, xh2 = (y1 - mean2) * rstd2, y1 = xh1 * g1 + b1
       float s1 = 0.f, s2 = 0.f;
-      float4 xh2[LN_MAX_CHUNKS];
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-        xh2[i].x = (xh1[i].x * g1[lane + 32 * i].x + b1[lane + 32 * i].x - mean2) * rstd2;
-        xh2[i].y = (xh1[i].y * g1[lane + 32 * i].y + b1[lane + 32 * i].y - mean2) * rstd2;
-        xh2[i].z = (xh1[i].z * g1[lane + 32 * i].z + b1[lane + 32 * i].z - mean2) * rstd2;
-        xh2[i].w = (xh1[i].w * g1[lane + 32 * i].w + b1[lane + 32 * i].w - mean2) * rstd2;
         if (lane + 32 * i < nchunk) {
+          const float4 G1 = g1[lane + 32 * i], B1 = b1[lane + 32 * i], G2 = g2[lane + 32 * i];
+          float4 xh2;
+          xh2.x = (xh1[i].x * G1.x + B1.x - mean2) * rstd2; xh2.y = (xh1[i].y * G1.y + B1.y - mean2) * rstd2;
+          xh2.z = (xh1[i].z * G1.z + B1.z - mean2) * rstd2; xh2.w = (xh1[i].w * G1.w + B1.w - mean2) * rstd2;
           float4 t = adg2[lane + 32 * i];
-          t.x += d[i].x * xh2[i].x; t.y += d[i].y * xh2[i].y; t.z += d[i].z * xh2[i].z; t.w += d[i].w * xh2[i].w;
+          t.x += d[i].x * xh2.x; t.y += d[i].y * xh2.y; t.z += d[i].z * xh2.z; t.w += d[i].w * xh2.w;
           adg2[lane + 32 * i] = t;
-          d[i].x *= g2[lane + 32 * i].x; d[i].y *= g2[lane + 32 * i].y; d[i].z *= g2[lane + 32 * i].z; d[i].w *= g2[lane + 32 * i].w;
+          d[i].x *= G2.x; d[i].y *= G2.y; d[i].z *= G2.z; d[i].w *= G2.w;
           s1 += d[i].x + d[i].y + d[i].z + d[i].w;
-          s2 += d[i].x * xh2[i].x + d[i].y * xh2[i].y + d[i].z * xh2[i].z + d[i].w * xh2[i].w;
+          s2 += d[i].x * xh2.x + d[i].y * xh2.y + d[i].z * xh2.z + d[i].w * xh2.w;
         }
       }
       s1 = warp_sum(s1) * invD;
       s2 = warp_sum(s2) * invD;
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-        d[i].x = rstd2 * (d[i].x - s1 - xh2[i].x * s2);
-        d[i].y = rstd2 * (d[i].y - s1 - xh2[i].y * s2);
-        d[i].z = rstd2 * (d[i].z - s1 - xh2[i].z * s2);
-        d[i].w = rstd2 * (d[i].w - s1 - xh2[i].w * s2);
+        if (lane + 32 * i < nchunk) {
+          const float4 G1 = g1[lane + 32 * i], B1 = b1[lane + 32 * i];
+          d[i].x = rstd2 * (d[i].x - s1 - (xh1[i].x * G1.x + B1.x - mean2) * rstd2 * s2);
+          d[i].y = rstd2 * (d[i].y - s1 - (xh1[i].y * G1.y + B1.y - mean2) * rstd2 * s2);
+          d[i].z = rstd2 * (d[i].z - s1 - (xh1[i].z * G1.z + B1.z - mean2) * rstd2 * s2);
+          d[i].w = rstd2 * (d[i].w - s1 - (xh1[i].w * G1.w + B1.w - mean2) * rstd2 * s2);
+        }
       }
     }
     // first LN
@@ -262,7 +265,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
           u.x += d[i].x; u.y += d[i].y; u.z += d[i].z; u.w += d[i].w;
           adb1[lane + 32 * i] = u;
         }
-        d[i].x *= g1[lane + 32 * i].x; d[i].y *= g1[lane + 32 * i].y; d[i].z *= g1[lane + 32 * i].z; d[i].w *= g1[lane + 32 * i].w;
+        const float4 G1 = g1[lane + 32 * i];
+        d[i].x *= G1.x; d[i].y *= G1.y; d[i].z *= G1.z; d[i].w *= G1.w;
         s1 += d[i].x + d[i].y + d[i].z + d[i].w;
         s2 += d[i].x * xh1[i].x + d[i].y * xh1[i].y + d[i].z * xh1[i].z + d[i].w * xh1[i].w;
       }
@@ -278,7 +282,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
         o.y = rstd1 * (d[i].y - s1 - xh1[i].y * s2);
         o.z = rstd1 * (d[i].z - s1 - xh1[i].z * s2);
         o.w = rstd1 * (d[i].w - s1 - xh1[i].w * s2);
-        o.x += rs[i].x; o.y += rs[i].y; o.z += rs[i].z; o.w += rs[i].w;
+        if (p.dres) {
+          const float4 r = reinterpret_cast<const float4*>(p.dres + row * p.lddres)[c];
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
         reinterpret_cast<float4*>(p.dx + row * p.lddx)[c] = o;
         if (p.dx_bf16)
           reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.dx_bf16) + row * p.lddxb)[c] =
@@ -369,6 +376,12 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
     cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 4 * 32 * 16);
     cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 6 * 32 * 16);
     cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 8 * 32 * 16);
+    // ~58 KB per CTA at D = 768: ask for the full shared-memory carve-out so that three CTAs fit (the default carve-out
+    // stops at two and shared memory, not registers, would set the occupancy)
+    cudaFuncSetAttribute(ln_bwd_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_done = true;
   }
   if (nc <= 2) ln_bwd_kernel<2><<<ln_grid(ln_bwd_kernel<2>, smem, rows), LN_WARPS * 32, smem, st>>>(p);
