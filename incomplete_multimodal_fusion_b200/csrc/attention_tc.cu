@@ -12,8 +12,12 @@
 //   never loaded; only the ragged end of a key range is masked in registers, and the MMA N / K extents
 //   shrink to the valid keys (multiples of 16).
 //
-//   TMEM budget 256 columns (S 128 | P 64 | O 64) and ~81 KB smem so two CTAs share an SM: while one CTA's
-//   softmax warps work, the other CTA's MMAs run.
+//   Key blocks are 64 wide and P is written IN PLACE over the S columns it was computed from (the P.V MMA and the
+//   next block's S MMA are issued in that order and the tensor pipe executes in order), so a CTA needs only 128 TMEM
+//   columns (S/P 64 | O 64) and ~65 KB of shared memory: THREE CTAs share an SM.  The kernel is paced by the softmax
+//   (16 ex2/clk/SM; clock instrumentation: a CTA spends ~60 % of its time in the exponent passes and ~20 % waiting for
+//   the next S), so what matters is how many independent CTAs keep the MUFU pipe busy while others wait on the tensor
+//   pipe or on TMA.
 #include "common.cuh"
 #include "mmf_b200.h"
 
@@ -24,11 +28,14 @@ namespace mmf {
 extern std::atomic<int64_t> g_launch_count;
 
 constexpr int TC_BM = 128;   // query rows per CTA (UMMA M)
-constexpr int TC_BN = 128;   // keys per block (UMMA N of S, K extent of P.V)
+constexpr int TC_BN = 64;    // keys per block (UMMA N of S, K extent of P.V)
 constexpr int TC_THREADS = 192;
-constexpr int TC_TILE_BYTES = 128 * 64 * 2;   // one 128 x 64 bf16 tile
-constexpr int TC_SMEM = 6 * TC_TILE_BYTES + 1024 + 128;   // 2xQ + 2x(K,V) + align + barriers
-constexpr uint32_t TMEM_S = 0, TMEM_P = 128, TMEM_O = 192, TMEM_COLS = 256;
+constexpr int TC_CTAS_PER_SM = 3;   // four would fit TMEM (4 x 128 columns) but not the 64-register tcgen05.ld of a whole S row
+constexpr int TC_QBUF = 2;          // Q tile buffers: the next head's Q arrives while the current head is in softmax
+constexpr int TC_TILE_BYTES = 128 * 64 * 2;      // one 128 x 64 bf16 tile (Q; also the backward kernels' 128-row tiles)
+constexpr int TC_KV_BYTES = TC_BN * 64 * 2;      // one key / value block
+constexpr int TC_SMEM = TC_QBUF * TC_TILE_BYTES + 4 * TC_KV_BYTES + 1024 + 128;   // Q + 2x(K,V) + align + barriers
+constexpr uint32_t TMEM_S = 0, TMEM_P = 0, TMEM_O = 64, TMEM_COLS = 128;
 
 struct AttnTcParams {
   __nv_bfloat16* o;
@@ -69,6 +76,47 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 
+// Row-wise softmax pieces on one 64-key block of S held in registers (one query row per thread); `nv` = valid keys.
+__device__ __forceinline__ float row_max64(const uint32_t (&v)[64], int nv) {
+  float m = -INFINITY;
+  if (nv >= 64) {
+#pragma unroll
+    for (int t = 0; t < 64; ++t) m = fmaxf(m, __uint_as_float(v[t]));
+  } else {
+#pragma unroll
+    for (int t = 0; t < 64; ++t)
+      if (t < nv) m = fmaxf(m, __uint_as_float(v[t]));
+  }
+  return m;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// P = exp2(s * scale_log2 - m_ref) packed to bf16 pairs (keys >= nv -> 0); returns the row sum
+__device__ __forceinline__ float exp_pack64(const uint32_t (&v)[64], uint32_t (&pk)[32], int nv, float scale_log2, float m_ref) {
+  float rs0 = 0.f, rs1 = 0.f;
+  if (nv >= 64) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * t]), scale_log2, -m_ref));
+      const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * t + 1]), scale_log2, -m_ref));
+      rs0 += p0; rs1 += p1;
+      pk[t] = pack_bf16(p0, p1);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const float p0 = 2 * t < nv ? ex2_approx(fmaf(__uint_as_float(v[2 * t]), scale_log2, -m_ref)) : 0.f;
+      const float p1 = 2 * t + 1 < nv ? ex2_approx(fmaf(__uint_as_float(v[2 * t + 1]), scale_log2, -m_ref)) : 0.f;
+      rs0 += p0; rs1 += p1;
+      pk[t] = pack_bf16(p0, p1);
+    }
+  }
+  return rs0 + rs1;
+}
+
 // key blocks of a query tile: the key range [k0, k1) is cut at the head/tail plane boundary, each part into
 // blocks of TC_BN keys.  Block j -> (global row of its first key, number of valid keys).
 struct KeyBlocks {
@@ -104,7 +152,7 @@ __device__ unsigned long long g_attn_clk[16];
 #define CLK(i, expr) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -137,9 +185,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                            // 2 buffers
-  uint8_t* sK = smem + 2 * TC_TILE_BYTES;        // 2 stages
-  uint8_t* sV = smem + 4 * TC_TILE_BYTES;        // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TC_TILE_BYTES);
+  uint8_t* sK = smem + TC_QBUF * TC_TILE_BYTES;  // 2 stages of 64 keys
+  uint8_t* sV = sK + 2 * TC_KV_BYTES;            // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * TC_KV_BYTES);
   uint64_t* q_full = bars;         // [2]
   uint64_t* q_empty = bars + 2;    // [2]
   uint64_t* kv_full = bars + 4;    // [2]
@@ -186,8 +234,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     if (lane == 0) {
       int g = 0;  // running key-block counter over all heads
       for (int h = 0; h < p.H; ++h) {
-        const int qs = h & 1;
-        mbar_wait(&q_empty[qs], ((h >> 1) & 1) ^ 1);
+        const int qs = h % TC_QBUF;
+        mbar_wait(&q_empty[qs], ((h / TC_QBUF) & 1) ^ 1);
         mbar_expect_tx(&q_full[qs], TC_TILE_BYTES);
         tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], h * 64, (int)q_row0);
         for (int j = 0; j < kb.nb; ++j, ++g) {
@@ -195,9 +243,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
           int64_t row; int nvalid;
           kb.get(j, row, nvalid);
-          mbar_expect_tx(&kv_full[st], 2 * TC_TILE_BYTES);
-          tma_load_2d(sK + st * TC_TILE_BYTES, &tmap_k, &kv_full[st], h * 64, (int)row);
-          tma_load_2d(sV + st * TC_TILE_BYTES, &tmap_v, &kv_full[st], h * 64, (int)row);
+          mbar_expect_tx(&kv_full[st], 2 * TC_KV_BYTES);
+          tma_load_2d(sK + st * TC_KV_BYTES, &tmap_k, &kv_full[st], h * 64, (int)row);
+          tma_load_2d(sV + st * TC_KV_BYTES, &tmap_v, &kv_full[st], h * 64, (int)row);
         }
       }
     }
@@ -209,7 +257,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       auto issue_s = [&](int h, int j, int gg) {
         const int st = gg & 1;
         if (j == 0) {
-          mbar_wait(&q_full[h & 1], (h >> 1) & 1);
+          mbar_wait(&q_full[h % TC_QBUF], (h / TC_QBUF) & 1);
         }
         mbar_wait(&kv_full[st], (gg >> 1) & 1);
         tc_fence_after();
@@ -217,8 +265,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         kb.get(j, row, nvalid);
         const int n16 = (nvalid + 15) & ~15;
         const uint32_t idesc = umma_idesc_bf16(TC_BM, n16, false, false);
-        const uint32_t q_addr = smem_u32(sQ + (h & 1) * TC_TILE_BYTES);
-        const uint32_t k_addr = smem_u32(sK + st * TC_TILE_BYTES);
+        const uint32_t q_addr = smem_u32(sQ + (h % TC_QBUF) * TC_TILE_BYTES);
+        const uint32_t k_addr = smem_u32(sK + st * TC_KV_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dh = 64 = 4 x 16
           umma_bf16(tmem + TMEM_S, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024), idesc, k > 0);
@@ -233,7 +281,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           mbar_wait(p_full, g & 1);     // softmax wrote P and is done reading S
           if (j == 0 && h > 0) mbar_wait(o_empty, (h - 1) & 1);   // previous head's O has been read out
           tc_fence_after();
-          const uint32_t v_addr = smem_u32(sV + st * TC_TILE_BYTES);
+          const uint32_t v_addr = smem_u32(sV + st * TC_KV_BYTES);
           const int ksteps = (nvalid + 15) >> 4;
           for (int k = 0; k < ksteps; ++k)   // 16 keys per step: P advances 8 packed columns, V 16 rows of 128 B
             umma_bf16_ts(tmem + TMEM_O, tmem + TMEM_P + k * 8, umma_smem_desc(v_addr + k * 2048, 8192, 1024), idesc_pv, (j > 0) || (k > 0));
@@ -242,7 +290,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             issue_s(h, j + 1, g + 1);          // in-order MMA pipe: S(next) completes after this P.V
           } else {
             umma_commit(o_full);
-            umma_commit(&q_empty[h & 1]);
+            umma_commit(&q_empty[h % TC_QBUF]);
             if (h + 1 < p.H) issue_s(h + 1, 0, g + 1);
           }
         }
@@ -255,9 +303,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const int i = r0 + row_in_tile;
     uint32_t raw[32];
+    uint32_t sreg[64];
     int g = 0;
 #ifdef MMF_ATTN_CLOCKS
-    const bool dbg_on = (blockIdx.y == 3) && (kb.nb == 5) && (r0 == p.n_head) && warp == 2 && lane == 0;
+    const bool dbg_on = (blockIdx.y == 3) && (kb.nb == 10) && (r0 == p.n_head) && warp == 2 && lane == 0;
     long long t_last = clock64();
 #endif
     for (int h = 0; h < p.H; ++h) {
@@ -269,21 +318,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_wait(s_full, g & 1);
         tc_fence_after();
         CLK(0, 0);
-        const int nchunk = (nvalid + 31) >> 5;
-        // pass A: row max over the valid keys
-        float mx = -INFINITY;
-        for (int c = 0; c < nchunk; ++c) {
-          tmem_ld_32x32(lane_addr + TMEM_S + c * 32, raw);
-          tmem_wait_ld();
-          if (c * 32 + 32 <= nvalid) {
-#pragma unroll
-            for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(raw[t]));
-          } else {
-#pragma unroll
-            for (int t = 0; t < 32; ++t)
-              if (c * 32 + t < nvalid) mx = fmaxf(mx, __uint_as_float(raw[t]));
-          }
-        }
+        // ONE read of the S row (64 keys -> 64 registers): TMEM reads run at only ~64 B/clk/SM, so a separate
+        // max pass + exp pass over S would cost as much as the exponentials themselves
+        tmem_ld_32x64(lane_addr + TMEM_S, sreg);
+        tmem_wait_ld();
+        const float mx = row_max64(sreg, nvalid);
         CLK(1, 0);
         const float m_new = mx * p.scale_log2;
         // lazy rescale: only when the max grew by more than 2^8 (warp-uniform decision: tcgen05.ld/st are warp-wide)
@@ -305,32 +344,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           }
           tmem_wait_st();
         }
-        // pass B: P = exp2(s*scale*log2e - m_ref) as packed bf16 -> TMEM
-        float rs = 0.f;
-        const int n16 = (nvalid + 15) & ~15;   // P.V reads ceil16(nvalid) keys
-        for (int c = 0; c * 32 < n16; ++c) {
-          tmem_ld_32x32(lane_addr + TMEM_S + c * 32, raw);
-          tmem_wait_ld();
-          uint32_t pk[16];
-          if (c * 32 + 32 <= nvalid) {
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-              const float p0 = exp2f(fmaf(__uint_as_float(raw[2 * t]), p.scale_log2, -m_ref));
-              const float p1 = exp2f(fmaf(__uint_as_float(raw[2 * t + 1]), p.scale_log2, -m_ref));
-              rs += p0 + p1;
-              pk[t] = pack_bf16(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-              const int c0 = c * 32 + 2 * t;
-              const float p0 = c0 < nvalid ? exp2f(fmaf(__uint_as_float(raw[2 * t]), p.scale_log2, -m_ref)) : 0.f;
-              const float p1 = c0 + 1 < nvalid ? exp2f(fmaf(__uint_as_float(raw[2 * t + 1]), p.scale_log2, -m_ref)) : 0.f;
-              rs += p0 + p1;
-              pk[t] = pack_bf16(p0, p1);
-            }
-          }
-          tmem_st_32x16(lane_addr + TMEM_P + c * 16, pk);
+        // P = exp2(s*scale*log2e - m_ref) as packed bf16, written in place over the S columns (P.V reads ceil16(nvalid) keys)
+        float rs;
+        {
+          uint32_t pk[32];
+          rs = exp_pack64(sreg, pk, nvalid, p.scale_log2, m_ref);
+          tmem_st_32x32(lane_addr + TMEM_P, pk);
         }
         l += rs;
         CLK(2, 0);
@@ -391,19 +410,7 @@ static EncodeTiledFn tc_encode_fn() {
   });
   return fn;
 }
-// [rows, cols] bf16 row-major (ld elements), box = 64 columns x 128 rows, 128B swizzle
-static int tc_make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld) {
-  EncodeTiledFn enc = tc_encode_fn();
-  if (!enc) return 1000;
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, 128};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 2000 + (int)r;
-}
+static int tc_make_tmap_box(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 // returns -1000 if this problem is not eligible for the tcgen05 kernel (caller falls through to the generic kernel)
 int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
@@ -412,9 +419,9 @@ int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   const int64_t rows = (int64_t)a->B * a->Nq;
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = tc_make_tmap(&tq, a->q, rows, (int64_t)a->H * 64, a->ldq))) return rc;
-  if ((rc = tc_make_tmap(&tk, a->k, rows, (int64_t)a->H * 64, a->ldk))) return rc;
-  if ((rc = tc_make_tmap(&tv, a->v, rows, (int64_t)a->H * 64, a->ldv))) return rc;
+  if ((rc = tc_make_tmap_box(&tq, a->q, rows, (int64_t)a->H * 64, a->ldq, TC_BM))) return rc;
+  if ((rc = tc_make_tmap_box(&tk, a->k, rows, (int64_t)a->H * 64, a->ldk, TC_BN))) return rc;
+  if ((rc = tc_make_tmap_box(&tv, a->v, rows, (int64_t)a->H * 64, a->ldv, TC_BN))) return rc;
   AttnTcParams p;
   p.o = reinterpret_cast<__nv_bfloat16*>(a->o); p.lse = a->lse; p.ldo = a->ldo;
   p.B = a->B; p.H = a->H; p.N = a->Nq; p.n_head = a->n_head_q; p.n_tail = a->n_tail_q;
@@ -425,6 +432,8 @@ int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e != cudaSuccess) return (int)e;
+    // the default carve-out is sized for fewer CTAs: ask for the whole shared memory so TC_CTAS_PER_SM CTAs fit
+    cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
   const int tiles = (a->Nq + TC_BM - 1) / TC_BM + (a->seg ? a->nseg : 0);
@@ -965,6 +974,8 @@ int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM);
     if (e != cudaSuccess) return (int)e;
+    cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
   const int tiles = (a->Nq + TC_BM - 1) / TC_BM + (a->seg ? a->nseg : 0);

@@ -133,7 +133,10 @@ def test_fwd_bwd_matches_oracle(variant, dim, heads, img, patch, batch, nenc, de
             continue
         e = rel(p.grad, g_ref)
         worst = max(worst, e)
-        assert e < GRAD_TOL, (k, e)
+        # the dem decoder sits behind an L1 loss: its gradient is sign(pred - target), which flips wherever bf16 rounding
+        # of the prediction crosses the target (same allowance as the golden-fixture test above)
+        tol = GOLDEN_GRAD_TOL if k.startswith("output_adapters.dem.") else GRAD_TOL
+        assert e < tol, (k, e)
     print("worst grad rel err", worst)
 
 
