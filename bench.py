@@ -272,9 +272,11 @@ def run_ours(args):
     if e2e:
         result["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
-        sps, cores, sec = cpu_reference_steps(args, 2, 1, args.cpu_batch)
+        sps, cores, sec = cpu_reference_steps(args, 10, 2, args.cpu_batch)
         result["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                                  "sample": f"oracle port, fp32, batch {args.cpu_batch}, 1 warm-up + 2 timed steps ({sec:.1f} s/step)"}
+                                  "sample": f"oracle port (fp32 restatement of the reference's step: fwd + losses + bwd + AdamW), same "
+                                            f"model, batch {args.cpu_batch} of the {args.batch}-sample workload per step, 2 warm-up + 10 timed "
+                                            f"steps ({sec:.2f} s/step)"}
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()

@@ -646,6 +646,7 @@ class EncoderStackFn(torch.autograd.Function):
             dW1 = _unpad_w1(wgrad(du, h), I, ipad)
             return dh, dW1, dW2.contiguous() if I != ipad else dW2
 
+        dXb_next = None
         for i in reversed(range(depth)):
             rec = saved[i]
             saved[i] = None
@@ -654,7 +655,7 @@ class EncoderStackFn(torch.autograd.Function):
             zo = base + i * per_layer + (ZB if fusion else 0)
             n1, an, n2, m0 = [params[zo + j].detach() for j in (0, 1, 5, 6)]
             # ---------------- zorro block backward ----------------
-            dX2b = K.cast_bf16(dX)
+            dX2b = dXb_next if dXb_next is not None else K.cast_bf16(dX)   # bf16 copy emitted by the previous LN backward
             dh2z, dW1, dW2 = ffn_bwd(dX2b, rec["gz"], rec["uz"], rec["h2z"], params[zo + 7], params[zo + 8], Mt)
             grads[zo + 7], grads[zo + 8] = dW1, dW2
             dX1 = torch.empty(Mt, D, dtype=f32, device=dev)
@@ -676,13 +677,13 @@ class EncoderStackFn(torch.autograd.Function):
             dWqkv = wgrad(dqkv, rec["h1"])
             grads[zo + 2], grads[zo + 3] = dWqkv[:HD], dWqkv[HD:]
             dZ = torch.empty(Mt, D, dtype=f32, device=dev)
-            dZb = torch.empty(Mt, D, dtype=bf16, device=dev) if fusion else None
+            dZb = torch.empty(Mt, D, dtype=bf16, device=dev) if (fusion or i > 0) else None
             dn1, dan = zeros(D), zeros(D)
             K.layernorm_bwd(dh1, X, n1, rec["st1"], dZ, dn1, g2=an, dres=dX1, dx_bf16=dZb, dg2=dan, x2=Xf2,
                             x_split=Mh if fusion else 0, rows=Mt)
             grads[zo], grads[zo + 1] = dn1, dan
             if not fusion:
-                dX = dZ
+                dX, dXb_next = dZ, dZb
                 _layer_hook(meta, grads, range(zo, zo + ZB))
                 continue
             # ---------------- fusion block backward (upstream: dZ[Mh:] = grad wrt Xf2) ----------------
@@ -723,7 +724,8 @@ class EncoderStackFn(torch.autograd.Function):
             K.layernorm_bwd(dhm, params[0].detach()[0].contiguous(), fn1, rec["stM"], dme_i, dfn1, g2=fan, dg2=dfan)
             K.add_inplace(dme, dme_i)
             dXin = torch.empty(Mt, D, dtype=f32, device=dev)
-            K.layernorm_bwd(dhk, X, fn1, rec["stA"], dXin, dfn1, g2=fan, dres=dZ, dg2=dfan)
+            dXb_next = torch.empty(Mt, D, dtype=bf16, device=dev) if i > 0 else None
+            K.layernorm_bwd(dhk, X, fn1, rec["stA"], dXin, dfn1, g2=fan, dres=dZ, dx_bf16=dXb_next, dg2=dfan)
             grads[fo], grads[fo + 1] = dfn1, dfan
             dX = dXin
             _layer_hook(meta, grads, range(fo, fo + 2 * ZB))
