@@ -1,9 +1,13 @@
-"""debug: per-phase clock totals of one fusion-tile CTA of the attention forward (needs scratch/dbg_libmmf.so)"""
+"""Per-phase clock totals of one fusion-tile CTA of the attention forward.  Needs a debug build of the library with
+-DMMF_ATTN_CLOCKS at scratch/dbg_libmmf.so:
+  for f in incomplete_multimodal_fusion_b200/csrc/*.cu; do nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 \
+      -Xcompiler -fPIC -DMMF_ATTN_CLOCKS -I include -I incomplete_multimodal_fusion_b200/csrc -c $f -o /tmp/$(basename $f .cu).o; done
+  nvcc -shared -o scratch/dbg_libmmf.so /tmp/*.o -gencode arch=compute_100a,code=sm_100a"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from incomplete_multimodal_fusion_b200 import _lib
-_lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dbg_libmmf.so")
+_lib.LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scratch", "dbg_libmmf.so")
 from incomplete_multimodal_fusion_b200 import kernels as K
 lib = _lib.load()
 raw = C.CDLL(_lib.LIB_PATH)
@@ -21,6 +25,6 @@ f(); torch.cuda.synchronize()
 raw.mmf_debug_attn_clocks(buf, 0)
 names = ["wait s_full", "ld + row max (pass A)", "exp + pack + st (pass B)", "wait_st+arrive", "loop top", "wait o_full", "head epilogue"]
 tot = sum(buf[i] for i in range(7))
-print("one fusion-tile CTA, 8 heads x 5 key blocks = 40 iterations; total cycles", tot)
+print("one fusion-tile CTA, 8 heads x 10 key blocks = 80 iterations; total cycles", tot)
 for i, n in enumerate(names):
-    print(f"  {n:28s} {buf[i]:10d} cycles  {100*buf[i]/tot:5.1f}%   per iteration {buf[i]/40:8.0f}")
+    print(f"  {n:28s} {buf[i]:10d} cycles  {100*buf[i]/tot:5.1f}%   per iteration {buf[i]/80:8.0f}")

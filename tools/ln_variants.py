@@ -8,7 +8,7 @@ import torch
 from incomplete_multimodal_fusion_b200 import _lib
 
 if len(sys.argv) > 1 and sys.argv[1] == "dbg":
-    _lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dbg_libmmf.so")
+    _lib.LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scratch", "dbg_libmmf.so")
 from incomplete_multimodal_fusion_b200 import kernels as K
 
 bf16, f32 = torch.bfloat16, torch.float32
