@@ -50,7 +50,6 @@ struct GemmParams {
   int64_t geglu_ipad;  // act==2: row offset of the gate half inside B
   float alpha;
   int32_t fast_ok;  // all pitches / pointers allow the vectorised epilogue
-  int32_t dbg;  // MMF_GEMM_DEBUG (profiling experiments only): 1 = no global I/O in the epilogue, 2 = also no staging, 3 = no tcgen05.ld
 };
 
 __device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
@@ -133,7 +132,7 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, float* stg, const
         const float2 a = unpack_bf16(old.x), b = unpack_bf16(old.y);
         x.x += a.x; x.y += a.y; x.z += b.x; x.w += b.y;
       }
-      if (p.dbg != 1) *reinterpret_cast<uint2*>(o) = pack4(x);
+      *reinterpret_cast<uint2*>(o) = pack4(x);
     }
   }
   __syncwarp();
@@ -375,7 +374,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (col0 >= p.N) break;  // warp-uniform
           tmem_ld_32x32(taddr + c * 32, raw);
           tmem_wait_ld();
-          if (p.dbg >= 2) continue;
           if (col0 + 32 <= p.N && p.fast_ok) {
             float4 resv[8];
             if (EPI == EPI_F32 && p.residual != nullptr) load_res8(resv, orow_i, res_i, col0 + (lane & 7) * 4);
@@ -683,7 +681,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           if (live) {
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
-            if (p.out2 && p.dbg != 5 && p.dbg != 7) {   // pre-activations [value | gate] for the backward pass
+            if (p.out2) {   // pre-activations [value | gate] for the backward pass
               pack_box(sbox, v0, lane, nullptr, 1.0f);
               pack_box(sbox + 4096, v1, lane, nullptr, 1.0f);
               fence_proxy_async_smem();
@@ -694,16 +692,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 tma_store_commit();
               }
             }
-            if (p.dbg != 6) {
 #pragma unroll
-              for (int t = 0; t < 64; ++t) v0[t] = __float_as_uint(gelu_fast(__uint_as_float(v1[t])) * __uint_as_float(v0[t]));
-            }
+            for (int t = 0; t < 64; ++t) v0[t] = __float_as_uint(gelu_fast(__uint_as_float(v1[t])) * __uint_as_float(v0[t]));
             if (lane == 0) tma_store_wait_read<0>();   // box 0 is read out (the GELU math above covered the wait)
             __syncwarp();
             pack_box(sbox, v0, lane, nullptr, 1.0f);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0 && p.dbg != 7) {
+            if (lane == 0) {
               tma_store_2d(&tmap_o, sbox, col_base, row0);
               tma_store_commit();
             }
@@ -747,20 +743,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         if (has_res && p.fast_ok && (int64_t)n0 + half * 128 + 32 <= p.N) load_res8(res_next, orow_i, res_i, (int64_t)n0 + half * 128 + cl);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
-        if (p.dbg == 4) {   // experiment: all four TMEM loads in flight at once, data discarded
-          uint32_t r2[32], r3[32], r4[32];
-          tmem_ld_32x32(taddr + (half * 4 + 0) * 32, raw);
-          tmem_ld_32x32(taddr + (half * 4 + 1) * 32, r2);
-          tmem_ld_32x32(taddr + (half * 4 + 2) * 32, r3);
-          tmem_ld_32x32(taddr + (half * 4 + 3) * 32, r4);
-          tmem_wait_ld();
-          if (raw[0] + r2[1] + r3[2] + r4[3] == 0x7fc12345u) reinterpret_cast<uint32_t*>(p.out)[0] = 1;
-        }
 #pragma unroll 1
-        for (int cc = 0; cc < 4 && p.dbg != 4; ++cc) {
+        for (int cc = 0; cc < 4; ++cc) {
           const int c = half * 4 + cc;
           const int64_t col0 = (int64_t)n0 + c * 32;
-          if (col0 < p.N && p.dbg < 3) {   // warp-uniform
+          if (col0 < p.N) {   // warp-uniform
             tmem_ld_32x32(taddr + c * 32, raw);
             float4 resv[8];
             if (has_res) {
@@ -769,7 +756,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               if (cc + 1 < 4 && p.fast_ok && col0 + 64 <= p.N) load_res8(res_next, orow_i, res_i, col0 + 32 + cl);
             }
             tmem_wait_ld();
-            if (p.dbg == 2) continue;
             if (col0 + 32 <= p.N && p.fast_ok) epi_chunk<EPI>(p, stg, raw, lane, orow_i, resv, col0);
             else epi_chunk_slow<EPI>(p, raw, raw, orow, res_row, col0, (int)min((int64_t)32, p.N - col0));
           }
@@ -886,8 +872,6 @@ static int launch_gemm(const MmfGemmArgs& a, cudaStream_t stream) {
   p.fast_ok = (a.ldo % 4 == 0) && al16(a.out) && (!a.residual || (a.ldr % 4 == 0 && al16(a.residual))) &&
               (!a.residual2 || al16(a.residual2)) && (!a.bias || al16(a.bias)) && (!a.out2 || (a.ldo2 % 4 == 0 && al16(a.out2))) &&
               (a.act != 2 || a.N % 4 == 0);
-  static const int dbg_env = getenv("MMF_GEMM_DEBUG") ? atoi(getenv("MMF_GEMM_DEBUG")) : 0;
-  p.dbg = dbg_env;
 
   static bool attr_set = false;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI>;
@@ -937,8 +921,6 @@ static int launch_gemm2(const MmfGemmArgs& a, cudaStream_t stream) {
   p.fast_ok = (a.ldo % 4 == 0) && al16(a.out) && (!a.residual || (a.ldr % 4 == 0 && al16(a.residual))) &&
               (!a.residual2 || al16(a.residual2)) && (!a.bias || al16(a.bias)) && (!a.out2 || (a.ldo2 % 4 == 0 && al16(a.out2))) &&
               (a.act != 2 || a.N % 4 == 0);
-  static const int dbg_env = getenv("MMF_GEMM_DEBUG") ? atoi(getenv("MMF_GEMM_DEBUG")) : 0;
-  p.dbg = dbg_env;
   CUtensorMap to = ta, to2 = ta;   // placeholders unless TS
   if (TS) {   // bf16 outputs as 32-row x 64-column boxes
     if ((rc = make_tmap(&to, a.out, a.M, a.N, a.ldo, 64, 32))) return rc;

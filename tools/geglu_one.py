@@ -25,4 +25,4 @@ elif mode == "plain":
     ms = t(lambda: K.gemm(a, w, u))
 else:
     ms = t(lambda: torch.matmul(a, w.t(), out=u))
-print(f"{mode:10s} dbg={os.environ.get('MMF_GEMM_DEBUG','0')}: {ms:.3f} ms {fl/ms:.0f} TFLOP/s")
+print(f"{mode:10s}: {ms:.3f} ms {fl/ms:.0f} TFLOP/s")

@@ -15,4 +15,4 @@ e0.record()
 for _ in range(20): K.gemm(a, w, out)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
-print(f"M={M} N={N} K={Kd} dbg={os.environ.get('MMF_GEMM_DEBUG','0')} 2cta={os.environ.get('MMF_GEMM_2CTA','1')}: {ms:.3f} ms {2*M*N*Kd/ms/1e9:.0f} TFLOP/s")
+print(f"M={M} N={N} K={Kd} 2cta={os.environ.get('MMF_GEMM_2CTA','1')}: {ms:.3f} ms {2*M*N*Kd/ms/1e9:.0f} TFLOP/s")
