@@ -54,7 +54,7 @@ typedef struct MmfGemmArgs {
   int64_t lda, ldb, ldo, ldr;
   int32_t a_mn, b_mn;
   int32_t out_f32;         /* 0: bf16 output, 1: f32 output */
-  int32_t act;             /* 0: none, 1: exact-erf GELU, 2: GEGLU (see below) */
+  int32_t act;             /* 0: none, 1: exact-erf GELU, 2: GEGLU, 3: GEGLU backward (see below) */
   int32_t split_k;         /* >=1.  >1: f32 atomic accumulation into a ZEROED `out`; requires out_f32=1,
                               act=0, bias=residual=NULL */
   int32_t res_period;      /* 0: residual row = r.  >0: residual row = map ? map[r % p] : r % p */
@@ -68,7 +68,11 @@ typedef struct MmfGemmArgs {
   int32_t accumulate;      /* 1: out += result (f32: atomic adds; bf16: read-modify-write) */
   /* act=2 (GEGLU, zorro_utils.py:115-118): B is the [2*I_pad, K] weight; tile columns pair value
    * row j with gate row I_pad + j; out[M, I_pad] = gelu(gate) * value; `out2` (optional, bf16,
-   * [M, 2*I_pad]) receives the pre-activation for the backward.  N must be passed as I_pad. */
+   * [M, 2*I_pad]) receives the pre-activation for the backward.  N must be passed as I_pad.
+   * act=3 (backward of the same GEGLU fused into the dgrad GEMM of the FFN's second Linear, autograd of
+   * zorro_utils.py:115-128): the accumulator is dg = alpha * A . B^T ([M, I_pad], never written); `out2` is an
+   * INPUT, the saved pre-activation [value | gate] (bf16 [M, 2*I_pad]); out (bf16 [M, 2*I_pad]) =
+   * [dg * gelu(gate) | dg * value * gelu'(gate)].  N = I_pad must be a multiple of 64; bf16, no bias/residual. */
 } MmfGemmArgs;
 int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream);
 

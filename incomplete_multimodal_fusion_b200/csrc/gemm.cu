@@ -66,7 +66,8 @@ enum : int {
   EPI_F32 = 2,      // out f32 = alpha*acc (+bias) (+residual), out2 (optional) = bf16 copy
   EPI_ATOMIC = 3,   // out f32 += alpha*acc   (split-K / accumulate)
   EPI_GEGLU = 4,    // out bf16 = gelu(gate)*value, out2 (optional) = [value | gate] bf16
-  EPI_BF16_ACC = 5  // out bf16 += alpha*acc
+  EPI_BF16_ACC = 5, // out bf16 += alpha*acc
+  EPI_GEGLU_BWD = 6 // acc = dg (gradient of the GEGLU output); out2 = saved [value | gate] (INPUT), out = [dvalue | dgate] bf16
 };
 
 // Per-warp 32x32 fp32 staging block, 128-byte rows, 16-byte groups XOR-swizzled with (row & 7): the row-per-lane
@@ -441,12 +442,61 @@ __device__ __forceinline__ void bias_scale64(uint32_t (&v)[64], const float* bia
   }
 }
 
-template <bool TS>
+// GEGLU backward fused into the dgrad GEMM that produces dg = dY . W2 (zorro_utils.py:115-128 under autograd): the
+// epilogue warps TMA-load the saved pre-activation boxes [value | gate] of their accumulator share into shared memory
+// while the tile's MMAs run, turn them IN PLACE into [dvalue | dgate] = [dg * gelu(gate) | dg * value * gelu'(gate)]
+// and hand the same boxes to the TMA store engine.  dg never goes to HBM (it was a bf16 [M, I] write + read) and the
+// elementwise pass over [M, 2I] rides in the shadow of the MMAs.  GB_ROUNDS 64-column rounds are buffered per warp.
+constexpr int GB_ROUNDS = 2;
+template <int EPI, bool TS>
 struct G2Cfg {
-  static constexpr int STAGES = TS ? 5 : 6;
-  static constexpr int STG_BYTES = TS ? 8 * 8192 : 8 * STG_FLOATS * 4;   // per epilogue warp: two 4 KB boxes / one 32x32 fp32 block
+  static constexpr bool GB = (EPI == EPI_GEGLU_BWD);
+  static constexpr int STAGES = GB ? (GB_ROUNDS == 2 ? 3 : 5) : (TS ? 5 : 6);
+  // per epilogue warp: two 4 KB boxes (GEGLU backward: two per buffered round) / one 32x32 fp32 block
+  static constexpr int STG_WARP = GB ? GB_ROUNDS * 8192 : (TS ? 8192 : STG_FLOATS * 4);
+  static constexpr int STG_BYTES = 8 * STG_WARP;
   static constexpr int SMEM_BYTES = STAGES * G2_STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
+
+// Phi(x), and phi(x) * sqrt(2 pi) = exp(-x^2 / 2), from the same Abramowitz-Stegun form as gelu_fast (2 MUFU)
+__device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& e) {
+  const float a = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
+  float q = fmaf(t, 1.061405429f, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * a * 1.4426950408889634f));
+  const float half_erfc = 0.5f * q * t * e;
+  cdf = x < 0.f ? half_erfc : 1.0f - half_erfc;
+}
+
+// One 64-column round of the fused GEGLU backward, in place on this lane's row of a (value, gate) box pair:
+// dg = alpha * acc;  value <- dg * gelu(gate);  gate <- dg * value * gelu'(gate)
+__device__ __forceinline__ void geglu_bwd_box(uint8_t* vbox, uint8_t* gbox, const uint32_t (&acc)[64], int lane, float alpha) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int off = lane * 128 + ((j ^ (lane & 7)) << 4);
+    const uint4 uv = *reinterpret_cast<const uint4*>(vbox + off);
+    const uint4 ug = *reinterpret_cast<const uint4*>(gbox + off);
+    const uint32_t* pv = &uv.x; const uint32_t* pg = &ug.x;
+    uint4 ov, og;
+    uint32_t* qv = &ov.x; uint32_t* qg = &og.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fv = unpack_bf16(pv[k]), fg = unpack_bf16(pg[k]);
+      const float d0 = __uint_as_float(acc[8 * j + 2 * k]) * alpha, d1 = __uint_as_float(acc[8 * j + 2 * k + 1]) * alpha;
+      float c0, e0, c1, e1;
+      gelu_cdf_pdf(fg.x, c0, e0);
+      gelu_cdf_pdf(fg.y, c1, e1);
+      qv[k] = pack_bf16(d0 * fg.x * c0, d1 * fg.y * c1);
+      qg[k] = pack_bf16(d0 * fv.x * fmaf(fg.x * 0.3989422804014327f, e0, c0), d1 * fv.y * fmaf(fg.y * 0.3989422804014327f, e1, c1));
+    }
+    *reinterpret_cast<uint4*>(vbox + off) = ov;
+    *reinterpret_cast<uint4*>(gbox + off) = og;
+  }
+}
 
 // 64 fp32 accumulator columns of this lane's row -> bf16 -> one 32-row x 128-byte box, 16-byte groups XOR-swizzled
 // with (row & 7) (= CU_TENSOR_MAP_SWIZZLE_128B for a 1024-byte aligned box)
@@ -470,19 +520,22 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                      const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
                      const GemmParams p) {
   constexpr bool geglu = (EPI == EPI_GEGLU);
-  constexpr int STAGES = G2Cfg<TS>::STAGES;
-  static_assert(!TS || EPI == EPI_BF16 || EPI == EPI_GEGLU || EPI == EPI_GELU, "TMA-store epilogue: bf16 outputs only");
+  constexpr bool geglu_bwd = (EPI == EPI_GEGLU_BWD);
+  constexpr int STAGES = G2Cfg<EPI, TS>::STAGES;
+  static_assert(!TS || EPI == EPI_BF16 || EPI == EPI_GEGLU || EPI == EPI_GELU || EPI == EPI_GEGLU_BWD, "TMA-store epilogue: bf16 outputs only");
+  static_assert(TS || !geglu_bwd, "the fused GEGLU backward exists for the TMA-store epilogue only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * G2_A_BYTES;
   uint8_t* stage_bytes = smem + STAGES * G2_STAGE_BYTES;   // 1024-byte aligned (TMA-store boxes need it)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_bytes + G2Cfg<TS>::STG_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_bytes + G2Cfg<EPI, TS>::STG_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]
   uint64_t* empty_bar = bars + STAGES;           // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* box_bar = bars + 2 * STAGES + 6;     // [8] GEGLU backward: one per epilogue warp (its pre-activation boxes landed)
   float* stage_all = reinterpret_cast<float*>(stage_bytes);
 
   const int warp = threadIdx.x >> 5;
@@ -501,7 +554,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     tma_prefetch_desc(&tmap_b);
     if (TS) {
       tma_prefetch_desc(&tmap_o);
-      if (geglu || EPI == EPI_GELU) tma_prefetch_desc(&tmap_o2);
+      if (geglu || geglu_bwd || EPI == EPI_GELU) tma_prefetch_desc(&tmap_o2);
     }
   }
   if (warp == 1) {
@@ -514,6 +567,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         mbar_init(&tmem_full[s], 1);
         mbar_init(&tmem_empty[s], 16);
       }
+      if (geglu_bwd)
+        for (int s = 0; s < 8; ++s) mbar_init(&box_bar[s], 1);
       mbar_fence_init();
     }
     __syncwarp();
@@ -605,7 +660,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     if constexpr (TS) {
-      uint8_t* sbox = stage_bytes + ew * 8192;   // two 4 KB boxes
+      uint8_t* sbox = stage_bytes + ew * G2Cfg<EPI, TS>::STG_WARP;   // two 4 KB boxes (per buffered round)
+      uint32_t box_phase = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         const int tile = w % tiles_mn;
         const int m0 = (tile / p.n_tiles) * 256 + (int)rank * 128;
@@ -613,6 +669,67 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int row0 = m0 + quarter * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * G2_BN;
         uint32_t v0[64], v1[64];
+        if constexpr (geglu_bwd) {
+          // this warp: rows [row0, +32), dg columns [col_base, +128) as two 64-column rounds; round r works on the
+          // boxes (value, gate) = u[:, col_base + 64r ..] and u[:, ipad + col_base + 64r ..]
+          const int col_base = n0 + half * 128;
+          const bool live0 = col_base < p.N && row0 < p.M, live1 = col_base + 64 < p.N && row0 < p.M;   // warp-uniform
+          const int ipad = (int)p.geglu_ipad;
+          auto load_round = [&](int r, uint8_t* dst) {
+            tma_load_2d(dst, &tmap_o2, &box_bar[ew], col_base + 64 * r, row0);
+            tma_load_2d(dst + 4096, &tmap_o2, &box_bar[ew], ipad + col_base + 64 * r, row0);
+          };
+          auto store_round = [&](int r, uint8_t* src) {
+            tma_store_2d(&tmap_o, src, col_base + 64 * r, row0);
+            tma_store_2d(&tmap_o, src + 4096, ipad + col_base + 64 * r, row0);
+            tma_store_commit();
+          };
+          if (live0 && lane == 0) {
+            tma_store_wait_read<0>();   // the previous tile's stores have drained this warp's boxes
+            if (GB_ROUNDS == 2) {
+              mbar_expect_tx(&box_bar[ew], live1 ? 16384 : 8192);
+              load_round(0, sbox);
+              if (live1) load_round(1, sbox + 8192);
+            } else {
+              mbar_expect_tx(&box_bar[ew], 8192);
+              load_round(0, sbox);
+            }
+          }
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          if (live0) tmem_ld_32x64(taddr + half * 128, v0);
+          if (live1) tmem_ld_32x64(taddr + half * 128 + 64, v1);
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          if (live0) {
+            mbar_wait(&box_bar[ew], box_phase);
+            box_phase ^= 1;
+            geglu_bwd_box(sbox, sbox + 4096, v0, lane, p.alpha);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) store_round(0, sbox);
+            if (live1) {
+              uint8_t* b1 = sbox + (GB_ROUNDS == 2 ? 8192 : 0);
+              if (GB_ROUNDS == 1) {
+                if (lane == 0) {
+                  tma_store_wait_read<0>();
+                  mbar_expect_tx(&box_bar[ew], 8192);
+                  load_round(1, b1);
+                }
+                mbar_wait(&box_bar[ew], box_phase);
+                box_phase ^= 1;
+              }
+              geglu_bwd_box(b1, b1 + 4096, v1, lane, p.alpha);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) store_round(1, b1);
+            }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         if constexpr (!geglu) {
@@ -923,13 +1040,14 @@ static int launch_gemm2(const MmfGemmArgs& a, cudaStream_t stream) {
               (a.act != 2 || a.N % 4 == 0);
   CUtensorMap to = ta, to2 = ta;   // placeholders unless TS
   if (TS) {   // bf16 outputs as 32-row x 64-column boxes
-    if ((rc = make_tmap(&to, a.out, a.M, a.N, a.ldo, 64, 32))) return rc;
-    if (a.out2 && (rc = make_tmap(&to2, a.out2, a.M, geglu ? 2 * a.N : a.N, a.ldo2, 64, 32))) return rc;
+    const bool gb = EPI == EPI_GEGLU_BWD;   // out = [dvalue | dgate], out2 = [value | gate]: both [M, 2N]
+    if ((rc = make_tmap(&to, a.out, a.M, gb ? 2 * a.N : a.N, a.ldo, 64, 32))) return rc;
+    if (a.out2 && (rc = make_tmap(&to2, a.out2, a.M, (geglu || gb) ? 2 * a.N : a.N, a.ldo2, 64, 32))) return rc;
   }
 
   static bool attr_set = false;
   auto kern = gemm2_tcgen05_kernel<EPI, TS>;
-  constexpr int SMEM = G2Cfg<TS>::SMEM_BYTES;
+  constexpr int SMEM = G2Cfg<EPI, TS>::SMEM_BYTES;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return (int)e;
@@ -959,7 +1077,15 @@ extern "C" int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream_) {
   if ((a.lda & 7) || (a.ldb & 7)) MMF_BAD_ARG(6);
   if (a.lda < (a.a_mn ? a.M : a.K) || a.ldb < (a.b_mn ? a.N : a.K) || a.ldo < a.N) MMF_BAD_ARG(7);
   if (a.split_k > 1 && (!a.out_f32 || a.act != 0 || a.bias || a.residual || a.out2)) MMF_BAD_ARG(8);
-  if (a.act < 0 || a.act > 2) MMF_BAD_ARG(9);
+  if (a.act < 0 || a.act > 3) MMF_BAD_ARG(9);
+  if (a.act == 3) {   // fused GEGLU backward: CTA-pair TMA-store kernel only, N = I_pad (a multiple of 64)
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (a.out_f32 || a.bias || a.residual || a.split_k > 1 || a.accumulate || !a.out2 || (a.N & 63) || a.out_period ||
+        (a.ldo & 7) || (a.ldo2 & 7) || a.ldo < 2 * a.N || a.ldo2 < 2 * a.N || !al16(a.out) || !al16(a.out2) ||
+        (a.block_n != 0 && a.block_n != 256))
+      MMF_BAD_ARG(21);
+    return launch_gemm2<EPI_GEGLU_BWD, true>(a, stream);
+  }
   if (a.act == 2 && (a.b_mn || a.out_f32 || a.bias || a.residual || (a.N & 7) || (a.out2 && (a.ldo2 & 7)) ||
                      (a.ldo & 7) || a.split_k > 1))
     MMF_BAD_ARG(10);

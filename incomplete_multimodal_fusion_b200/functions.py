@@ -636,10 +636,10 @@ class EncoderStackFn(torch.autograd.Function):
         def ffn_bwd(dXo_b, g, u, h, w1_param, w2_param, rows):
             """returns dh (bf16 [rows, D]), dW1, dW2"""
             w2b = w_bf16(w2_param, cols_pad=ipad)
-            dg = torch.empty(rows, ipad, dtype=bf16, device=dev)
-            K.gemm(dXo_b, w2b, dg, b_mn=True)
+            # dg = dXo . W2 stays in TMEM: the GEMM's epilogue turns it into du = [dvalue | dgate] against the saved u
+            du = torch.empty_like(u)
+            K.gemm(dXo_b, w2b, du, b_mn=True, act=3, out2=u)
             dW2 = wgrad(dXo_b, g)[:, :I]
-            du = K.geglu_bwd(u, dg, torch.empty_like(u))
             w1b = w_geglu_bf16(w1_param, ipad)
             dh = torch.empty(rows, D, dtype=bf16, device=dev)
             K.gemm(du, w1b, dh, b_mn=True)

@@ -61,7 +61,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, 
          res_row_map=None, res_period=0, out_period=0, out_batch_rows=0, split_k=1, alpha=1.0, out2=None, block_n=0,
          accumulate=False, M=None, N=None, K=None):
     """out[M,N] = epilogue(alpha * A . B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn),
-    both bf16 row-major 2-D.  act=2 (GEGLU): b is [2*Ipad, K] and N = Ipad."""
+    both bf16 row-major 2-D.  act=2 (GEGLU): b is [2*Ipad, K] and N = Ipad.  act=3 (GEGLU backward fused into the
+    dgrad GEMM): out2 = saved [value | gate] (input), out = [dvalue | dgate], both [M, 2*Ipad]; N = Ipad."""
     assert a.dtype == bf16 and b.dtype == bf16
     if M is None:
         M = a.shape[1] if a_mn else a.shape[0]
@@ -110,7 +111,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, act=0, residual=None, 
     e1.record()
     n_eff = 2 * N if act == 2 else N
     kind = "wgrad" if (a_mn and b_mn) else ("dgrad" if b_mn else "fwd")
-    GEMM_TIMING.append((e0, e1, 2.0 * M * n_eff * K, kind, (kind + ("_geglu" if act == 2 else ""), M, n_eff, K)))
+    GEMM_TIMING.append((e0, e1, 2.0 * M * n_eff * K, kind, (kind + {2: "_geglu", 3: "_geglubwd"}.get(act, ""), M, n_eff, K)))
     return out
 
 

@@ -111,6 +111,27 @@ def test_gemm_geglu(I):
     assert rel(pre, u) < 6e-3
 
 
+@pytest.mark.parametrize("M,I", [(333, 512), (4096 + 77, 2048), (1000, 2752), (256, 64), (40000, 1024)])
+def test_gemm_geglu_backward_fused(M, I):
+    # du = [dg * gelu(gate) | dg * value * gelu'(gate)] with dg = dY . W2 formed in TMEM only (act=3), against
+    # autograd of the reference expression (zorro_utils.py:115-118) in fp32 and against the unfused kernels
+    D = 256
+    dY = rnd(M, D, dtype=bf16, seed=20, scale=0.5)
+    W2 = rnd(D, I, dtype=bf16, seed=21, scale=0.1)          # stored [K = D, N = I]: the dgrad layout (b_mn)
+    u = rnd(M, 2 * I, dtype=bf16, seed=22)
+    uf = u.float().requires_grad_(True)
+    dg = dY.float() @ W2.float()
+    (F.gelu(uf[:, I:]) * uf[:, :I]).backward(dg)
+    du = torch.full((M, 2 * I), float("nan"), dtype=bf16, device="cuda")
+    K().gemm(dY, W2, du, b_mn=True, act=3, out2=u)
+    assert torch.isfinite(du.float()).all()
+    assert rel(du, uf.grad) < 6e-3
+    dg_b = torch.empty(M, I, dtype=bf16, device="cuda")
+    K().gemm(dY, W2, dg_b, b_mn=True)
+    du2 = K().geglu_bwd(u, dg_b, torch.empty_like(u))
+    assert rel(du, du2) < 8e-3
+
+
 def test_gemm_large_persistent():
     # more tiles than SMs: exercises the persistent loop, both accumulator stages and ring wrap-around
     M, N, K_ = 4096 + 64, 2048, 1024

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""In-step kernel timeline of the bench workload through torch.profiler (CUPTI): per-kernel totals as they run inside a
+warm step (not ncu's serialised cold-cache replays), the GPU idle time between kernels and the largest gaps.
+
+  python tools/timeline_step.py --batch 256 [--out gpurun_out/timeline.txt]"""
+import argparse
+import os
+import sys
+from collections import defaultdict
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+from bench import synthetic_batch  # noqa: E402
+from incomplete_multimodal_fusion_b200.training import PretrainStep, build_pretrain_model  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--size", default="base")
+ap.add_argument("--variant", default="crossattn")
+ap.add_argument("--nenc", type=int, default=294)
+ap.add_argument("--image", type=int, default=224)
+ap.add_argument("--out", default="")
+a = ap.parse_args()
+torch.manual_seed(0)
+model = build_pretrain_model(a.size, a.variant, image_size=a.image).cuda()
+step = PretrainStep(model, num_encoded_tokens=a.nenc, global_batch=a.batch)
+x = {k: v.cuda() for k, v in synthetic_batch(a.batch, a.image, 1234).items()}
+for i in range(4):
+    torch.manual_seed(1 + i)
+    step(x)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    torch.manual_seed(9)
+    step(x)
+    torch.cuda.synchronize()
+
+evs = []
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None:
+        evs.append((e.time_range.start, e.time_range.end, e.name))
+evs.sort()
+tot = defaultdict(float)
+cnt = defaultdict(int)
+for s, e, n in evs:
+    key = n.split("<")[0].split("(")[0][:60]
+    tot[key] += (e - s) / 1e3
+    cnt[key] += 1
+span = (evs[-1][1] - evs[0][0]) / 1e3
+busy_end = evs[0][0]
+idle = 0.0
+gaps = []
+for s, e, n in evs:
+    if s > busy_end:
+        idle += (s - busy_end) / 1e3
+        gaps.append(((s - busy_end) / 1e3, n[:70]))
+    busy_end = max(busy_end, e)
+lines = ["span %.2f ms, sum of kernel time %.2f ms, idle %.2f ms, %d device activities" % (span, sum(tot.values()), idle, len(evs))]
+for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:45]:
+    lines.append("%9.3f ms %5.1f%% n=%4d  %s" % (v, 100 * v / span, cnt[k], k))
+lines.append("largest gaps (ms, kernel that followed):")
+for g, n in sorted(gaps, reverse=True)[:15]:
+    lines.append("   %.3f  %s" % (g, n))
+small = sum(g for g, _ in gaps if g < 0.02)
+lines.append("gaps < 20 us: %.2f ms in %d gaps" % (small, sum(1 for g, _ in gaps if g < 0.02)))
+txt = "\n".join(lines)
+print(txt)
+if a.out:
+    open(a.out, "w").write(txt + "\n")
