@@ -3,7 +3,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from incomplete_multimodal_fusion_b200 import kernels as K
+from incomplete_multimodal_fusion_b200 import _lib, kernels as K
+if os.environ.get("MMF_LIB"):   # e.g. scratch/dbg_libmmf.so built from another revision
+    _lib.LIB_PATH = os.path.abspath(os.environ["MMF_LIB"])
 M, D, I = 125440, 768, 2048
 a = (torch.randn(M, D, device="cuda") * .1).bfloat16(); w = (torch.randn(2 * I, D, device="cuda") * .1).bfloat16()
 g = torch.empty(M, I, dtype=torch.bfloat16, device="cuda"); u = torch.empty(M, 2 * I, dtype=torch.bfloat16, device="cuda")
@@ -21,6 +23,13 @@ if mode == "geglu":
     ms = t(lambda: K.gemm(a, w, g, act=2, out2=u))
 elif mode == "geglu_noU":
     ms = t(lambda: K.gemm(a, w, g, act=2))
+elif mode == "bwd":      # fused GEGLU backward (dgrad of FFN-2 + elementwise) next to the two-kernel form
+    dy = (torch.randn(M, D, device="cuda") * .1).bfloat16(); w2 = (torch.randn(D, I, device="cuda") * .1).bfloat16()
+    u.normal_(); du = torch.empty_like(u)
+    ms = t(lambda: K.gemm(dy, w2, du, b_mn=True, act=3, out2=u))
+    ms2 = t(lambda: (K.gemm(dy, w2, g, b_mn=True), K.geglu_bwd(u, g, du)))
+    fl = 2 * M * I * D / 1e9
+    print(f"unfused   : {ms2:.3f} ms")
 elif mode == "plain":
     ms = t(lambda: K.gemm(a, w, u))
 else:
