@@ -462,24 +462,80 @@ struct G2Cfg {
   static constexpr int SMEM_BYTES = STAGES * G2_STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
 
-// Phi(x), and phi(x) * sqrt(2 pi) = exp(-x^2 / 2), from the same Abramowitz-Stegun form as gelu_fast (2 MUFU)
-__device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& e) {
-  const float a = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
-  float q = fmaf(t, 1.061405429f, -1.453152027f);
-  q = fmaf(q, t, 1.421413741f);
-  q = fmaf(q, t, -0.284496736f);
-  q = fmaf(q, t, 0.254829592f);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * a * 1.4426950408889634f));
-  const float half_erfc = 0.5f * q * t * e;
-  cdf = x < 0.f ? half_erfc : 1.0f - half_erfc;
+// Packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two elements per issue slot.  The GEGLU backward below is
+// paced by the epilogue warps' instruction issue, not by the MMAs or HBM, so its polynomial work runs on pairs.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+#define F2C(c) f2_pack((c), (c))
+
+// (gelu(g0) * v0, gelu(g1) * v1): gelu_fast (common.cuh) on a pair, polynomial and products as packed fp32x2
+__device__ __forceinline__ void geglu_fwd_pair(float& v0, float& v1, float g0, float g1) {
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(g0), 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(g1), 1.0f)));
+  const uint64_t t = f2_pack(t0, t1), x = f2_pack(g0, g1);
+  uint64_t q = f2_fma(t, F2C(0.5f * 1.061405429f), F2C(0.5f * -1.453152027f));
+  q = f2_fma(q, t, F2C(0.5f * 1.421413741f));
+  q = f2_fma(q, t, F2C(0.5f * -0.284496736f));
+  q = f2_fma(q, t, F2C(0.5f * 0.254829592f));
+  float a0, a1, e0, e1;
+  f2_unpack(f2_mul(f2_mul(x, x), F2C(-0.5f * 1.4426950408889634f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  float h0, h1;
+  f2_unpack(f2_mul(f2_mul(q, t), f2_pack(e0, e1)), h0, h1);   // Phi(-|x|)
+  const uint64_t cdf = f2_pack(g0 < 0.f ? h0 : 1.0f - h0, g1 < 0.f ? h1 : 1.0f - h1);
+  f2_unpack(f2_mul(f2_mul(x, cdf), f2_pack(v0, v1)), v0, v1);
+}
+
+// GEGLU backward on one bf16 pair: (dvalue, dgate) = (dg * gelu(gate), dg * value * gelu'(gate)), exact-erf GELU through
+// the same Abramowitz-Stegun erfc form as gelu_fast: Phi(-|x|) = q(t) * t * exp(-x^2/2) / 2, t = 1 / (1 + 0.3275911 |x| / sqrt2);
+// gelu'(x) = Phi(x) + x * exp(-x^2/2) / sqrt(2 pi).  4 MUFU + ~22 issue slots per pair.
+__device__ __forceinline__ void geglu_bwd_pair(uint32_t vraw, uint32_t graw, float d0, float d1, uint64_t alpha2, uint32_t& ov, uint32_t& og) {
+  const float2 fv = unpack_bf16(vraw), fg = unpack_bf16(graw);
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(fg.x), 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(fg.y), 1.0f)));
+  const uint64_t t = f2_pack(t0, t1), x = f2_pack(fg.x, fg.y);
+  uint64_t q = f2_fma(t, F2C(0.5f * 1.061405429f), F2C(0.5f * -1.453152027f));
+  q = f2_fma(q, t, F2C(0.5f * 1.421413741f));
+  q = f2_fma(q, t, F2C(0.5f * -0.284496736f));
+  q = f2_fma(q, t, F2C(0.5f * 0.254829592f));
+  float a0, a1, e0, e1;
+  f2_unpack(f2_mul(f2_mul(x, x), F2C(-0.5f * 1.4426950408889634f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const uint64_t e = f2_pack(e0, e1);
+  float h0, h1;
+  f2_unpack(f2_mul(f2_mul(q, t), e), h0, h1);                 // Phi(-|x|)
+  const uint64_t cdf = f2_pack(fg.x < 0.f ? h0 : 1.0f - h0, fg.y < 0.f ? h1 : 1.0f - h1);
+  const uint64_t d = f2_mul(f2_pack(d0, d1), alpha2);
+  float o0, o1;
+  f2_unpack(f2_mul(d, f2_mul(x, cdf)), o0, o1);
+  ov = pack_bf16(o0, o1);
+  const uint64_t gp = f2_fma(f2_mul(x, e), F2C(0.3989422804014327f), cdf);
+  f2_unpack(f2_mul(f2_mul(d, f2_pack(fv.x, fv.y)), gp), o0, o1);
+  og = pack_bf16(o0, o1);
 }
 
 // 32 columns of the fused GEGLU backward, in place on this lane's row of a (value, gate) box pair (32 rows x 64 bytes,
-// CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index XOR address bits 7-8):
-// dg = alpha * acc;  value <- dg * gelu(gate);  gate <- dg * value * gelu'(gate)
+// CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index XOR address bits 7-8)
 __device__ __forceinline__ void geglu_bwd_box32(uint8_t* vbox, uint8_t* gbox, const uint32_t* acc, int lane, float alpha) {
+  const uint64_t alpha2 = f2_pack(alpha, alpha);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
@@ -489,15 +545,8 @@ __device__ __forceinline__ void geglu_bwd_box32(uint8_t* vbox, uint8_t* gbox, co
     uint4 ov, og;
     uint32_t* qv = &ov.x; uint32_t* qg = &og.x;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 fv = unpack_bf16(pv[k]), fg = unpack_bf16(pg[k]);
-      const float d0 = __uint_as_float(acc[8 * j + 2 * k]) * alpha, d1 = __uint_as_float(acc[8 * j + 2 * k + 1]) * alpha;
-      float c0, e0, c1, e1;
-      gelu_cdf_pdf(fg.x, c0, e0);
-      gelu_cdf_pdf(fg.y, c1, e1);
-      qv[k] = pack_bf16(d0 * fg.x * c0, d1 * fg.y * c1);
-      qg[k] = pack_bf16(d0 * fv.x * fmaf(fg.x * 0.3989422804014327f, e0, c0), d1 * fv.y * fmaf(fg.y * 0.3989422804014327f, e1, c1));
-    }
+    for (int k = 0; k < 4; ++k)
+      geglu_bwd_pair(pv[k], pg[k], __uint_as_float(acc[8 * j + 2 * k]), __uint_as_float(acc[8 * j + 2 * k + 1]), alpha2, qv[k], qg[k]);
     *reinterpret_cast<uint4*>(vbox + off) = ov;
     *reinterpret_cast<uint4*>(gbox + off) = og;
   }
@@ -812,7 +861,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             // above, keeps raw and activated values live together and spills (measured: 0.746 vs 0.679 ms at cfg 2).
             if (p.one) {
 #pragma unroll
-              for (int t = 0; t < 64; ++t) v0[t] = __float_as_uint(gelu_fast(__uint_as_float(v1[t])) * __uint_as_float(v0[t]));
+              for (int t = 0; t < 64; t += 2) {
+                float a = __uint_as_float(v0[t]), b = __uint_as_float(v0[t + 1]);
+                geglu_fwd_pair(a, b, __uint_as_float(v1[t]), __uint_as_float(v1[t + 1]));
+                v0[t] = __float_as_uint(a); v0[t + 1] = __float_as_uint(b);
+              }
             }
             if (lane == 0) tma_store_wait_read<0>();   // box 0 is read out (the GELU math above covered the wait)
             __syncwarp();
