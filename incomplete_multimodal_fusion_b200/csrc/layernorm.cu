@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "mmf_b200.h"
 #include <atomic>
+#include <cstdlib>
 
 namespace mmf {
 extern std::atomic<int64_t> g_launch_count;
@@ -50,7 +51,9 @@ __device__ __forceinline__ void ln_stage_params(float4* sg1, float4* sb1, float4
   __syncthreads();
 }
 
-template <int NC>
+// FULL: D == NC * 128, every chunk of every lane is in range.  The `chunk < nchunk` tests then fold away at compile time;
+// with them each chunk is its own predicated basic block and the row's arithmetic cannot be interleaved.
+template <int NC, bool FULL>
 __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_fwd_kernel(const LnParams p) {
   constexpr int LN_MAX_CHUNKS = NC;
   const int lane = threadIdx.x & 31;
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_fwd_kerne
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
       const int c = lane + 32 * i;
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < nchunk) v[i] = xr[c];
+      if (FULL || c < nchunk) v[i] = xr[c];
     }
     if (p.delta && row >= p.delta_row0) {
       const uint2* dr = reinterpret_cast<const uint2*>(p.delta + (row - p.delta_row0) * p.lddelta);
@@ -76,10 +79,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_fwd_kerne
       uint2 u[LN_MAX_CHUNKS];
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i)
-        if (lane + 32 * i < nchunk) u[i] = dr[lane + 32 * i];
+        if (FULL || lane + 32 * i < nchunk) u[i] = dr[lane + 32 * i];
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-        if (lane + 32 * i < nchunk) {
+        if (FULL || lane + 32 * i < nchunk) {
           const float2 lo = unpack_bf16(u[i].x), hi = unpack_bf16(u[i].y);
           v[i].x += lo.x; v[i].y += lo.y; v[i].z += hi.x; v[i].w += hi.y;
           xo[lane + 32 * i] = v[i];
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_fwd_kerne
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
       const int c = lane + 32 * i;
-      if (c < nchunk) {
+      if (FULL || c < nchunk) {
         const float a = v[i].x - mean1, b = v[i].y - mean1, cc = v[i].z - mean1, d = v[i].w - mean1;
         q += a * a + b * b + cc * cc + d * d;
       }
@@ -111,12 +114,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_fwd_kerne
       s = 0.f;
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i)
-        if (lane + 32 * i < nchunk) s += v[i].x + v[i].y + v[i].z + v[i].w;
+        if (FULL || lane + 32 * i < nchunk) s += v[i].x + v[i].y + v[i].z + v[i].w;
       mean2 = warp_sum(s) * invD;
       q = 0.f;
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-        if (lane + 32 * i < nchunk) {
+        if (FULL || lane + 32 * i < nchunk) {
           const float a = v[i].x - mean2, b = v[i].y - mean2, cc = v[i].z - mean2, d = v[i].w - mean2;
           q += a * a + b * b + cc * cc + d * d;
         }
@@ -134,12 +137,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_fwd_kerne
       float4* yr = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + row * p.ldy);
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i)
-        if (lane + 32 * i < nchunk) yr[lane + 32 * i] = v[i];
+        if (FULL || lane + 32 * i < nchunk) yr[lane + 32 * i] = v[i];
     } else {
       uint2* yr = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy);
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i)
-        if (lane + 32 * i < nchunk) yr[lane + 32 * i] = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+        if (FULL || lane + 32 * i < nchunk) yr[lane + 32 * i] = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
     }
     if (p.stats && lane == 0) reinterpret_cast<float4*>(p.stats)[row] = make_float4(mean1, rstd1, mean2, rstd2);
   }
@@ -169,8 +172,13 @@ struct LnBwdParams {
   float* dg2;         // optional (double LN)
 };
 
-template <int NC>
-__global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_bwd_kernel(const LnBwdParams p) {
+// PF (software pipelining across rows): ncu shows the plain row loop stalled on its own loads (long-scoreboard 9.7 per
+// issue at 24 warps per SM; no pipe above 50 %): a warp has nothing in flight while it does a row's ~1300 instructions.
+// With PF the NEXT row's x and dy are requested before the current row's arithmetic starts (NC float4 + NC uint2 more
+// live registers: 2 CTAs per SM instead of 3), and the residual-branch gradient is fetched in one batch ahead of the
+// first LayerNorm's reductions instead of chunk by chunk behind the dx stores.
+template <int NC, bool PF, bool FULL>
+__global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) ln_bwd_kernel(const LnBwdParams p) {
   constexpr int LN_MAX_CHUNKS = NC;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -194,30 +202,50 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_bwd_kerne
     if (dbl) adg2[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.db1) adb1[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < p.rows; row += (int64_t)gridDim.x * LN_WARPS) {
-    const float4 st = __ldg(reinterpret_cast<const float4*>(p.stats) + row);
+  const int64_t row_first = (int64_t)blockIdx.x * LN_WARPS + warp, row_step = (int64_t)gridDim.x * LN_WARPS;
+  const bool pf_dy = PF && !p.dy_f32;   // bf16 upstream gradients ride the prefetch; the rare fp32 ones are read in place
+  float4 nx[PF ? LN_MAX_CHUNKS : 1];
+  uint2 ndy[PF ? LN_MAX_CHUNKS : 1];
+  float4 nst = make_float4(0.f, 1.f, 0.f, 1.f);
+  auto fetch_row = [&](int64_t r) {
+    const float4* xr = reinterpret_cast<const float4*>((p.x2 && r >= p.x_split) ? p.x2 + (r - p.x_split) * p.ldx : p.x + r * p.ldx);
+    const uint2* dr = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + r * p.lddy);
+    nst = __ldg(reinterpret_cast<const float4*>(p.stats) + r);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      const int c = lane + 32 * i;
+      if (FULL || c < nchunk) {
+        nx[PF ? i : 0] = xr[c];
+        if (pf_dy) ndy[PF ? i : 0] = dr[c];
+      }
+    }
+  };
+  if (PF && row_first < p.rows) fetch_row(row_first);
+  for (int64_t row = row_first; row < p.rows; row += row_step) {
+    const float4 st = PF ? nst : __ldg(reinterpret_cast<const float4*>(p.stats) + row);
     const float mean1 = st.x, rstd1 = st.y, mean2 = st.z, rstd2 = st.w;
     const float4* xr = reinterpret_cast<const float4*>(
         (p.x2 && row >= p.x_split) ? p.x2 + (row - p.x_split) * p.ldx : p.x + row * p.ldx);
-    float4 xh1[LN_MAX_CHUNKS], d[LN_MAX_CHUNKS];
+    float4 xh1[LN_MAX_CHUNKS], d[LN_MAX_CHUNKS], rs[PF ? LN_MAX_CHUNKS : 1];
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {  // all global loads of the row are issued before any arithmetic
       const int c = lane + 32 * i;
       xh1[i] = d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < nchunk) {
-        xh1[i] = xr[c];
+      if (FULL || c < nchunk) {
+        xh1[i] = PF ? nx[PF ? i : 0] : xr[c];
         if (p.dy_f32) {
           d[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + row * p.lddy)[c];
         } else {
-          const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + row * p.lddy)[c];
+          const uint2 u = PF ? ndy[PF ? i : 0] : reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + row * p.lddy)[c];
           const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
           d[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
       }
     }
+    if (PF && row + row_step < p.rows) fetch_row(row + row_step);   // in flight during this row's arithmetic
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-      const bool in = lane + 32 * i < nchunk;
+      const bool in = FULL || lane + 32 * i < nchunk;
       xh1[i].x = in ? (xh1[i].x - mean1) * rstd1 : 0.f; xh1[i].y = in ? (xh1[i].y - mean1) * rstd1 : 0.f;
       xh1[i].z = in ? (xh1[i].z - mean1) * rstd1 : 0.f; xh1[i].w = in ? (xh1[i].w - mean1) * rstd1 : 0.f;
     }
@@ -226,7 +254,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_bwd_kerne
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-        if (lane + 32 * i < nchunk) {
+        if (FULL || lane + 32 * i < nchunk) {
           const float4 G1 = g1[lane + 32 * i], B1 = b1[lane + 32 * i], G2 = g2[lane + 32 * i];
           float4 xh2;
           xh2.x = (xh1[i].x * G1.x + B1.x - mean2) * rstd2; xh2.y = (xh1[i].y * G1.y + B1.y - mean2) * rstd2;
@@ -243,7 +271,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_bwd_kerne
       s2 = warp_sum(s2) * invD;
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-        if (lane + 32 * i < nchunk) {
+        if (FULL || lane + 32 * i < nchunk) {
           const float4 G1 = g1[lane + 32 * i], B1 = b1[lane + 32 * i];
           d[i].x = rstd2 * (d[i].x - s1 - (xh1[i].x * G1.x + B1.x - mean2) * rstd2 * s2);
           d[i].y = rstd2 * (d[i].y - s1 - (xh1[i].y * G1.y + B1.y - mean2) * rstd2 * s2);
@@ -253,10 +281,17 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_bwd_kerne
       }
     }
     // first LN
+    if (PF) {
+#pragma unroll
+      for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.dres && (FULL || lane + 32 * i < nchunk)) rs[i] = reinterpret_cast<const float4*>(p.dres + row * p.lddres)[lane + 32 * i];
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
-      if (lane + 32 * i < nchunk) {
+      if (FULL || lane + 32 * i < nchunk) {
         float4 t = adg1[lane + 32 * i];
         t.x += d[i].x * xh1[i].x; t.y += d[i].y * xh1[i].y; t.z += d[i].z * xh1[i].z; t.w += d[i].w * xh1[i].w;
         adg1[lane + 32 * i] = t;
@@ -276,13 +311,15 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_bwd_kerne
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
       const int c = lane + 32 * i;
-      if (c < nchunk) {
+      if (FULL || c < nchunk) {
         float4 o;
         o.x = rstd1 * (d[i].x - s1 - xh1[i].x * s2);
         o.y = rstd1 * (d[i].y - s1 - xh1[i].y * s2);
         o.z = rstd1 * (d[i].z - s1 - xh1[i].z * s2);
         o.w = rstd1 * (d[i].w - s1 - xh1[i].w * s2);
-        if (p.dres) {
+        if (PF) {
+          o.x += rs[PF ? i : 0].x; o.y += rs[PF ? i : 0].y; o.z += rs[PF ? i : 0].z; o.w += rs[PF ? i : 0].w;
+        } else if (p.dres) {
           const float4 r = reinterpret_cast<const float4*>(p.dres + row * p.lddres)[c];
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
@@ -344,10 +381,12 @@ extern "C" int mmf_layernorm_fwd(const float* x, const float* x2, int64_t x_spli
              reinterpret_cast<const __nv_bfloat16*>(delta), delta_row0, lddelta, xout, ldxout};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nc = ceil_div(D, 128);
-  if (nc <= 2) ln_fwd_kernel<2><<<ln_grid(ln_fwd_kernel<2>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p);
-  else if (nc <= 4) ln_fwd_kernel<4><<<ln_grid(ln_fwd_kernel<4>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p);
-  else if (nc <= 6) ln_fwd_kernel<6><<<ln_grid(ln_fwd_kernel<6>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p);
-  else ln_fwd_kernel<8><<<ln_grid(ln_fwd_kernel<8>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p);
+#define MMF_LN_FWD_LAUNCH(NCV, F) ln_fwd_kernel<NCV, F><<<ln_grid(ln_fwd_kernel<NCV, F>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p)
+  if (nc <= 2) { if (D == 256) MMF_LN_FWD_LAUNCH(2, true); else MMF_LN_FWD_LAUNCH(2, false); }
+  else if (nc <= 4) { if (D == 512) MMF_LN_FWD_LAUNCH(4, true); else MMF_LN_FWD_LAUNCH(4, false); }
+  else if (nc <= 6) { if (D == 768) MMF_LN_FWD_LAUNCH(6, true); else MMF_LN_FWD_LAUNCH(6, false); }
+  else { if (D == 1024) MMF_LN_FWD_LAUNCH(8, true); else MMF_LN_FWD_LAUNCH(8, false); }
+#undef MMF_LN_FWD_LAUNCH
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
   return 0;
@@ -370,24 +409,33 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
   const int ncp = nc <= 2 ? 2 : (nc <= 4 ? 4 : (nc <= 6 ? 6 : 8));
   const int narr = 1 + (g2 ? 1 : 0) + (db1 ? 1 : 0);
   const size_t smem = (size_t)narr * LN_WARPS * ncp * 32 * sizeof(float4);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(ln_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 2 * 32 * 16);
-    cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 4 * 32 * 16);
-    cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 6 * 32 * 16);
-    cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * 8 * 32 * 16);
-    // ~58 KB per CTA at D = 768: ask for the full shared-memory carve-out so that three CTAs fit (the default carve-out
-    // stops at two and shared memory, not registers, would set the occupancy)
-    cudaFuncSetAttribute(ln_bwd_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(ln_bwd_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(ln_bwd_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(ln_bwd_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_done = true;
-  }
-  if (nc <= 2) ln_bwd_kernel<2><<<ln_grid(ln_bwd_kernel<2>, smem, rows), LN_WARPS * 32, smem, st>>>(p);
-  else if (nc <= 4) ln_bwd_kernel<4><<<ln_grid(ln_bwd_kernel<4>, smem, rows), LN_WARPS * 32, smem, st>>>(p);
-  else if (nc <= 6) ln_bwd_kernel<6><<<ln_grid(ln_bwd_kernel<6>, smem, rows), LN_WARPS * 32, smem, st>>>(p);
-  else ln_bwd_kernel<8><<<ln_grid(ln_bwd_kernel<8>, smem, rows), LN_WARPS * 32, smem, st>>>(p);
+  // ~58 KB per CTA at D = 768: ask for the full shared-memory carve-out so that three CTAs fit (the default carve-out
+  // stops at two and shared memory, not registers, would set the occupancy)
+  // row prefetch: 0.382 -> 0.329 ms at the cfg-2 shape (D = 768); at D = 1024 its registers spill, so it stays off there
+  static const int variant = getenv("MMF_LN_BWD_PF") ? atoi(getenv("MMF_LN_BWD_PF")) : 1;
+  const bool early = variant != 0 && nc <= 6;
+#define MMF_LN_BWD_LAUNCH(NCV, E, F)                                                                                       \
+  do {                                                                                                                    \
+    static bool attr_done = false;                                                                                        \
+    if (!attr_done) {                                                                                                     \
+      cudaFuncSetAttribute(ln_bwd_kernel<NCV, E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * NCV * 32 * 16); \
+      cudaFuncSetAttribute(ln_bwd_kernel<NCV, E, F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+      attr_done = true;                                                                                                   \
+    }                                                                                                                     \
+    ln_bwd_kernel<NCV, E, F><<<ln_grid(ln_bwd_kernel<NCV, E, F>, smem, rows), LN_WARPS * 32, smem, st>>>(p);               \
+  } while (0)
+#define MMF_LN_BWD_DISPATCH(E, F)                       \
+  do {                                                  \
+    if (nc <= 2) MMF_LN_BWD_LAUNCH(2, E, F);            \
+    else if (nc <= 4) MMF_LN_BWD_LAUNCH(4, E, F);       \
+    else if (nc <= 6) MMF_LN_BWD_LAUNCH(6, E, F);       \
+    else MMF_LN_BWD_LAUNCH(8, E, F);                    \
+  } while (0)
+  const bool full = D == 256 || D == 512 || D == 768 || D == 1024;   // = NC * 128 of the kernel chosen below
+  if (early) { if (full) MMF_LN_BWD_DISPATCH(true, true); else MMF_LN_BWD_DISPATCH(true, false); }
+  else { if (full) MMF_LN_BWD_DISPATCH(false, true); else MMF_LN_BWD_DISPATCH(false, false); }
+#undef MMF_LN_BWD_DISPATCH
+#undef MMF_LN_BWD_LAUNCH
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
   return 0;

@@ -48,3 +48,9 @@ ms = t(lambda: K.layernorm_bwd(dy, x, g1, st, dx, dg1, g2=g2, dres=dres, dg2=dg2
 print("no bf16 copy    %.3f ms %5.0f GB/s" % (ms, Mt * D * 14 / ms / 1e6))
 ms = t(lambda: K.layernorm_bwd(dy, x, g1, st, dx, dg1, dres=dres, dx_bf16=dxb))
 print("single LN       %.3f ms %5.0f GB/s" % (ms, Mt * D * 16 / ms / 1e6))
+ms = t(lambda: K.layernorm_fwd(x, g1, y, g2=g2, stats=st))
+print("fwd ln2         %.3f ms %5.0f GB/s" % (ms, Mt * D * 6 / ms / 1e6))
+delta = torch.randn(Mt, D, device="cuda").bfloat16()
+xo = torch.empty(Mt, D, device="cuda")
+ms = t(lambda: K.layernorm_fwd(x, g1, y, g2=g2, stats=st, delta=delta, xout=xo))
+print("fwd ln2 + delta %.3f ms %5.0f GB/s" % (ms, Mt * D * 12 / ms / 1e6))
