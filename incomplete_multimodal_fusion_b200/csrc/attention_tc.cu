@@ -47,6 +47,7 @@ struct AttnTcParams {
   float scale_log2;           // scale * log2(e)
   const int32_t* seg;
   int nseg;
+  int tiles;                  // query tiles per sample the grid was sized for (upper bound)
 };
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
@@ -145,6 +146,34 @@ struct KeyBlocks {
   }
 };
 
+
+// CTA -> (query tile, sample, head range) for the kernels whose CTAs own a query tile.  Tiles of the LAST segment (the
+// fusion tokens: they visit every key block, ~4.5x the work of a modality tile at cfg 2) are numbered first, for all
+// samples, and the light tiles afterwards: with the natural order the last heavy CTAs start late and the grid ends on a
+// long tail (2.9 waves of 3 CTAs per SM); forward 0.29 -> 0.24 ms at cfg 2.  A heavy tile can also be split into
+// TC_HSPLIT CTAs over the heads (measured: no further gain, so 1).  `tiles` = the host's upper bound of tiles per sample;
+// the grid is (tiles + (TC_HSPLIT - 1) * heavy_max) * B CTAs, surplus ones exit.
+constexpr int TC_HSPLIT = 1;
+__device__ __forceinline__ void lpt_tile(const int32_t* seg, int nseg, int tiles, int B, int H, int& tile, int& b, int& h0, int& h1) {
+  const int L = blockIdx.x;
+  h0 = 0; h1 = H;
+  if (seg == nullptr) { tile = L % tiles; b = L / tiles; if (b >= B) tile = 1 << 20; return; }
+  int first_heavy = 0;
+  for (int s = 0; s + 1 < nseg; ++s) first_heavy += (seg[s + 1] - seg[s] + TC_BM - 1) / TC_BM;
+  const int th = (seg[nseg] - seg[nseg - 1] + TC_BM - 1) / TC_BM;
+  const int hs = (H % TC_HSPLIT == 0) ? TC_HSPLIT : 1;
+  if (L < th * B * hs) {
+    const int part = L % hs, t = L / hs;
+    b = t / th; tile = first_heavy + t % th;
+    h0 = part * (H / hs); h1 = h0 + H / hs;
+    return;
+  }
+  const int tl = tiles - th, L2 = L - th * B * hs;
+  b = L2 / tl;
+  const int t = L2 % tl;
+  tile = (t < first_heavy && b < B) ? t : (1 << 20);   // surplus indices land past the last tile
+}
+
 #ifdef MMF_ATTN_CLOCKS
 __device__ unsigned long long g_attn_clk[16];
 #define CLK(i, expr) do { if (dbg_on) { const long long t__ = clock64(); g_attn_clk[i] += (unsigned long long)(t__ - t_last); t_last = t__; } } while (0)
@@ -157,9 +186,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                    const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // ---- which query tile? (tiles are cut per segment) ----
-  int r0 = 0, r1 = 0, k0 = 0, k1 = 0;
+  int r0 = 0, r1 = 0, k0 = 0, k1 = 0, b = 0, h0 = 0, h1 = 0;
   {
-    int tile = blockIdx.x;
+    int tile;
+    lpt_tile(p.seg, p.nseg, p.tiles, p.B, p.H, tile, b, h0, h1);
     bool found = false;
     if (p.seg == nullptr) {
       r0 = tile * TC_BM; r1 = min(r0 + TC_BM, p.N); k0 = 0; k1 = p.N; found = r0 < p.N;
@@ -178,9 +208,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
     if (!found) return;
   }
+  const int nh = h1 - h0;   // this CTA's heads are h0 .. h1-1; h below counts from h0
   // One CTA serves this query tile for ALL heads of one sample: barriers / TMEM are set up once and the TMA
   // producer runs ahead into the next head's Q/K/V while the current head is in softmax.
-  const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -233,19 +263,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int g = 0;  // running key-block counter over all heads
-      for (int h = 0; h < p.H; ++h) {
+      for (int h = 0; h < nh; ++h) {
         const int qs = h % TC_QBUF;
         mbar_wait(&q_empty[qs], ((h / TC_QBUF) & 1) ^ 1);
         mbar_expect_tx(&q_full[qs], TC_TILE_BYTES);
-        tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], h * 64, (int)q_row0);
+        tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], (h0 + h) * 64, (int)q_row0);
         for (int j = 0; j < kb.nb; ++j, ++g) {
           const int st = g & 1;
           mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
           int64_t row; int nvalid;
           kb.get(j, row, nvalid);
           mbar_expect_tx(&kv_full[st], 2 * TC_KV_BYTES);
-          tma_load_2d(sK + st * TC_KV_BYTES, &tmap_k, &kv_full[st], h * 64, (int)row);
-          tma_load_2d(sV + st * TC_KV_BYTES, &tmap_v, &kv_full[st], h * 64, (int)row);
+          tma_load_2d(sK + st * TC_KV_BYTES, &tmap_k, &kv_full[st], (h0 + h) * 64, (int)row);
+          tma_load_2d(sV + st * TC_KV_BYTES, &tmap_v, &kv_full[st], (h0 + h) * 64, (int)row);
         }
       }
     }
@@ -273,7 +303,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         umma_commit(s_full);
       };
       issue_s(0, 0, 0);
-      for (int h = 0; h < p.H; ++h) {
+      for (int h = 0; h < nh; ++h) {
         for (int j = 0; j < kb.nb; ++j, ++g) {
           const int st = g & 1;
           int64_t row; int nvalid;
@@ -291,7 +321,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           } else {
             umma_commit(o_full);
             umma_commit(&q_empty[h % TC_QBUF]);
-            if (h + 1 < p.H) issue_s(h + 1, 0, g + 1);
+            if (h + 1 < nh) issue_s(h + 1, 0, g + 1);
           }
         }
       }
@@ -306,10 +336,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint32_t sreg[64];
     int g = 0;
 #ifdef MMF_ATTN_CLOCKS
-    const bool dbg_on = (blockIdx.y == 3) && (kb.nb == 10) && (r0 == p.n_head) && warp == 2 && lane == 0;
+    const bool dbg_on = (b == 3) && (r0 == p.n_head) && warp == 2 && lane == 0;   // first fusion tile of sample 3
+    if (dbg_on) g_attn_clk[15] = (unsigned long long)kb.nb * nh;
     long long t_last = clock64();
 #endif
-    for (int h = 0; h < p.H; ++h) {
+    for (int h = 0; h < nh; ++h) {
       float m_ref = -INFINITY, l = 0.f;
       for (int j = 0; j < kb.nb; ++j, ++g) {
         int64_t row; int nvalid;
@@ -364,7 +395,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tc_fence_after();
       CLK(5, 0);
       const float inv = 1.0f / l;
-      __nv_bfloat16* orow = p.o + (q_row0 + row_in_tile) * p.ldo + h * 64;
+      __nv_bfloat16* orow = p.o + (q_row0 + row_in_tile) * p.ldo + (h0 + h) * 64;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         tmem_ld_32x32(lane_addr + TMEM_O + c * 32, raw);
@@ -382,7 +413,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);   // the MMA warp may overwrite O for the next head
-      if (p.lse && i < r1) p.lse[((int64_t)b * p.H + h) * p.N + i] = (m_ref + log2f(l)) * 0.6931471805599453f;
+      if (p.lse && i < r1) p.lse[((int64_t)b * p.H + h0 + h) * p.N + i] = (m_ref + log2f(l)) * 0.6931471805599453f;
       CLK(6, 0);
     }
   }
@@ -437,7 +468,9 @@ int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
     attr = true;
   }
   const int tiles = (a->Nq + TC_BM - 1) / TC_BM + (a->seg ? a->nseg : 0);
-  attn_fwd_tc_kernel<<<dim3(tiles, a->B), TC_THREADS, TC_SMEM, stream>>>(tq, tk, tv, p);
+  p.tiles = tiles;
+  const int heavy_max = a->seg ? (a->Nq + TC_BM - 1) / TC_BM : 0;
+  attn_fwd_tc_kernel<<<(tiles + (TC_HSPLIT - 1) * heavy_max) * a->B, TC_THREADS, TC_SMEM, stream>>>(tq, tk, tv, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
@@ -488,6 +521,7 @@ struct AttnBwdTcParams {
   float scale, scale_log2;
   const int32_t* seg;
   int nseg;
+  int tiles;             // tiles per sample the grids were sized for (upper bound)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -505,9 +539,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                       const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                       const AttnBwdTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  int r0 = 0, r1 = 0, k0 = 0, k1 = 0;
+  int r0 = 0, r1 = 0, k0 = 0, k1 = 0, b = 0, h0 = 0, h1 = 0;
   {
-    int tile = blockIdx.x;
+    int tile;
+    lpt_tile(p.seg, p.nseg, p.tiles, p.B, p.H, tile, b, h0, h1);
     bool found = false;
     if (p.seg == nullptr) {
       r0 = tile * TC_BM; r1 = min(r0 + TC_BM, p.N); k0 = 0; k1 = p.N; found = r0 < p.N;
@@ -526,7 +561,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     }
     if (!found) return;
   }
-  const int b = blockIdx.y;
+  const int nh = h1 - h0;   // this CTA's heads are h0 .. h1-1; h below counts from h0
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // 2 buffers of 128x64
@@ -572,20 +607,20 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       int g = 0;
-      for (int h = 0; h < p.H; ++h) {
+      for (int h = 0; h < nh; ++h) {
         const int qs = h & 1;
         mbar_wait(&q_empty[qs], ((h >> 1) & 1) ^ 1);
         mbar_expect_tx(&q_full[qs], 2 * TC_TILE_BYTES);
-        tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], h * 64, (int)q_row0);
-        tma_load_2d(sdO + qs * TC_TILE_BYTES, &tmap_do, &q_full[qs], h * 64, (int)q_row0);
+        tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], (h0 + h) * 64, (int)q_row0);
+        tma_load_2d(sdO + qs * TC_TILE_BYTES, &tmap_do, &q_full[qs], (h0 + h) * 64, (int)q_row0);
         for (int j = 0; j < kb.nb; ++j, ++g) {
           const int st = g & 1;
           mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
           int tok, nvalid; int64_t row;
           kb.get(j, tok, row, nvalid);
           mbar_expect_tx(&kv_full[st], 2 * BW_BLK_BYTES);
-          tma_load_2d(sK + st * BW_BLK_BYTES, &tmap_k, &kv_full[st], h * 64, (int)row);
-          tma_load_2d(sV + st * BW_BLK_BYTES, &tmap_v, &kv_full[st], h * 64, (int)row);
+          tma_load_2d(sK + st * BW_BLK_BYTES, &tmap_k, &kv_full[st], (h0 + h) * 64, (int)row);
+          tma_load_2d(sV + st * BW_BLK_BYTES, &tmap_v, &kv_full[st], (h0 + h) * 64, (int)row);
         }
       }
     }
@@ -610,7 +645,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         umma_commit(s_full);
       };
       issue_s(0, 0, 0);
-      for (int h = 0; h < p.H; ++h) {
+      for (int h = 0; h < nh; ++h) {
         for (int j = 0; j < kb.nb; ++j, ++g) {
           const int st = g & 1;
           int tok, nvalid; int64_t row;
@@ -628,7 +663,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           } else {
             umma_commit(acc_full);
             umma_commit(&q_empty[h & 1]);
-            if (h + 1 < p.H) issue_s(h + 1, 0, g + 1);
+            if (h + 1 < nh) issue_s(h + 1, 0, g + 1);
           }
         }
       }
@@ -641,8 +676,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const bool row_ok = i < r1;
     uint32_t rs[32], rd[32];
     int g = 0;
-    for (int h = 0; h < p.H; ++h) {
-      const int64_t stat_idx = ((int64_t)b * p.H + h) * p.N + i;
+    for (int h = 0; h < nh; ++h) {
+      const int64_t stat_idx = ((int64_t)b * p.H + h0 + h) * p.N + i;
       const float lse2 = row_ok ? p.lse[stat_idx] * 1.4426950408889634f : INFINITY;   // invalid rows -> P = 0
       const float dl = row_ok ? p.delta[stat_idx] : 0.f;
       for (int j = 0; j < kb.nb; ++j, ++g) {
@@ -672,7 +707,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
       mbar_wait(acc_full, h & 1);
       tc_fence_after();
-      __nv_bfloat16* orow = p.dq + (q_row0 + row_in_tile) * p.lddq + h * 64;
+      __nv_bfloat16* orow = p.dq + (q_row0 + row_in_tile) * p.lddq + (h0 + h) * 64;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         tmem_ld_32x32(lane_addr + DQ_ACC + c * 32, rs);
@@ -979,7 +1014,9 @@ int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
     attr = true;
   }
   const int tiles = (a->Nq + TC_BM - 1) / TC_BM + (a->seg ? a->nseg : 0);
-  attn_bwd_dq_tc_kernel<<<dim3(tiles, a->B), TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
+  p.tiles = tiles;
+  const int heavy_max = a->seg ? (a->Nq + TC_BM - 1) / TC_BM : 0;
+  attn_bwd_dq_tc_kernel<<<(tiles + (TC_HSPLIT - 1) * heavy_max) * a->B, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
   attn_bwd_dkv_tc_kernel<<<dim3(tiles, a->B), TC_THREADS, DKV_SMEM, stream>>>(k128, v128, q64, do64, p);
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();

@@ -48,6 +48,35 @@ def enable_gemm_timing(flag: bool = True):
     return GEMM_TIMING
 
 
+# Same idea for the non-GEMM kernels bench.py reports a roofline for: name -> [(start, end, meta)]
+KERNEL_TIMING = None
+
+
+def enable_kernel_timing(flag: bool = True):
+    global KERNEL_TIMING
+    KERNEL_TIMING = {} if flag else None
+    return KERNEL_TIMING
+
+
+class _Timed:
+    """with _Timed(name, meta): launch  -- records CUDA events on the launch stream when KERNEL_TIMING is enabled"""
+
+    def __init__(self, name, meta):
+        self.name, self.meta = name, meta
+
+    def __enter__(self):
+        if KERNEL_TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if KERNEL_TIMING is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            KERNEL_TIMING.setdefault(self.name, []).append((self.e0, e1, self.meta))
+        return False
+
+
 def launch_count() -> int:
     return int(_L().mmf_launch_count())
 
@@ -124,9 +153,12 @@ def layernorm_fwd(x, g1, y, *, b1=None, eps1=1e-5, g2=None, eps2=1e-5, stats=Non
     if delta is not None:
         assert delta.dtype == bf16 and xout is not None and xout.dtype == f32
         assert delta.shape[0] >= rows - delta_row0 and xout.shape[0] >= rows - delta_row0
-    check(_L().mmf_layernorm_fwd(_p(x), _p(x2), x_split, rows, D, _ld(x), _p(g1), _p(b1), eps1, _p(g2), eps2, _p(y), _ld(y),
-                                 int(y.dtype == f32), _p(stats), _p(delta), delta_row0, _ld(delta) if delta is not None else 0,
-                                 _p(xout), _ld(xout) if xout is not None else 0, _stream()), "mmf_layernorm_fwd")
+    # algorithmic bytes: read x (4), write y (2 or 4), + delta rows: read delta (2), write xout (4)
+    nbytes = rows * D * (4 + y.element_size()) + (max(rows - delta_row0, 0) * D * 6 if delta is not None else 0)
+    with _Timed("ln_fwd", nbytes):
+        check(_L().mmf_layernorm_fwd(_p(x), _p(x2), x_split, rows, D, _ld(x), _p(g1), _p(b1), eps1, _p(g2), eps2, _p(y), _ld(y),
+                                     int(y.dtype == f32), _p(stats), _p(delta), delta_row0, _ld(delta) if delta is not None else 0,
+                                     _p(xout), _ld(xout) if xout is not None else 0, _stream()), "mmf_layernorm_fwd")
     return y
 
 
@@ -135,10 +167,13 @@ def layernorm_bwd(dy, x, g1, stats, dx, dg1, *, b1=None, g2=None, dres=None, dx_
     assert dy.dtype in (bf16, f32) and x.dtype == f32 and dx.dtype == f32
     rows = rows if rows is not None else dy.shape[0]
     D = dy.shape[1]
-    check(_L().mmf_layernorm_bwd(_p(dy), _ld(dy), int(dy.dtype == f32), _p(x), _p(x2), x_split, rows, D, _ld(x), _p(g1), _p(b1),
-                                 _p(g2), _p(stats), _p(dres), _ld(dres) if dres is not None else 0, _p(dx), _ld(dx),
-                                 _p(dx_bf16), _ld(dx_bf16) if dx_bf16 is not None else 0, _p(dg1), _p(db1), _p(dg2), _stream()),
-          "mmf_layernorm_bwd")
+    # algorithmic bytes: read dy, x (4) (+ dres 4), write dx (4) (+ bf16 copy 2)
+    nbytes = rows * D * (dy.element_size() + 8 + (4 if dres is not None else 0) + (2 if dx_bf16 is not None else 0))
+    with _Timed("ln_bwd", nbytes):
+        check(_L().mmf_layernorm_bwd(_p(dy), _ld(dy), int(dy.dtype == f32), _p(x), _p(x2), x_split, rows, D, _ld(x), _p(g1), _p(b1),
+                                     _p(g2), _p(stats), _p(dres), _ld(dres) if dres is not None else 0, _p(dx), _ld(dx),
+                                     _p(dx_bf16), _ld(dx_bf16) if dx_bf16 is not None else 0, _p(dg1), _p(db1), _p(dg2), _stream()),
+              "mmf_layernorm_bwd")
     return dx
 
 
@@ -160,7 +195,8 @@ def _attn_args(q, k, v, o, lse, B, H, Nq, Nk, dh, scale, n_head_q, n_head_k, seg
 def attn_fwd(q, k, v, o, lse, *, B, H, Nq, Nk, dh, scale, n_head_q=None, n_head_k=None, seg=None, nseg=0):
     """q/k/v/o: bf16 2-D token-major views (column slices of a fused qkv buffer are fine)."""
     a = _attn_args(q, k, v, o, lse, B, H, Nq, Nk, dh, scale, n_head_q, n_head_k, seg, nseg)
-    check(_L().mmf_attn_fwd(C.byref(a), _stream()), "mmf_attn_fwd")
+    with _Timed("attn_fwd", (B, H, Nq, Nk, dh, seg, nseg)):
+        check(_L().mmf_attn_fwd(C.byref(a), _stream()), "mmf_attn_fwd")
     return o
 
 
@@ -170,7 +206,8 @@ def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, delta, *, B, H, Nq, Nk, dh, scale
     a.d_o, a.lddo, a.delta = _p(d_o), d_o.stride(0), _p(delta)
     a.dq, a.dk, a.dv = _p(dq), _p(dk), _p(dv)
     a.lddq, a.lddk, a.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
-    check(_L().mmf_attn_bwd(C.byref(a), _stream()), "mmf_attn_bwd")
+    with _Timed("attn_bwd", (B, H, Nq, Nk, dh, seg, nseg)):
+        check(_L().mmf_attn_bwd(C.byref(a), _stream()), "mmf_attn_bwd")
 
 
 def _slot_args(q, kv_tok, kv_me, slotmap, seg, B, F, H, S, n_head, scale):

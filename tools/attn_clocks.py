@@ -25,6 +25,7 @@ f(); torch.cuda.synchronize()
 raw.mmf_debug_attn_clocks(buf, 0)
 names = ["wait s_full", "ld + row max (pass A)", "exp + pack + st (pass B)", "wait_st+arrive", "loop top", "wait o_full", "head epilogue"]
 tot = sum(buf[i] for i in range(7))
-print("one fusion-tile CTA, 8 heads x 10 key blocks = 80 iterations; total cycles", tot)
+its = max(int(buf[15]), 1)
+print("one fusion-tile CTA, heads x key blocks = %d iterations; total cycles" % its, tot)
 for i, n in enumerate(names):
-    print(f"  {n:28s} {buf[i]:10d} cycles  {100*buf[i]/tot:5.1f}%   per iteration {buf[i]/80:8.0f}")
+    print(f"  {n:28s} {buf[i]:10d} cycles  {100*buf[i]/tot:5.1f}%   per iteration {buf[i]/its:8.0f}")
