@@ -174,6 +174,21 @@ __device__ __forceinline__ void lpt_tile(const int32_t* seg, int nseg, int tiles
   tile = (t < first_heavy && b < B) ? t : (1 << 20);   // surplus indices land past the last tile
 }
 
+// The same idea for the dK/dV kernel, whose CTAs own a KEY tile: there the modality tiles are the heavier ones (their
+// keys are read by their own segment's queries and by every fusion query), so all samples' modality tiles come first.
+__device__ __forceinline__ void lpt_key_tile(const int32_t* seg, int nseg, int tiles, int B, int& tile, int& b) {
+  const int L = blockIdx.x;
+  if (seg == nullptr) { tile = L % tiles; b = L / tiles; if (b >= B) tile = 1 << 20; return; }
+  int nmod = 0;
+  for (int s = 0; s + 1 < nseg; ++s) nmod += (seg[s + 1] - seg[s] + TC_BM - 1) / TC_BM;
+  const int th = (seg[nseg] - seg[nseg - 1] + TC_BM - 1) / TC_BM;
+  if (nmod > 0 && L < nmod * B) { b = L / nmod; tile = L % nmod; return; }
+  const int tl = tiles - nmod, L2 = L - nmod * B;
+  b = L2 / tl;
+  const int t = L2 % tl;
+  tile = (t < th && b < B) ? nmod + t : (1 << 20);
+}
+
 #ifdef MMF_ATTN_CLOCKS
 __device__ unsigned long long g_attn_clk[16];
 #define CLK(i, expr) do { if (dbg_on) { const long long t__ = clock64(); g_attn_clk[i] += (unsigned long long)(t__ - t_last); t_last = t__; } } while (0)
@@ -745,9 +760,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
                        const AttnBwdTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // key tile (cut per segment) and the query ranges that attend to it
-  int c0 = 0, c1 = 0, qa0 = 0, qe0 = 0, qa1 = 0, qe1 = 0;
+  int c0 = 0, c1 = 0, qa0 = 0, qe0 = 0, qa1 = 0, qe1 = 0, b = 0;
   {
-    int tile = blockIdx.x;
+    int tile;
+    lpt_key_tile(p.seg, p.nseg, p.tiles, p.B, tile, b);
     bool found = false;
     if (p.seg == nullptr) {
       c0 = tile * TC_BM; c1 = min(c0 + TC_BM, p.N); qa0 = 0; qe0 = p.N; found = c0 < p.N;
@@ -767,7 +783,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
     }
     if (!found) return;
   }
-  const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;                                   // 2 buffers of 128x64 (per head)
@@ -911,12 +926,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
           tmem_wait_ld();
           uint32_t pk[16], dk_[16];
 #pragma unroll
-          for (int t = 0; t < 16; ++t) {
-            const int q0 = c * 32 + 2 * t;
-            const float p0 = ex2(fmaf(__uint_as_float(rs[2 * t]), p.scale_log2, -ls[q0]));        // lse = +inf beyond nvalid -> 0
-            const float p1 = ex2(fmaf(__uint_as_float(rs[2 * t + 1]), p.scale_log2, -ls[q0 + 1]));
-            pk[t] = pack_bf16(p0, p1);
-            dk_[t] = pack_bf16(p0 * (__uint_as_float(rd[2 * t]) - dl[q0]), p1 * (__uint_as_float(rd[2 * t + 1]) - dl[q0 + 1]));
+          for (int t = 0; t < 8; ++t) {   // four query columns per step: one 16-byte broadcast read of lse and of delta
+            const float4 l4 = reinterpret_cast<const float4*>(ls)[c * 8 + t], d4 = reinterpret_cast<const float4*>(dl)[c * 8 + t];
+            const float p0 = ex2(fmaf(__uint_as_float(rs[4 * t]), p.scale_log2, -l4.x));        // lse = +inf beyond nvalid -> 0
+            const float p1 = ex2(fmaf(__uint_as_float(rs[4 * t + 1]), p.scale_log2, -l4.y));
+            const float p2 = ex2(fmaf(__uint_as_float(rs[4 * t + 2]), p.scale_log2, -l4.z));
+            const float p3 = ex2(fmaf(__uint_as_float(rs[4 * t + 3]), p.scale_log2, -l4.w));
+            pk[2 * t] = pack_bf16(p0, p1);
+            pk[2 * t + 1] = pack_bf16(p2, p3);
+            dk_[2 * t] = pack_bf16(p0 * (__uint_as_float(rd[4 * t]) - d4.x), p1 * (__uint_as_float(rd[4 * t + 1]) - d4.y));
+            dk_[2 * t + 1] = pack_bf16(p2 * (__uint_as_float(rd[4 * t + 2]) - d4.z), p3 * (__uint_as_float(rd[4 * t + 3]) - d4.w));
           }
           tmem_st_32x16(lane_addr + KV_ST + c * 16, pk);     // P^T over consumed S^T columns
           tmem_st_32x16(lane_addr + KV_DPT + c * 16, dk_);   // dS^T over consumed dP^T columns
@@ -1017,7 +1036,7 @@ int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   p.tiles = tiles;
   const int heavy_max = a->seg ? (a->Nq + TC_BM - 1) / TC_BM : 0;
   attn_bwd_dq_tc_kernel<<<(tiles + (TC_HSPLIT - 1) * heavy_max) * a->B, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
-  attn_bwd_dkv_tc_kernel<<<dim3(tiles, a->B), TC_THREADS, DKV_SMEM, stream>>>(k128, v128, q64, do64, p);
+  attn_bwd_dkv_tc_kernel<<<tiles * a->B, TC_THREADS, DKV_SMEM, stream>>>(k128, v128, q64, do64, p);
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;

@@ -525,6 +525,25 @@ def _unpad_w1(dw1, I, ipad):
     return torch.cat([dw1[:I], dw1[ipad:ipad + I]], 0)
 
 
+class _ZeroArena:
+    """One zero-filled fp32 buffer per encoder layer for every gradient the layer accumulates into (split-K weight
+    gradients, LayerNorm gammas): a single memset instead of a dozen small fill launches per layer."""
+
+    def __init__(self, numel: int, device):
+        self.buf = torch.zeros(numel, dtype=f32, device=device)
+        self.off = 0
+
+    def take(self, *shape) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        if self.off + n > self.buf.numel():          # (bound was too tight: fall back to a private buffer)
+            return torch.zeros(*shape, dtype=f32, device=self.buf.device)
+        v = self.buf[self.off:self.off + n].view(*shape)
+        self.off += (n + 3) // 4 * 4                  # keep every view 16-byte aligned
+        return v
+
+
 def _layer_hook(meta, grads, slots):
     """hand one encoder layer's parameter gradients to the data-parallel reducer while the backward continues
     (training.GradAllReduce.reduce_now); the hook returns the tensors autograd should install instead"""
@@ -631,7 +650,10 @@ class EncoderStackFn(torch.autograd.Function):
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
         dme = torch.zeros(Fn, D, dtype=f32, device=dev) if fusion else None
         dX = dX.contiguous()
-        zeros = lambda n: torch.zeros(n, dtype=f32, device=dev)
+        # per layer: every parameter gradient (weights at their padded GEGLU width) + the mask-embedding k/v gradient
+        layer_elems = (2 if fusion else 1) * (4 * D + 4 * HD * D + 3 * ipad * D + 64) + (Fn * 2 * HD if fusion else 0)
+        arena = None
+        zeros = lambda n: arena.take(n)
 
         def ffn_bwd(dXo_b, g, u, h, w1_param, w2_param, rows):
             """returns dh (bf16 [rows, D]), dW1, dW2"""
@@ -639,17 +661,18 @@ class EncoderStackFn(torch.autograd.Function):
             # dg = dXo . W2 stays in TMEM: the GEMM's epilogue turns it into du = [dvalue | dgate] against the saved u
             du = torch.empty_like(u)
             K.gemm(dXo_b, w2b, du, b_mn=True, act=3, out2=u)
-            dW2 = wgrad(dXo_b, g)[:, :I]
+            dW2 = wgrad(dXo_b, g, out=arena.take(D, ipad))[:, :I]
             w1b = w_geglu_bf16(w1_param, ipad)
             dh = torch.empty(rows, D, dtype=bf16, device=dev)
             K.gemm(du, w1b, dh, b_mn=True)
-            dW1 = _unpad_w1(wgrad(du, h), I, ipad)
+            dW1 = _unpad_w1(wgrad(du, h, out=arena.take(2 * ipad, D)), I, ipad)
             return dh, dW1, dW2.contiguous() if I != ipad else dW2
 
         dXb_next = None
         for i in reversed(range(depth)):
             rec = saved[i]
             saved[i] = None
+            arena = _ZeroArena(layer_elems, dev)
             X = rec["X"]
             Xf2 = rec.get("Xf2")
             zo = base + i * per_layer + (ZB if fusion else 0)
@@ -665,7 +688,7 @@ class EncoderStackFn(torch.autograd.Function):
             grads[zo + 5], grads[zo + 6] = dn2, dm0
             do = torch.empty(Mt, HD, dtype=bf16, device=dev)
             K.gemm(dX1b, w_bf16(params[zo + 4]), do, b_mn=True)
-            grads[zo + 4] = wgrad(dX1b, rec["o"])
+            grads[zo + 4] = wgrad(dX1b, rec["o"], out=arena.take(D, HD))
             qkv = rec["qkv"]
             dqkv = torch.empty_like(qkv)
             delta = torch.empty(B, H, N, dtype=f32, device=dev)
@@ -674,7 +697,7 @@ class EncoderStackFn(torch.autograd.Function):
                        n_head_q=nenc, n_head_k=nenc, seg=seg, nseg=nseg)
             dh1 = torch.empty(Mt, D, dtype=bf16, device=dev)
             K.gemm(dqkv, w_cat_bf16([params[zo + 2], params[zo + 3]]), dh1, b_mn=True)
-            dWqkv = wgrad(dqkv, rec["h1"])
+            dWqkv = wgrad(dqkv, rec["h1"], out=arena.take(3 * HD, D))
             grads[zo + 2], grads[zo + 3] = dWqkv[:HD], dWqkv[HD:]
             dZ = torch.empty(Mt, D, dtype=f32, device=dev)
             dZb = torch.empty(Mt, D, dtype=bf16, device=dev) if (fusion or i > 0) else None
@@ -698,21 +721,21 @@ class EncoderStackFn(torch.autograd.Function):
             grads[fo + 5], grads[fo + 6] = dfn2, dfm0
             da = torch.empty(Mf, HD, dtype=bf16, device=dev)
             K.gemm(dXf1b, w_bf16(params[fo + 4]), da, b_mn=True)
-            grads[fo + 4] = wgrad(dXf1b, rec["a"])
+            grads[fo + 4] = wgrad(dXf1b, rec["a"], out=arena.take(D, HD))
             # dkv [Mt, 2HD] and dq [Mf, HD] share one buffer, [dk | dv | dq] per row (the dq columns of the modality rows
             # stay unused): the fusion rows' dgrad is then ONE GEMM over K = 3HD against [Wkv; Wq] instead of a second,
             # read-modify-write GEMM into the same rows
             dkvq = torch.empty(Mt, 3 * HD, dtype=bf16, device=dev)
             dkv, dq = dkvq[:, :2 * HD], dkvq[Mh:, 2 * HD:]
-            dkvm = torch.zeros(Fn, 2 * HD, dtype=f32, device=dev)
+            dkvm = arena.take(Fn, 2 * HD)
             K.slot_attn_bwd(rec["q"], rec["kv"], rec["kvm"], meta["slotmap"], seg, da, dq, dkv, dkvm, B=B, F=Fn, H=H, S=nseg,
                             n_head=nenc, scale=scale)
             wkvb = w_bf16(params[fo + 3])
             dhk = torch.empty(Mt, D, dtype=bf16, device=dev)
             K.gemm(dkv[:Mh], wkvb, dhk[:Mh], b_mn=True)
             K.gemm(dkvq[Mh:], w_cat_bf16([params[fo + 3], params[fo + 2]]), dhk[Mh:], b_mn=True)
-            dWkv = wgrad(dkv, rec["hk"])
-            grads[fo + 2] = wgrad(dq, rec["hk"][Mh:])
+            dWkv = wgrad(dkv, rec["hk"], out=arena.take(2 * HD, D))
+            grads[fo + 2] = wgrad(dq, rec["hk"][Mh:], out=arena.take(HD, D))
             # mask-embedding rows (batch-invariant keys/values)
             dkvmb = K.cast_bf16(dkvm)
             dhm = torch.empty(Fn, D, dtype=bf16, device=dev)
