@@ -132,7 +132,10 @@ def reference_loss(ref, out, x, cfg):
     return total
 
 
-def model_case(name, cfg, batch, nenc, mask_seed, uniformly, task_masks=None):
+def model_case(name, cfg, batch, nenc, mask_seed, uniformly, task_masks=None, autocast=False):
+    """autocast=True: the same run under torch.autocast('cpu', bfloat16) -- the reference's OWN code in bf16.  (CUDA
+    autocast cannot run in the GPU-less authoring container; the CPU policy casts the same Linear / conv / matmul calls
+    to bf16 and keeps the fp32 residual stream and LayerNorms, but leaves softmax in bf16 where CUDA autocast upcasts.)"""
     from oracle import init_state_dict
     from oracle.functional import perturb_state_dict
     ref = load_reference()
@@ -140,14 +143,15 @@ def model_case(name, cfg, batch, nenc, mask_seed, uniformly, task_masks=None):
     model = build_reference_model(cfg, sd)
     x = make_inputs(cfg, batch, seed=1234)
     torch.manual_seed(mask_seed)
-    out = model(x, mask_inputs=True, task_masks=task_masks, num_encoded_tokens=nenc, alphas=1.0,
-                sample_tasks_uniformly=uniformly)
-    loss = reference_loss(ref, out, x, cfg)
+    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+        out = model(x, mask_inputs=True, task_masks=task_masks, num_encoded_tokens=nenc, alphas=1.0,
+                    sample_tasks_uniformly=uniformly)
+        loss = reference_loss(ref, out, x, cfg)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
     fx = {
         "cfg": cfg.__dict__.copy(), "batch": batch, "nenc": nenc, "mask_seed": mask_seed,
-        "uniformly": uniformly, "input_seed": 1234, "sd_seed": 0, "perturb_seed": 7,
+        "uniformly": uniformly, "input_seed": 1234, "sd_seed": 0, "perturb_seed": 7, "autocast": "cpu bf16" if autocast else None,
         "task_masks_in": task_masks,
         "preds": {t: v.detach() for t, v in out[0].items()},
         "task_masks": {t: v for t, v in out[1].items()},
@@ -265,6 +269,9 @@ def main():
     from oracle import OracleConfig
     only = sys.argv[1:]     # e.g. `make_golden.py lstm_s2dsm` regenerates just that fixture
     small = dict(dim=128, depth=2, heads=2, dim_head=64, image_size=32, patch=8, dec_dim=64, dec_depth=1, dec_heads=2)
+    if not only or "bf16" in only:
+        model_case("crossattn_simple_bf16", OracleConfig(variant="crossattn", decoder="simple", **small), 2, 24, 1, False, autocast=True)
+        model_case("crossattn_uniform_bf16", OracleConfig(variant="crossattn", decoder="simple", **small), 3, 20, 11, True, autocast=True)
     if not only:
         model_case("crossattn_simple", OracleConfig(variant="crossattn", decoder="simple", **small), 2, 24, 1, False)
         model_case("plain_xattn", OracleConfig(variant="plain", decoder="xattn", **small), 2, 24, 3, True)

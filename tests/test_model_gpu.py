@@ -29,6 +29,35 @@ def _golden(golden_dir, name):
     return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
 
 
+# bf16 tier against the reference's OWN bf16 run (torch.autocast('cpu', bfloat16), tests/golden/*_bf16.pt): two
+# independently rounded bf16 computations, each ~6e-3 from the fp32 result (test_reference_bf16_autocast_golden_noise_floor),
+# measured on B200: activations 7e-3 (inside north_star's 1e-2), worst small-tensor gradient 4.6e-2 on the 2-sample case
+# (the L1 sign flips described at GOLDEN_GRAD_TOL, now present on both sides) and 2.6e-2 on the 3-sample case
+BF16_ACT_TOL = 1e-2
+BF16_GRAD_TOL = 7e-2
+
+
+@pytest.mark.parametrize("name", ["crossattn_simple_bf16", "crossattn_uniform_bf16"])
+def test_matches_reference_bf16_autocast_golden(golden_dir, name):
+    fx = _golden(golden_dir, name)
+    cfg = OracleConfig(**fx["cfg"])
+    model = build_model(cfg, default_sd(cfg))
+    x = make_inputs(cfg, fx["batch"], fx["input_seed"], "cuda")
+    tm = {t: m.cuda() for t, m in fx["task_masks"].items()}
+    out = model(x, task_masks=tm, num_encoded_tokens=fx["nenc"])
+    errs = {t: rel(out[0][t], fx["preds"][t].cuda()) for t in fx["preds"]}
+    errs["return_tokens"] = rel(out[2], fx["return_tokens"].cuda())
+    errs["fusion_tokens"] = rel(out[4], fx["fusion_tokens"].cuda())
+    assert max(errs.values()) < BF16_ACT_TOL, errs
+    loss = pretrain_loss_ours(out, x, cfg.patch)
+    assert abs(float(loss) - float(fx["loss"])) < 1e-2 * abs(float(fx["loss"]))
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    gerr = {k: rel(grads[k], g.cuda()) for k, g in fx["grads"].items() if float(g.norm()) > 1e-6}
+    assert max(gerr.values()) < BF16_GRAD_TOL, sorted(gerr.items(), key=lambda kv: -kv[1])[:5]
+    print("bf16 golden %s: max activation err %.4f, max gradient err %.4f" % (name, max(errs.values()), max(gerr.values())))
+
+
 @pytest.mark.parametrize("name", ["crossattn_simple", "crossattn_uniform"])
 def test_forward_matches_reference_golden(golden_dir, name):
     """explicit task_masks taken from the reference's run -> same visible tokens -> compare every output"""
