@@ -249,6 +249,38 @@ int mmf_mask_build(const float* noise1, const float* noise2, const float* share,
 int mmf_dino_loss(const void* student, int64_t lds, const void* teacher, int64_t ldt, int32_t is_f32, int32_t B, int32_t D,
                   float student_temp, float teacher_temp, float* row_loss, float* dstudent, mmf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step around the path: multi-tensor AdamW and gradient norm / clip coefficient.
+ * Replaces torch.optim.AdamW as configured by utils/optim_factory.py:138-176 (betas (0.9, 0.95), decoupled weight
+ * decay on every parameter) and the grad-norm / clip of utils/native_scaler.py:20-82 (one torch.norm per parameter).
+ * `tensors` is a DEVICE array, one entry per parameter tensor; (chunk_tensor[c], chunk_index[c]) maps launch block c
+ * to elements [chunk_index * chunk_elems, +chunk_elems) of tensor chunk_tensor (DEVICE int32 arrays).  n == 0 skips
+ * a tensor (no gradient this step).  Update, per element (torch.optim.AdamW, amsgrad off, maximize off):
+ *   g *= *grad_scale (if given);  p *= 1 - lr*wd;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;
+ *   p -= (lr / bias_correction1) * m / (sqrt(v) / sqrt(bias_correction2) + eps)
+ * w16a / w16b (nullable): bf16 images of p refreshed in the same pass (what autocast's weight cast produces each
+ * forward in the reference); element i of p goes to image element (i / cols) * pitch16 + i % cols, or i if cols == 0.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct MmfAdamWTensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  void* w16a;
+  void* w16b;
+  int64_t n;
+  int64_t pitch16a, pitch16b;
+  int32_t cols;
+  float bias_correction1, bias_correction2;   /* 1 - beta^step of THIS tensor */
+} MmfAdamWTensor;
+int mmf_adamw_step(const MmfAdamWTensor* tensors, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t nchunks,
+                   int32_t chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   const float* grad_scale, mmf_stream_t stream);
+/* sqnorm (device scalar, overwritten) = sum of g^2 over all tensors; norm (nullable) = sqrt; clip_coef (nullable) =
+ * min(1, max_norm / (norm + 1e-6)) (torch.nn.utils.clip_grad_norm_), 1 if max_norm <= 0.  No host synchronisation. */
+int mmf_grad_norm(const MmfAdamWTensor* tensors, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t nchunks,
+                  int32_t chunk_elems, float max_norm, float* sqnorm, float* norm, float* clip_coef, mmf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,14 @@ class PoolAttnArgs(C.Structure):
     ]
 
 
+class AdamWTensor(C.Structure):
+    _fields_ = [
+        ("p", c_vp), ("g", c_vp), ("m", c_vp), ("v", c_vp), ("w16a", c_vp), ("w16b", c_vp),
+        ("n", c_i64), ("pitch16a", c_i64), ("pitch16b", c_i64),
+        ("cols", c_i32), ("bias_correction1", c_f32), ("bias_correction2", c_f32),
+    ]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES).  Must list every symbol of mmf_b200.h.
 SIGNATURES = {
     "mmf_abi_version": [],
@@ -91,6 +99,8 @@ SIGNATURES = {
     "mmf_add_inplace_f32": [c_vp, c_vp, c_i64, c_vp],
     "mmf_add_bf16_f32": [c_vp, c_vp, c_vp, c_i64, c_vp],
     "mmf_dino_loss": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp],
+    "mmf_adamw_step": [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp],
+    "mmf_grad_norm": [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp],
     "mmf_mask_build": [c_vp, c_vp, c_vp, c_i32, C.POINTER(c_i32), c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
 }
 _RESTYPES = {"mmf_launch_count": c_i64, "mmf_reset_launch_count": None}

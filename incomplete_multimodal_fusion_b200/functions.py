@@ -54,6 +54,15 @@ class _WeightCache:
 
 WEIGHTS = _WeightCache()
 
+# torch's fused optimisers (observed: AdamW(fused=True), torch 2.11) update parameters WITHOUT bumping their version
+# counters, so version stamps alone would keep serving the pre-update images.  Any torch optimiser step therefore drops
+# the cache; `optim.FusedAdamW` (not a torch Optimizer) refreshes the images itself and re-stamps them instead.
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+    register_optimizer_step_post_hook(lambda _opt, _args, _kwargs: WEIGHTS.clear())
+except ImportError:   # pragma: no cover  (older torch: callers must invalidate by hand)
+    pass
+
 
 def w_bf16(w: torch.Tensor, rows_pad: Optional[int] = None, cols_pad: Optional[int] = None) -> torch.Tensor:
     """bf16 image of a 2-D (or conv 4-D, flattened) fp32 weight, zero padded."""

@@ -134,7 +134,7 @@ class PretrainStep:
 
     def __init__(self, model, num_encoded_tokens: int, patch_size: int = 16, blr: float = 1e-4, global_batch: int = 256,
                  weight_decay: float = 0.05, sample_tasks_uniformly: bool = True, alphas: float = 1.0,
-                 contrastive_weight: float = 0.3):
+                 contrastive_weight: float = 0.3, max_grad_norm: Optional[float] = None, torch_optimizer: bool = False):
         self.model = model
         self.nenc = num_encoded_tokens
         self.uniformly = sample_tasks_uniformly
@@ -142,8 +142,13 @@ class PretrainStep:
         self.cw = contrastive_weight
         self.losses = {d: DOMAIN_CONF[d]["loss"](patch_size=patch_size, stride=1) for d in DOMAIN_CONF}
         self.hard_negative = HardNegtive_loss()
-        self.opt = torch.optim.AdamW(model.parameters(), lr=blr * global_batch / 256, betas=(0.9, 0.95),
-                                     weight_decay=weight_decay, fused=True)
+        if torch_optimizer:   # torch's own fused AdamW (kept for A/B runs and the CPU tests)
+            self.opt = torch.optim.AdamW(model.parameters(), lr=blr * global_batch / 256, betas=(0.9, 0.95),
+                                         weight_decay=weight_decay, fused=True)
+        else:
+            from .optim import FusedAdamW
+            self.opt = FusedAdamW(model.parameters(), lr=blr * global_batch / 256, betas=(0.9, 0.95), weight_decay=weight_decay,
+                                  max_grad_norm=max_grad_norm)
         self.reducer = GradAllReduce(list(model.parameters()))
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         if self.world > 1:

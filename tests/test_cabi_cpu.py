@@ -29,7 +29,8 @@ def test_struct_layouts_match_header_field_order():
     src = open(os.path.join(ROOT, "include", "mmf_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     for cname, cls in (("MmfGemmArgs", _lib.GemmArgs), ("MmfAttnArgs", _lib.AttnArgs),
-                       ("MmfSlotAttnArgs", _lib.SlotAttnArgs), ("MmfPoolAttnArgs", _lib.PoolAttnArgs)):
+                       ("MmfSlotAttnArgs", _lib.SlotAttnArgs), ("MmfPoolAttnArgs", _lib.PoolAttnArgs),
+                       ("MmfAdamWTensor", _lib.AdamWTensor)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
         names = []
         for decl in body.split(";"):
