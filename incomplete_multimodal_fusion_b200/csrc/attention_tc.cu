@@ -507,21 +507,20 @@ constexpr int BW_BLK_BYTES = BW_BLK * 64 * 2;     // 64 x 64 bf16 tile = 8 KB
 
 // blocks of BW_BLK token indices over up to two index ranges (each range lies inside one plane)
 struct RowBlocks {
-  int a[2], e[2], nbr[2], nb;
+  int a0, e0, a1, e1, nb0, nb;   // scalars, not arrays: a runtime index would put them in local memory
   int n_head, n_tail, b;
   int64_t head_rows;
-  __device__ void init(int a0, int e0, int a1, int e1, int n_head_, int n_tail_, int64_t head_rows_, int b_) {
+  __device__ void init(int a0_, int e0_, int a1_, int e1_, int n_head_, int n_tail_, int64_t head_rows_, int b_) {
     n_head = n_head_; n_tail = n_tail_; head_rows = head_rows_; b = b_;
-    a[0] = a0; e[0] = max(e0, a0); a[1] = a1; e[1] = max(e1, a1);
-    nbr[0] = (e[0] - a[0] + BW_BLK - 1) / BW_BLK;
-    nbr[1] = (e[1] - a[1] + BW_BLK - 1) / BW_BLK;
-    nb = nbr[0] + nbr[1];
+    a0 = a0_; e0 = max(e0_, a0_); a1 = a1_; e1 = max(e1_, a1_);
+    nb0 = (e0 - a0 + BW_BLK - 1) / BW_BLK;
+    nb = nb0 + (e1 - a1 + BW_BLK - 1) / BW_BLK;
   }
   // block j -> first token index, global row of that token, number of valid rows
   __device__ void get(int j, int& tok, int64_t& row, int& nvalid) const {
-    const int r = j < nbr[0] ? 0 : 1;
-    tok = a[r] + (j - (r ? nbr[0] : 0)) * BW_BLK;
-    nvalid = min(BW_BLK, e[r] - tok);
+    const bool second = j >= nb0;
+    tok = second ? a1 + (j - nb0) * BW_BLK : a0 + j * BW_BLK;
+    nvalid = min(BW_BLK, (second ? e1 : e0) - tok);
     row = tok < n_head ? (int64_t)b * n_head + tok : head_rows + (int64_t)b * n_tail + (tok - n_head);
   }
 };
@@ -901,22 +900,48 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
     const bool key_ok = c0 + row_in_tile < c1;
     uint32_t rs[32], rd[32];
     int g = 0;
+#ifdef MMF_ATTN_CLOCKS
+    const bool dbg_on = (b == 3) && (c0 == 0) && warp == 2 && lane == 0;   // first modality key tile of sample 3
+    if (dbg_on) g_attn_clk[15] = (unsigned long long)qb.nb * p.H;
+    long long t_last = clock64();
+#endif
+    // lse*log2e and delta of a block's 64 query rows are staged in shared memory by the first 64 elementwise threads.
+    // The values of block g+1 are fetched (global loads into registers) right after the barrier of block g and written
+    // to the other stage at the end of block g: their latency hides behind the block's arithmetic.  Fetched where they
+    // are needed they cost ~2000 clk per block, 40 % of this CTA's time (tools/attn_clocks_bwd.py).
+    float nl = 0.f, nd = 0.f;   // raw loaded values: nothing may consume them before the stage write (in-order issue
+    bool nok = false;           // would park the warp on the load right after the barrier)
+    auto fetch = [&](int hh, int jj) {
+      int tok, nvalid; int64_t row;
+      qb.get(jj, tok, row, nvalid);
+      const int64_t sb = ((int64_t)b * p.H + hh) * p.N;
+      nok = tid128 < nvalid;
+      const int64_t at = sb + tok + (nok ? tid128 : 0);
+      nl = p.lse[at];
+      nd = p.delta[at];
+    };
+    auto stage = [&](int stg) {
+      s_lse[stg * BW_BLK + tid128] = nok ? nl * 1.4426950408889634f : INFINITY;   // +inf beyond nvalid -> P = 0
+      s_dl[stg * BW_BLK + tid128] = nok ? nd : 0.f;
+    };
+    if (tid128 < BW_BLK && qb.nb > 0) {
+      fetch(0, 0);
+      stage(0);
+    }
     for (int h = 0; h < p.H; ++h) {
-      const int64_t stat_base = ((int64_t)b * p.H + h) * p.N;
       for (int j = 0; j < qb.nb; ++j, ++g) {
         const int st = g & 1;
         int tok, nvalid; int64_t row;
         qb.get(j, tok, row, nvalid);
-        // stage lse*log2e and delta of the block's query rows (buffer st was last read two blocks ago, before the
-        // ds_full arrival that the s_full wait below transitively orders)
-        if (tid128 < BW_BLK) {
-          const bool ok = tid128 < nvalid;
-          s_lse[st * BW_BLK + tid128] = ok ? p.lse[stat_base + tok + tid128] * 1.4426950408889634f : INFINITY;
-          s_dl[st * BW_BLK + tid128] = ok ? p.delta[stat_base + tok + tid128] : 0.f;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four elementwise warps only
+        CLK(4, 0);
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four elementwise warps: stage st is complete, st^1 is free
+        const int hn = (j + 1 < qb.nb) ? h : h + 1, jn = (j + 1 < qb.nb) ? j + 1 : 0;
+        const bool stage_next = tid128 < BW_BLK && hn < p.H;
+        if (stage_next) fetch(hn, jn);
+        CLK(5, 0);
         mbar_wait(s_full, g & 1);
         tc_fence_after();
+        CLK(0, 0);
         const float* ls = s_lse + st * BW_BLK;
         const float* dl = s_dl + st * BW_BLK;
 #pragma unroll
@@ -940,10 +965,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
           tmem_st_32x16(lane_addr + KV_ST + c * 16, pk);     // P^T over consumed S^T columns
           tmem_st_32x16(lane_addr + KV_DPT + c * 16, dk_);   // dS^T over consumed dP^T columns
         }
+        CLK(2, 0);
+        if (stage_next) stage(st ^ 1);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ds_full);
+        CLK(3, 0);
       }
       if (qb.nb == 0) continue;
       mbar_wait(acc_full, h & 1);
@@ -975,6 +1003,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
+      CLK(6, 0);
     }
   }
   tc_fence_before();
