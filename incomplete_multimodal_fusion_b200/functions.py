@@ -589,6 +589,10 @@ class EncoderStackFn(torch.autograd.Function):
         # read-modify-write in a GEMM epilogue).
         S = X.contiguous()
         pend = None
+        # optional pyramid taps (downstream ViTBaseline, multimae_big_imcomplete.py:651-653): the fusion tokens after the
+        # listed blocks are returned as extra outputs, in ascending block order
+        taps = sorted(meta.get("taps") or [])
+        tap_out = []
         for i in range(depth):
             lp = [p.detach() for p in params[base + i * per_layer: base + (i + 1) * per_layer]]
             rec = {}
@@ -636,15 +640,23 @@ class EncoderStackFn(torch.autograd.Function):
             rec.update(h1=h1, st1=st1, qkv=qkv, o=o, lse=lse, X1=X1, h2z=h2z, st2=st2, gz=gz, uz=uz)
             saved.append(rec)
             S, pend = X1, dZ
+            if i in taps and i != depth - 1:   # fusion tokens after block i (stream + its pending delta), fp32 [B*F, D]
+                tap_out.append(K.add_bf16(S[Mh:], pend[Mh:]))
         X = K.add_bf16(S, pend) if pend is not None else S
+        if (depth - 1) in taps:
+            tap_out.append(X[Mh:].clone())   # (an output may not be a view of another output)
         ctx.meta = meta
         ctx.saved = saved
         ctx.params = params
+        ctx.taps = taps
+        if taps:
+            return (X,) + tuple(tap_out)
         return X
 
     @staticmethod
-    def backward(ctx, dX):
+    def backward(ctx, dX, *dtaps):
         meta, saved, params = ctx.meta, ctx.saved, ctx.params
+        tap_grad = {i: g for i, g in zip(ctx.taps, dtaps) if g is not None}
         B, D, H, Fn, nenc, fusion = meta["B"], meta["D"], meta["H"], meta["F"], meta["nenc"], meta["fusion"]
         depth, I = meta["depth"], meta["I"]
         ipad = _pad64(I)
@@ -659,6 +671,8 @@ class EncoderStackFn(torch.autograd.Function):
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
         dme = torch.zeros(Fn, D, dtype=f32, device=dev) if fusion else None
         dX = dX.contiguous()
+        if tap_grad:
+            dX = dX.clone()     # tap gradients are accumulated into it in place below
         # per layer: every parameter gradient (weights at their padded GEGLU width) + the mask-embedding k/v gradient
         layer_elems = (2 if fusion else 1) * (4 * D + 4 * HD * D + 3 * ipad * D + 64) + (Fn * 2 * HD if fusion else 0)
         arena = None
@@ -682,6 +696,9 @@ class EncoderStackFn(torch.autograd.Function):
             rec = saved[i]
             saved[i] = None
             arena = _ZeroArena(layer_elems, dev)
+            if i in tap_grad:   # dX is the gradient w.r.t. block i's output: the tap is its fusion plane
+                K.add_inplace(dX[Mh:], tap_grad[i].contiguous().float().view(Mf, D))
+                dXb_next = None                         # the bf16 copy emitted by the previous LayerNorm backward is stale
             X = rec["X"]
             Xf2 = rec.get("Xf2")
             zo = base + i * per_layer + (ZB if fusion else 0)

@@ -265,10 +265,61 @@ def mask_case():
     print("masks", len(cases))
 
 
+def load_reference_downstream():
+    """the downstream package's modules the ViTBaseline file needs, loaded in memory as `refdown` (the package __init__
+    pulls in detectron2; the four files below are self-contained and unpatched)"""
+    if "refdown" in sys.modules:
+        return sys.modules["refdown"]
+    base = os.path.join(REF, "downstream", "instance_segmentation", "modeling", "multimae")
+    pkg = types.ModuleType("refdown")
+    pkg.__path__ = [base]
+    sys.modules["refdown"] = pkg
+    for mod in ("multimae_utils", "zorro_utils", "input_adapters", "multimae_big_imcomplete"):
+        m = types.ModuleType("refdown." + mod)
+        m.__package__ = "refdown"
+        m.__file__ = os.path.join(base, mod + ".py")
+        sys.modules["refdown." + mod] = m
+        exec(compile(_read(m.__file__), m.__file__, "exec"), m.__dict__)
+        setattr(pkg, mod, m)
+    return pkg
+
+
+def vitbaseline_case(cfg):
+    """downstream ViTBaseline (multimae_big_imcomplete.py), eval mode, for the 7 non-empty modality subsets"""
+    from oracle.vit_baseline import vit_baseline_state_dict
+    ref = load_reference_downstream()
+    mod = ref.multimae_big_imcomplete
+    Adapter, FusAdapter = ref.input_adapters.PatchedInputAdapter, ref.input_adapters.FusionInputAdapter
+    ia = OrderedDict((t, Adapter(num_channels=C, stride_level=1, patch_size_full=cfg.patch, image_size=cfg.image_size))
+                     for t, C in cfg.channels.items())
+    ia["fusion"] = FusAdapter(num_channels=1, stride_level=1, patch_size_full=cfg.patch, image_size=cfg.image_size)
+    model = mod.ViTBaseline(pretrained="/nonexistent", pretrain_size=cfg.image_size, input_adapters=ia, output_adapters=None,
+                            in_domains=list(cfg.channels), dim_tokens=cfg.dim, depth=cfg.depth, dim_head=cfg.dim_head,
+                            heads=cfg.heads, ff_mult=cfg.ff_mult, num_fusion_tokens=cfg.num_patches).eval()
+    sd = vit_baseline_state_dict(cfg, seed=0)
+    res = torch.nn.Module.load_state_dict(model, sd, strict=True)      # (the class overrides load_state_dict leniently)
+    assert not res.missing_keys and not res.unexpected_keys
+    x = make_inputs(cfg, 2, seed=77)
+    out = {}
+    for bits in range(1, 8):
+        present = [t for i, t in enumerate(("s1", "s2", "dem")) if bits >> i & 1]
+        model.in_domains = present          # eval mode encodes `in_domains`; the caller narrows it to what is available
+        with torch.no_grad():
+            feats = model({t: x[t] for t in present})
+        out["+".join(present)] = [f.clone() for f in feats]
+    torch.save({"cfg": cfg.__dict__.copy(), "input_seed": 77, "batch": 2, "sd_seed": 0, "flags": list(model.flags),
+                "state_dict_keys": [(k, tuple(v.shape)) for k, v in model.state_dict().items()], "results": out},
+               os.path.join(HERE, "vitbaseline.pt"))
+    print("vitbaseline", list(out), [tuple(f.shape) for f in out["s1+s2+dem"]])
+
+
 def main():
     from oracle import OracleConfig
     only = sys.argv[1:]     # e.g. `make_golden.py lstm_s2dsm` regenerates just that fixture
     small = dict(dim=128, depth=2, heads=2, dim_head=64, image_size=32, patch=8, dec_dim=64, dec_depth=1, dec_heads=2)
+    if not only or "vitbaseline" in only:
+        vitbaseline_case(OracleConfig(variant="crossattn", decoder="simple", dim=64, depth=4, heads=1, dim_head=64, image_size=32,
+                                      patch=8, dec_dim=64, dec_depth=1, dec_heads=2))
     if not only or "bf16" in only:
         model_case("crossattn_simple_bf16", OracleConfig(variant="crossattn", decoder="simple", **small), 2, 24, 1, False, autocast=True)
         model_case("crossattn_uniform_bf16", OracleConfig(variant="crossattn", decoder="simple", **small), 3, 20, 11, True, autocast=True)

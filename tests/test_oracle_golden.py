@@ -179,3 +179,22 @@ def test_reference_bf16_autocast_golden_noise_floor(golden_dir, name):
     assert set(b16["grad_norms"]) == set(f32["grad_norms"])
     worst = max(rel(b16["grads"][k], g) for k, g in f32["grads"].items() if float(g.norm()) > 1e-6)
     assert worst < 5e-2, worst
+
+
+def test_vit_baseline_matches_reference(golden_dir):
+    """downstream ViTBaseline: the oracle's pyramid features for the 7 modality subsets against the
+    reference class's own outputs; absent modalities have neither tokens nor a modality-attention slot"""
+    from oracle.vit_baseline import vit_baseline_flags, vit_baseline_forward, vit_baseline_state_dict
+    fx = _load(golden_dir, "vitbaseline")
+    cfg = _cfg(fx["cfg"])
+    sd = vit_baseline_state_dict(cfg, seed=fx["sd_seed"])
+    assert {k: tuple(v.shape) for k, v in sd.items()} == dict(fx["state_dict_keys"])        # the reference class's schema
+    assert vit_baseline_flags(cfg.depth) == fx["flags"]
+    x = _inputs(cfg, fx["batch"], fx["input_seed"])
+    for name, feats in fx["results"].items():
+        present = name.split("+")
+        with torch.no_grad():
+            out = vit_baseline_forward(sd, cfg, OrderedDict((t, x[t]) for t in present), in_domains=present)
+        for a, b in zip(out, feats):
+            assert a.shape == b.shape
+            assert float((a - b).norm() / b.norm()) < 1e-5, name
