@@ -690,10 +690,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const bool row_ok = i < r1;
     uint32_t rs[32], rd[32];
     int g = 0;
+    // this row's lse / delta of the NEXT head are requested while the current head is processed (fetched at the head's
+    // start they cost a full memory round trip per head, i.e. per 2 key blocks on a modality tile)
+    const int64_t stat0 = ((int64_t)b * p.H + h0) * p.N + (row_ok ? i : r0);
+    float lse_raw = p.lse[stat0], dl_raw = p.delta[stat0];
     for (int h = 0; h < nh; ++h) {
-      const int64_t stat_idx = ((int64_t)b * p.H + h0 + h) * p.N + i;
-      const float lse2 = row_ok ? p.lse[stat_idx] * 1.4426950408889634f : INFINITY;   // invalid rows -> P = 0
-      const float dl = row_ok ? p.delta[stat_idx] : 0.f;
+      const float lse2 = row_ok ? lse_raw * 1.4426950408889634f : INFINITY;   // invalid rows -> P = 0
+      const float dl = row_ok ? dl_raw : 0.f;
+      if (h + 1 < nh) {
+        lse_raw = p.lse[stat0 + (int64_t)(h + 1) * p.N];
+        dl_raw = p.delta[stat0 + (int64_t)(h + 1) * p.N];
+      }
       for (int j = 0; j < kb.nb; ++j, ++g) {
         int tok, nvalid; int64_t row;
         kb.get(j, tok, row, nvalid);
@@ -795,11 +802,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   uint64_t* kvt_empty = bars + 2;   // [2]
   uint64_t* qb_full = bars + 4;     // [2] Q / dO block
   uint64_t* qb_empty = bars + 6;    // [2]
-  uint64_t* s_full = bars + 8;
-  uint64_t* ds_full = bars + 9;
-  uint64_t* acc_full = bars + 10;
-  uint64_t* acc_empty = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_full = bars + 8;      // [2] S^T / dP^T of one 32-query half of the block
+  uint64_t* ds_full = bars + 10;    // [2] P^T / dS^T of that half written (S^T / dP^T consumed)
+  uint64_t* acc_full = bars + 12;
+  uint64_t* acc_empty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int64_t k_row0 = c0 < p.n_head ? (int64_t)b * p.n_head + c0 : p.head_rows + (int64_t)b * p.n_tail + (c0 - p.n_head);
   RowBlocks qb;
@@ -814,7 +821,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         mbar_init(&kvt_full[s], 1); mbar_init(&kvt_empty[s], 1);
         mbar_init(&qb_full[s], 1); mbar_init(&qb_empty[s], 1);
       }
-      mbar_init(s_full, 1); mbar_init(ds_full, 4); mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+      for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], 4); }
+      mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
       mbar_fence_init();
     }
     __syncwarp();
@@ -848,46 +856,67 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(TC_BM, BW_BLK, false, false);   // S^T[128 keys x 64 q] = K . Q^T
+      // A block of 64 queries is handled as two 32-query halves with their own S^T / dP^T columns and barriers: while
+      // the elementwise warps turn half B into P^T / dS^T, the tensor pipe accumulates half A into dV / dK and computes
+      // half A of the NEXT block (and vice versa), so neither side waits for the other in steady state.  (With one
+      // 64-query unit per block the elementwise warps spent 27 % of their time waiting for S: tools/attn_clocks_bwd.py.)
+      const uint32_t idesc_s = umma_idesc_bf16(TC_BM, 32, false, false);       // S^T[128 keys x 32 q] = K . Q^T (one half)
       const uint32_t idesc_acc = umma_idesc_bf16(TC_BM, 64, false, true);      // dV/dK[128 x 64dh] += A(TMEM)[128 x q] . B (MN-major)
       int g = 0;
-      auto issue_s = [&](int h, int j, int gg) {
+      auto issue_s = [&](int h, int j, int gg, int hf) {
         const int st = gg & 1;
-        if (j == 0) mbar_wait(&kvt_full[h & 1], (h >> 1) & 1);
-        mbar_wait(&qb_full[st], (gg >> 1) & 1);
+        if (hf == 0) {   // half A exists in every block: it carries the waits for the block's operands
+          if (j == 0) mbar_wait(&kvt_full[h & 1], (h >> 1) & 1);
+          mbar_wait(&qb_full[st], (gg >> 1) & 1);
+        }
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + (h & 1) * TC_TILE_BYTES), v_addr = smem_u32(sV + (h & 1) * TC_TILE_BYTES);
-        const uint32_t q_addr = smem_u32(sQ + st * BW_BLK_BYTES), do_addr = smem_u32(sdO + st * BW_BLK_BYTES);
+        const uint32_t q_addr = smem_u32(sQ + st * BW_BLK_BYTES) + hf * 4096, do_addr = smem_u32(sdO + st * BW_BLK_BYTES) + hf * 4096;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + KV_ST, umma_smem_desc(k_addr + k * 32, 16, 1024), umma_smem_desc(q_addr + k * 32, 16, 1024), idesc_s, k > 0);
+          umma_bf16(tmem + KV_ST + hf * 32, umma_smem_desc(k_addr + k * 32, 16, 1024), umma_smem_desc(q_addr + k * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + KV_DPT, umma_smem_desc(v_addr + k * 32, 16, 1024), umma_smem_desc(do_addr + k * 32, 16, 1024), idesc_s, k > 0);
-        umma_commit(s_full);
+          umma_bf16(tmem + KV_DPT + hf * 32, umma_smem_desc(v_addr + k * 32, 16, 1024), umma_smem_desc(do_addr + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(&s_full[hf]);
       };
-      if (qb.nb > 0) issue_s(0, 0, 0);
+      int used0 = 0, used1 = 0;   // completed waits on ds_full[0] / ds_full[1]
+      if (qb.nb > 0) {
+        int tok, nvalid; int64_t row;
+        qb.get(0, tok, row, nvalid);
+        issue_s(0, 0, 0, 0);
+        if (nvalid > 32) issue_s(0, 0, 0, 1);
+      }
       for (int h = 0; h < p.H; ++h) {
         for (int j = 0; j < qb.nb; ++j, ++g) {
           const int st = g & 1;
-          int tok, nvalid; int64_t row;
+          int tok, nvalid, nvalid_next = 0; int64_t row;
           qb.get(j, tok, row, nvalid);
-          mbar_wait(ds_full, g & 1);
-          if (j == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);
-          tc_fence_after();
+          const int hn = (j + 1 < qb.nb) ? h : h + 1, jn = (j + 1 < qb.nb) ? j + 1 : 0;
+          const bool has_next = hn < p.H;
+          if (has_next) qb.get(jn, tok, row, nvalid_next);
           const uint32_t q_addr = smem_u32(sQ + st * BW_BLK_BYTES), do_addr = smem_u32(sdO + st * BW_BLK_BYTES);
-          const int ksteps = (nvalid + 15) >> 4;
-          for (int k = 0; k < ksteps; ++k)   // dV += P^T . dO
-            umma_bf16_ts(tmem + KV_DV, tmem + KV_ST + k * 8, umma_smem_desc(do_addr + k * 2048, 8192, 1024), idesc_acc, (j > 0) || (k > 0));
-          for (int k = 0; k < ksteps; ++k)   // dK += dS^T . Q
-            umma_bf16_ts(tmem + KV_DK, tmem + KV_DPT + k * 8, umma_smem_desc(q_addr + k * 2048, 8192, 1024), idesc_acc, (j > 0) || (k > 0));
-          umma_commit(&qb_empty[st]);
-          if (j + 1 < qb.nb) {
-            issue_s(h, j + 1, g + 1);
-          } else {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int nvh = min(32, nvalid - 32 * hf);
+            if (nvh > 0) {
+              if (hf == 0) { mbar_wait(&ds_full[0], used0 & 1); ++used0; } else { mbar_wait(&ds_full[1], used1 & 1); ++used1; }
+              if (j == 0 && hf == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);   // previous head's dV / dK have been read out
+              tc_fence_after();
+              const int ksteps = (nvh + 15) >> 4;
+              for (int k = 0; k < ksteps; ++k)   // dV += P^T . dO
+                umma_bf16_ts(tmem + KV_DV, tmem + KV_ST + hf * 32 + k * 8, umma_smem_desc(do_addr + (2 * hf + k) * 2048, 8192, 1024),
+                             idesc_acc, (j > 0) || (hf > 0) || (k > 0));
+              for (int k = 0; k < ksteps; ++k)   // dK += dS^T . Q
+                umma_bf16_ts(tmem + KV_DK, tmem + KV_DPT + hf * 32 + k * 8, umma_smem_desc(q_addr + (2 * hf + k) * 2048, 8192, 1024),
+                             idesc_acc, (j > 0) || (hf > 0) || (k > 0));
+            }
+            if (hf == 1) umma_commit(&qb_empty[st]);   // every MMA reading this Q / dO stage has been issued
+            if (has_next && nvalid_next > 32 * hf) issue_s(hn, jn, g + 1, hf);   // its columns are free: in-order tensor pipe
+          }
+          if (j + 1 == qb.nb) {
             umma_commit(acc_full);
             umma_commit(&kvt_empty[h & 1]);
-            if (h + 1 < p.H) issue_s(h + 1, 0, g + 1);
           }
         }
       }
@@ -900,6 +929,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
     const bool key_ok = c0 + row_in_tile < c1;
     uint32_t rs[32], rd[32];
     int g = 0;
+    int used0 = 0, used1 = 0;   // completed waits on s_full[0] / s_full[1]
 #ifdef MMF_ATTN_CLOCKS
     const bool dbg_on = (b == 3) && (c0 == 0) && warp == 2 && lane == 0;   // first modality key tile of sample 3
     if (dbg_on) g_attn_clk[15] = (unsigned long long)qb.nb * p.H;
@@ -939,13 +969,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         const bool stage_next = tid128 < BW_BLK && hn < p.H;
         if (stage_next) fetch(hn, jn);
         CLK(5, 0);
-        mbar_wait(s_full, g & 1);
-        tc_fence_after();
-        CLK(0, 0);
         const float* ls = s_lse + st * BW_BLK;
         const float* dl = s_dl + st * BW_BLK;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 2; ++c) {   // the block's two 32-query halves (see the MMA warp)
+          if (nvalid <= 32 * c) continue;
+          if (c == 0) { mbar_wait(&s_full[0], used0 & 1); ++used0; } else { mbar_wait(&s_full[1], used1 & 1); ++used1; }
+          tc_fence_after();
+          CLK(0, 0);
           tmem_ld_32x32(lane_addr + KV_ST + c * 32, rs);
           tmem_ld_32x32(lane_addr + KV_DPT + c * 32, rd);
           tmem_wait_ld();
@@ -962,15 +993,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
             dk_[2 * t] = pack_bf16(p0 * (__uint_as_float(rd[4 * t]) - d4.x), p1 * (__uint_as_float(rd[4 * t + 1]) - d4.y));
             dk_[2 * t + 1] = pack_bf16(p2 * (__uint_as_float(rd[4 * t + 2]) - d4.z), p3 * (__uint_as_float(rd[4 * t + 3]) - d4.w));
           }
-          tmem_st_32x16(lane_addr + KV_ST + c * 16, pk);     // P^T over consumed S^T columns
-          tmem_st_32x16(lane_addr + KV_DPT + c * 16, dk_);   // dS^T over consumed dP^T columns
+          tmem_st_32x16(lane_addr + KV_ST + c * 32, pk);     // P^T in place over the half's consumed S^T columns
+          tmem_st_32x16(lane_addr + KV_DPT + c * 32, dk_);   // dS^T in place over its dP^T columns
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ds_full[c]);
+          CLK(1, 0);
         }
         CLK(2, 0);
         if (stage_next) stage(st ^ 1);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ds_full);
         CLK(3, 0);
       }
       if (qb.nb == 0) continue;

@@ -23,7 +23,7 @@ buf = (C.c_ulonglong * 16)()
 raw.mmf_debug_attn_clocks(buf, 1)
 f(); torch.cuda.synchronize()
 raw.mmf_debug_attn_clocks(buf, 0)
-names = ["wait s_full", "-", "ld + exp + pack + st", "wait_st + arrive", "loop top + stage lse/delta (global loads)", "bar.sync", "head epilogue (+wait acc)"]
+names = ["wait s_full (both halves)", "ld + exp + pack + st + arrive (both halves)", "-", "stage next lse/delta", "loop top", "bar.sync + issue next lse/delta loads", "head epilogue (+wait acc)"]
 tot = sum(buf[i] for i in range(7))
 its = max(int(buf[15]), 1)
 print("one modality key-tile CTA of dK/dV, heads x query blocks = %d iterations; total cycles" % its, tot)
