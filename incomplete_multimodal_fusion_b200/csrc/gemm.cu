@@ -462,26 +462,6 @@ struct G2Cfg {
   static constexpr int SMEM_BYTES = STAGES * G2_STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
 
-// Packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two elements per issue slot.  The GEGLU backward below is
-// paced by the epilogue warps' instruction issue, not by the MMAs or HBM, so its polynomial work runs on pairs.
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-#define F2C(c) f2_pack((c), (c))
-
 // (gelu(g0) * v0, gelu(g1) * v1): gelu_fast (common.cuh) on a pair, polynomial and products as packed fp32x2
 __device__ __forceinline__ void geglu_fwd_pair(float& v0, float& v1, float g0, float g1) {
   float t0, t1;

@@ -176,7 +176,9 @@ struct LnBwdParams {
 // issue at 24 warps per SM; no pipe above 50 %): a warp has nothing in flight while it does a row's ~1300 instructions.
 // With PF the NEXT row's x and dy are requested before the current row's arithmetic starts (NC float4 + NC uint2 more
 // live registers: 2 CTAs per SM instead of 3), and the residual-branch gradient is fetched in one batch ahead of the
-// first LayerNorm's reductions instead of chunk by chunk behind the dx stores.
+// first LayerNorm's reductions instead of chunk by chunk behind the dx stores.  Tried and dropped: two rows per warp
+// (spills, 0.42 ms) and packed fp32x2 row arithmetic (the pair packing moves cost more than the FFMA2s save: 0.41 ms
+// against 0.33 ms for this form at the cfg-2 shape).
 template <int NC, bool PF, bool FULL>
 __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) ln_bwd_kernel(const LnBwdParams p) {
   constexpr int LN_MAX_CHUNKS = NC;
