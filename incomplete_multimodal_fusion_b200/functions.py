@@ -553,16 +553,28 @@ class _ZeroArena:
         return v
 
 
-def _layer_hook(meta, grads, slots):
+def _layer_hook(meta, grads, slots, arena=None):
     """hand one encoder layer's parameter gradients to the data-parallel reducer while the backward continues
-    (training.GradAllReduce.reduce_now); the hook returns the tensors autograd should install instead"""
-    hook = meta.get("grad_hook")
-    if hook is None:
+    (training.GradAllReduce).  Gradients that live in the layer's zero arena are reduced IN PLACE as one contiguous
+    buffer (`grad_hook_inplace`: no packing copy); anything else goes through `grad_hook`, which returns the tensors
+    autograd should install instead."""
+    hook, inplace = meta.get("grad_hook"), meta.get("grad_hook_inplace")
+    if hook is None and inplace is None:
         return
     slots = [j for j in slots if grads[j] is not None]
-    out = hook([grads[j].contiguous() for j in slots])
-    for j, g in zip(slots, out):
-        grads[j] = g
+    rest = slots
+    if inplace is not None and arena is not None and arena.off > 0:
+        lo = arena.buf.data_ptr()
+        hi = lo + arena.off * 4
+        inside = [j for j in slots if grads[j].is_contiguous() and lo <= grads[j].data_ptr() and
+                  grads[j].data_ptr() + grads[j].numel() * 4 <= hi]
+        if inside:
+            inplace(arena.buf[:arena.off], [grads[j] for j in inside])
+            rest = [j for j in slots if j not in set(inside)]
+    if rest and hook is not None:
+        out = hook([grads[j].contiguous() for j in rest])
+        for j, g in zip(rest, out):
+            grads[j] = g
 
 
 class EncoderStackFn(torch.autograd.Function):
@@ -733,7 +745,7 @@ class EncoderStackFn(torch.autograd.Function):
             grads[zo], grads[zo + 1] = dn1, dan
             if not fusion:
                 dX, dXb_next = dZ, dZb
-                _layer_hook(meta, grads, range(zo, zo + ZB))
+                _layer_hook(meta, grads, range(zo, zo + ZB), arena)
                 continue
             # ---------------- fusion block backward (upstream: dZ[Mh:] = grad wrt Xf2) ----------------
             fo = base + i * per_layer
@@ -777,7 +789,7 @@ class EncoderStackFn(torch.autograd.Function):
             K.layernorm_bwd(dhk, X, fn1, rec["stA"], dXin, dfn1, g2=fan, dres=dZ, dx_bf16=dXb_next, dg2=dfan)
             grads[fo], grads[fo + 1] = dfn1, dfan
             dX = dXin
-            _layer_hook(meta, grads, range(fo, fo + 2 * ZB))
+            _layer_hook(meta, grads, range(fo, fo + 2 * ZB), arena)
         if fusion:
             grads[0] = dme.view(1, Fn, D)
         ctx.saved = None

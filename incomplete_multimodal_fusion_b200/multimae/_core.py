@@ -265,7 +265,8 @@ class MultiMAEBase(nn.Module):
                 slotmap[m, ix.long()] = torch.arange(ix.numel(), dtype=torch.int32, device=device)
         meta = dict(B=B, D=D, H=Hh, F=n_tail, nenc=nenc, fusion=self.FUSION_BLOCKS, depth=self.depth,
                     I=int(D * self.ff_mult * 2 / 3), seg=zmask.seg, nseg=zmask.nseg, slotmap=slotmap,
-                    grad_hook=getattr(self, 'grad_hook', None))
+                    grad_hook=getattr(self, 'grad_hook', None),
+                    grad_hook_inplace=getattr(self, 'grad_hook_inplace', None))
         params = []
         if self.FUSION_BLOCKS:
             params.append(self.mask_embedding)

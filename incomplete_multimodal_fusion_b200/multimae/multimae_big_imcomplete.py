@@ -115,7 +115,7 @@ class ViTBaseline(MultiMAE):
         X = Fn.EmbedFn.apply(meta_e, self.fusion_tokens, *mod_args)
         meta = dict(B=B, D=D, H=Hh, F=Fn_tok, nenc=nenc, fusion=True, depth=self.depth, I=int(D * self.ff_mult * 2 / 3),
                     seg=zmask.seg, nseg=zmask.nseg, slotmap=slotmap.contiguous(), grad_hook=getattr(self, 'grad_hook', None),
-                    taps=list(self.flags))
+                    grad_hook_inplace=getattr(self, 'grad_hook_inplace', None), taps=list(self.flags))
         params = [self.mask_embedding]
         for fus, blk in zip(self.fus_blocks, self.blocks):
             params += block_params(fus) + block_params(blk)

@@ -111,6 +111,24 @@ class GradAllReduce:
         self._reduced.update(v.data_ptr() for v in views)
         return views
 
+    def reduce_inplace(self, flat: torch.Tensor, views: List[torch.Tensor]):
+        """all-reduce a contiguous buffer that already holds gradients (the encoder backward's per-layer zero arena;
+        `views` are the parameter gradients inside it): no packing copy, the views stay the `.grad`s"""
+        if not self.enabled() or flat.numel() == 0:
+            return
+        if flat.device.type != "cuda":
+            dist.all_reduce(flat, group=self.group)
+        else:
+            if self.stream is None:
+                self.stream = torch.cuda.Stream()
+            ready = torch.cuda.Event()
+            ready.record()
+            self._keep.append(flat)      # alive until finish() has joined the side stream
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ready)
+                dist.all_reduce(flat, group=self.group)
+        self._reduced.update(v.data_ptr() for v in views)
+
     def finish(self):
         """call after backward(): reduces the remaining gradients; returns with every reduction visible to the current stream"""
         if self.enabled():
@@ -153,6 +171,7 @@ class PretrainStep:
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         if self.world > 1:
             model.grad_hook = self.reducer.reduce_now   # per-layer reduction from inside the encoder backward
+            model.grad_hook_inplace = self.reducer.reduce_inplace
 
     def loss(self, out, targets):
         preds, masks = out[0], out[1]

@@ -33,6 +33,14 @@ def _worker(rank, world, port, out):
         got = red.reduce_now(layer)
         assert torch.allclose(got[0], torch.full((3, 4), float(sum(r + step for r in range(world)))))
         assert torch.allclose(got[1], torch.full((5,), float(sum(10 * r + step for r in range(world)))))
+        # ... or, when they already sit in one contiguous buffer (the backward's per-layer arena), in place
+        flat = torch.zeros(40)
+        va, vb = flat[:12].view(3, 4), flat[16:21]
+        va.fill_(float(rank + 1)); vb.fill_(float(2 * rank + step))
+        red.reduce_inplace(flat[:24], [va, vb])
+        assert torch.allclose(va, torch.full((3, 4), float(sum(r + 1 for r in range(world)))))
+        assert torch.allclose(vb, torch.full((5,), float(sum(2 * r + step for r in range(world)))))
+        assert float(flat[24:].abs().sum()) == 0.0 and va.data_ptr() in red._reduced
         params[1].grad = got[1][:7] if got[1].numel() >= 7 else torch.full_like(params[1], 1.0 + rank)
         # ... the remaining parameters at the end
         for i in (0, 2, 3):
