@@ -101,6 +101,107 @@ __global__ void masked_loss_bwd_kernel(const TP* __restrict__ pred, const float*
   (void)F;
 }
 
+// Vectorised form for patch widths that are multiples of 8 (every configuration of the reference: P = 16): a thread
+// owns 8 consecutive pixels of one patch row (16-byte bf16 / 2 x 16-byte fp32 loads), a warp owns 32 such pieces of the
+// same sample; only pieces of MASKED patches are read.  work[] as in the scalar kernel.
+template <typename TP>
+__global__ void __launch_bounds__(256) masked_loss_fwd_vec_kernel(const TP* __restrict__ pred, const float* __restrict__ target,
+                                                                  const int64_t* __restrict__ mask, int64_t mask_bstride, int C, int H,
+                                                                  int W, int P, int kind, float* __restrict__ work, int64_t B) {
+  const int b = blockIdx.y;
+  const int nw = W / P, W8 = W >> 3, P8 = P >> 3;
+  const int pieces = C * H * W8;                      // 8-pixel pieces of this sample
+  float acc = 0.f;
+  int cnt = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pieces; i += gridDim.x * blockDim.x) {
+    const int x8 = i % W8, y = (i / W8) % H, c = i / (W8 * H);
+    const int patch = (y / P) * nw + x8 / P8;
+    if (mask != nullptr && mask[b * mask_bstride + patch] == 0) continue;
+    const int64_t off = (((int64_t)b * C + c) * H + y) * W + x8 * 8;
+    float pv[8];
+    if (sizeof(TP) == 2) {
+      const uint4 u = *reinterpret_cast<const uint4*>(pred + off);
+      const uint32_t* pu = &u.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16(pu[k]); pv[2 * k] = f.x; pv[2 * k + 1] = f.y; }
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(pred + off), bq = *reinterpret_cast<const float4*>(pred + off + 4);
+      pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; pv[4] = bq.x; pv[5] = bq.y; pv[6] = bq.z; pv[7] = bq.w;
+    }
+    const float4 t0 = *reinterpret_cast<const float4*>(target + off), t1 = *reinterpret_cast<const float4*>(target + off + 4);
+    const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float d = pv[k] - tv[k];
+      acc += kind == 0 ? d * d : fabsf(d);
+    }
+    if (c == 0) cnt += 8;
+  }
+  __shared__ float red[2][8];
+  acc = warp_sum(acc);
+  float fc = warp_sum((float)cnt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = acc; red[1][warp] = fc; }
+  __syncthreads();
+  if (warp == 0) {
+    acc = lane < 8 ? red[0][lane] : 0.f;
+    fc = lane < 8 ? red[1][lane] : 0.f;
+    acc = warp_sum(acc);
+    fc = warp_sum(fc);
+    if (lane == 0) {
+      if (acc != 0.f) atomicAdd(work + b, acc / (float)C);
+      if (fc != 0.f) atomicAdd(work + B + b, fc);
+    }
+  }
+}
+
+template <typename TP>
+__global__ void __launch_bounds__(256) masked_loss_bwd_vec_kernel(const TP* __restrict__ pred, const float* __restrict__ target,
+                                                                  const int64_t* __restrict__ mask, int64_t mask_bstride, int C, int H,
+                                                                  int W, int P, int kind, const float* __restrict__ work, int64_t B,
+                                                                  const float* __restrict__ dloss, TP* __restrict__ dpred) {
+  const int b = blockIdx.y;
+  const int nw = W / P, W8 = W >> 3, P8 = P >> 3;
+  const int pieces = C * H * W8;
+  const float g = dloss[0], nvalid = work[2 * B], cntb = work[B + b];
+  const float coef_m = (cntb > 0.f && nvalid > 0.f) ? g / (nvalid * cntb * (float)C) : 0.f;
+  const float coef_u = g / ((float)B * (float)C * (float)H * (float)W);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pieces; i += gridDim.x * blockDim.x) {
+    const int x8 = i % W8, y = (i / W8) % H, c = i / (W8 * H);
+    float coef = coef_u;
+    if (mask != nullptr) coef = mask[b * mask_bstride + (y / P) * nw + x8 / P8] != 0 ? coef_m : 0.f;
+    const int64_t off = (((int64_t)b * C + c) * H + y) * W + x8 * 8;
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    if (coef != 0.f) {
+      float pv[8];
+      if (sizeof(TP) == 2) {
+        const uint4 u = *reinterpret_cast<const uint4*>(pred + off);
+        const uint32_t* pu = &u.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16(pu[k]); pv[2 * k] = f.x; pv[2 * k + 1] = f.y; }
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(pred + off), bq = *reinterpret_cast<const float4*>(pred + off + 4);
+        pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; pv[4] = bq.x; pv[5] = bq.y; pv[6] = bq.z; pv[7] = bq.w;
+      }
+      const float4 t0 = *reinterpret_cast<const float4*>(target + off), t1 = *reinterpret_cast<const float4*>(target + off + 4);
+      const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = pv[k] - tv[k];
+        o[k] = kind == 0 ? 2.f * d * coef : (d > 0.f ? coef : (d < 0.f ? -coef : 0.f));
+      }
+    }
+    if (sizeof(TP) == 2) {
+      *reinterpret_cast<uint4*>(dpred + off) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    } else {
+      *reinterpret_cast<float4*>(dpred + off) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dpred + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
 }  // namespace mmf
 
 using namespace mmf;
@@ -119,7 +220,18 @@ extern "C" int mmf_masked_loss_fwd(const void* pred, int32_t pred_f32, const flo
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 grid(gx, (unsigned)B);
-  if (pred_f32) masked_loss_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B);
+  const bool vec = (P % 8 == 0) && (W % 8 == 0) && (reinterpret_cast<uintptr_t>(pred) % 16 == 0) && (reinterpret_cast<uintptr_t>(target) % 16 == 0);
+  if (vec) {
+    const int64_t pieces = (int64_t)C * H * (W / 8);
+    if (pieces > INT32_MAX) MMF_BAD_ARG(3);
+    int vx = (int)ceil_div64(pieces, 256 * 4);
+    const int vcap = (int)ceil_div64(148 * 16, B);
+    if (vx > vcap) vx = vcap;
+    if (vx < 1) vx = 1;
+    dim3 vgrid(vx, (unsigned)B);
+    if (pred_f32) masked_loss_fwd_vec_kernel<float><<<vgrid, 256, 0, st>>>((const float*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B);
+    else masked_loss_fwd_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B);
+  } else if (pred_f32) masked_loss_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B);
   else masked_loss_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B);
   // without a mask the mean is over B*C*H*W: per-sample sums were divided by C already
   masked_loss_finalize_kernel<<<1, 32, 0, st>>>(work, B, mask != nullptr, (float)H * (float)W, loss);
@@ -137,7 +249,19 @@ extern "C" int mmf_masked_loss_bwd(const void* pred, int32_t pred_f32, const flo
   const int64_t total = B * C * H * W;
   int64_t g = ceil_div64(total, 256);
   if (g > 148 * 16) g = 148 * 16;
-  if (pred_f32) masked_loss_bwd_kernel<float><<<(int)g, 256, 0, st>>>((const float*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B, dloss, (float*)dpred);
+  const bool vec = (P % 8 == 0) && (W % 8 == 0) && B <= 65535 && (reinterpret_cast<uintptr_t>(pred) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(target) % 16 == 0) && (reinterpret_cast<uintptr_t>(dpred) % 16 == 0) &&
+                   (int64_t)C * H * (W / 8) <= INT32_MAX;
+  if (vec) {
+    const int64_t pieces = (int64_t)C * H * (W / 8);
+    int vx = (int)ceil_div64(pieces, 256 * 4);
+    const int vcap = (int)ceil_div64(148 * 16, B);
+    if (vx > vcap) vx = vcap;
+    if (vx < 1) vx = 1;
+    dim3 vgrid(vx, (unsigned)B);
+    if (pred_f32) masked_loss_bwd_vec_kernel<float><<<vgrid, 256, 0, st>>>((const float*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B, dloss, (float*)dpred);
+    else masked_loss_bwd_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B, dloss, (__nv_bfloat16*)dpred);
+  } else if (pred_f32) masked_loss_bwd_kernel<float><<<(int)g, 256, 0, st>>>((const float*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B, dloss, (float*)dpred);
   else masked_loss_bwd_kernel<__nv_bfloat16><<<(int)g, 256, 0, st>>>((const __nv_bfloat16*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B, dloss, (__nv_bfloat16*)dpred);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();

@@ -339,12 +339,13 @@ def test_pool_attention_fwd_bwd_uniform_rows():
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", [0, 1])
 @pytest.mark.parametrize("pdt", [bf16, f32])
-def test_masked_loss(kind, pdt):
+@pytest.mark.parametrize("P", [8, 4, 16])       # 8 / 16: the vectorised kernels (8 pixels per thread); 4: the scalar ones
+def test_masked_loss(kind, pdt, P):
     import oracle
-    B, Cc, H, W, P = 5, 3, 32, 32, 8
+    B, Cc, H, W = 5, 3, 32, 32
     pred = rnd(B, Cc, H, W, dtype=pdt, seed=1).requires_grad_(True)
     tgt = rnd(B, Cc, H, W, seed=2)
-    mask = (torch.rand(B, 16, device="cuda") > 0.5).long()
+    mask = (torch.rand(B, (H // P) * (W // P), device="cuda") > 0.5).long()
     mask[1] = 0                                      # nanmean path
     fn = oracle.masked_mse_loss if kind == 0 else oracle.masked_l1_loss
     for m in (mask, None, torch.zeros_like(mask)):
