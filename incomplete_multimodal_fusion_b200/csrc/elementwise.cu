@@ -101,6 +101,39 @@ __global__ void colsum_kernel(const T* __restrict__ x, int64_t rows, int cols, i
   }
 }
 
+// bf16 rows, cols % 256 == 0: a thread owns 8 adjacent columns (16-byte loads), 32 column-threads x 8 row-lanes per CTA,
+// four rows in flight per thread; the row-lanes are combined in shared memory before one atomic per column
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int64_t ld,
+                                                         float* __restrict__ out, int rows_per_cta) {
+  const int tcol = threadIdx.x & 31, trow = threadIdx.x >> 5;
+  const int64_t col = ((int64_t)blockIdx.x * 32 + tcol) * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  auto add8 = [&](const uint4& u) {
+    const uint32_t* pu = &u.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16(pu[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+  };
+  int64_t r = r0 + trow;
+  for (; r + 24 < r1; r += 32) {
+    const uint4 a = *reinterpret_cast<const uint4*>(x + r * ld + col), b = *reinterpret_cast<const uint4*>(x + (r + 8) * ld + col),
+                c = *reinterpret_cast<const uint4*>(x + (r + 16) * ld + col), d = *reinterpret_cast<const uint4*>(x + (r + 24) * ld + col);
+    add8(a); add8(b); add8(c); add8(d);
+  }
+  for (; r < r1; r += 8) add8(*reinterpret_cast<const uint4*>(x + r * ld + col));
+  __shared__ float red[8][32][9];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[trow][tcol][k] = acc[k];
+  __syncthreads();
+  const int c = threadIdx.x;   // 256 columns of this CTA, one per thread
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) s += red[t][c >> 3][c & 7];
+  atomicAdd(out + (int64_t)blockIdx.x * 256 + c, s);
+}
+
 // ------------------------------------------------------------------------------------------------
 // out[b, r, :] (f32, batch stride) = src[r, :]   -- batch-invariant rows (fusion tokens + pos-emb)
 // and its backward: dsrc[r, :] = sum_b dout[b, r, :]
@@ -268,6 +301,17 @@ extern "C" int mmf_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t
 extern "C" int mmf_colsum(const void* x, int32_t x_f32, int64_t rows, int64_t cols, int64_t ld, float* out, mmf_stream_t stream) {
   if (!x || !out) MMF_BAD_ARG(1);
   if (rows * cols == 0) return 0;
+  if (!x_f32 && cols % 256 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int gxv = (int)(cols / 256);
+    int gyv = (int)ceil_div64(148 * 4, gxv);
+    if (gyv > rows / 32) gyv = (int)(rows / 32 > 0 ? rows / 32 : 1);
+    const int rpc = (int)ceil_div64(rows, gyv);
+    gyv = (int)ceil_div64(rows, rpc);
+    colsum_vec_kernel<<<dim3(gxv, gyv), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, ld, out, rpc);
+    MMF_COUNT_LAUNCH();
+    MMF_LAUNCH_CHECK();
+    return 0;
+  }
   const int threads = 128;
   const int gx = (int)ceil_div64(cols, threads);
   int gy = (int)ceil_div64(148 * 8, gx);

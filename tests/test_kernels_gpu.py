@@ -395,6 +395,11 @@ def test_elementwise():
     out = torch.zeros(200, device="cuda")
     k.colsum(x, out)
     assert rel(out, x.float().sum(0)) < 1e-5
+    for rows, cols in ((5001, 256), (777, 768), (31, 1024), (50176, 256)):   # the vectorised kernel (cols % 256 == 0)
+        x = rnd(rows, cols, dtype=bf16, seed=8)
+        out = torch.zeros(cols, device="cuda")
+        k.colsum(x, out)
+        assert rel(out, x.float().sum(0)) < 1e-5, (rows, cols)
     # bcast / reduce
     src = rnd(10, 64, seed=7)
     dst = torch.zeros(4, 25, 64, device="cuda")
