@@ -374,18 +374,53 @@ __global__ void pool_attn_fwd_kernel(const PoolParams p) {
   }
   sum = warp_sum(sum);
   __syncwarp();
+  // weighted sum of the values: lane-per-key like the score pass (each lane accumulates all 64 dims over its keys: N/32
+  // independent 128-byte row reads instead of N dependent 4-byte ones), then a transposing reduction: after the
+  // butterfly lane l holds dims 2l, 2l+1
   float2 o = make_float2(0.f, 0.f);
   if (sum > 0.f) {
-    for (int j = 0; j < p.N; ++j) {
+    float acc[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) acc[d] = 0.f;
+    for (int j = lane; j < p.N; j += 32) {
       const float w = sc[j];
-      if (w != 0.f) {
-        const int64_t row = j < p.n_head ? (int64_t)b * p.n_head + j : head_rows + (int64_t)b * p.n_tail + (j - p.n_head);
-        const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.kv + row * p.ldkv + HD + h * 64 + 2 * lane));
-        o.x += w * v.x; o.y += w * v.y;
+      if (w == 0.f) continue;
+      const int64_t row = j < p.n_head ? (int64_t)b * p.n_head + j : head_rows + (int64_t)b * p.n_tail + (j - p.n_head);
+      const __nv_bfloat16* vr = p.kv + row * p.ldkv + HD + h * 64;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(vr + c * 8);
+        const uint32_t* pu = &u.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16(pu[k]);
+          acc[c * 8 + 2 * k] += w * f.x; acc[c * 8 + 2 * k + 1] += w * f.y;
+        }
       }
     }
+    // reduce-scatter over the warp: at step s (16, 8, 4, 2, 1) a lane keeps the half of its remaining dims selected
+    // by bit s of its lane id and receives the partner's partial sums for that half
+    float buf[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+      const bool hi = (lane & 16) != 0;
+      const float send = hi ? acc[d] : acc[d + 32], keep = hi ? acc[d + 32] : acc[d];
+      buf[d] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int s = 8, n = 16; s >= 1; s >>= 1, n >>= 1) {
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        if (d < n) {
+          const bool hi = (lane & s) != 0;
+          const float send = hi ? buf[d] : buf[d + n], keep = hi ? buf[d + n] : buf[d];
+          buf[d] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+    }
+    // lane l now holds the two dims [32*b4 + 16*b3 + 8*b2 + 4*b1 + 2*b0 + {0, 1}] with b_i the bits of l: 2l, 2l + 1
     const float inv = 1.0f / sum;
-    o.x *= inv; o.y *= inv;
+    o.x = buf[0] * inv; o.y = buf[1] * inv;
   }
   *reinterpret_cast<uint32_t*>(p.out + ((int64_t)b * p.R + r) * HD + h * 64 + 2 * lane) = pack_bf16(o.x, o.y);
   if (lane == 0) {
@@ -398,7 +433,7 @@ __global__ void pool_attn_fwd_kernel(const PoolParams p) {
 // backward: 4 lanes per key (16 of the 64 dims each), 64 keys per 256-thread block, looping over the
 // R queries.  delta[b,r,h] = dout.out sits right after the (max,sum) pairs in `stat`.
 __global__ void __launch_bounds__(256) pool_attn_bwd_kernel(const PoolParams p) {
-  __shared__ float qs[16][64], ds_[16][64], mxs[16], sums[16], dls[16];
+  __shared__ float qs[16][64], ds_[16][64], dqs[16][64], mxs[16], sums[16], dls[16];
   const int h = blockIdx.y, b = blockIdx.z;
   const int HD = p.H * 64;
   const int tid = threadIdx.x, sub = tid & 3;
@@ -406,6 +441,7 @@ __global__ void __launch_bounds__(256) pool_attn_bwd_kernel(const PoolParams p) 
     const int r = t / 64, d = t % 64;
     qs[r][d] = __bfloat162float(p.q[b * p.q_bstride + (int64_t)r * HD + h * 64 + d]);
     ds_[r][d] = __bfloat162float(p.dout[((int64_t)b * p.R + r) * HD + h * 64 + d]);
+    dqs[r][d] = 0.f;   // dq of this CTA's 64 keys: combined in shared memory, one global atomic per (r, dim) at the end
   }
   if (tid < p.R) {
     const int64_t brh = ((int64_t)b * p.R + tid) * p.H + h;
@@ -458,9 +494,14 @@ __global__ void __launch_bounds__(256) pool_attn_bwd_kernel(const PoolParams p) 
         c += __shfl_xor_sync(0xffffffffu, c, 4);
         c += __shfl_xor_sync(0xffffffffu, c, 8);
         c += __shfl_xor_sync(0xffffffffu, c, 16);
-        if ((tid & 31) < 4 && c != 0.f) atomicAdd(p.dq + b * p.dq_bstride + (int64_t)r * HD + h * 64 + sub * 16 + d, c);
+        if ((tid & 31) < 4 && c != 0.f) atomicAdd(&dqs[r][sub * 16 + d], c);
       }
     }
+  }
+  __syncthreads();
+  for (int t = tid; t < p.R * 64; t += blockDim.x) {
+    const float c = dqs[t / 64][t % 64];
+    if (c != 0.f) atomicAdd(p.dq + b * p.dq_bstride + (int64_t)(t / 64) * HD + h * 64 + (t % 64), c);
   }
   if (valid) {
     __nv_bfloat16* ok = p.dkv + row * p.lddkv + h * 64 + sub * 16;
