@@ -28,6 +28,7 @@ from .multimae_utils import trunc_normal_
 from .zorro_utils import Attention, AttentionBiLSTM, Block, Block_Fusion, LayerNorm, Mlp, TokenTypes, ZorroMask, block_params
 
 MODALITIES = ('s1', 's2', 'dem')   # hard-coded token order of the reference (multimae.py:378-407)
+_MASK_STREAMS = {}                 # device index -> the mask sampler's side stream (see _sample_masks)
 
 
 class MultiMAEBase(nn.Module):
@@ -131,17 +132,33 @@ class MultiMAEBase(nn.Module):
         sizes = [t.shape[1] for t in input_tokens.values()]
         alphas = [alphas] * len(sizes) if isinstance(alphas, float) else alphas
         if sample_tasks_uniformly:
-            share = Dirichlet(self.sample_alphas(1, len(sizes), alphas=alphas)).sample().to(device)
+            share_cpu = Dirichlet(self.sample_alphas(1, len(sizes), alphas=alphas)).sample()
         else:
-            share = Dirichlet(torch.Tensor(alphas)).sample((1,)).to(device)
-        noise1 = torch.cat([torch.rand(1, n, device=device) for n in sizes], dim=1)
-        noise2 = torch.rand_like(noise1)
+            share_cpu = Dirichlet(torch.Tensor(alphas)).sample((1,))
         Fn_tok = self.fusion_tokens.shape[1]
         want_slot = self.FUSION_BLOCKS and all(n == Fn_tok for n in sizes)
-        mask, ids_restore, ids_keep, idx, counts, seg, slotmap = K.mask_build(
-            noise1.view(-1), noise2.view(-1), share.float().view(-1).contiguous(), sizes, num_encoded_tokens, Fn_tok, want_slot)
+        # The draws and the mask builder run on their own (high-priority) stream: the per-modality token counts are the
+        # one thing the host has to read back per step, and read on the main stream that copy would wait for everything
+        # still queued there -- the whole previous step -- and leave the GPU idle until the host has queued new work.
+        # The mask depends on the random draws only (whose Philox offsets are assigned in host call order, whatever the
+        # stream), so the values are unchanged.
+        main = torch.cuda.current_stream(device)
+        side = _MASK_STREAMS.get(device.index)
+        if side is None:
+            side = _MASK_STREAMS[device.index] = torch.cuda.Stream(device=device, priority=-1)
+        with torch.cuda.stream(side):
+            share = share_cpu.to(device)
+            noise1 = torch.cat([torch.rand(1, n, device=device) for n in sizes], dim=1)
+            noise2 = torch.rand_like(noise1)
+            mask, ids_restore, ids_keep, idx, counts, seg, slotmap = K.mask_build(
+                noise1.view(-1), noise2.view(-1), share.float().view(-1).contiguous(), sizes, num_encoded_tokens, Fn_tok, want_slot)
+            counts_host = counts.tolist()          # synchronises the side stream only
+        main.wait_stream(side)
+        for t in (mask, ids_restore, ids_keep, idx, counts, seg, slotmap):
+            if t is not None:
+                t.record_stream(main)
         return dict(tasks=list(input_tokens.keys()), sizes=sizes, B=B, mask=mask, ids_restore=ids_restore, ids_keep=ids_keep,
-                    idx=idx, counts=counts, seg=seg, slotmap=slotmap)
+                    idx=idx, counts=counts, counts_host=counts_host, seg=seg, slotmap=slotmap)
 
     def generate_random_masks(self, input_tokens: Dict[str, torch.Tensor], num_encoded_tokens: int,
                               alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False):
@@ -214,7 +231,7 @@ class MultiMAEBase(nn.Module):
         if task_masks is None:
             r = self._sample_masks(carriers, nenc, alphas=alphas, sample_tasks_uniformly=sample_tasks_uniformly)
             task_masks, ids_keep, ids_restore = self._public_masks(r)
-            cnt = r["counts"].tolist()                                  # the one host sync of the step: token counts
+            cnt = r["counts_host"]                                      # the one host read-back of the step: token counts
             off = [0]
             for n in r["sizes"]:
                 off.append(off[-1] + n)

@@ -90,7 +90,7 @@ class ViTBaseline(MultiMAE):
             nenc = int(total * 0.9) if self.training else total          # (:576-580)
         if task_masks is None:
             r = self._sample_masks(carriers, nenc, alphas=alphas, sample_tasks_uniformly=sample_tasks_uniformly)
-            cnt = r["counts"].tolist()
+            cnt = r["counts_host"]
             off = [0]
             for n in r["sizes"]:
                 off.append(off[-1] + n)
