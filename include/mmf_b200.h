@@ -250,6 +250,19 @@ int mmf_dino_loss(const void* student, int64_t lds, const void* teacher, int64_t
                   float student_temp, float teacher_temp, float* row_loss, float* dstudent, mmf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Masked cross-entropy over class maps (criterion.py:24-58 MaskedCrossEntropyLoss with label_smoothing = 0; the loss of
+ * the 4th, semantic, modality `dnw` in pretrain_mmae_my.py:68-75).  logits [B, C, H, W] (bf16 or f32),
+ * target [B, H, W] int64 class ids, mask [B, (H/P)*(W/P)] int64 (1 = masked patch, counted) or NULL.  Per pixel
+ * logsumexp_c - logit[target]; per sample sum / #masked pixels; batch nanmean; all-zero mask -> 0.  P and W must be
+ * multiples of 8.  work: f32 [2B + 2] scratch shared by forward and backward (as for the reconstruction losses).
+ * ---------------------------------------------------------------------------------------------- */
+int mmf_masked_ce_fwd(const void* logits, int32_t logits_f32, const int64_t* target, const int64_t* mask, int64_t mask_bstride,
+                      int64_t B, int32_t C, int32_t H, int32_t W, int32_t P, float* work, float* loss, mmf_stream_t stream);
+int mmf_masked_ce_bwd(const void* logits, int32_t logits_f32, const int64_t* target, const int64_t* mask, int64_t mask_bstride,
+                      int64_t B, int32_t C, int32_t H, int32_t W, int32_t P, const float* work, const float* dloss, void* dlogits,
+                      mmf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Training step around the path: multi-tensor AdamW and gradient norm / clip coefficient.
  * Replaces torch.optim.AdamW as configured by utils/optim_factory.py:138-176 (betas (0.9, 0.95), decoupled weight
  * decay on every parameter) and the grad-norm / clip of utils/native_scaler.py:20-82 (one torch.norm per parameter).

@@ -87,6 +87,8 @@ SIGNATURES = {
     "mmf_pool_attn_bwd": [C.POINTER(PoolAttnArgs), c_vp],
     "mmf_masked_loss_fwd": [c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp],
     "mmf_masked_loss_bwd": [c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],
+    "mmf_masked_ce_fwd": [c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp],
+    "mmf_masked_ce_bwd": [c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],
     "mmf_cast_f32_bf16": [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_f32, c_vp],
     "mmf_geglu_bwd": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp],
     "mmf_gelu_bwd": [c_vp, c_vp, c_vp, c_i64, c_vp],

@@ -202,6 +202,112 @@ __global__ void __launch_bounds__(256) masked_loss_bwd_vec_kernel(const TP* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Masked cross-entropy (criterion.py:24-58 MaskedCrossEntropyLoss, label_smoothing = 0): per pixel
+// logsumexp_c(logits) - logits[target]; patch-mask weighted, per-sample normalised, batch nanmean (same work[] /
+// finalize as the reconstruction losses).  A thread owns 8 consecutive pixels and walks the C class planes.
+// ------------------------------------------------------------------------------------------------
+template <typename TP>
+__device__ __forceinline__ void ld8(const TP* p, float (&v)[8]) {
+  if (sizeof(TP) == 2) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t* pu = &u.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16(pu[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+
+template <typename TP, bool BWD>
+__global__ void __launch_bounds__(256) masked_ce_kernel(const TP* __restrict__ logits, const int64_t* __restrict__ target,
+                                                        const int64_t* __restrict__ mask, int64_t mask_bstride, int C, int H, int W,
+                                                        int P, float* __restrict__ work, int64_t B, const float* __restrict__ dloss,
+                                                        TP* __restrict__ dlogits) {
+  const int b = blockIdx.y;
+  const int nw = W / P, W8 = W >> 3, P8 = P >> 3;
+  const int pieces = H * W8;
+  const int64_t plane = (int64_t)H * W;
+  float acc = 0.f, cnt = 0.f;
+  float coef_m = 0.f, coef_u = 0.f;
+  if (BWD) {
+    const float g = dloss[0], nvalid = work[2 * B], cntb = work[B + b];
+    coef_m = (cntb > 0.f && nvalid > 0.f) ? g / (nvalid * cntb) : 0.f;
+    coef_u = g / ((float)B * (float)H * (float)W);
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pieces; i += gridDim.x * blockDim.x) {
+    const int x8 = i % W8, y = i / W8;
+    const bool on = mask == nullptr || mask[b * mask_bstride + (y / P) * nw + x8 / P8] != 0;
+    const int64_t pix = (int64_t)y * W + x8 * 8;
+    const TP* base = logits + (int64_t)b * C * plane + pix;
+    if (!on) {
+      if (BWD) {
+        for (int c = 0; c < C; ++c) {
+          if (sizeof(TP) == 2) *reinterpret_cast<uint4*>(dlogits + (int64_t)b * C * plane + c * plane + pix) = make_uint4(0, 0, 0, 0);
+          else {
+            *reinterpret_cast<float4*>(dlogits + (int64_t)b * C * plane + c * plane + pix) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dlogits + (int64_t)b * C * plane + c * plane + pix + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      continue;
+    }
+    int64_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = target[(int64_t)b * plane + pix + k];
+    float m[8], s[8], tl[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { m[k] = -INFINITY; s[k] = 0.f; tl[k] = 0.f; }
+    for (int c = 0; c < C; ++c) {
+      float v[8];
+      ld8<TP>(base + c * plane, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float mn = fmaxf(m[k], v[k]);
+        s[k] = s[k] * __expf(m[k] - mn) + __expf(v[k] - mn);
+        m[k] = mn;
+        if (t[k] == c) tl[k] = v[k];
+      }
+    }
+    if (!BWD) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += m[k] + __logf(s[k]) - tl[k];
+      cnt += 8.f;
+    } else {
+      const float coef = mask != nullptr ? coef_m : coef_u;
+      for (int c = 0; c < C; ++c) {
+        float v[8], o[8];
+        ld8<TP>(base + c * plane, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (__expf(v[k] - m[k]) / s[k] - (t[k] == c ? 1.f : 0.f)) * coef;
+        TP* dst = dlogits + (int64_t)b * C * plane + c * plane + pix;
+        if (sizeof(TP) == 2) {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        } else {
+          *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+  }
+  if (!BWD) {
+    __shared__ float red[2][8];
+    acc = warp_sum(acc);
+    cnt = warp_sum(cnt);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = acc; red[1][warp] = cnt; }
+    __syncthreads();
+    if (warp == 0) {
+      acc = lane < 8 ? red[0][lane] : 0.f;
+      cnt = lane < 8 ? red[1][lane] : 0.f;
+      acc = warp_sum(acc);
+      cnt = warp_sum(cnt);
+      if (lane == 0 && cnt != 0.f) { atomicAdd(work + b, acc); atomicAdd(work + B + b, cnt); }
+    }
+  }
+}
+
 }  // namespace mmf
 
 using namespace mmf;
@@ -263,6 +369,46 @@ extern "C" int mmf_masked_loss_bwd(const void* pred, int32_t pred_f32, const flo
     else masked_loss_bwd_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B, dloss, (__nv_bfloat16*)dpred);
   } else if (pred_f32) masked_loss_bwd_kernel<float><<<(int)g, 256, 0, st>>>((const float*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B, dloss, (float*)dpred);
   else masked_loss_bwd_kernel<__nv_bfloat16><<<(int)g, 256, 0, st>>>((const __nv_bfloat16*)pred, target, mask, mask_bstride, C, H, W, P, kind, work, B, dloss, (__nv_bfloat16*)dpred);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+static int ce_grid(int64_t pieces, int64_t B) {
+  int vx = (int)mmf::ceil_div64(pieces, 256 * 2);
+  const int vcap = (int)mmf::ceil_div64(148 * 16, B);
+  if (vx > vcap) vx = vcap;
+  return vx < 1 ? 1 : vx;
+}
+
+extern "C" int mmf_masked_ce_fwd(const void* logits, int32_t logits_f32, const int64_t* target, const int64_t* mask,
+                                 int64_t mask_bstride, int64_t B, int32_t C, int32_t H, int32_t W, int32_t P, float* work,
+                                 float* loss, mmf_stream_t stream) {
+  if (!logits || !target || !work || !loss) MMF_BAD_ARG(1);
+  if (B <= 0 || B > 65535 || C <= 0 || P <= 0 || H % P || W % P || (P & 7) || (W & 7)) MMF_BAD_ARG(2);
+  if (reinterpret_cast<uintptr_t>(logits) & 15) MMF_BAD_ARG(3);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(work, 0, (2 * B + 2) * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(ce_grid((int64_t)H * (W / 8), B), (unsigned)B);
+  if (logits_f32) masked_ce_kernel<float, false><<<grid, 256, 0, st>>>((const float*)logits, target, mask, mask_bstride, C, H, W, P, work, B, nullptr, nullptr);
+  else masked_ce_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)logits, target, mask, mask_bstride, C, H, W, P, work, B, nullptr, nullptr);
+  masked_loss_finalize_kernel<<<1, 32, 0, st>>>(work, B, mask != nullptr, (float)H * (float)W, loss);
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmf_masked_ce_bwd(const void* logits, int32_t logits_f32, const int64_t* target, const int64_t* mask,
+                                 int64_t mask_bstride, int64_t B, int32_t C, int32_t H, int32_t W, int32_t P, const float* work,
+                                 const float* dloss, void* dlogits, mmf_stream_t stream) {
+  if (!logits || !target || !work || !dloss || !dlogits) MMF_BAD_ARG(1);
+  if (B <= 0 || B > 65535 || C <= 0 || P <= 0 || H % P || W % P || (P & 7) || (W & 7)) MMF_BAD_ARG(2);
+  if ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) MMF_BAD_ARG(3);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(ce_grid((int64_t)H * (W / 8), B), (unsigned)B);
+  if (logits_f32) masked_ce_kernel<float, true><<<grid, 256, 0, st>>>((const float*)logits, target, mask, mask_bstride, C, H, W, P, const_cast<float*>(work), B, dloss, (float*)dlogits);
+  else masked_ce_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)logits, target, mask, mask_bstride, C, H, W, P, const_cast<float*>(work), B, dloss, (__nv_bfloat16*)dlogits);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
   return 0;

@@ -382,6 +382,29 @@ class MaskedLossFn(torch.autograd.Function):
         return dpred, None, None, None, None
 
 
+class MaskedCEFn(torch.autograd.Function):
+    """criterion.py:24-58 (label_smoothing 0) fused: logsumexp - target logit, patch mask, per-sample mean, batch nanmean"""
+
+    @staticmethod
+    def forward(ctx, logits, target, mask, P):
+        logits = logits.contiguous()
+        target = target.contiguous()
+        B = logits.shape[0]
+        work = torch.empty(2 * B + 2, dtype=f32, device=logits.device)
+        loss = torch.empty(1, dtype=f32, device=logits.device)
+        K.masked_ce_fwd(logits, target, mask, P, work, loss)
+        ctx.save_for_backward(logits, target, mask, work)
+        ctx.P = P
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, target, mask, work = ctx.saved_tensors
+        dlogits = torch.empty_like(logits)
+        K.masked_ce_bwd(logits, target, mask, ctx.P, work, dloss.reshape(1).to(f32).contiguous(), dlogits)
+        return dlogits, None, None, None
+
+
 class DinoLossFn(torch.autograd.Function):
     """criterion.py:328-335 fused (forward + student gradient in one launch); the teacher gets no gradient"""
 

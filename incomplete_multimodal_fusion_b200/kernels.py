@@ -274,6 +274,23 @@ def masked_loss_bwd(pred, target, mask, P, kind, work, dloss, dpred):
                                    _p(dloss), _p(dpred), _stream()), "mmf_masked_loss_bwd")
 
 
+def masked_ce_fwd(logits, target, mask, P, work, loss):
+    B, Cc, H, W = logits.shape
+    assert logits.is_contiguous() and target.is_contiguous() and target.dtype == torch.int64 and target.shape == (B, H, W)
+    mb = mask.stride(0) if mask is not None else 0
+    if mask is not None:
+        assert mask.dtype == torch.int64 and mask.stride(1) == 1
+    check(_L().mmf_masked_ce_fwd(_p(logits), int(logits.dtype == f32), _p(target), _p(mask), mb, B, Cc, H, W, P, _p(work),
+                                 _p(loss), _stream()), "mmf_masked_ce_fwd")
+
+
+def masked_ce_bwd(logits, target, mask, P, work, dloss, dlogits):
+    B, Cc, H, W = logits.shape
+    mb = mask.stride(0) if mask is not None else 0
+    check(_L().mmf_masked_ce_bwd(_p(logits), int(logits.dtype == f32), _p(target), _p(mask), mb, B, Cc, H, W, P, _p(work),
+                                 _p(dloss), _p(dlogits), _stream()), "mmf_masked_ce_bwd")
+
+
 def cast_bf16(src, dst=None, *, rows_pad=None, cols_pad=None, scale=1.0):
     """f32 [rows, cols] -> bf16 [rows_pad, cols_pad] (zero padded)."""
     assert src.dtype == f32 and src.dim() == 2

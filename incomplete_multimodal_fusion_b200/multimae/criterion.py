@@ -40,6 +40,30 @@ class MaskedL1Loss(_MaskedReconLoss):
     KIND = 1
 
 
+class MaskedCrossEntropyLoss(nn.Module):
+    """criterion.py:24-58: cross-entropy over class maps with the patch mask (the loss of the semantic modality `dnw`,
+    pretrain_mmae_my.py:68-75).  input [B, C, H, W] logits (bf16 or fp32), target [B, H, W] int64, mask [B, n_patches]."""
+
+    def __init__(self, patch_size: int = 16, stride: int = 1, label_smoothing: float = 0.0):
+        super().__init__()
+        self.patch_size = patch_size
+        self.stride = stride
+        self.scale_factor = patch_size // stride
+        self.label_smoothing = label_smoothing
+        if label_smoothing != 0.0:
+            raise NotImplementedError("label smoothing is not built (0.0 in the reference's script, pretrain_mmae_my.py:74)")
+
+    def forward(self, input, target, mask=None):
+        if not input.is_cuda:
+            raise RuntimeError("MaskedCrossEntropyLoss runs on CUDA only (no CPU fallback)")
+        if mask is not None:
+            mask = mask.to(torch.int64)
+            if mask.dim() == 2 and mask.shape[0] == 1 and input.shape[0] > 1:
+                mask = mask.expand(input.shape[0], -1)
+            mask = mask.contiguous()
+        return Fn.MaskedCEFn.apply(input, target.to(torch.int64), mask, self.scale_factor)
+
+
 class HardNegtive_loss(nn.Module):
     """Debiased hard-negative contrastive loss (criterion.py:214-268).  The [2B, D] x [D, 2B] similarity runs on the
     tcgen05 GEMM with bf16 operands (torch.mm under the reference's autocast, Appendix A #19); normalisation, exp / log

@@ -27,7 +27,7 @@ __all__ = [
     "sample_alphas", "generate_random_masks", "masks_from_task_masks", "build_input_info",
     "zorro_mask_from_counts", "pool_mask_from_counts",
     "vit_block", "simple_output_adapter", "xattn_output_adapter",
-    "multimae_forward", "masked_mse_loss", "masked_l1_loss", "hard_negative_loss", "dino_loss",
+    "multimae_forward", "masked_mse_loss", "masked_l1_loss", "masked_ce_loss", "hard_negative_loss", "dino_loss",
     "pretrain_loss", "count_params",
 ]
 
@@ -595,6 +595,22 @@ def masked_mse_loss(pred, target, mask=None, patch: int = 16):
 def masked_l1_loss(pred, target, mask=None, patch: int = 16):
     """MaskedL1Loss.forward (norm_pix=False), criterion.py:142-172."""
     return _masked_recon(F.l1_loss(pred, target, reduction="none"), mask, patch)
+
+
+def masked_ce_loss(logits, target, mask=None, patch: int = 16):
+    """MaskedCrossEntropyLoss.forward, criterion.py:37-58 (label_smoothing = 0): per-pixel cross-entropy over the class
+    axis, patch mask nearest-upsampled to pixels, per-sample sum / mask sum, batch nanmean; an all-zero mask returns 0."""
+    loss = F.cross_entropy(logits.float(), target, reduction="none")
+    if mask is None:
+        return loss.mean()
+    if mask.sum() == 0:
+        return torch.zeros((), device=loss.device)
+    H, W = logits.shape[-2:]
+    nh, nw = H // patch, W // patch
+    m = mask.reshape(mask.shape[0], nh, nw).float()
+    m = F.interpolate(m.unsqueeze(1), size=(H, W), mode="nearest").squeeze(1)
+    loss = (loss * m).flatten(1).sum(1) / m.flatten(1).sum(1)
+    return loss.nanmean()
 
 
 def hard_negative_loss(out_1, out_2, tau_plus=0.1, beta=1.0, temperature=0.5):

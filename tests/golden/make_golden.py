@@ -243,6 +243,13 @@ def loss_case():
         "hardneg": ref.criterion.HardNegtive_loss()(a, b),
         "dino": ref.criterion.dino_loss_func(a, b),
     }
+    # masked cross-entropy over class maps (criterion.py:24-58): drawn AFTER everything above so the older entries keep
+    # their values
+    logits = torch.randn(3, 5, 32, 32, generator=g)
+    cls = torch.randint(0, 5, (3, 32, 32), generator=g)
+    ce = ref.criterion.MaskedCrossEntropyLoss(patch_size=8)
+    fx.update({"ce": ce(logits, cls, mask), "ce_nomask": ce(logits, cls),
+               "ce_zeromask": ce(logits, cls, torch.zeros_like(mask)).float()})
     torch.save(fx, os.path.join(HERE, "losses.pt"))
     print("losses", {k: float(v) for k, v in fx.items() if k != "seed"})
 

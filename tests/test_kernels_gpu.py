@@ -367,6 +367,48 @@ def test_masked_loss(kind, pdt, P):
             assert rel(dpred[keep], pred.grad[keep]) < (1e-5 if pdt == f32 else 6e-3)
 
 
+@pytest.mark.parametrize("pdt", [bf16, f32])
+@pytest.mark.parametrize("C,P", [(9, 16), (5, 8), (33, 8)])
+def test_masked_cross_entropy(pdt, C, P, golden_dir):
+    """MaskedCrossEntropyLoss (criterion.py:24-58) fused: value and gradient against the oracle restatement (itself pinned by
+    the reference's golden in test_losses_match_reference), masked / unmasked / all-zero-mask, through the drop-in class"""
+    import oracle
+    from incomplete_multimodal_fusion_b200.multimae.criterion import MaskedCrossEntropyLoss
+    B, H, W = 4, 32, 32
+    logits = rnd(B, C, H, W, dtype=pdt, seed=3, scale=2.0).requires_grad_(True)
+    target = torch.randint(0, C, (B, H, W), device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    mask = (torch.rand(B, (H // P) * (W // P), device="cuda") > 0.4).long()
+    mask[2] = 0                                      # nanmean path
+    crit = MaskedCrossEntropyLoss(patch_size=P)
+    for m in (mask, None, torch.zeros_like(mask)):
+        lref = logits.detach().float().requires_grad_(True)
+        ref = oracle.masked_ce_loss(lref, target, m, P)
+        logits.grad = None
+        out = crit(logits, target, mask=m)
+        assert abs(float(out) - float(ref)) <= 2e-5 * max(1.0, abs(float(ref)))
+        if ref.requires_grad:
+            (ref * 1.3).backward()
+            (out * 1.3).backward()
+            keep = torch.ones(B, dtype=torch.bool, device="cuda") if m is None else m.sum(1) > 0
+            if (~keep).any():      # 0/0 sample: the reference's autograd sends NaN, the kernel 0 (as for the MSE / L1 losses)
+                assert float(logits.grad[~keep].float().abs().max()) == 0.0
+            assert rel(logits.grad[keep], lref.grad[keep]) < (6e-3 if pdt == bf16 else 1e-5)
+    with pytest.raises(NotImplementedError):
+        MaskedCrossEntropyLoss(patch_size=P, label_smoothing=0.1)
+    # and the reference's golden value on the same inputs
+    import os
+    fx = torch.load(os.path.join(golden_dir, "losses.pt"), weights_only=False)
+    g = torch.Generator().manual_seed(fx["seed"])
+    _ = (torch.randn(3, 2, 32, 32, generator=g), torch.randn(3, 2, 32, 32, generator=g))
+    gmask = (torch.rand(3, 16, generator=g) > 0.5).long()
+    gmask[2] = 0
+    _ = (torch.randn(6, 48, generator=g), torch.randn(6, 48, generator=g))
+    glogits = torch.randn(3, 5, 32, 32, generator=g)
+    gcls = torch.randint(0, 5, (3, 32, 32), generator=g)
+    got = MaskedCrossEntropyLoss(patch_size=8)(glogits.cuda(), gcls.cuda(), mask=gmask.cuda())
+    assert abs(float(got) - float(fx["ce"])) < 2e-5 * float(fx["ce"])
+
+
 def test_elementwise():
     import oracle
     k = K()

@@ -100,6 +100,12 @@ def test_losses_match_reference(golden_dir):
     assert float(oracle.masked_mse_loss(pred, tgt, torch.zeros_like(mask), 8)) == float(fx["mse_zeromask"]) == 0.0
     torch.testing.assert_close(oracle.hard_negative_loss(a, b), fx["hardneg"])
     torch.testing.assert_close(oracle.dino_loss(a, b), fx["dino"])
+    # masked cross-entropy over class maps (criterion.py:24-58; the loss of the semantic modality)
+    logits = torch.randn(3, 5, 32, 32, generator=g)
+    cls = torch.randint(0, 5, (3, 32, 32), generator=g)
+    torch.testing.assert_close(oracle.masked_ce_loss(logits, cls, mask, 8), fx["ce"])
+    torch.testing.assert_close(oracle.masked_ce_loss(logits, cls, None, 8), fx["ce_nomask"])
+    assert float(oracle.masked_ce_loss(logits, cls, torch.zeros_like(mask), 8)) == float(fx["ce_zeromask"]) == 0.0
 
 
 def test_mask_sampler_bit_exact(golden_dir):
