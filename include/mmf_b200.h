@@ -215,6 +215,11 @@ int mmf_reduce_batch(const float* src, float* dst, int64_t batch, int64_t rows, 
  * out[b*n_keep + i, (c ph pw)] = bf16(img[b, c, py*P+ph, px*P+pw]), patch idx[i] = py*(W/P)+px */
 int mmf_im2col_gather(const float* img, const int32_t* idx, void* out, int64_t batch, int32_t C, int32_t H, int32_t W,
                       int32_t P, int32_t n_keep, int64_t ld_out, mmf_stream_t stream);
+/* one-hot im2col of a class map for the VISIBLE patches (SemSegInputAdapter.forward, input_adapters.py:299-328, the
+ * 4th `dnw` modality of multimae_quadruplet.py): out[b*n_keep + i, cls*P*P + ph*P + pw] = 1 for every pixel of patch
+ * idx[i]; `out` (bf16, ld_out >= num_classes*P*P) must be zeroed by the caller; cls is [B, H, W] int64 */
+int mmf_onehot_im2col(const int64_t* cls, const int32_t* idx, void* out, int64_t batch, int32_t H, int32_t W, int32_t P,
+                      int32_t n_keep, int32_t num_classes, int64_t ld_out, mmf_stream_t stream);
 /* 'b (nh nw) (c ph pw) -> b c (nh ph) (nw pw)' bf16 (output_adapters_simple.py:183-186); inverse=1 for the gradient */
 int mmf_unpatchify_bf16(void* tokens, void* image, int64_t batch, int32_t C, int32_t H, int32_t W, int32_t P,
                         int32_t inverse, mmf_stream_t stream);

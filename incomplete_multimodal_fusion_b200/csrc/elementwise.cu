@@ -186,6 +186,27 @@ __global__ void im2col_gather_kernel(const float* __restrict__ img, const int32_
   }
 }
 
+// One-hot im2col of a class map (SemSegInputAdapter, input_adapters.py:209-328): row b*n_keep + i of `out`
+// ([.., num_classes*P*P] bf16, ZEROED by the caller) gets a 1 at column cls*P*P + ph*P + pw for every pixel of visible
+// patch idx[i].  With it the adapter's embedding lookup + Conv2d(k = s = P) becomes one GEMM against the
+// [num_classes*P*P, D] table  T[c, ph, pw, :] = W[:, :, ph, pw] . class_emb[c]  (exact in bf16: the operand is 0 / 1).
+__global__ void onehot_im2col_kernel(const int64_t* __restrict__ cls, const int32_t* __restrict__ idx, __nv_bfloat16* __restrict__ out,
+                                     int64_t batch, int H, int W, int P, int n_keep, int num_classes, int64_t ld_out) {
+  const int nw = W / P;
+  const int64_t total = batch * n_keep * P * P;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int pw = (int)(t % P);
+    int64_t l = t / P;
+    const int ph = (int)(l % P); l /= P;
+    const int i = (int)(l % n_keep);
+    const int64_t b = l / n_keep;
+    const int patch = idx[i];
+    const int py = patch / nw, px = patch % nw;
+    const int64_t c = cls[(b * H + (py * P + ph)) * (int64_t)W + px * P + pw];
+    if (c >= 0 && c < num_classes) out[(b * n_keep + i) * ld_out + (c * P + ph) * P + pw] = __float2bfloat16(1.0f);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Un-patchify 'b (nh nw) (c ph pw) -> b c (nh ph) (nw pw)' (output_adapters_simple.py:183-186), bf16,
 // and its inverse (for the gradient).  8-element (16 B) granules; requires P % 8 == 0.
@@ -360,6 +381,18 @@ extern "C" int mmf_im2col_gather(const float* img, const int32_t* idx, void* out
   const int64_t total = batch * n_keep * C * P * (P / 4);
   im2col_gather_kernel<<<ew_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       img, idx, reinterpret_cast<__nv_bfloat16*>(out), batch, C, H, W, P, n_keep, ld_out);
+  MMF_COUNT_LAUNCH();
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmf_onehot_im2col(const int64_t* cls, const int32_t* idx, void* out, int64_t batch, int32_t H, int32_t W, int32_t P,
+                                 int32_t n_keep, int32_t num_classes, int64_t ld_out, mmf_stream_t stream) {
+  if (!cls || !idx || !out) MMF_BAD_ARG(1);
+  if (P <= 0 || H % P || W % P || num_classes <= 0 || ld_out < (int64_t)num_classes * P * P) MMF_BAD_ARG(2);
+  if (batch * n_keep == 0) return 0;
+  onehot_im2col_kernel<<<ew_grid(batch * n_keep * P * P, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      cls, idx, reinterpret_cast<__nv_bfloat16*>(out), batch, H, W, P, n_keep, num_classes, ld_out);
   MMF_COUNT_LAUNCH();
   MMF_LAUNCH_CHECK();
   return 0;

@@ -463,25 +463,46 @@ class MatmulNTFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 class EmbedFn(torch.autograd.Function):
     """Builds the planar token stream X [B*nenc + B*F, D] (f32):
-      head plane: for each modality m (in s1, s2, dem order) its n_m visible patches, projected with the
+      head plane: for each modality m (in s1, s2, dem[, dnw] order) its n_m visible patches, projected with the
                   conv weight viewed as [D, C*P*P] + bias + sin-cos pos-emb (input_adapters.py:97-119
                   restricted to the visible patches, multimae.py:378-383)
       tail plane: fusion_tokens + fusion pos-emb broadcast over the batch (multimae.py:353-354).
-    args: meta (dict), fusion_tokens [1,F,D], then per modality (image, proj_weight, proj_bias)."""
+    args: meta (dict), fusion_tokens [1,F,D], then per modality its tensors: kind "patch" (default) -> (image, proj_weight,
+    proj_bias); kind "semseg" (meta["kinds"][m], SemSegInputAdapter input_adapters.py:209-328) -> (class map [B,H,W]
+    int64, class_emb weight [NC, E], proj_weight [D, E, P, P], proj_bias).  A semantic map is embedded as ONE GEMM of the
+    visible patches' one-hot rows [B*n, NC*P*P] against the table T[c, ph, pw, :] = W[:, :, ph, pw] . class_emb[c]: the
+    embedding lookup and the Conv2d(k = s = P) of the reference folded together (the table is parameter-sized algebra,
+    113 MFLOP at ViT-B, done with torch.einsum in fp32; every batch-sized contraction is mmf_gemm_bf16)."""
+
+    @staticmethod
+    def _arity(kind):
+        return 4 if kind == "semseg" else 3
 
     @staticmethod
     def forward(ctx, meta, fusion_tokens, *mod_args):
         B, D, P, Fn, nenc = meta["B"], meta["D"], meta["P"], meta["F"], meta["nenc"]
+        kinds = meta.get("kinds") or ["patch"] * len(meta["idx"])
         dev = fusion_tokens.device
         Mh = B * nenc
         X = torch.empty(Mh + B * Fn, D, dtype=f32, device=dev)
         saved = []
         off = 0
+        ap = 0
         for m, idx in enumerate(meta["idx"]):
-            img, w, b = mod_args[3 * m: 3 * m + 3]
+            args = mod_args[ap: ap + EmbedFn._arity(kinds[m])]
+            ap += EmbedFn._arity(kinds[m])
             n = idx.numel()
             A = None
-            if n > 0:
+            if n > 0 and kinds[m] == "semseg":
+                cls, emb, w, b = args
+                NC = emb.shape[0]
+                A = torch.zeros(B * n, NC * P * P, dtype=bf16, device=dev)
+                K.onehot_im2col(cls.contiguous(), idx, A, P, NC)
+                table = torch.einsum("deuv,ce->dcuv", w.detach().float(), emb.detach().float()).reshape(D, NC * P * P)
+                K.gemm(A, K.cast_bf16(table.contiguous()), X[off:], bias=b.detach(), residual=meta["pos"][m], res_row_map=idx,
+                       res_period=n, out_period=n, out_batch_rows=nenc)
+            elif n > 0:
+                img, w, b = args
                 C = img.shape[1]
                 A = torch.empty(B * n, C * P * P, dtype=bf16, device=dev)
                 K.im2col_gather(img.contiguous(), idx, A, P)
@@ -493,29 +514,51 @@ class EmbedFn(torch.autograd.Function):
             fus = (fusion_tokens.detach()[0] + meta["pos_fusion"]).contiguous()
             K.bcast_rows(fus, X[Mh:], B, Fn, D, Fn * D)
         ctx.meta = meta
+        ctx.kinds = kinds
         ctx.saved_A = saved
-        ctx.mod_shapes = [(mod_args[3 * m + 1].shape, ) for m in range(len(meta["idx"]))]
+        ctx.mod_params = []          # what the parameter gradients need besides A
+        ap = 0
+        for m in range(len(meta["idx"])):
+            args = mod_args[ap: ap + EmbedFn._arity(kinds[m])]
+            ap += EmbedFn._arity(kinds[m])
+            ctx.mod_params.append((args[1].detach(), args[2].detach(), meta.get("padding_idx", {}).get(m)) if kinds[m] == "semseg"
+                                  else (args[1].shape,))
         return X
 
     @staticmethod
     def backward(ctx, dX):
         meta = ctx.meta
-        B, D, Fn, nenc = meta["B"], meta["D"], meta["F"], meta["nenc"]
+        B, D, P, Fn, nenc = meta["B"], meta["D"], meta["P"], meta["F"], meta["nenc"]
         Mh = B * nenc
         dX = dX.contiguous()
         grads: List[Optional[torch.Tensor]] = []
         off = 0
         for m, idx in enumerate(meta["idx"]):
             n = idx.numel()
-            wshape = ctx.mod_shapes[m][0]
+            semseg = ctx.kinds[m] == "semseg"
             if n == 0:
-                grads += [None, torch.zeros(wshape, dtype=f32, device=dX.device), torch.zeros(D, dtype=f32, device=dX.device)]
+                if semseg:
+                    emb, w, _ = ctx.mod_params[m]
+                    grads += [None, torch.zeros_like(emb), torch.zeros_like(w), torch.zeros(D, dtype=f32, device=dX.device)]
+                else:
+                    grads += [None, torch.zeros(ctx.mod_params[m][0], dtype=f32, device=dX.device),
+                              torch.zeros(D, dtype=f32, device=dX.device)]
                 continue
             dY = torch.empty(B * n, D, dtype=bf16, device=dX.device)
             K.gather_rows(dX, dY, batch=B, n=n, d=D, src_batch_rows=nenc, row_off=off)
-            dW = wgrad(dY, ctx.saved_A[m]).view(wshape)
             db = K.colsum(dY, torch.zeros(D, dtype=f32, device=dX.device))
-            grads += [None, dW, db]
+            if semseg:
+                emb, w, pad = ctx.mod_params[m]
+                NC = emb.shape[0]
+                dT = wgrad(dY, ctx.saved_A[m]).view(D, NC, P, P)                       # gradient of the table
+                dw = torch.einsum("dcuv,ce->deuv", dT, emb.float())
+                demb = torch.einsum("dcuv,deuv->ce", dT, w.float())
+                if pad is not None:
+                    demb[pad] = 0                                                        # nn.Embedding(padding_idx=...)
+                grads += [None, demb, dw, db]
+            else:
+                dW = wgrad(dY, ctx.saved_A[m]).view(ctx.mod_params[m][0])
+                grads += [None, dW, db]
             off += n
         dfus = None
         if Fn > 0:

@@ -338,6 +338,15 @@ def im2col_gather(img, idx, out, P):
     return out
 
 
+def onehot_im2col(cls, idx, out, P, num_classes):
+    """cls [B, H, W] int64 class map -> out (zeroed bf16 [B*n, num_classes*P*P]) one-hot rows of the visible patches"""
+    B, H, W = cls.shape
+    assert cls.is_contiguous() and cls.dtype == torch.int64 and idx.dtype == torch.int32 and out.dtype == bf16
+    check(_L().mmf_onehot_im2col(_p(cls), _p(idx), _p(out), B, H, W, P, idx.numel(), num_classes, _ld(out), _stream()),
+          "mmf_onehot_im2col")
+    return out
+
+
 def unpatchify(tokens, image, Cc, H, W, P, inverse=False):
     B = image.shape[0]
     assert tokens.is_contiguous() and image.is_contiguous() and tokens.dtype == bf16 and image.dtype == bf16

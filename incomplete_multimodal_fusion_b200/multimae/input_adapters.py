@@ -41,14 +41,16 @@ class _SpatialAdapterBase(nn.Module):
         if self.pos_emb.requires_grad:
             raise NotImplementedError("learnable positional embeddings are not built (never enabled by the reference scripts)")
 
+    POS_RESIZE_MODE = 'bicubic'
+
     def pos_table(self, n_h: int, n_w: int) -> torch.Tensor:
         """[n_h*n_w, D] fp32 rows of the positional table (bicubic resize only if the grid differs,
-        input_adapters.py:113 -- the identity at the native size)."""
+        input_adapters.py:113 -- the identity at the native size; the semantic adapter resizes bilinearly, :321)."""
         key = (n_h, n_w, self.pos_emb.data_ptr(), self.pos_emb._version, self.pos_emb.device)
         if self._pos_cache is None or self._pos_cache[0] != key:
             pe = self.pos_emb.detach()
             if pe.shape[-2:] != (n_h, n_w):
-                pe = torch.nn.functional.interpolate(pe, size=(n_h, n_w), mode='bicubic', align_corners=False)
+                pe = torch.nn.functional.interpolate(pe, size=(n_h, n_w), mode=self.POS_RESIZE_MODE, align_corners=False)
             self._pos_cache = (key, pe.flatten(2).transpose(1, 2)[0].contiguous())
         return self._pos_cache[1]
 
@@ -89,6 +91,68 @@ class PatchedInputAdapter(_SpatialAdapterBase):
         meta = dict(B=B, D=self.dim_tokens, P=self.P_H, F=0, nenc=n, idx=[idx], pos=[self.pos_table(n_h, n_w)],
                     pos_fusion=torch.zeros(0, self.dim_tokens, device=x.device))
         X = Fn.EmbedFn.apply(meta, torch.zeros(1, 0, self.dim_tokens, device=x.device), x.float(), self.proj.weight, self.proj.bias)
+        return X.view(B, n, self.dim_tokens)
+
+
+class SemSegInputAdapter(_SpatialAdapterBase):
+    """Adapter for semantic class maps (input_adapters.py:209-328; the `dnw` modality of pretrain_mmae_my.py:68-75): a
+    learned class embedding per pixel, then Conv2d(dim_class_emb -> D, k = s = P), plus the positional table.  The two are
+    folded into one GEMM over one-hot patch rows (functions.EmbedFn, kind "semseg"); parameters, names and shapes are the
+    reference's (`class_emb.weight`, `proj.weight`, `proj.bias`, `pos_emb`)."""
+    POS_RESIZE_MODE = 'bilinear'
+    KIND = 'semseg'
+
+    def __init__(self, num_classes: int, stride_level: int, patch_size_full: Union[int, Tuple[int, int]],
+                 dim_tokens: Optional[int] = None, sincos_pos_emb: int = True, learnable_pos_emb: int = False,
+                 image_size: Union[int, Tuple[int]] = 224, dim_class_emb: int = 64, interpolate_class_emb: bool = False,
+                 emb_padding_idx: int = None):
+        super().__init__(None, stride_level, patch_size_full, dim_tokens, sincos_pos_emb, learnable_pos_emb, image_size)
+        del self.num_channels
+        self.num_classes = num_classes
+        self.dim_class_emb = dim_class_emb
+        self.interpolate_class_emb = interpolate_class_emb
+        self.emb_padding_idx = emb_padding_idx
+        if self.emb_padding_idx is not None:
+            self.num_classes += 1
+        if interpolate_class_emb:
+            raise NotImplementedError("interpolate_class_emb=True is not built (False in the reference's script, pretrain_mmae_my.py:71)")
+        if self.dim_tokens is not None:
+            self.init(dim_tokens=dim_tokens)
+
+    def init(self, dim_tokens: int = 768):
+        self.dim_tokens = dim_tokens
+        self._make_pos_emb(dim_tokens)
+        self.class_emb = nn.Embedding(num_embeddings=self.num_classes, embedding_dim=self.dim_class_emb, padding_idx=self.emb_padding_idx)
+        trunc_normal_(self.class_emb.weight, std=0.02)
+        self.proj = nn.Conv2d(in_channels=self.dim_class_emb, out_channels=self.dim_tokens,
+                              kernel_size=(self.P_H, self.P_W), stride=(self.P_H, self.P_W))
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'pos_emb', 'class_emb'}
+
+    def grid(self, H, W):
+        assert self.dim_tokens is not None, 'Need to call init(dim_tokens) function first'
+        assert (H % self.P_H == 0) and (W % self.P_W == 0), \
+            f'Image sizes {H}x{W} must be divisible by patch sizes {self.P_H}x{self.P_W}'
+        assert self.P_H == self.P_W, 'square patches only'
+        return H // self.P_H, W // self.P_W
+
+    def embed_args(self, x):
+        """this modality's tensors for functions.EmbedFn"""
+        return [x.to(torch.int64), self.class_emb.weight, self.proj.weight, self.proj.bias]
+
+    def forward(self, x):
+        """[B, H, W] int64 class ids -> [B, n_h*n_w, D] fp32: every patch embedded (reference semantics)"""
+        B, H, W = x.shape
+        if not x.is_cuda:
+            raise RuntimeError("SemSegInputAdapter runs on CUDA only (no CPU fallback)")
+        n_h, n_w = self.grid(H, W)
+        n = n_h * n_w
+        idx = torch.arange(n, dtype=torch.int32, device=x.device)
+        meta = dict(B=B, D=self.dim_tokens, P=self.P_H, F=0, nenc=n, idx=[idx], pos=[self.pos_table(n_h, n_w)], kinds=["semseg"],
+                    padding_idx={0: self.emb_padding_idx}, pos_fusion=torch.zeros(0, self.dim_tokens, device=x.device))
+        X = Fn.EmbedFn.apply(meta, torch.zeros(1, 0, self.dim_tokens, device=x.device), *self.embed_args(x))
         return X.view(B, n, self.dim_tokens)
 
 

@@ -23,7 +23,7 @@ __all__ = [
     "OracleConfig", "S1", "S2", "DEM", "FUSION",
     "sincos_posemb_2d", "init_state_dict", "perturb_state_dict",
     "zorro_layer_norm", "zorro_attention", "geglu_feed_forward", "biased_mlp",
-    "zorro_block", "fusion_block", "patch_embed", "add_fusion_posemb",
+    "zorro_block", "fusion_block", "patch_embed", "semseg_embed", "add_fusion_posemb",
     "sample_alphas", "generate_random_masks", "masks_from_task_masks", "build_input_info",
     "zorro_mask_from_counts", "pool_mask_from_counts",
     "vit_block", "simple_output_adapter", "xattn_output_adapter",
@@ -294,6 +294,19 @@ def patch_embed(sd, pfx: str, img, cfg: OracleConfig):
     pe = sd[pfx + "pos_emb"]
     if pe.shape[-2:] != (H // P, W // P):
         pe = F.interpolate(pe, size=(H // P, W // P), mode="bicubic", align_corners=False)
+    return y + pe.flatten(2).transpose(1, 2)
+
+
+def semseg_embed(sd, pfx: str, x, patch: int, padding_idx=None, lowp=None):
+    """SemSegInputAdapter.forward, input_adapters.py:299-328 (interpolate_class_emb=False): class embedding per pixel,
+    Conv2d(k = s = P) + bias, flatten, + the positional table (bilinear resize if the grid differs).  x: [B, H, W] int64."""
+    emb = F.embedding(x, sd[pfx + "class_emb.weight"], padding_idx=padding_idx)            # [B, H, W, E]
+    y = F.conv2d(emb.permute(0, 3, 1, 2), sd[pfx + "proj.weight"], sd[pfx + "proj.bias"], stride=patch)
+    y = y.flatten(2).transpose(1, 2)
+    pe = sd[pfx + "pos_emb"]
+    nh, nw = x.shape[1] // patch, x.shape[2] // patch
+    if pe.shape[-2:] != (nh, nw):
+        pe = F.interpolate(pe, size=(nh, nw), mode="bilinear")
     return y + pe.flatten(2).transpose(1, 2)
 
 

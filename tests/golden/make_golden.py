@@ -272,6 +272,28 @@ def mask_case():
     print("masks", len(cases))
 
 
+def semseg_case():
+    """SemSegInputAdapter (input_adapters.py:209-328) on its own: tokens and parameter gradients for a random class map,
+    with and without a padding class"""
+    ref = load_reference()
+    out = {}
+    for name, pad in (("plain", None), ("padded", 3)):
+        torch.manual_seed(21)
+        ad = ref.input_adapters.SemSegInputAdapter(num_classes=9, stride_level=1, patch_size_full=8, dim_tokens=64, image_size=32,
+                                                   dim_class_emb=16, interpolate_class_emb=False, emb_padding_idx=pad)
+        g = torch.Generator().manual_seed(22)
+        with torch.no_grad():
+            ad.proj.bias.copy_(torch.randn(64, generator=g) * 0.1)
+        x = torch.randint(0, ad.num_classes, (3, 32, 32), generator=g)
+        w = torch.randn(3, 16, 64, generator=g)
+        tok = ad(x)
+        (tok * w).sum().backward()
+        out[name] = {"state_dict": {k: v.detach().clone() for k, v in ad.state_dict().items()}, "x": x, "w": w, "tokens": tok.detach(),
+                     "padding_idx": pad, "grads": {k: p.grad.clone() for k, p in ad.named_parameters() if p.grad is not None}}
+    torch.save(out, os.path.join(HERE, "semseg_adapter.pt"))
+    print("semseg_adapter", {k: tuple(v["tokens"].shape) for k, v in out.items()}, list(out["plain"]["grads"]))
+
+
 def load_reference_downstream():
     """the downstream package's modules the ViTBaseline file needs, loaded in memory as `refdown` (the package __init__
     pulls in detectron2; the four files below are self-contained and unpatched)"""
@@ -324,6 +346,8 @@ def main():
     from oracle import OracleConfig
     only = sys.argv[1:]     # e.g. `make_golden.py lstm_s2dsm` regenerates just that fixture
     small = dict(dim=128, depth=2, heads=2, dim_head=64, image_size=32, patch=8, dec_dim=64, dec_depth=1, dec_heads=2)
+    if not only or "semseg" in only:
+        semseg_case()
     if not only or "vitbaseline" in only:
         vitbaseline_case(OracleConfig(variant="crossattn", decoder="simple", dim=64, depth=4, heads=1, dim_head=64, image_size=32,
                                       patch=8, dec_dim=64, dec_depth=1, dec_heads=2))

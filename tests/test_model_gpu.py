@@ -248,3 +248,22 @@ def test_lstm_s2dsm_variant_matches_reference_golden_and_oracle(golden_dir):
         if g_ref is None or float(g_ref.norm()) < 1e-7:
             continue
         assert rel(p.grad, g_ref) < GOLDEN_GRAD_TOL, (k, rel(p.grad, g_ref))
+
+
+def test_semseg_input_adapter_matches_reference_golden(golden_dir):
+    """SemSegInputAdapter: class embedding + patch projection as one one-hot GEMM; same state_dict as the
+    reference adapter (strict load), tokens and parameter gradients against its golden run, padding class included"""
+    from incomplete_multimodal_fusion_b200.multimae.input_adapters import SemSegInputAdapter
+    fx = _golden(golden_dir, "semseg_adapter")
+    for name, c in fx.items():
+        ad = SemSegInputAdapter(num_classes=9, stride_level=1, patch_size_full=8, dim_tokens=64, image_size=32, dim_class_emb=16,
+                                interpolate_class_emb=False, emb_padding_idx=c["padding_idx"]).cuda()
+        ad.load_state_dict(c["state_dict"], strict=True)
+        tok = ad(c["x"].cuda())
+        assert tok.shape == c["tokens"].shape and rel(tok, c["tokens"].cuda()) < ACT_TOL, (name, rel(tok, c["tokens"].cuda()))
+        (tok * c["w"].cuda()).sum().backward()
+        for k, g in c["grads"].items():
+            got = dict(ad.named_parameters())[k].grad
+            assert rel(got, g.cuda()) < GRAD_TOL, (name, k, rel(got, g.cuda()))
+        if c["padding_idx"] is not None:
+            assert float(ad.class_emb.weight.grad[c["padding_idx"]].abs().max()) == 0.0

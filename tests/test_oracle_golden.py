@@ -204,3 +204,15 @@ def test_vit_baseline_matches_reference(golden_dir):
         for a, b in zip(out, feats):
             assert a.shape == b.shape
             assert float((a - b).norm() / b.norm()) < 1e-5, name
+
+
+def test_semseg_adapter_matches_reference(golden_dir):
+    """SemSegInputAdapter: the oracle's restatement against the reference adapter's tokens and gradients"""
+    fx = _load(golden_dir, "semseg_adapter")
+    for name, c in fx.items():
+        sd = {"a." + k: v.clone().requires_grad_(k != "pos_emb") for k, v in c["state_dict"].items()}
+        tok = oracle.semseg_embed(sd, "a.", c["x"], 8, padding_idx=c["padding_idx"])
+        torch.testing.assert_close(tok, c["tokens"], rtol=1e-5, atol=1e-6)
+        (tok * c["w"]).sum().backward()
+        for k, g in c["grads"].items():
+            torch.testing.assert_close(sd["a." + k].grad, g, rtol=1e-4, atol=1e-6)
