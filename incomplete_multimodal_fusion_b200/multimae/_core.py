@@ -36,6 +36,7 @@ class MultiMAEBase(nn.Module):
     LSTM_FUSION = False                # one BiLSTM-initialised fusion token per visible token (multimae_lstm_s2dsm.py)
     MODALITIES = MODALITIES            # token order of the variant's forward
     TYPE_IDS = {'s1': TokenTypes.S1.value, 's2': TokenTypes.S2.value, 'dem': TokenTypes.DEM.value}
+    FUSION_TYPE_ID = TokenTypes.FUSION.value   # (the 4-modality variant renumbers: multimae_quadruplet.py)
 
     def __init__(self, input_adapters: Dict[str, nn.Module], output_adapters: Optional[Dict[str, nn.Module]],
                  num_global_tokens: int = 1, dim_tokens: int = 768, depth: int = 12, dim_head: int = 64, heads: int = 8,
@@ -255,14 +256,20 @@ class MultiMAEBase(nn.Module):
         zmask = ZorroMask(counts, n_tail, device)
 
         # ---- tokens: visible-patch embedding + fusion tokens, planar layout ----
-        mod_args = []
-        for t in MODALITIES:
+        mod_args, kinds, pads = [], [], {}
+        for m, t in enumerate(MODALITIES):
             ad = self.input_adapters[t]
-            mod_args += [x[t].float(), ad.proj.weight, ad.proj.bias]
+            kinds.append(getattr(ad, 'KIND', 'patch'))
+            if kinds[-1] == 'semseg':          # class map [B, H, W] (SemSegInputAdapter): embedded through a one-hot GEMM
+                mod_args += ad.embed_args(x[t])
+                pads[m] = ad.emb_padding_idx
+            else:
+                mod_args += [x[t].float(), ad.proj.weight, ad.proj.bias]
         fus_ad = self.input_adapters['fusion']
         pos_fusion = fus_ad.pos_table(H // fus_ad.P_H, W // fus_ad.P_W)
         meta_e = dict(B=B, D=D, P=self.input_adapters[first].P_H, F=0 if self.LSTM_FUSION else Fn_tok, nenc=nenc, idx=idx,
-                      pos=[self.input_adapters[t].pos_table(*grids[t]) for t in MODALITIES], pos_fusion=pos_fusion)
+                      pos=[self.input_adapters[t].pos_table(*grids[t]) for t in MODALITIES], pos_fusion=pos_fusion, kinds=kinds,
+                      padding_idx=pads)
         X = Fn.EmbedFn.apply(meta_e, self.fusion_tokens, *mod_args)
         complete_fusion = None
         if self.LSTM_FUSION:
@@ -314,10 +321,10 @@ class MultiMAEBase(nn.Module):
         queries = torch.cat(queries, 0)
         Rt = queries.shape[0]
         N = nenc + n_tail
-        types = torch.repeat_interleave(torch.tensor([self.TYPE_IDS[t] for t in MODALITIES] + [TokenTypes.FUSION.value],
+        types = torch.repeat_interleave(torch.tensor([self.TYPE_IDS[t] for t in MODALITIES] + [self.FUSION_TYPE_ID],
                                                      device=device), torch.tensor(counts + [n_tail], device=device))
         pmask = torch.zeros(Rt, N, dtype=torch.uint8, device=device)
-        pmask[:R] = ((rtypes[:, None] == types[None, :]) | (rtypes[:, None] == TokenTypes.FUSION.value)).to(torch.uint8)
+        pmask[:R] = ((rtypes[:, None] == types[None, :]) | (rtypes[:, None] == self.FUSION_TYPE_ID)).to(torch.uint8)
         mode = torch.zeros(Rt, dtype=torch.int32, device=device)
         if self.FUSION_BLOCKS:
             for j, ix in enumerate(idx):           # per-modality pools over the fusion tokens at that modality's

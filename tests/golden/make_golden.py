@@ -82,6 +82,8 @@ def load_reference():
     load("multimae", quiet)
     load("multimae_crossattn", quiet)
     load("multimae_lstm_s2dsm", quiet)
+    load("zorro_utils_quadruplet")
+    load("multimae_quadruplet", quiet)
     return pkg
 
 
@@ -294,6 +296,55 @@ def semseg_case():
     print("semseg_adapter", {k: tuple(v["tokens"].shape) for k, v in out.items()}, list(out["plain"]["grads"]))
 
 
+def quadruplet_case():
+    """4-modality model (multimae_quadruplet.py) with the semantic `dnw` input and the masked cross-entropy loss"""
+    from oracle.quadruplet import NUM_CLASSES, quad_config, quad_state_dict
+    from oracle.functional import perturb_state_dict
+    ref = load_reference()
+    cfg = quad_config(dim=128, depth=2, heads=2, dim_head=64, image_size=32, patch=8, dec_dim=64, dec_depth=1, dec_heads=2)
+    sd = perturb_state_dict(quad_state_dict(cfg, seed=0), seed=7)
+    Adapter, Sem, Fus = ref.input_adapters.PatchedInputAdapter, ref.input_adapters.SemSegInputAdapter, ref.input_adapters.FusionInputAdapter
+    ia = OrderedDict((t, Adapter(num_channels=cfg.channels[t], stride_level=1, patch_size_full=cfg.patch, image_size=cfg.image_size))
+                     for t in ("s1", "s2", "dem"))
+    ia["dnw"] = Sem(num_classes=NUM_CLASSES, stride_level=1, patch_size_full=cfg.patch, image_size=cfg.image_size, dim_class_emb=16,
+                    interpolate_class_emb=False)
+    ia["fusion"] = Fus(num_channels=1, stride_level=1, patch_size_full=cfg.patch, image_size=cfg.image_size)
+    Out = ref.output_adapters_simple.SpatialOutputAdapter
+    oa = OrderedDict((t, Out(num_channels=cfg.channels[t], stride_level=1, patch_size_full=cfg.patch, dim_tokens=cfg.dec_dim,
+                             depth=cfg.dec_depth, num_heads=cfg.dec_heads, use_task_queries=True, task=t,
+                             context_tasks=list(cfg.channels), image_size=cfg.image_size, use_xattn=True)) for t in cfg.out_tasks)
+    T = ref.zorro_utils_quadruplet.TokenTypes
+    model = ref.multimae_quadruplet.MultiMAE(input_adapters=ia, output_adapters=oa, dim_tokens=cfg.dim, depth=cfg.depth,
+                                             dim_head=cfg.dim_head, heads=cfg.heads, ff_mult=cfg.ff_mult,
+                                             num_fusion_tokens=cfg.num_patches,
+                                             return_token_types=(T.S1, T.S2, T.DEM, T.DNW, T.FUSION),
+                                             norm_layer=ref.zorro_utils_quadruplet.LayerNorm)
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    g = torch.Generator().manual_seed(1234)
+    x = OrderedDict((t, torch.randn(3, cfg.channels[t], 32, 32, generator=g)) for t in ("s1", "s2", "dem"))
+    x["dnw"] = torch.randint(0, NUM_CLASSES, (3, 32, 32), generator=g)
+    torch.manual_seed(5)
+    out = model(x, mask_inputs=True, num_encoded_tokens=28, alphas=1.0, sample_tasks_uniformly=False)
+    mse, l1 = ref.criterion.MaskedMSELoss(patch_size=cfg.patch), ref.criterion.MaskedL1Loss(patch_size=cfg.patch)
+    ce = ref.criterion.MaskedCrossEntropyLoss(patch_size=cfg.patch)
+    preds, masks = out[0], out[1]
+    loss = mse(preds["s1"].float(), x["s1"], mask=masks["s1"]) + mse(preds["s2"].float(), x["s2"], mask=masks["s2"]) + \
+        l1(preds["dem"].float(), x["dem"], mask=masks["dem"]) + ce(preds["dnw"].float(), x["dnw"], mask=masks["dnw"])
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    torch.save({"cfg_kwargs": dict(dim=128, depth=2, heads=2, dim_head=64, image_size=32, patch=8, dec_dim=64, dec_depth=1, dec_heads=2),
+                "batch": 3, "nenc": 28, "mask_seed": 5, "input_seed": 1234,
+                "preds": {t: v.detach() for t, v in preds.items()}, "task_masks": dict(masks), "return_tokens": out[2].detach(),
+                "ori_tokens": out[3].detach(), "fusion_tokens": out[4].detach(), "loss": loss.detach(),
+                "grad_norms": {k: v.norm() for k, v in grads.items()},
+                "grads": {k: v for k, v in grads.items() if v.numel() <= 4096 or k.endswith("blocks.0.attn.to_q.weight")
+                          or k == "input_adapters.dnw.class_emb.weight"},
+                "state_dict_keys": [(k, tuple(v.shape)) for k, v in model.state_dict().items()]},
+               os.path.join(HERE, "quadruplet.pt"))
+    print("quadruplet loss", float(loss), "counts", [int((m[0] == 0).sum()) for m in masks.values()], "n_grads", len(grads))
+
+
 def load_reference_downstream():
     """the downstream package's modules the ViTBaseline file needs, loaded in memory as `refdown` (the package __init__
     pulls in detectron2; the four files below are self-contained and unpatched)"""
@@ -348,6 +399,8 @@ def main():
     small = dict(dim=128, depth=2, heads=2, dim_head=64, image_size=32, patch=8, dec_dim=64, dec_depth=1, dec_heads=2)
     if not only or "semseg" in only:
         semseg_case()
+    if not only or "quadruplet" in only:
+        quadruplet_case()
     if not only or "vitbaseline" in only:
         vitbaseline_case(OracleConfig(variant="crossattn", decoder="simple", dim=64, depth=4, heads=1, dim_head=64, image_size=32,
                                       patch=8, dec_dim=64, dec_depth=1, dec_heads=2))

@@ -216,3 +216,35 @@ def test_semseg_adapter_matches_reference(golden_dir):
         (tok * c["w"]).sum().backward()
         for k, g in c["grads"].items():
             torch.testing.assert_close(sd["a." + k].grad, g, rtol=1e-4, atol=1e-6)
+
+
+def test_quadruplet_variant_matches_reference(golden_dir):
+    """4-modality model (multimae_quadruplet.py): semantic `dnw` input through SemSegInputAdapter, five-type
+    zorro / pool masks, cross-entropy on the dnw decoder -- the oracle against the reference model's own run"""
+    from oracle.quadruplet import NUM_CLASSES, quad_config, quad_forward, quad_loss, quad_state_dict
+    fx = _load(golden_dir, "quadruplet")
+    cfg = quad_config(**fx["cfg_kwargs"])
+    sd = oracle.perturb_state_dict(quad_state_dict(cfg, seed=0), seed=7)
+    assert {k: tuple(v.shape) for k, v in sd.items() if not k.endswith(".beta")} == \
+        {k: s for k, s in fx["state_dict_keys"] if not k.endswith(".beta")}
+    for k, v in sd.items():
+        if not (k.endswith(".beta") or k.endswith("pos_emb")):
+            v.requires_grad_(True)
+    g = torch.Generator().manual_seed(fx["input_seed"])
+    x = OrderedDict((t, torch.randn(fx["batch"], cfg.channels[t], 32, 32, generator=g)) for t in ("s1", "s2", "dem"))
+    x["dnw"] = torch.randint(0, NUM_CLASSES, (fx["batch"], 32, 32), generator=g)
+    torch.manual_seed(fx["mask_seed"])
+    out = quad_forward(sd, cfg, x, num_encoded_tokens=fx["nenc"])
+    for t in fx["task_masks"]:
+        assert torch.equal(out[1][t], fx["task_masks"][t])
+    for t in fx["preds"]:
+        torch.testing.assert_close(out[0][t], fx["preds"][t], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out[2], fx["return_tokens"], rtol=1e-4, atol=1e-5)
+    loss = quad_loss(out, x, cfg)
+    torch.testing.assert_close(loss, fx["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    got = {k: v.grad for k, v in sd.items() if v.grad is not None}
+    assert set(fx["grad_norms"]) <= set(got)
+    for k, gr in fx["grads"].items():
+        if float(gr.norm()) > 1e-7:
+            assert float((got[k] - gr).norm() / gr.norm()) < 1e-4, k
