@@ -613,6 +613,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / multicast commit lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // Programmatic dependent launch: the grid may have been scheduled before the previous kernel of the stream has
+  // finished (the prologue above -- barrier init, TMEM allocation, descriptor prefetch -- touches no global data);
+  // everything below reads or writes memory other kernels own, so every thread waits for them here.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs, each its own halves) ------------------------------
@@ -1098,7 +1102,19 @@ static int launch_gemm2(const MmfGemmArgs& a, cudaStream_t stream) {
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.split_k;
   const int max_clusters = num_sms() / 2;
   const int clusters = (int)(total < max_clusters ? total : max_clusters);
-  kern<<<2 * clusters, G2Cfg<EPI, TS>::THREADS, SMEM, stream>>>(ta, tb, to, to2, p);
+  static const bool pdl = !(getenv("MMF_PDL") && atoi(getenv("MMF_PDL")) == 0);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(G2Cfg<EPI, TS>::THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, p);
+  if (le != cudaSuccess) return (int)le;
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
   return 0;
