@@ -191,8 +191,12 @@ def run_ours(args):
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"     # NCCL prints its version banner on STDOUT; rank 0 prints one JSON line only
     torch.cuda.set_device(local)
+    reserve = int(os.environ.get("MMF_RESERVE_SMS", "0"))
     if world > 1:
+        if reserve > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        kernels.set_gemm_reserved_sms(reserve)
     dev = torch.device("cuda", local)
 
     torch.manual_seed(0)

@@ -32,6 +32,9 @@ int mmf_abi_version(void);
  * `gpu_launches`). */
 int64_t mmf_launch_count(void);
 void mmf_reset_launch_count(void);
+/* Data-parallel runs: leave `n` SMs out of the persistent GEMM grids so that a concurrent NCCL all-reduce (capped to the
+ * same number of CTAs, NCCL_MAX_CTAS) does not delay GEMM CTAs that are statically assigned to the SMs it occupies. */
+void mmf_set_gemm_reserved_sms(int32_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators), bf16 x bf16 -> fp32 accumulate.

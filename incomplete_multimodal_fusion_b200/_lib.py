@@ -74,6 +74,7 @@ SIGNATURES = {
     "mmf_abi_version": [],
     "mmf_launch_count": [],
     "mmf_reset_launch_count": [],
+    "mmf_set_gemm_reserved_sms": [c_i32],
     "mmf_gemm_bf16": [C.POINTER(GemmArgs), c_vp],
     "mmf_layernorm_fwd": [c_vp, c_vp, c_i64, c_i64, c_i32, c_i64, c_vp, c_vp, c_f32, c_vp, c_f32, c_vp, c_i64, c_i32, c_vp,
                           c_vp, c_i64, c_i64, c_vp, c_i64, c_vp],
@@ -106,7 +107,7 @@ SIGNATURES = {
     "mmf_grad_norm": [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp],
     "mmf_mask_build": [c_vp, c_vp, c_vp, c_i32, C.POINTER(c_i32), c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
 }
-_RESTYPES = {"mmf_launch_count": c_i64, "mmf_reset_launch_count": None}
+_RESTYPES = {"mmf_launch_count": c_i64, "mmf_reset_launch_count": None, "mmf_set_gemm_reserved_sms": None}
 
 
 def lib_path() -> str:

@@ -17,6 +17,7 @@
 namespace mmf {
 
 std::atomic<int64_t> g_launch_count{0};
+std::atomic<int> g_reserved_sms{0};   // SMs the persistent GEMM grids leave free (for a concurrent NCCL all-reduce)
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
@@ -1100,7 +1101,8 @@ static int launch_gemm2(const MmfGemmArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.split_k;
-  const int max_clusters = num_sms() / 2;
+  int max_clusters = (num_sms() - g_reserved_sms.load(std::memory_order_relaxed)) / 2;
+  if (max_clusters < 1) max_clusters = 1;
   const int clusters = (int)(total < max_clusters ? total : max_clusters);
   static const bool pdl = !(getenv("MMF_PDL") && atoi(getenv("MMF_PDL")) == 0);
   cudaLaunchConfig_t cfg = {};
@@ -1206,5 +1208,6 @@ extern "C" int mmf_gemm_bf16(const MmfGemmArgs* args, mmf_stream_t stream_) {
 }
 
 extern "C" int mmf_abi_version(void) { return 1; }
+extern "C" void mmf_set_gemm_reserved_sms(int32_t n) { mmf::g_reserved_sms.store(n < 0 ? 0 : n); }
 extern "C" int64_t mmf_launch_count(void) { return mmf::g_launch_count.load(); }
 extern "C" void mmf_reset_launch_count(void) { mmf::g_launch_count.store(0); }

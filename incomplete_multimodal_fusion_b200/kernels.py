@@ -81,6 +81,11 @@ def launch_count() -> int:
     return int(_L().mmf_launch_count())
 
 
+def set_gemm_reserved_sms(n: int):
+    """leave n SMs out of the persistent GEMM grids (data-parallel runs: room for the concurrent NCCL all-reduce)"""
+    _L().mmf_set_gemm_reserved_sms(int(n))
+
+
 def reset_launch_count():
     _L().mmf_reset_launch_count()
 
