@@ -758,7 +758,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
 // ---------------------------------------- dK, dV ----------------------------------------
 constexpr uint32_t KV_ST = 0, KV_DPT = 64, KV_DV = 128, KV_DK = 192;   // P^T aliases S^T, dS^T aliases dP^T
-constexpr int DKV_SMEM = 4 * TC_TILE_BYTES + 4 * BW_BLK_BYTES + 2 * 2 * BW_BLK * 4 + 1024 + 256;
+constexpr int DKV_SMEM = 4 * TC_TILE_BYTES + 4 * BW_BLK_BYTES + 4 * 2 * 2 * BW_BLK * 4 + 1024 + 256;   // + per-warp lse / delta stages
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
@@ -795,9 +795,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   uint8_t* sV = smem + 2 * TC_TILE_BYTES;
   uint8_t* sQ = smem + 4 * TC_TILE_BYTES;               // 2 stages of 64x64
   uint8_t* sdO = sQ + 2 * BW_BLK_BYTES;
-  float* s_lse = reinterpret_cast<float*>(sdO + 2 * BW_BLK_BYTES);   // [2][64]
-  float* s_dl = s_lse + 2 * BW_BLK;                                  // [2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dl + 2 * BW_BLK);
+  float* s_lse = reinterpret_cast<float*>(sdO + 2 * BW_BLK_BYTES);   // [4 warps][2 stages][64]
+  float* s_dl = s_lse + 4 * 2 * BW_BLK;                              // [4 warps][2 stages][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dl + 4 * 2 * BW_BLK);
   uint64_t* kvt_full = bars;        // [2] K and V tile of a head
   uint64_t* kvt_empty = bars + 2;   // [2]
   uint64_t* qb_full = bars + 4;     // [2] Q / dO block
@@ -924,7 +924,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   } else {
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;      // key row of this thread
-    const int tid128 = threadIdx.x - 64;              // 0..127 over the four elementwise warps
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const bool key_ok = c0 + row_in_tile < c1;
     uint32_t rs[32], rd[32];
@@ -935,26 +934,30 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
     if (dbg_on) g_attn_clk[15] = (unsigned long long)qb.nb * p.H;
     long long t_last = clock64();
 #endif
-    // lse*log2e and delta of a block's 64 query rows are staged in shared memory by the first 64 elementwise threads.
-    // The values of block g+1 are fetched (global loads into registers) right after the barrier of block g and written
-    // to the other stage at the end of block g: their latency hides behind the block's arithmetic.  Fetched where they
-    // are needed they cost ~2000 clk per block, 40 % of this CTA's time (tools/attn_clocks_bwd.py).
-    float nl = 0.f, nd = 0.f;   // raw loaded values: nothing may consume them before the stage write (in-order issue
-    bool nok = false;           // would park the warp on the load right after the barrier)
+    // lse*log2e and delta of a block's 64 query rows are staged in shared memory PER WARP (each warp keeps its own two
+    // stages; lane l fetches rows l and l + 32), so the four elementwise warps never meet at a barrier.  The values of
+    // block g+1 are fetched (global loads into registers) at the start of block g and written to the other stage at its
+    // end: their latency hides behind the block's arithmetic.  Fetched where they are needed they cost ~2000 clk per
+    // block, 40 % of this CTA's time (tools/attn_clocks_bwd.py).
+    float* w_lse = s_lse + quarter * 2 * BW_BLK;
+    float* w_dl = s_dl + quarter * 2 * BW_BLK;
+    float nl0 = 0.f, nl1 = 0.f, nd0 = 0.f, nd1 = 0.f;   // raw loaded values: nothing may consume them before the stage
+    bool nok0 = false, nok1 = false;                    // write (in-order issue would park the warp on the loads)
     auto fetch = [&](int hh, int jj) {
       int tok, nvalid; int64_t row;
       qb.get(jj, tok, row, nvalid);
-      const int64_t sb = ((int64_t)b * p.H + hh) * p.N;
-      nok = tid128 < nvalid;
-      const int64_t at = sb + tok + (nok ? tid128 : 0);
-      nl = p.lse[at];
-      nd = p.delta[at];
+      const int64_t sb = ((int64_t)b * p.H + hh) * p.N + tok;
+      nok0 = lane < nvalid; nok1 = lane + 32 < nvalid;
+      nl0 = p.lse[sb + (nok0 ? lane : 0)]; nd0 = p.delta[sb + (nok0 ? lane : 0)];
+      nl1 = p.lse[sb + (nok1 ? lane + 32 : 0)]; nd1 = p.delta[sb + (nok1 ? lane + 32 : 0)];
     };
     auto stage = [&](int stg) {
-      s_lse[stg * BW_BLK + tid128] = nok ? nl * 1.4426950408889634f : INFINITY;   // +inf beyond nvalid -> P = 0
-      s_dl[stg * BW_BLK + tid128] = nok ? nd : 0.f;
+      w_lse[stg * BW_BLK + lane] = nok0 ? nl0 * 1.4426950408889634f : INFINITY;        // +inf beyond nvalid -> P = 0
+      w_lse[stg * BW_BLK + lane + 32] = nok1 ? nl1 * 1.4426950408889634f : INFINITY;
+      w_dl[stg * BW_BLK + lane] = nok0 ? nd0 : 0.f;
+      w_dl[stg * BW_BLK + lane + 32] = nok1 ? nd1 : 0.f;
     };
-    if (tid128 < BW_BLK && qb.nb > 0) {
+    if (qb.nb > 0) {
       fetch(0, 0);
       stage(0);
     }
@@ -964,13 +967,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         int tok, nvalid; int64_t row;
         qb.get(j, tok, row, nvalid);
         CLK(4, 0);
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four elementwise warps: stage st is complete, st^1 is free
+        __syncwarp();   // this warp's stage st is complete (written at the end of the previous block), st^1 is free
         const int hn = (j + 1 < qb.nb) ? h : h + 1, jn = (j + 1 < qb.nb) ? j + 1 : 0;
-        const bool stage_next = tid128 < BW_BLK && hn < p.H;
+        const bool stage_next = hn < p.H;
         if (stage_next) fetch(hn, jn);
         CLK(5, 0);
-        const float* ls = s_lse + st * BW_BLK;
-        const float* dl = s_dl + st * BW_BLK;
+        const float* ls = w_lse + st * BW_BLK;
+        const float* dl = w_dl + st * BW_BLK;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {   // the block's two 32-query halves (see the MMA warp)
           if (nvalid <= 32 * c) continue;
