@@ -103,13 +103,43 @@ def _wgrad_split(tokens: int, out_elems: int) -> int:
     return max(1, min(want, tokens // 1024 if tokens >= 2048 else 1, 32))
 
 
+# ------------------------------------------------------------------------------------------------
+# Zero-initialised fp32 gradient accumulators outside the encoder stack (decoder / pooling / embedding weights, biases,
+# LayerNorm gammas: ~100 small tensors per step).  A training step may open an arena (one zero-filled buffer, one
+# memset); without one every accumulator is its own torch.zeros as before.
+# ------------------------------------------------------------------------------------------------
+_STEP_ARENA = None   # (buffer, offset) of the step in flight; module-global: autograd runs backward on its own thread
+
+
+def begin_step_arena(numel: int, device):
+    global _STEP_ARENA
+    _STEP_ARENA = [torch.zeros(int(numel), dtype=f32, device=device), 0]
+
+
+def end_step_arena():
+    global _STEP_ARENA
+    _STEP_ARENA = None
+
+
+def zeros_f32(*shape, device):
+    a = _STEP_ARENA
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if a is None or a[0].device != device or a[1] + n > a[0].numel():
+        return torch.zeros(*shape, dtype=f32, device=device)
+    v = a[0][a[1]:a[1] + n].view(*shape)
+    a[1] += (n + 3) // 4 * 4          # 16-byte aligned views
+    return v
+
+
 def wgrad(dy: torch.Tensor, x: torch.Tensor, out_rows: Optional[int] = None, out_cols: Optional[int] = None,
           out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """dW[n_out, k_in] = dy^T x with dy [T, n_out], x [T, k_in] both bf16 token-major (MN-major operands)."""
     n_out = out_rows or dy.shape[1]
     k_in = out_cols or x.shape[1]
     if out is None:
-        out = torch.zeros(n_out, k_in, dtype=f32, device=dy.device)
+        out = zeros_f32(n_out, k_in, device=dy.device)
     K.gemm(dy, x, out, a_mn=True, b_mn=True, split_k=_wgrad_split(dy.shape[0], n_out * k_in), accumulate=accumulate,
            M=n_out, N=k_in, K=dy.shape[0])
     return out
@@ -170,7 +200,7 @@ class LinearFn(torch.autograd.Function):
             dw = wgrad(dyb, xb) if M > 0 else torch.zeros_like(weight)
             dw = dw.view(weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros(weight.shape[0], dtype=f32, device=dy.device)
+            db = zeros_f32(weight.shape[0], device=dy.device)
             if M > 0:
                 K.colsum(dyb, db)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
@@ -200,8 +230,8 @@ class LayerNormFn(torch.autograd.Function):
         dy = dy.contiguous()
         D = x.shape[1]
         dx = torch.empty_like(x)
-        dg = torch.zeros(D, dtype=f32, device=x.device)
-        db = torch.zeros(D, dtype=f32, device=x.device) if bias is not None else None
+        dg = zeros_f32(D, device=x.device)
+        db = zeros_f32(D, device=x.device) if bias is not None else None
         K.layernorm_bwd(dy, x, gamma.detach(), stats, dx, dg, b1=None if bias is None else bias.detach(), db1=db)
         return dx, dg, db, None, None
 
@@ -232,8 +262,8 @@ class AddLayerNormFn(torch.autograd.Function):
     def backward(ctx, dxout, dy):
         xout, gamma, bias, stats = ctx.saved_tensors
         D = xout.shape[1]
-        dg = torch.zeros(D, dtype=f32, device=xout.device)
-        db = torch.zeros(D, dtype=f32, device=xout.device) if bias is not None else None
+        dg = zeros_f32(D, device=xout.device)
+        db = zeros_f32(D, device=xout.device) if bias is not None else None
         if dy is None:      # only the residual stream was used downstream
             dx = dxout.contiguous()
             return dx, to_bf16(dx), dg, db, None
@@ -333,7 +363,7 @@ class PoolAttnFn(torch.autograd.Function):
         q, kv, mask_u8, mode, out, stat = ctx.saved_tensors
         B, R, H, N, n_head, scale = ctx.dims
         dout = to_bf16(dout.contiguous())
-        dq = torch.zeros(R, H * 64, dtype=f32, device=q.device)
+        dq = zeros_f32(R, H * 64, device=q.device)
         dkv = torch.empty_like(kv)
         K.pool_attn_bwd(q, kv, mask_u8, mode, out, stat, dout, dq, dkv, B=B, R=R, H=H, N=N, n_head=n_head, scale=scale,
                         q_batched=False)
@@ -546,7 +576,7 @@ class EmbedFn(torch.autograd.Function):
                 continue
             dY = torch.empty(B * n, D, dtype=bf16, device=dX.device)
             K.gather_rows(dX, dY, batch=B, n=n, d=D, src_batch_rows=nenc, row_off=off)
-            db = K.colsum(dY, torch.zeros(D, dtype=f32, device=dX.device))
+            db = K.colsum(dY, zeros_f32(D, device=dX.device))
             if semseg:
                 emb, w, pad = ctx.mod_params[m]
                 NC = emb.shape[0]

@@ -11,6 +11,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.distributed as dist
 
+from . import functions as Fn
 from .multimae import multimae as _plain
 from .multimae import multimae_crossattn as _cross
 from .multimae import multimae_lstm_s2dsm as _lstm
@@ -168,6 +169,10 @@ class PretrainStep:
             self.opt = FusedAdamW(model.parameters(), lr=blr * global_batch / 256, betas=(0.9, 0.95), weight_decay=weight_decay,
                                   max_grad_norm=max_grad_norm)
         self.reducer = GradAllReduce(list(model.parameters()))
+        # zero arena for the gradient accumulators outside the encoder stack: every parameter that is not an encoder-block
+        # tensor, twice over (transient accumulators such as padded weight gradients share it)
+        enc = {id(p) for n, p in model.named_parameters() if n.startswith("blocks.") or n.startswith("fus_blocks.")}
+        self._arena_elems = 2 * sum(p.numel() + 4 for p in model.parameters() if p.requires_grad and id(p) not in enc) + 1024
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         if self.world > 1:
             model.grad_hook = self.reducer.reduce_now   # per-layer reduction from inside the encoder backward
@@ -190,7 +195,11 @@ class PretrainStep:
         self.opt.zero_grad(set_to_none=True)
         out = self.model(inputs, num_encoded_tokens=self.nenc, alphas=self.alphas, sample_tasks_uniformly=self.uniformly)
         loss = self.loss(out, inputs)
-        (loss / self.world if self.world > 1 else loss).backward()   # 1/world here -> the all-reduce is a plain sum
+        Fn.begin_step_arena(self._arena_elems, loss.device)
+        try:
+            (loss / self.world if self.world > 1 else loss).backward()   # 1/world here -> the all-reduce is a plain sum
+        finally:
+            Fn.end_step_arena()
         self.reducer.finish()
         self.opt.step()
         return loss.detach()
