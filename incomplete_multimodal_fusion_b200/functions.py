@@ -603,10 +603,12 @@ class EmbedFn(torch.autograd.Function):
 ZB = 9  # tensors per (zorro or fusion) block: norm1.g, attn.norm.g, to_q.W, to_kv.W, to_out.W, norm2.g, mlp.0.g, mlp.1.W, mlp.3.W
 
 
-def _ln2(x, g1, g2, x2=None, split=0, rows=None, delta=None, delta_row0=0, xout=None):
-    """fused double LayerNorm of (x [+ delta]) -> bf16; see kernels.layernorm_fwd for the residual-add arguments"""
+def _ln2(x, g1, g2, x2=None, split=0, rows=None, delta=None, delta_row0=0, xout=None, y=None):
+    """fused double LayerNorm of (x [+ delta]) -> bf16 (into `y` if given); see kernels.layernorm_fwd for the residual-add
+    arguments"""
     rows = rows if rows is not None else x.shape[0]
-    y = torch.empty(rows, x.shape[1], dtype=bf16, device=x.device)
+    if y is None:
+        y = torch.empty(rows, x.shape[1], dtype=bf16, device=x.device)
     st = torch.empty(rows, 4, dtype=f32, device=x.device)
     K.layernorm_fwd(x, g1, y, g2=g2, stats=st, x2=x2, x_split=split, rows=rows, delta=delta, delta_row0=delta_row0, xout=xout)
     return y, st
@@ -708,15 +710,18 @@ class EncoderStackFn(torch.autograd.Function):
             Xin = S if pend is None else torch.empty(Mt, D, dtype=f32, device=S.device)
             if fusion:
                 fn1, fan, fwq, fwkv, fwo, fn2, fm0, fw1, fw2 = lp[:ZB]
-                hk, stA = _ln2(S, fn1, fan, delta=pend, xout=Xin if pend is not None else None)
+                # the normalised mask-embedding rows ride at the end of the token rows: ONE k/v projection (and, in the
+                # backward, one dgrad and one wgrad) per layer instead of a second, 196-row launch of each
+                hk_all = torch.empty(Mt + Fn, D, dtype=bf16, device=S.device)
+                hk, hm = hk_all[:Mt], hk_all[Mt:]
+                _, stA = _ln2(S, fn1, fan, delta=pend, xout=Xin if pend is not None else None, y=hk)
+                _, stM = _ln2(me.contiguous(), fn1, fan, y=hm)
                 wkv = w_bf16(params[base + i * per_layer + 3])
-                kv = torch.empty(Mt, 2 * HD, dtype=bf16, device=S.device)
-                K.gemm(hk, wkv, kv)
+                kv_all = torch.empty(Mt + Fn, 2 * HD, dtype=bf16, device=S.device)
+                K.gemm(hk_all, wkv, kv_all)
+                kv, kvm = kv_all[:Mt], kv_all[Mt:]
                 q = torch.empty(Mf, HD, dtype=bf16, device=S.device)
                 K.gemm(hk[Mh:], w_bf16(params[base + i * per_layer + 2]), q)
-                hm, stM = _ln2(me.contiguous(), fn1, fan)
-                kvm = torch.empty(Fn, 2 * HD, dtype=bf16, device=S.device)
-                K.gemm(hm, wkv, kvm)
                 a = torch.empty(Mf, HD, dtype=bf16, device=S.device)
                 K.slot_attn_fwd(q, kv, kvm, meta["slotmap"], seg, a, None, B=B, F=Fn, H=H, S=nseg, n_head=nenc, scale=scale)
                 dA = torch.empty(Mf, D, dtype=bf16, device=S.device)
@@ -726,7 +731,8 @@ class EncoderStackFn(torch.autograd.Function):
                 dF, g, u = _ffn_fwd(h2, w_geglu_bf16(params[base + i * per_layer + 7], ipad),
                                     w_bf16(params[base + i * per_layer + 8], cols_pad=ipad), ipad)
                 Xf2 = torch.empty(Mf, D, dtype=f32, device=S.device)
-                rec.update(hk=hk, stA=stA, kv=kv, q=q, hm=hm, stM=stM, kvm=kvm, a=a, Xf1=Xf1, h2=h2, stB=stB, g=g, u=u, Xf2=Xf2)
+                rec.update(hk=hk, hk_all=hk_all, stA=stA, kv=kv, q=q, hm=hm, stM=stM, kvm=kvm, a=a, Xf1=Xf1, h2=h2, stB=stB, g=g, u=u,
+                           Xf2=Xf2)
             zo = base + i * per_layer + (ZB if fusion else 0)
             n1, an, wq, wkv_, wo, n2, m0, w1, w2 = [p.detach() for p in params[zo: zo + ZB]]
             if fusion:   # rows >= Mh: Xf2 = Xf1 + ffn (written by this launch), rows < Mh: the block input
@@ -859,23 +865,22 @@ class EncoderStackFn(torch.autograd.Function):
             # dkv [Mt, 2HD] and dq [Mf, HD] share one buffer, [dk | dv | dq] per row (the dq columns of the modality rows
             # stay unused): the fusion rows' dgrad is then ONE GEMM over K = 3HD against [Wkv; Wq] instead of a second,
             # read-modify-write GEMM into the same rows
-            dkvq = torch.empty(Mt, 3 * HD, dtype=bf16, device=dev)
-            dkv, dq = dkvq[:, :2 * HD], dkvq[Mh:, 2 * HD:]
+            # rows [0, Mt): tokens; rows [Mt, Mt + Fn): the mask-embedding rows (batch-invariant keys / values), so that
+            # their k/v gradient shares the token rows' dgrad and wgrad launches
+            dkvq = torch.empty(Mt + Fn, 3 * HD, dtype=bf16, device=dev)
+            dkv, dq = dkvq[:Mt, :2 * HD], dkvq[Mh:Mt, 2 * HD:]
             dkvm = arena.take(Fn, 2 * HD)
             K.slot_attn_bwd(rec["q"], rec["kv"], rec["kvm"], meta["slotmap"], seg, da, dq, dkv, dkvm, B=B, F=Fn, H=H, S=nseg,
                             n_head=nenc, scale=scale)
+            K.cast_bf16(dkvm, dkvq[Mt:, :2 * HD])
             wkvb = w_bf16(params[fo + 3])
-            dhk = torch.empty(Mt, D, dtype=bf16, device=dev)
-            K.gemm(dkv[:Mh], wkvb, dhk[:Mh], b_mn=True)
-            K.gemm(dkvq[Mh:], w_cat_bf16([params[fo + 3], params[fo + 2]]), dhk[Mh:], b_mn=True)
-            dWkv = wgrad(dkv, rec["hk"], out=arena.take(2 * HD, D))
+            dhk_all = torch.empty(Mt + Fn, D, dtype=bf16, device=dev)
+            dhk, dhm = dhk_all[:Mt], dhk_all[Mt:]
+            K.gemm(dkvq[:Mh, :2 * HD], wkvb, dhk_all[:Mh], b_mn=True)
+            K.gemm(dkvq[Mh:Mt], w_cat_bf16([params[fo + 3], params[fo + 2]]), dhk_all[Mh:Mt], b_mn=True)
+            K.gemm(dkvq[Mt:, :2 * HD], wkvb, dhm, b_mn=True)
+            grads[fo + 3] = wgrad(dkvq[:, :2 * HD], rec["hk_all"], out=arena.take(2 * HD, D))
             grads[fo + 2] = wgrad(dq, rec["hk"][Mh:], out=arena.take(HD, D))
-            # mask-embedding rows (batch-invariant keys/values)
-            dkvmb = K.cast_bf16(dkvm)
-            dhm = torch.empty(Fn, D, dtype=bf16, device=dev)
-            K.gemm(dkvmb, wkvb, dhm, b_mn=True)
-            wgrad(dkvmb, rec["hm"], out=dWkv, accumulate=True)
-            grads[fo + 3] = dWkv
             dfn1, dfan = zeros(D), zeros(D)
             dme_i = torch.empty(Fn, D, dtype=f32, device=dev)
             K.layernorm_bwd(dhm, params[0].detach()[0].contiguous(), fn1, rec["stM"], dme_i, dfn1, g2=fan, dg2=dfan)
