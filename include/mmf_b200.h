@@ -223,6 +223,18 @@ int mmf_im2col_gather(const float* img, const int32_t* idx, void* out, int64_t b
  * idx[i]; `out` (bf16, ld_out >= num_classes*P*P) must be zeroed by the caller; cls is [B, H, W] int64 */
 int mmf_onehot_im2col(const int64_t* cls, const int32_t* idx, void* out, int64_t batch, int32_t H, int32_t W, int32_t P,
                       int32_t n_keep, int32_t num_classes, int64_t ld_out, mmf_stream_t stream);
+/* Device half of the input pipeline (reference utils/multimodal_dfc2023.py:99-141 load_dsm / load_rgb /
+ * load_sar after the rasterio decode, and the RandomCrop of :53-94), one launch per modality:
+ *   src [B, C, Hs, Ws] raw raster, src_dtype 0 = uint8, 1 = uint16, 2 = float32 (8-byte aligned);
+ *   mode 0: nan_to_num -> cv2.resize(INTER_AREA) by the integer `factor` -> (float64(x) - mean[c]) / std[c] -> fp32  (load_rgb)
+ *   mode 1: 10 log10(x + 1e-7), clip [-25, 0], nan_to_num -> resize -> the same z-score (load_sar; float32 rasters only)
+ *   mode 2: nan_to_num -> resize -> (x - mean) / sqrt(var + 1e-6) with the resized image's own fp32 mean / variance (load_dsm)
+ *   then the window [top[b], top[b] + Ho) x [left[b], left[b] + Wo) of the RESIZED image -> out [B, C, Ho, Wo] fp32.
+ * mean_host / std_host: HOST arrays of C doubles (modes 0, 1); crop_top / crop_left: DEVICE int32 [B] or both null (then
+ * Ho = Hs / factor, Wo = Ws / factor).  The caller guarantees top[b] + Ho <= Hs / factor (same for left). */
+int mmf_raster_prep(const void* src, int32_t src_dtype, int64_t batch, int32_t C, int32_t Hs, int32_t Ws, int32_t factor,
+                    int32_t mode, const double* mean_host, const double* std_host, const int32_t* crop_top,
+                    const int32_t* crop_left, int32_t Ho, int32_t Wo, float* out, mmf_stream_t stream);
 /* 'b (nh nw) (c ph pw) -> b c (nh ph) (nw pw)' bf16 (output_adapters_simple.py:183-186); inverse=1 for the gradient */
 int mmf_unpatchify_bf16(void* tokens, void* image, int64_t batch, int32_t C, int32_t H, int32_t W, int32_t P,
                         int32_t inverse, mmf_stream_t stream);

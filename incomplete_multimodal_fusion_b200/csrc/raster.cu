@@ -1,0 +1,201 @@
+// Device half of the input pipeline: everything the reference's dataset does to a raster AFTER the GeoTIFF
+// decode (utils/multimodal_dfc2023.py:99-141 load_dsm / load_rgb / load_sar, the RandomCrop of :53-94), one launch per
+// modality on the raw, still-integer (or fp32) batch:
+//     transform (SAR: 10 log10(x + 1e-7), clip to [-25, 0]; nan_to_num)  ->  cv2.resize(.., INTER_AREA) by an integer
+//     factor  ->  float32  ->  z-score with per-band constants (rgb, sar) or the image's own mean / variance (dsm)
+//     ->  crop window (top, left) per sample  ->  fp32 [B, C, Ho, Wo], the tensor the patch embedding reads.
+// The host then ships uint8 / uint16 rasters at native size (RGB: 1 byte per value instead of the 4 of the normalised
+// fp32 tensor) and never touches the pixels.
+//
+// cv2's INTER_AREA for integer factors is restated exactly (probed against cv2 4.13, pinned by tests/golden/raster.pt):
+//   integers, factor 2 : (a + b + c + d + 2) >> 2
+//   integers, factor f : rint(float(sum) * (1.f / f^2)), round-half-even, saturated
+//   float32,  factor 2 : ((a + b) + (c + d)) * 0.25f
+//   float32,  factor f : the f^2 values in row-major order, summed as sum += ((s0 + s1) + s2) + s3 per group of four,
+//                        then singly; result sum * (1.f / f^2)
+// and numpy's float64 z-score ((float32 - float64) / float64, rounded once to float32) is done in fp64.
+#include "common.cuh"
+#include "mmf_b200.h"
+#include <atomic>
+#include <float.h>
+
+namespace mmf {
+extern std::atomic<int64_t> g_launch_count;
+
+constexpr int RASTER_MAX_C = 8;
+constexpr int RASTER_MAX_F = 8;
+
+struct RasterParams {
+  const void* src;       // [B, C, Hs, Ws] raw raster
+  int64_t B;
+  int C, Hs, Ws, f, Hr, Wr, mode, Ho, Wo;
+  double mean[RASTER_MAX_C], stdv[RASTER_MAX_C];
+  const int32_t* top;    // [B] crop origin in the RESIZED image, or null (0)
+  const int32_t* left;
+  float* out;            // [B, C, Ho, Wo]
+};
+
+template <typename T> struct RasterT;
+template <> struct RasterT<uint8_t> { static constexpr bool is_int = true; static constexpr int maxv = 255; };
+template <> struct RasterT<uint16_t> { static constexpr bool is_int = true; static constexpr int maxv = 65535; };
+template <> struct RasterT<float> { static constexpr bool is_int = false; static constexpr int maxv = 0; };
+
+// np.nan_to_num on float32
+__device__ __forceinline__ float nan_to_num(float v) {
+  if (v != v) return 0.f;
+  if (v > FLT_MAX) return FLT_MAX;
+  if (v < -FLT_MAX) return -FLT_MAX;
+  return v;
+}
+
+// per-pixel transform ahead of the resize (load_sar: multimodal_dfc2023.py:131-133; load_rgb / load_dsm: nan_to_num)
+template <int MODE>
+__device__ __forceinline__ float pre_transform(float x) {
+  if (MODE == 1) {
+    float v = __fmul_rn(10.f, log10f(__fadd_rn(x, 1e-7f)));
+    if (v == v) v = fminf(fmaxf(v, -25.f), 0.f);   // np.clip keeps NaN; nan_to_num then zeroes it
+    return nan_to_num(v);
+  }
+  return nan_to_num(x);
+}
+
+// value of the resized image at (y, x) of plane `img` -- cv2.resize(INTER_AREA) by the integer factor f, as float32
+template <typename T, int MODE>
+__device__ __forceinline__ float resized_at(const T* __restrict__ img, int y, int x, int Ws, int f) {
+  const T* s = img + (int64_t)y * f * Ws + (int64_t)x * f;
+  if constexpr (RasterT<T>::is_int) {
+    if (f == 1) return (float)s[0];
+    if (f == 2) return (float)(((int)s[0] + (int)s[1] + (int)s[Ws] + (int)s[Ws + 1] + 2) >> 2);
+    int sum = 0;
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) sum += (int)s[(int64_t)dy * Ws + dx];
+    const float r = rintf(__fmul_rn((float)sum, 1.f / (float)(f * f)));
+    return fminf(fmaxf(r, 0.f), (float)RasterT<T>::maxv);
+  } else {
+    if (f == 1) return pre_transform<MODE>(s[0]);
+    if (f == 2) {
+      const float2 r0 = *reinterpret_cast<const float2*>(s), r1 = *reinterpret_cast<const float2*>(s + Ws);
+      return __fmul_rn(__fadd_rn(__fadd_rn(pre_transform<MODE>(r0.x), pre_transform<MODE>(r0.y)),
+                                 __fadd_rn(pre_transform<MODE>(r1.x), pre_transform<MODE>(r1.y))), 0.25f);
+    }
+    const int area = f * f;
+    float sum = 0.f;
+    int k = 0;
+    auto at = [&](int kk) { return pre_transform<MODE>(s[(int64_t)(kk / f) * Ws + (kk % f)]); };
+    for (; k + 4 <= area; k += 4)
+      sum = __fadd_rn(sum, __fadd_rn(__fadd_rn(__fadd_rn(at(k), at(k + 1)), at(k + 2)), at(k + 3)));
+    for (; k < area; ++k) sum = __fadd_rn(sum, at(k));
+    return __fmul_rn(sum, 1.f / (float)area);
+  }
+}
+
+// modes 0 (constant z-score) and 1 (SAR: dB, clip, constant z-score): one thread per output pixel
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) raster_const_kernel(const RasterParams p) {
+  const int64_t total = p.B * p.C * p.Ho * p.Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % p.Wo), oy = (int)((i / p.Wo) % p.Ho);
+    const int c = (int)((i / ((int64_t)p.Wo * p.Ho)) % p.C);
+    const int64_t b = i / ((int64_t)p.Wo * p.Ho * p.C);
+    const int y = oy + (p.top ? p.top[b] : 0), x = ox + (p.left ? p.left[b] : 0);
+    const T* img = reinterpret_cast<const T*>(p.src) + (b * p.C + c) * (int64_t)p.Hs * p.Ws;
+    const float v = resized_at<T, MODE>(img, y, x, p.Ws, p.f);
+    p.out[i] = (float)(((double)v - p.mean[c]) / p.stdv[c]);
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();   // sh may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+  return t;
+}
+
+// mode 2 (load_dsm, multimodal_dfc2023.py:99-112): the image's own mean and variance over the WHOLE resized raster
+// (all bands), then the crop.  One CTA per sample, three sweeps over its source (1 MB at 512 x 512 fp32: L2 resident).
+template <typename T>
+__global__ void __launch_bounds__(1024) raster_standardize_kernel(const RasterParams p) {
+  __shared__ double sh[32];
+  const int64_t b = blockIdx.x;
+  const T* img = reinterpret_cast<const T*>(p.src) + b * p.C * (int64_t)p.Hs * p.Ws;
+  const int n = p.C * p.Hr * p.Wr;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = i % p.Wr, y = (i / p.Wr) % p.Hr, c = i / (p.Wr * p.Hr);
+    acc += (double)resized_at<T, 0>(img + (int64_t)c * p.Hs * p.Ws, y, x, p.Ws, p.f);
+  }
+  const float mean = (float)(block_sum(acc, sh) / (double)n);
+  acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = i % p.Wr, y = (i / p.Wr) % p.Hr, c = i / (p.Wr * p.Hr);
+    const float d = __fsub_rn(resized_at<T, 0>(img + (int64_t)c * p.Hs * p.Ws, y, x, p.Ws, p.f), mean);
+    acc += (double)__fmul_rn(d, d);
+  }
+  const float var = (float)(block_sum(acc, sh) / (double)n);
+  const float den = __fsqrt_rn(__fadd_rn(var, 1e-6f));
+  const int top = p.top ? p.top[b] : 0, left = p.left ? p.left[b] : 0;
+  const int m = p.C * p.Ho * p.Wo;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const int ox = i % p.Wo, oy = (i / p.Wo) % p.Ho, c = i / (p.Wo * p.Ho);
+    const float v = resized_at<T, 0>(img + (int64_t)c * p.Hs * p.Ws, oy + top, ox + left, p.Ws, p.f);
+    p.out[b * m + i] = __fdiv_rn(__fsub_rn(v, mean), den);
+  }
+}
+
+template <typename T>
+static int raster_launch(const RasterParams& p, cudaStream_t st) {
+  if (p.mode == 2) {
+    raster_standardize_kernel<T><<<(unsigned)p.B, 1024, 0, st>>>(p);
+  } else {
+    const int64_t total = p.B * p.C * p.Ho * p.Wo;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t need = ceil_div64(total, 256), cap = (int64_t)sms * 8;
+    const unsigned grid = (unsigned)(need < cap ? need : cap);
+    if (p.mode == 1) raster_const_kernel<T, 1><<<grid, 256, 0, st>>>(p);
+    else raster_const_kernel<T, 0><<<grid, 256, 0, st>>>(p);
+  }
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mmf
+
+extern "C" int mmf_raster_prep(const void* src, int32_t src_dtype, int64_t batch, int32_t C, int32_t Hs, int32_t Ws,
+                               int32_t factor, int32_t mode, const double* mean_host, const double* std_host,
+                               const int32_t* crop_top, const int32_t* crop_left, int32_t Ho, int32_t Wo, float* out,
+                               mmf_stream_t stream) {
+  using namespace mmf;
+  if (!src || !out) MMF_BAD_ARG(1);
+  if (batch <= 0) return 0;
+  if (C <= 0 || C > RASTER_MAX_C || Hs <= 0 || Ws <= 0) MMF_BAD_ARG(2);
+  if (factor < 1 || factor > RASTER_MAX_F || Hs % factor || Ws % factor) MMF_BAD_ARG(3);   // integer INTER_AREA factors only
+  if (mode < 0 || mode > 2) MMF_BAD_ARG(4);
+  if (mode == 1 && src_dtype != 2) MMF_BAD_ARG(5);      // the dB transform is restated for float32 rasters
+  if (mode != 2 && (!mean_host || !std_host)) MMF_BAD_ARG(6);
+  const int Hr = Hs / factor, Wr = Ws / factor;
+  if (Ho <= 0 || Wo <= 0 || Ho > Hr || Wo > Wr) MMF_BAD_ARG(7);
+  if ((crop_top == nullptr) != (crop_left == nullptr)) MMF_BAD_ARG(8);
+  if (!crop_top && (Ho != Hr || Wo != Wr)) MMF_BAD_ARG(9);   // a smaller window needs its origin
+  if (src_dtype == 2 && (reinterpret_cast<uintptr_t>(src) & 7)) MMF_BAD_ARG(10);
+  RasterParams p{};
+  p.src = src; p.B = batch; p.C = C; p.Hs = Hs; p.Ws = Ws; p.f = factor; p.Hr = Hr; p.Wr = Wr; p.mode = mode;
+  p.Ho = Ho; p.Wo = Wo; p.top = crop_top; p.left = crop_left; p.out = out;
+  for (int c = 0; c < C; ++c) {
+    p.mean[c] = mode == 2 ? 0.0 : mean_host[c];
+    p.stdv[c] = mode == 2 ? 1.0 : std_host[c];
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (src_dtype) {
+    case 0: return raster_launch<uint8_t>(p, st);
+    case 1: return raster_launch<uint16_t>(p, st);
+    case 2: return raster_launch<float>(p, st);
+    default: MMF_BAD_ARG(11);
+  }
+}

@@ -343,6 +343,28 @@ def im2col_gather(img, idx, out, P):
     return out
 
 
+_RASTER_DTYPES = {torch.uint8: 0, torch.uint16: 1, torch.float32: 2}
+RASTER_ZSCORE, RASTER_SAR_DB, RASTER_STANDARDIZE = 0, 1, 2
+
+
+def raster_prep(src, mode, factor, mean=None, std=None, crop_top=None, crop_left=None, out_hw=None, out=None):
+    """raw raster batch [B, C, Hs, Ws] (uint8 / uint16 / float32) -> normalised fp32 [B, C, Ho, Wo]; see mmf_raster_prep"""
+    assert src.dim() == 4 and src.is_contiguous() and src.dtype in _RASTER_DTYPES, "raster_prep: contiguous uint8/uint16/float32 [B,C,H,W]"
+    B, Cc, Hs, Ws = src.shape
+    Ho, Wo = out_hw if out_hw is not None else (Hs // factor, Ws // factor)
+    if out is None:
+        out = torch.empty(B, Cc, Ho, Wo, dtype=f32, device=src.device)
+    assert out.is_contiguous() and out.dtype == f32 and tuple(out.shape) == (B, Cc, Ho, Wo)
+    for t in (crop_top, crop_left):
+        assert t is None or (t.dtype == torch.int32 and t.numel() == B and t.is_contiguous())
+    dbl = C.c_double * max(Cc, 1)
+    m = dbl(*[float(v) for v in mean]) if mean is not None else None
+    sd = dbl(*[float(v) for v in std]) if std is not None else None
+    check(_L().mmf_raster_prep(_p(src), _RASTER_DTYPES[src.dtype], B, Cc, Hs, Ws, factor, mode, m, sd, _p(crop_top), _p(crop_left),
+                               Ho, Wo, _p(out), _stream()), "mmf_raster_prep")
+    return out
+
+
 def onehot_im2col(cls, idx, out, P, num_classes):
     """cls [B, H, W] int64 class map -> out (zeroed bf16 [B*n, num_classes*P*P]) one-hot rows of the visible patches"""
     B, H, W = cls.shape
