@@ -179,6 +179,41 @@ def other_kernels(ktiming, steps, pk):
     return out
 
 
+def raster_pipeline_figures(batch, image, dev, pk):
+    """SURVEY 8f-4, outside the timed step: the three mmf_raster_prep launches that turn one raw decoded batch (512 x 512
+    uint8 optical, fp32 SAR / DSM) into the step's normalised fp32 crops; algorithmic bytes = source under the crop
+    window (whole source for the per-image standardisation) + fp32 output."""
+    import numpy as np
+    import torch
+    from incomplete_multimodal_fusion_b200.utils import multimodal_dfc2023 as D
+    S, f = 512, 2
+    crop_hw = min(image, 255)
+    raw = {"rgb": torch.randint(0, 256, (batch, 3, S, S), dtype=torch.uint8, device=dev),
+           "sar": torch.rand(batch, 1, S, S, device=dev) + 0.01, "dsm": torch.rand(batch, 1, S, S, device=dev) * 30}
+    np.random.seed(0)
+    top, left = D.RandomCrop(crop_hw).draw(batch)
+    crop = (top, left, (crop_hw, crop_hw))
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, fn, key, whole in (("rgb_u8_zscore", D.prepare_rgb, "rgb", False), ("sar_f32_db_zscore", D.prepare_sar, "sar", False),
+                                 ("dsm_f32_standardise", D.prepare_dsm, "dsm", True)):
+        src = raw[key]
+        for _ in range(2):
+            fn(src, crop)
+        e0.record()
+        for _ in range(5):
+            fn(src, crop)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        rd = src.numel() * src.element_size() if whole else batch * src.shape[1] * (crop_hw * f) ** 2 * src.element_size()
+        wr = batch * src.shape[1] * crop_hw * crop_hw * 4
+        out[name] = {"ms": round(ms, 4), "gbs": round((rd + wr) / ms / 1e6, 1), "frac_of_hbm_peak": round((rd + wr) / ms / 1e6 / pk["hbm"], 3)}
+    out["raw_h2d_mb_per_batch"] = round(sum(v.numel() * v.element_size() for v in raw.values()) / 1e6, 1)
+    out["shape"] = "batch %d, 512x512 rasters -> INTER_AREA 256x256 -> %d crops" % (batch, crop_hw)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -318,6 +353,7 @@ def run_ours(args):
         return
     pk = peaks()
     other = other_kernels(ktiming, 2, pk)
+    other["input_pipeline"] = raster_pipeline_figures(args.batch, args.image, dev, pk)
     gb = [(k, v) for k, v in by_shape.items() if k[0].endswith("_geglubwd")]
     if gb:   # dgrad GEMM + fused GEGLU backward: tensor flops AND the elementwise pass's algorithmic bytes (u read, du write, A read)
         t = sum(v[0] for _, v in gb)
