@@ -205,6 +205,14 @@ class MultiMAEBase(nn.Module):
         return info
 
     # ---- forward ----
+    def _device_const(self, key, device, make):
+        """small constant device tensors, built once per (key, device) instead of a pageable H2D copy per step"""
+        cache = self.__dict__.setdefault('_const_cache', {})
+        k = (key, str(device))
+        if k not in cache:
+            cache[k] = make().to(device)
+        return cache[k]
+
     def forward(self, x: Union[Dict[str, torch.Tensor], torch.Tensor], mask_inputs: bool = True,
                 task_masks: Dict[str, torch.Tensor] = None, num_encoded_tokens: int = 128,
                 alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False,
@@ -321,8 +329,13 @@ class MultiMAEBase(nn.Module):
         queries = torch.cat(queries, 0)
         Rt = queries.shape[0]
         N = nenc + n_tail
-        types = torch.repeat_interleave(torch.tensor([self.TYPE_IDS[t] for t in MODALITIES] + [self.FUSION_TYPE_ID],
-                                                     device=device), torch.tensor(counts + [n_tail], device=device))
+        # token type of every position from the device segment table (a repeat_interleave with device repeats reads its
+        # output size back: a full host synchronisation in the middle of the step, after which the small decoder / loss
+        # kernels ran host-bound)
+        type_ids = self._device_const(('type_ids', tuple(MODALITIES)), device,
+                                      lambda: torch.tensor([self.TYPE_IDS[t] for t in MODALITIES] + [self.FUSION_TYPE_ID]))
+        pos = self._device_const(('arange', N), device, lambda: torch.arange(N, dtype=torch.int32))
+        types = type_ids[(pos[:, None] >= zmask.seg[None, 1:-1]).sum(1)]
         pmask = torch.zeros(Rt, N, dtype=torch.uint8, device=device)
         pmask[:R] = ((rtypes[:, None] == types[None, :]) | (rtypes[:, None] == self.FUSION_TYPE_ID)).to(torch.uint8)
         mode = torch.zeros(Rt, dtype=torch.int32, device=device)

@@ -51,19 +51,23 @@ span = (evs[-1][1] - evs[0][0]) / 1e3
 busy_end = evs[0][0]
 idle = 0.0
 gaps = []
+prev = ""
 for s, e, n in evs:
     if s > busy_end:
         idle += (s - busy_end) / 1e3
-        gaps.append(((s - busy_end) / 1e3, n[:70]))
+        gaps.append(((s - busy_end) / 1e3, n[:70], prev[:40], (s - evs[0][0]) / 1e3))
+    if e >= busy_end:
+        prev = n
     busy_end = max(busy_end, e)
 lines = ["span %.2f ms, sum of kernel time %.2f ms, idle %.2f ms, %d device activities" % (span, sum(tot.values()), idle, len(evs))]
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:45]:
     lines.append("%9.3f ms %5.1f%% n=%4d  %s" % (v, 100 * v / span, cnt[k], k))
 lines.append("largest gaps (ms, kernel that followed):")
-for g, n in sorted(gaps, reverse=True)[:15]:
-    lines.append("   %.3f  %s" % (g, n))
-small = sum(g for g, _ in gaps if g < 0.02)
-lines.append("gaps < 20 us: %.2f ms in %d gaps" % (small, sum(1 for g, _ in gaps if g < 0.02)))
+ap_top = int(os.environ.get("MMF_TIMELINE_GAPS", "15"))
+for g, n, pv, at in sorted(gaps, reverse=True)[:ap_top]:
+    lines.append("   %.3f  at %7.2f ms  %s   <- after %s" % (g, at, n, pv))
+small = sum(g[0] for g in gaps if g[0] < 0.02)
+lines.append("gaps < 20 us: %.2f ms in %d gaps" % (small, sum(1 for g in gaps if g[0] < 0.02)))
 txt = "\n".join(lines)
 print(txt)
 if a.out:
