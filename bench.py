@@ -192,7 +192,7 @@ def raster_pipeline_figures(batch, image, dev, pk):
            "sar": torch.rand(batch, 1, S, S, device=dev) + 0.01, "dsm": torch.rand(batch, 1, S, S, device=dev) * 30}
     np.random.seed(0)
     top, left = D.RandomCrop(crop_hw).draw(batch)
-    crop = (top, left, (crop_hw, crop_hw))
+    crop = D.upload_crop((top, left, (crop_hw, crop_hw)), batch, dev)
     out = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for name, fn, key, whole in (("rgb_u8_zscore", D.prepare_rgb, "rgb", False), ("sar_f32_db_zscore", D.prepare_sar, "sar", False),

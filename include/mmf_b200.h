@@ -225,7 +225,7 @@ int mmf_onehot_im2col(const int64_t* cls, const int32_t* idx, void* out, int64_t
                       int32_t n_keep, int32_t num_classes, int64_t ld_out, mmf_stream_t stream);
 /* Device half of the input pipeline (reference utils/multimodal_dfc2023.py:99-141 load_dsm / load_rgb /
  * load_sar after the rasterio decode, and the RandomCrop of :53-94), one launch per modality:
- *   src [B, C, Hs, Ws] raw raster, src_dtype 0 = uint8, 1 = uint16, 2 = float32 (8-byte aligned);
+ *   src [B, C, Hs, Ws] raw raster, src_dtype 0 = uint8, 1 = uint16, 2 = float32, aligned to two elements;
  *   mode 0: nan_to_num -> cv2.resize(INTER_AREA) by the integer `factor` -> (float64(x) - mean[c]) / std[c] -> fp32  (load_rgb)
  *   mode 1: 10 log10(x + 1e-7), clip [-25, 0], nan_to_num -> resize -> the same z-score (load_sar; float32 rasters only)
  *   mode 2: nan_to_num -> resize -> (x - mean) / sqrt(var + 1e-6) with the resized image's own fp32 mean / variance (load_dsm)

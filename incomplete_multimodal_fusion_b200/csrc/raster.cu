@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "mmf_b200.h"
 #include <atomic>
+#include <cooperative_groups.h>
 #include <float.h>
 
 namespace mmf {
@@ -59,13 +60,23 @@ __device__ __forceinline__ float pre_transform(float x) {
   return nan_to_num(x);
 }
 
-// value of the resized image at (y, x) of plane `img` -- cv2.resize(INTER_AREA) by the integer factor f, as float32
-template <typename T, int MODE>
-__device__ __forceinline__ float resized_at(const T* __restrict__ img, int y, int x, int Ws, int f) {
+// value of the resized image at (y, x) of plane `img` -- cv2.resize(INTER_AREA) by the integer factor f, as float32.
+// F = compile-time factor (1, 2) or 0 = runtime `f`; factor 2 reads each source row's pixel pair with one load.
+template <typename T, int MODE, int F>
+__device__ __forceinline__ float resized_at(const T* __restrict__ img, int y, int x, int Ws, int f_rt) {
+  const int f = F ? F : f_rt;
   const T* s = img + (int64_t)y * f * Ws + (int64_t)x * f;
   if constexpr (RasterT<T>::is_int) {
     if (f == 1) return (float)s[0];
-    if (f == 2) return (float)(((int)s[0] + (int)s[1] + (int)s[Ws] + (int)s[Ws + 1] + 2) >> 2);
+    if (f == 2) {
+      if constexpr (sizeof(T) == 1) {
+        const uint32_t a = *reinterpret_cast<const uint16_t*>(s), b = *reinterpret_cast<const uint16_t*>(s + Ws);
+        return (float)(((a & 0xff) + (a >> 8) + (b & 0xff) + (b >> 8) + 2) >> 2);
+      } else {
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(s), b = *reinterpret_cast<const uint32_t*>(s + Ws);
+        return (float)(((a & 0xffff) + (a >> 16) + (b & 0xffff) + (b >> 16) + 2) >> 2);
+      }
+    }
     int sum = 0;
     for (int dy = 0; dy < f; ++dy)
       for (int dx = 0; dx < f; ++dx) sum += (int)s[(int64_t)dy * Ws + dx];
@@ -94,7 +105,8 @@ __device__ __forceinline__ float resized_at(const T* __restrict__ img, int y, in
 // contiguous per warp.  uint8 rasters: the resized value is one of 256 integers, so the fp64 z-score is taken from a
 // per-CTA table (one fp64 division per thread instead of one per pixel) -- same bits.
 constexpr int RASTER_ROWS = 8;
-template <typename T, int MODE>
+constexpr int RASTER_U = 4;   // pixels per lane per round: their source loads are all issued before the first store
+template <typename T, int MODE, int F>
 __global__ void __launch_bounds__(RASTER_ROWS * 32) raster_const_kernel(const RasterParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.y;
@@ -102,6 +114,7 @@ __global__ void __launch_bounds__(RASTER_ROWS * 32) raster_const_kernel(const Ra
   constexpr bool LUT = sizeof(T) == 1;
   __shared__ float lut[LUT ? 256 : 1];
   const double mean = p.mean[c], stdv = p.stdv[c];
+  const double rstd = 1.0 / stdv;   // dB path only (log10f already sits ~1 ulp from numpy's): no fp64 division per pixel
   if (LUT) {
     lut[threadIdx.x] = (float)(((double)threadIdx.x - mean) / stdv);   // RASTER_ROWS * 32 == 256 threads
     __syncthreads();
@@ -111,31 +124,53 @@ __global__ void __launch_bounds__(RASTER_ROWS * 32) raster_const_kernel(const Ra
   const int y = oy + (p.top ? p.top[b] : 0), x0 = p.left ? p.left[b] : 0;
   const T* img = reinterpret_cast<const T*>(p.src) + (b * p.C + c) * (int64_t)p.Hs * p.Ws;
   float* orow = p.out + ((b * p.C + c) * p.Ho + oy) * (int64_t)p.Wo;
-  // (a variant that issued 8 pixels' loads per lane before the first store measured slower: 0.19 vs 0.14 ms)
-  for (int ox = lane; ox < p.Wo; ox += 32) {
-    const float v = resized_at<T, MODE>(img, y, x0 + ox, p.Ws, p.f);
-    orow[ox] = LUT ? lut[(int)v] : (float)(((double)v - mean) / stdv);
+  for (int base = 0; base < p.Wo; base += 32 * RASTER_U) {
+    float v[RASTER_U];
+#pragma unroll
+    for (int u = 0; u < RASTER_U; ++u) {
+      const int ox = min(base + 32 * u + lane, p.Wo - 1);   // clamped: no predicated loads, the store is guarded
+      v[u] = resized_at<T, MODE, F>(img, y, x0 + ox, p.Ws, p.f);
+    }
+#pragma unroll
+    for (int u = 0; u < RASTER_U; ++u) {
+      const int ox = base + 32 * u + lane;
+      if (ox < p.Wo)
+        orow[ox] = LUT ? lut[(int)v[u]] : (MODE == 1 ? (float)(((double)v[u] - mean) * rstd) : (float)(((double)v[u] - mean) / stdv));
+    }
   }
 }
 
 // mode 2 (load_dsm, multimodal_dfc2023.py:99-112): the image's own mean and variance over the WHOLE resized raster
-// (all bands), then the crop.  One CTA per sample (512 threads: all 256 samples of a batch are co-resident), a warp per
-// row.  Sweep 1 accumulates sum(x) and sum(x^2) in fp64 (the variance about the fp32-rounded mean m follows as
-// (sum(x^2) - 2 m sum(x) + n m^2) / n, exact to fp64 rounding), sweep 2 re-reads the crop window (L2) and writes it.
-template <typename T>
-__global__ void __launch_bounds__(512) raster_standardize_kernel(const RasterParams p) {
-  __shared__ double sh[2][16];
+// (all bands), then the crop.  A cluster of RASTER_CL CTAs per sample (one CTA per sample left 148 SMs with 256 uneven
+// jobs), a warp per row.  Sweep 1 accumulates sum(x) and sum(x^2) in fp64 (the variance about the fp32-rounded mean m
+// follows as (sum(x^2) - 2 m sum(x) + n m^2) / n, exact to fp64 rounding); the CTAs' partial sums meet through
+// distributed shared memory, summed in rank order by every CTA (same bits everywhere); sweep 2 re-reads the crop window
+// (L2) and writes it.
+constexpr int RASTER_CL = 4;
+template <typename T, int F>
+__global__ void __cluster_dims__(RASTER_CL, 1, 1) __launch_bounds__(256) raster_standardize_kernel(const RasterParams p) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double sh[2][8];
+  __shared__ double part[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const int64_t b = blockIdx.x;
+  const int rank = (int)cluster.block_rank();
+  const int64_t b = blockIdx.x / RASTER_CL;
   const T* img = reinterpret_cast<const T*>(p.src) + b * p.C * (int64_t)p.Hs * p.Ws;
   double s1 = 0.0, s2 = 0.0;
-  for (int r = warp; r < p.C * p.Hr; r += nwarp) {
+  for (int r = rank * nwarp + warp; r < p.C * p.Hr; r += RASTER_CL * nwarp) {
     const int c = r / p.Hr, y = r - c * p.Hr;
     const T* plane = img + (int64_t)c * p.Hs * p.Ws;
-    for (int x = lane; x < p.Wr; x += 32) {
-      const double v = (double)resized_at<T, 0>(plane, y, x, p.Ws, p.f);
-      s1 += v;
-      s2 += v * v;
+    for (int base = 0; base < p.Wr; base += 32 * RASTER_U) {
+      float v[RASTER_U];
+#pragma unroll
+      for (int u = 0; u < RASTER_U; ++u) v[u] = resized_at<T, 0, F>(plane, y, min(base + 32 * u + lane, p.Wr - 1), p.Ws, p.f);
+#pragma unroll
+      for (int u = 0; u < RASTER_U; ++u)
+        if (base + 32 * u + lane < p.Wr) {
+          s1 += (double)v[u];
+          s2 += (double)v[u] * (double)v[u];
+        }
     }
   }
 #pragma unroll
@@ -145,32 +180,59 @@ __global__ void __launch_bounds__(512) raster_standardize_kernel(const RasterPar
   }
   if (lane == 0) { sh[0][warp] = s1; sh[1][warp] = s2; }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    s1 = s2 = 0.0;
+    for (int w = 0; w < nwarp; ++w) { s1 += sh[0][w]; s2 += sh[1][w]; }
+    part[0] = s1; part[1] = s2;
+  }
+  cluster.sync();
   s1 = s2 = 0.0;
-  for (int w = 0; w < nwarp; ++w) { s1 += sh[0][w]; s2 += sh[1][w]; }
+  for (int r = 0; r < RASTER_CL; ++r) {
+    const double* q = cluster.map_shared_rank(part, r);
+    s1 += q[0]; s2 += q[1];
+  }
+  cluster.sync();   // no CTA leaves (or reuses `part`) while a peer still reads it
   const double n = (double)p.C * p.Hr * p.Wr;
   const float mean = (float)(s1 / n);
   const double md = (double)mean;
   const float var = (float)(fmax(s2 - 2.0 * md * s1 + n * md * md, 0.0) / n);
   const float den = __fsqrt_rn(__fadd_rn(var, 1e-6f));
   const int top = p.top ? p.top[b] : 0, left = p.left ? p.left[b] : 0;
-  for (int r = warp; r < p.C * p.Ho; r += nwarp) {
+  for (int r = rank * nwarp + warp; r < p.C * p.Ho; r += RASTER_CL * nwarp) {
     const int c = r / p.Ho, oy = r - c * p.Ho;
     const T* plane = img + (int64_t)c * p.Hs * p.Ws;
     float* orow = p.out + ((b * p.C + c) * p.Ho + oy) * (int64_t)p.Wo;
-    for (int ox = lane; ox < p.Wo; ox += 32)
-      orow[ox] = __fdiv_rn(__fsub_rn(resized_at<T, 0>(plane, oy + top, ox + left, p.Ws, p.f), mean), den);
+    for (int base = 0; base < p.Wo; base += 32 * RASTER_U) {
+      float v[RASTER_U];
+#pragma unroll
+      for (int u = 0; u < RASTER_U; ++u)
+        v[u] = resized_at<T, 0, F>(plane, oy + top, min(base + 32 * u + lane, p.Wo - 1) + left, p.Ws, p.f);
+#pragma unroll
+      for (int u = 0; u < RASTER_U; ++u)
+        if (base + 32 * u + lane < p.Wo) orow[base + 32 * u + lane] = __fdiv_rn(__fsub_rn(v[u], mean), den);
+    }
   }
 }
 
 template <typename T>
 static int raster_launch(const RasterParams& p, cudaStream_t st) {
   if (p.mode == 2) {
-    raster_standardize_kernel<T><<<(unsigned)p.B, 512, 0, st>>>(p);
+    const unsigned grid = (unsigned)(p.B * RASTER_CL);
+    if (p.f == 2) raster_standardize_kernel<T, 2><<<grid, 256, 0, st>>>(p);
+    else if (p.f == 1) raster_standardize_kernel<T, 1><<<grid, 256, 0, st>>>(p);
+    else raster_standardize_kernel<T, 0><<<grid, 256, 0, st>>>(p);
   } else {
     if (p.B > 65535) return -12;
     const dim3 grid((unsigned)ceil_div(p.Ho, RASTER_ROWS), (unsigned)p.C, (unsigned)p.B);
-    if (p.mode == 1) raster_const_kernel<T, 1><<<grid, RASTER_ROWS * 32, 0, st>>>(p);
-    else raster_const_kernel<T, 0><<<grid, RASTER_ROWS * 32, 0, st>>>(p);
+#define MMF_RASTER_LAUNCH(MODE)                                                                         \
+  do {                                                                                                  \
+    if (p.f == 2) raster_const_kernel<T, MODE, 2><<<grid, RASTER_ROWS * 32, 0, st>>>(p);                \
+    else if (p.f == 1) raster_const_kernel<T, MODE, 1><<<grid, RASTER_ROWS * 32, 0, st>>>(p);           \
+    else raster_const_kernel<T, MODE, 0><<<grid, RASTER_ROWS * 32, 0, st>>>(p);                         \
+  } while (0)
+    if (p.mode == 1) MMF_RASTER_LAUNCH(1);
+    else MMF_RASTER_LAUNCH(0);
+#undef MMF_RASTER_LAUNCH
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
@@ -195,7 +257,8 @@ extern "C" int mmf_raster_prep(const void* src, int32_t src_dtype, int64_t batch
   if (Ho <= 0 || Wo <= 0 || Ho > Hr || Wo > Wr) MMF_BAD_ARG(7);
   if ((crop_top == nullptr) != (crop_left == nullptr)) MMF_BAD_ARG(8);
   if (!crop_top && (Ho != Hr || Wo != Wr)) MMF_BAD_ARG(9);   // a smaller window needs its origin
-  if (src_dtype == 2 && (reinterpret_cast<uintptr_t>(src) & 7)) MMF_BAD_ARG(10);
+  const int elem = src_dtype == 0 ? 1 : (src_dtype == 1 ? 2 : 4);
+  if (reinterpret_cast<uintptr_t>(src) & (uintptr_t)(2 * elem - 1)) MMF_BAD_ARG(10);   // factor 2 reads pixel pairs with one load
   RasterParams p{};
   p.src = src; p.B = batch; p.C = C; p.Hs = Hs; p.Ws = Ws; p.f = factor; p.Hr = Hr; p.Wr = Wr; p.mode = mode;
   p.Ho = Ho; p.Wo = Wo; p.top = crop_top; p.left = crop_left; p.out = out;

@@ -350,6 +350,8 @@ RASTER_ZSCORE, RASTER_SAR_DB, RASTER_STANDARDIZE = 0, 1, 2
 def raster_prep(src, mode, factor, mean=None, std=None, crop_top=None, crop_left=None, out_hw=None, out=None):
     """raw raster batch [B, C, Hs, Ws] (uint8 / uint16 / float32) -> normalised fp32 [B, C, Ho, Wo]; see mmf_raster_prep"""
     assert src.dim() == 4 and src.is_contiguous() and src.dtype in _RASTER_DTYPES, "raster_prep: contiguous uint8/uint16/float32 [B,C,H,W]"
+    if src.data_ptr() % (2 * src.element_size()):
+        src = src.clone()          # a view at an odd element offset: the factor-2 path reads pixel pairs with one load
     B, Cc, Hs, Ws = src.shape
     Ho, Wo = out_hw if out_hw is not None else (Hs // factor, Ws // factor)
     if out is None:

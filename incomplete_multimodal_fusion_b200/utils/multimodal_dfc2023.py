@@ -57,12 +57,20 @@ def _crop_args(crop, batch, size, device):
     if crop is None:
         return None, None, size
     top, left, hw = crop
+    if torch.is_tensor(top) and top.is_cuda:      # origins already uploaded (``upload_crop``): validated there, no copy here
+        return top, left, tuple(hw)
     top, left = np.asarray(top, np.int32), np.asarray(left, np.int32)
     if top.shape != (batch,) or left.shape != (batch,):
         raise ValueError("crop origins must be [batch]")
     if top.min() < 0 or left.min() < 0 or top.max() + hw[0] > size[0] or left.max() + hw[1] > size[1]:
         raise ValueError("crop window leaves the resized raster")
     return torch.from_numpy(top).to(device), torch.from_numpy(left).to(device), tuple(hw)
+
+
+def upload_crop(crop, batch, device, size=RESIZE):
+    """validate the crop origins once and move them to the device: the same window then serves all modalities of the batch
+    without a host -> device copy per launch"""
+    return _crop_args(crop, batch, size, device)
 
 
 def _prepare(raw, mode, mean, std, crop, size):
@@ -93,6 +101,9 @@ def prepare_dsm(raw, crop=None, size=RESIZE):
 def prepare_rgb_sar_dsm(sample, use_rgb=True, use_sar=True, use_dsm=True, crop=None):
     """load_rgb_sar_dsm (:151-177) + RandomCrop + collate on decoded batches: ``sample`` maps 'rgb' / 'sar' / 'dsm' to raw
     CUDA tensors; ``crop`` = (top[B], left[B], (h, w)) from ``RandomCrop.draw`` or None.  Returns the reference's keys."""
+    if crop is not None:
+        first = next(v for v in sample.values() if v is not None)
+        crop = upload_crop(crop, first.shape[0], first.device)
     return {
         's1': prepare_sar(sample["sar"], crop) if use_sar else None,
         's2': prepare_rgb(sample["rgb"], crop) if use_rgb else None,

@@ -32,7 +32,7 @@ sar = torch.rand(B, 1, S, S, device="cuda") + 0.01
 dsm = torch.rand(B, 1, S, S, device="cuda") * 30
 np.random.seed(0)
 top, left = D.RandomCrop(CR).draw(B)
-crop = (top, left, (CR, CR))
+crop = D.upload_crop((top, left, (CR, CR)), B, "cuda")
 f = S // 256
 for name, fn, src, whole in (("rgb u8 zscore", D.prepare_rgb, rgb, False), ("sar f32 dB+zscore", D.prepare_sar, sar, False),
                              ("dsm f32 standardise", D.prepare_dsm, dsm, True)):
