@@ -78,6 +78,16 @@ class HardNegtive_loss(nn.Module):
         eye = torch.eye(batch_size, dtype=torch.bool, device=device)
         return ~torch.cat([torch.cat([eye, eye], 1), torch.cat([eye, eye], 1)], 0)
 
+    def _negative_index(self, batch_size, device):
+        """[2B, 2B - 2] int64: column of the j-th True of get_negative_mask's row r (what masked_select walks)"""
+        cache = self.__dict__.setdefault('_neg_index_cache', {})
+        key = (batch_size, str(device))
+        if key not in cache:
+            j = torch.arange(2 * batch_size - 2, device=device)[None, :]
+            b = (torch.arange(2 * batch_size, device=device) % batch_size)[:, None]
+            cache[key] = j + (j >= b).long() + (j >= b + batch_size - 1).long()
+        return cache[key]
+
     def forward(self, out_1, out_2):
         B = out_1.shape[0]
         if not out_1.is_cuda:
@@ -86,7 +96,9 @@ class HardNegtive_loss(nn.Module):
         o2 = F.normalize(out_2.float(), dim=1)
         out = torch.cat([o1, o2], dim=0)
         neg = torch.exp(Fn.MatmulNTFn.apply(out, out) / self.temperature)
-        neg = neg.masked_select(self.get_negative_mask(B, out.device)).view(2 * B, -1)
+        # the negatives of row r are all columns but r mod B and (r mod B) + B, in ascending order: a gather through a static
+        # index instead of masked_select (whose output size is read back: a host synchronisation per loss call)
+        neg = torch.gather(neg, 1, self._negative_index(B, out.device))
         pos = torch.exp((o1 * o2).sum(-1) / self.temperature)
         pos = torch.cat([pos, pos], 0)
         if self.estimator == 'hard':

@@ -169,6 +169,60 @@ def test_fwd_bwd_matches_oracle(variant, dim, heads, img, patch, batch, nenc, de
     print("worst grad rel err", worst)
 
 
+def test_full_vitb_config_matches_oracle_and_is_batch_invariant():
+    """BASELINE cfg 2 at its real width (ViT-B/16 fusion-block variant, 224 x 224, 294 visible tokens, cross-attention
+    decoders -- the bench model): (1) batch 8 against the fp32 oracle on the same masks, forward, loss and every parameter
+    gradient; (2) the full batch of 256 (M_t = 125,440 token rows: the shapes bench.py times) -- a sample's predictions do
+    not depend on the batch it rides in, so the first 8 samples must reproduce the batch-8 run."""
+    cfg = OracleConfig(variant="crossattn", dim=768, depth=12, heads=8, image_size=224, patch=16, dec_dim=256,
+                       dec_depth=2, dec_heads=8, decoder="xattn")
+    sd = default_sd(cfg)
+    model = build_model(cfg, sd)
+    x256 = make_inputs(cfg, 256, 21, "cuda")
+    x = OrderedDict((k, v[:8].contiguous()) for k, v in x256.items())
+    torch.manual_seed(9)
+    out = model(x, num_encoded_tokens=294, sample_tasks_uniformly=True)
+    loss = pretrain_loss_ours(out, x, cfg.patch)
+    loss.backward()
+
+    sd_o = OrderedDict((k, v.cuda().requires_grad_(not (k.endswith(".beta") or k.endswith("pos_emb")))) for k, v in sd.items())
+    torch.manual_seed(9)
+    ref = oracle.multimae_forward(sd_o, cfg, x, num_encoded_tokens=294, sample_tasks_uniformly=True)
+    ref_loss, _ = oracle.pretrain_loss(ref, x, cfg)
+    ref_loss.backward()
+    for t in ref[1]:
+        assert torch.equal(out[1][t], ref[1][t])
+    for t in ref[0]:
+        assert rel(out[0][t], ref[0][t]) < ACT_TOL, (t, rel(out[0][t], ref[0][t]))
+    for i in range(2, len(ref)):
+        assert rel(out[i], ref[i]) < ACT_TOL, (i, rel(out[i], ref[i]))
+    assert abs(float(loss) - float(ref_loss)) < ACT_TOL * abs(float(ref_loss))
+    worst = 0.0
+    for k, p in model.named_parameters():
+        g_ref = sd_o[k].grad
+        if g_ref is None or float(g_ref.norm()) < 1e-7:
+            continue
+        e = rel(p.grad, g_ref)
+        worst = max(worst, e)
+        assert e < (GOLDEN_GRAD_TOL if k.startswith("output_adapters.dem.") else GRAD_TOL), (k, e)
+    print("ViT-B full config: worst grad rel err", worst)
+    del ref, ref_loss, sd_o
+    model.zero_grad(set_to_none=True)
+
+    with torch.no_grad():
+        torch.manual_seed(9)
+        out8 = model(x, num_encoded_tokens=294, sample_tasks_uniformly=True)
+        torch.manual_seed(9)
+        big = model(x256, num_encoded_tokens=294, sample_tasks_uniformly=True)
+    for t in out8[1]:
+        assert torch.equal(big[1][t][:8], out8[1][t])                   # one mask row per step, whatever the batch
+    for t in out8[0]:
+        assert rel(big[0][t][:8], out8[0][t]) < 1e-6, (t, rel(big[0][t][:8], out8[0][t]))
+    for i in range(2, len(out8)):
+        assert rel(big[i][:8], out8[i]) < 1e-6, (i, rel(big[i][:8], out8[i]))
+    assert all(torch.isfinite(v.float()).all() for v in big[0].values())
+
+
 def test_reference_autocast_noise_floor():
     """How far the reference's OWN bf16-autocast arithmetic is from its fp32 arithmetic (oracle emulation), next to
     our distance from fp32: our path must not be noisier than that floor by more than 2x."""
