@@ -169,25 +169,28 @@ def test_fwd_bwd_matches_oracle(variant, dim, heads, img, patch, batch, nenc, de
     print("worst grad rel err", worst)
 
 
-def test_full_vitb_config_matches_oracle_and_is_batch_invariant():
+@pytest.mark.parametrize("dim,depth,image,nenc,big", [(768, 12, 224, 294, 256), (1024, 3, 256, 384, 0)])
+def test_full_vitb_config_matches_oracle_and_is_batch_invariant(dim, depth, image, nenc, big):
     """BASELINE cfg 2 at its real width (ViT-B/16 fusion-block variant, 224 x 224, 294 visible tokens, cross-attention
     decoders -- the bench model): (1) batch 8 against the fp32 oracle on the same masks, forward, loss and every parameter
     gradient; (2) the full batch of 256 (M_t = 125,440 token rows: the shapes bench.py times) -- a sample's predictions do
-    not depend on the batch it rides in, so the first 8 samples must reproduce the batch-8 run."""
-    cfg = OracleConfig(variant="crossattn", dim=768, depth=12, heads=8, image_size=224, patch=16, dec_dim=256,
+    not depend on the batch it rides in, so the first 8 samples must reproduce the batch-8 run.  Second case: the ViT-L/16
+    width of cfg 5 (D = 1024, GEGLU width 2730 padded to 2752, 256 x 256 tiles, 384 visible tokens), three layers deep,
+    part (1) only."""
+    cfg = OracleConfig(variant="crossattn", dim=dim, depth=depth, heads=8, image_size=image, patch=16, dec_dim=256,
                        dec_depth=2, dec_heads=8, decoder="xattn")
     sd = default_sd(cfg)
     model = build_model(cfg, sd)
-    x256 = make_inputs(cfg, 256, 21, "cuda")
+    x256 = make_inputs(cfg, max(big, 8), 21, "cuda")
     x = OrderedDict((k, v[:8].contiguous()) for k, v in x256.items())
     torch.manual_seed(9)
-    out = model(x, num_encoded_tokens=294, sample_tasks_uniformly=True)
+    out = model(x, num_encoded_tokens=nenc, sample_tasks_uniformly=True)
     loss = pretrain_loss_ours(out, x, cfg.patch)
     loss.backward()
 
     sd_o = OrderedDict((k, v.cuda().requires_grad_(not (k.endswith(".beta") or k.endswith("pos_emb")))) for k, v in sd.items())
     torch.manual_seed(9)
-    ref = oracle.multimae_forward(sd_o, cfg, x, num_encoded_tokens=294, sample_tasks_uniformly=True)
+    ref = oracle.multimae_forward(sd_o, cfg, x, num_encoded_tokens=nenc, sample_tasks_uniformly=True)
     ref_loss, _ = oracle.pretrain_loss(ref, x, cfg)
     ref_loss.backward()
     for t in ref[1]:
@@ -205,15 +208,17 @@ def test_full_vitb_config_matches_oracle_and_is_batch_invariant():
         e = rel(p.grad, g_ref)
         worst = max(worst, e)
         assert e < (GOLDEN_GRAD_TOL if k.startswith("output_adapters.dem.") else GRAD_TOL), (k, e)
-    print("ViT-B full config: worst grad rel err", worst)
+    print("full-width config D=%d: worst grad rel err" % dim, worst)
     del ref, ref_loss, sd_o
     model.zero_grad(set_to_none=True)
+    if not big:
+        return
 
     with torch.no_grad():
         torch.manual_seed(9)
-        out8 = model(x, num_encoded_tokens=294, sample_tasks_uniformly=True)
+        out8 = model(x, num_encoded_tokens=nenc, sample_tasks_uniformly=True)
         torch.manual_seed(9)
-        big = model(x256, num_encoded_tokens=294, sample_tasks_uniformly=True)
+        big = model(x256, num_encoded_tokens=nenc, sample_tasks_uniformly=True)
     for t in out8[1]:
         assert torch.equal(big[1][t][:8], out8[1][t])                   # one mask row per step, whatever the batch
     for t in out8[0]:
