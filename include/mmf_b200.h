@@ -235,6 +235,11 @@ int mmf_onehot_im2col(const int64_t* cls, const int32_t* idx, void* out, int64_t
 int mmf_raster_prep(const void* src, int32_t src_dtype, int64_t batch, int32_t C, int32_t Hs, int32_t Ws, int32_t factor,
                     int32_t mode, const double* mean_host, const double* std_host, const int32_t* crop_top,
                     const int32_t* crop_left, int32_t Ho, int32_t Wo, float* out, mmf_stream_t stream);
+/* Truncated depth standardisation (pretrain_mmae.py:452-459, --standardize_depth): per sample of n = C*H*W fp32 values,
+ * mean and UNBIASED variance of sorted(x)[k_lo : k_hi] (the reference: k_lo = int(0.1 n), k_hi = int(0.9 n)), then
+ * out = (x - mean) / sqrt(var + 1e-6) over the whole sample.  Radix select in shared memory, no sort; n <= 56,320. */
+int mmf_trunc_standardize(const float* x, float* out, int64_t batch, int32_t n, int32_t k_lo, int32_t k_hi,
+                          mmf_stream_t stream);
 /* 'b (nh nw) (c ph pw) -> b c (nh ph) (nw pw)' bf16 (output_adapters_simple.py:183-186); inverse=1 for the gradient */
 int mmf_unpatchify_bf16(void* tokens, void* image, int64_t batch, int32_t C, int32_t H, int32_t W, int32_t P,
                         int32_t inverse, mmf_stream_t stream);

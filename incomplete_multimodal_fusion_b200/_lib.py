@@ -100,6 +100,7 @@ SIGNATURES = {
     "mmf_onehot_im2col": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_vp],
     "mmf_raster_prep": [c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                         c_vp, c_vp, c_i32, c_i32, c_vp, c_vp],
+    "mmf_trunc_standardize": [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp],
     "mmf_unpatchify_bf16": [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "mmf_gather_rows": [c_vp, c_i32, c_i64, c_i64, c_i64, c_vp, c_vp, c_i32, c_i64, c_i64, c_i32, c_i32, c_vp],
     "mmf_add_inplace_f32": [c_vp, c_vp, c_i64, c_vp],

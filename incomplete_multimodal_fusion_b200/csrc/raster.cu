@@ -214,6 +214,101 @@ __global__ void __cluster_dims__(RASTER_CL, 1, 1) __launch_bounds__(256) raster_
   }
 }
 
+// Truncated depth standardisation of the training loop (pretrain_mmae.py:452-459, `--standardize_depth`): per sample,
+// sort the n = C*H*W values, keep sorted[k_lo : k_hi] (the reference drops the bottom and top 10 %), and standardise the
+// WHOLE image with that slice's mean and unbiased variance.  No sort here: the sample sits in shared memory (n <= 56 K
+// floats), two 4-pass radix selects on order-preserving keys find v_lo = sorted[k_lo] and v_hi = sorted[k_hi - 1]; the
+// slice is then {v_lo < x < v_hi} plus the right number of copies of the two boundary values (ties), summed in fp64.
+constexpr int TRUNC_THREADS = 1024;
+__device__ __forceinline__ uint32_t order_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// value of rank k (0-based, ascending) among xs[0..n): 8 bits per pass, shared-memory histogram of the keys that match
+// the prefix found so far
+__device__ float radix_select(const float* xs, int n, int k, uint32_t* hist, uint32_t* bcast) {
+  uint32_t prefix = 0, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = order_key(xs[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t acc = 0;
+      int bkt = 0;
+      for (; bkt < 256; ++bkt) {
+        if (acc + hist[bkt] > (uint32_t)k) break;
+        acc += hist[bkt];
+      }
+      bcast[0] = (uint32_t)bkt;
+      bcast[1] = acc;
+    }
+    __syncthreads();
+    prefix |= bcast[0] << shift;
+    mask |= 255u << shift;
+    k -= (int)bcast[1];
+    __syncthreads();
+  }
+  const uint32_t u = (prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix;
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(TRUNC_THREADS) trunc_standardize_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                          int n, int k_lo, int k_hi) {
+  extern __shared__ float xs[];
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t bcast[2];
+  __shared__ double shd[32];
+  const float* xi = x + (int64_t)blockIdx.x * n;
+  float* oi = out + (int64_t)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = xi[i];
+  __syncthreads();
+  const float v_lo = radix_select(xs, n, k_lo, hist, bcast);
+  const float v_hi = radix_select(xs, n, k_hi - 1, hist, bcast);
+  const int m = k_hi - k_lo;
+  // counts of the boundary values inside the slice
+  double c_le_lo = 0.0, c_lt_hi = 0.0, s_mid = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = xs[i];
+    c_le_lo += v <= v_lo ? 1.0 : 0.0;
+    c_lt_hi += v < v_hi ? 1.0 : 0.0;
+    s_mid += (v > v_lo && v < v_hi) ? (double)v : 0.0;
+  }
+  c_le_lo = block_sum_d(c_le_lo, shd);
+  c_lt_hi = block_sum_d(c_lt_hi, shd);
+  s_mid = block_sum_d(s_mid, shd);
+  double n_lo, n_hi;
+  if (v_lo == v_hi) { n_lo = (double)m; n_hi = 0.0; }
+  else { n_lo = c_le_lo - (double)k_lo; n_hi = (double)k_hi - c_lt_hi; }
+  const double mean = (s_mid + n_lo * (double)v_lo + n_hi * (double)v_hi) / (double)m;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = xs[i];
+    const double d = (double)v - mean;
+    q += (v > v_lo && v < v_hi) ? d * d : 0.0;
+  }
+  q = block_sum_d(q, shd);
+  q += n_lo * ((double)v_lo - mean) * ((double)v_lo - mean) + n_hi * ((double)v_hi - mean) * ((double)v_hi - mean);
+  const float var = (float)(q / (double)(m - 1));   // torch.var: unbiased
+  const float mean_f = (float)mean;
+  const float den = __fsqrt_rn(__fadd_rn(var, 1e-6f));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) oi[i] = __fdiv_rn(__fsub_rn(xs[i], mean_f), den);
+}
+
 template <typename T>
 static int raster_launch(const RasterParams& p, cudaStream_t st) {
   if (p.mode == 2) {
@@ -273,4 +368,24 @@ extern "C" int mmf_raster_prep(const void* src, int32_t src_dtype, int64_t batch
     case 2: return raster_launch<float>(p, st);
     default: MMF_BAD_ARG(11);
   }
+}
+
+extern "C" int mmf_trunc_standardize(const float* x, float* out, int64_t batch, int32_t n, int32_t k_lo, int32_t k_hi,
+                                     mmf_stream_t stream) {
+  using namespace mmf;
+  if (!x || !out) MMF_BAD_ARG(1);
+  if (batch <= 0) return 0;
+  const size_t smem = (size_t)n * sizeof(float);
+  if (n <= 1 || smem > 220 * 1024) MMF_BAD_ARG(2);      // the sample lives in shared memory
+  if (k_lo < 0 || k_hi > n || k_hi - k_lo < 2) MMF_BAD_ARG(3);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(trunc_standardize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  trunc_standardize_kernel<<<(unsigned)batch, TRUNC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, n, k_lo, k_hi);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMF_LAUNCH_CHECK();
+  return 0;
 }

@@ -367,6 +367,17 @@ def raster_prep(src, mode, factor, mean=None, std=None, crop_top=None, crop_left
     return out
 
 
+def trunc_standardize(x, lo=0.1, hi=0.9):
+    """x fp32 [B, ...]: per sample (x - mean) / sqrt(var + 1e-6) with the mean / unbiased variance of the sorted values
+    between the `lo` and `hi` quantile positions (pretrain_mmae.py:452-459)"""
+    assert x.dtype == f32 and x.is_contiguous() and x.dim() >= 2
+    B = x.shape[0]
+    n = x.numel() // B
+    out = torch.empty_like(x)
+    check(_L().mmf_trunc_standardize(_p(x), _p(out), B, n, int(lo * n), int(hi * n), _stream()), "mmf_trunc_standardize")
+    return out
+
+
 def onehot_im2col(cls, idx, out, P, num_classes):
     """cls [B, H, W] int64 class map -> out (zeroed bf16 [B*n, num_classes*P*P]) one-hot rows of the visible patches"""
     B, H, W = cls.shape

@@ -109,3 +109,12 @@ def prepare_rgb_sar_dsm(sample, use_rgb=True, use_sar=True, use_dsm=True, crop=N
         's2': prepare_rgb(sample["rgb"], crop) if use_rgb else None,
         'dem': prepare_dsm(sample["dsm"], crop) if use_dsm else None,
     }
+
+
+def standardize_depth(dem):
+    """The training loop's truncated depth standardisation (pretrain_mmae.py:452-459, ``--standardize_depth``): per sample,
+    mean and variance of the values left after dropping the bottom and top 10 %, applied to the whole image.  One launch
+    (radix select in shared memory) instead of the reference's full ``torch.sort`` of every sample."""
+    if not dem.is_cuda:
+        raise RuntimeError("standardize_depth: CUDA tensors only (no CPU fallback)")
+    return K.trunc_standardize(dem.float().contiguous())

@@ -87,3 +87,11 @@ def draw_crops(batch, hw, h=256, w=256):
         top[b] = np.random.randint(0, h - hw[0])
         left[b] = np.random.randint(0, w - hw[1])
     return top, left
+
+
+def standardize_depth(dem):
+    """pretrain_mmae.py:452-459 verbatim in meaning (torch; ``rearrange(.., 'b c h w -> b (c h w)')`` = flatten(1))"""
+    import torch
+    trunc = torch.sort(dem.flatten(1), dim=1)[0]
+    trunc = trunc[:, int(0.1 * trunc.shape[1]): int(0.9 * trunc.shape[1])]
+    return (dem - trunc.mean(dim=1)[:, None, None, None]) / torch.sqrt(trunc.var(dim=1)[:, None, None, None] + 1e-6)

@@ -123,3 +123,28 @@ def test_device_pipeline_rejects_what_it_does_not_restate():
     with pytest.raises(ValueError):
         D.prepare_rgb(torch.zeros(2, 3, 256, 256, dtype=torch.uint8, device="cuda"),
                       crop=(np.array([40, 0]), np.array([0, 0]), (224, 224)))            # window leaves the raster
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["normal", "ties", "constant", "negative"])
+def test_standardize_depth_matches_reference_expression(kind):
+    """the sort-free truncated standardisation against the reference's expression (pretrain_mmae.py:452-459) in fp64-free
+    torch on the CPU: continuous values, heavy ties (boundary values repeated inside and outside the kept slice), a
+    constant image (variance 0 -> division by sqrt(1e-6)) and negative values (key order of the radix select)"""
+    from incomplete_multimodal_fusion_b200.utils import multimodal_dfc2023 as D
+    g = torch.Generator().manual_seed(4)
+    B, H = 6, 224
+    if kind == "normal":
+        dem = torch.randn(B, 1, H, H, generator=g) * 7 + 5
+    elif kind == "ties":
+        dem = torch.randint(0, 12, (B, 1, H, H), generator=g).float()
+    elif kind == "constant":
+        dem = torch.full((B, 1, H, H), 3.25)
+    else:
+        dem = -torch.rand(B, 1, H, H, generator=g) * 100 + 20
+    want = O.standardize_depth(dem.double()).float() if kind != "constant" else O.standardize_depth(dem)
+    got = D.standardize_depth(dem.cuda()).cpu()
+    scale = float(want.abs().max().clamp_min(1.0))
+    assert float((got - want).abs().max()) <= 2e-5 * scale, (kind, float((got - want).abs().max()))
+    ref32 = O.standardize_depth(dem)            # the reference's own fp32 arithmetic sits at the same distance
+    assert float((got - ref32).abs().max()) <= 2e-4 * scale
