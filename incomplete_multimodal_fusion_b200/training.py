@@ -153,8 +153,10 @@ class PretrainStep:
 
     def __init__(self, model, num_encoded_tokens: int, patch_size: int = 16, blr: float = 1e-4, global_batch: int = 256,
                  weight_decay: float = 0.05, sample_tasks_uniformly: bool = True, alphas: float = 1.0,
-                 contrastive_weight: float = 0.3, max_grad_norm: Optional[float] = None, torch_optimizer: bool = False):
+                 contrastive_weight: float = 0.3, max_grad_norm: Optional[float] = None, torch_optimizer: bool = False,
+                 standardize_depth: bool = False):
         self.model = model
+        self.standardize_depth = standardize_depth   # pretrain_mmae.py:87-89, 452-459 (off by default there too)
         self.nenc = num_encoded_tokens
         self.uniformly = sample_tasks_uniformly
         self.alphas = alphas
@@ -193,6 +195,9 @@ class PretrainStep:
 
     def __call__(self, inputs: Dict[str, torch.Tensor]) -> torch.Tensor:
         self.opt.zero_grad(set_to_none=True)
+        if self.standardize_depth and 'dem' in inputs:
+            from .utils.multimodal_dfc2023 import standardize_depth
+            inputs = dict(inputs, dem=standardize_depth(inputs['dem']))
         out = self.model(inputs, num_encoded_tokens=self.nenc, alphas=self.alphas, sample_tasks_uniformly=self.uniformly)
         loss = self.loss(out, inputs)
         Fn.begin_step_arena(self._arena_elems, loss.device)
