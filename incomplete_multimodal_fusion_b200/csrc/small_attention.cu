@@ -433,7 +433,10 @@ __global__ void pool_attn_fwd_kernel(const PoolParams p) {
 // backward: 4 lanes per key (16 of the 64 dims each), 64 keys per 256-thread block, looping over the
 // R queries.  delta[b,r,h] = dout.out sits right after the (max,sum) pairs in `stat`.
 __global__ void __launch_bounds__(256) pool_attn_bwd_kernel(const PoolParams p) {
-  __shared__ float qs[16][64], ds_[16][64], dqs[16][64], mxs[16], sums[16], dls[16];
+  // dq_r = sum_j ds_rj k_j is taken in a second phase from shared copies of the block's 64 keys and its [R, 64] ds
+  // values: thread (r, dim) runs over the keys (the first form reduced every (r, dim) product over the warp's keys with
+  // three shuffles and a shared atomic: 340 shuffles per thread)
+  __shared__ float qs[16][64], ds_[16][64], dss[16][64], ks[64][65], mxs[16], sums[16], dls[16];
   const int h = blockIdx.y, b = blockIdx.z;
   const int HD = p.H * 64;
   const int tid = threadIdx.x, sub = tid & 3;
@@ -441,7 +444,6 @@ __global__ void __launch_bounds__(256) pool_attn_bwd_kernel(const PoolParams p) 
     const int r = t / 64, d = t % 64;
     qs[r][d] = __bfloat162float(p.q[b * p.q_bstride + (int64_t)r * HD + h * 64 + d]);
     ds_[r][d] = __bfloat162float(p.dout[((int64_t)b * p.R + r) * HD + h * 64 + d]);
-    dqs[r][d] = 0.f;   // dq of this CTA's 64 keys: combined in shared memory, one global atomic per (r, dim) at the end
   }
   if (tid < p.R) {
     const int64_t brh = ((int64_t)b * p.R + tid) * p.H + h;
@@ -471,6 +473,8 @@ __global__ void __launch_bounds__(256) pool_attn_bwd_kernel(const PoolParams p) 
       }
     }
   }
+#pragma unroll
+  for (int d = 0; d < 16; ++d) ks[tid >> 2][sub * 16 + d] = kf[d];
   for (int r = 0; r < p.R; ++r) {
     const float sum = sums[r];
     float dp = 0.f, sdot = 0.f;
@@ -487,21 +491,15 @@ __global__ void __launch_bounds__(256) pool_attn_bwd_kernel(const PoolParams p) 
     }
 #pragma unroll
     for (int d = 0; d < 16; ++d) { dk[d] += dsj * qs[r][sub * 16 + d]; dv[d] += pj * ds_[r][sub * 16 + d]; }
-    if (sum > 0.f) {  // dq_r += sum_j ds_j k_j : reduce the 8 keys of the warp, then one atomic per dim
-#pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        float c = dsj * kf[d];
-        c += __shfl_xor_sync(0xffffffffu, c, 4);
-        c += __shfl_xor_sync(0xffffffffu, c, 8);
-        c += __shfl_xor_sync(0xffffffffu, c, 16);
-        if ((tid & 31) < 4 && c != 0.f) atomicAdd(&dqs[r][sub * 16 + d], c);
-      }
-    }
+    if (sub == 0) dss[r][tid >> 2] = dsj;   // 0 for masked / invalid keys and for uniform or empty rows
   }
   __syncthreads();
   for (int t = tid; t < p.R * 64; t += blockDim.x) {
-    const float c = dqs[t / 64][t % 64];
-    if (c != 0.f) atomicAdd(p.dq + b * p.dq_bstride + (int64_t)(t / 64) * HD + h * 64 + (t % 64), c);
+    const int r = t >> 6, d = t & 63;
+    float c = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) c += dss[r][k] * ks[k][d];
+    if (c != 0.f) atomicAdd(p.dq + b * p.dq_bstride + (int64_t)r * HD + h * 64 + d, c);
   }
   if (valid) {
     __nv_bfloat16* ok = p.dkv + row * p.lddkv + h * 64 + sub * 16;
