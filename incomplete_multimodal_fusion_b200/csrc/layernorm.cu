@@ -179,7 +179,9 @@ struct LnBwdParams {
 // first LayerNorm's reductions instead of chunk by chunk behind the dx stores.  Tried and dropped: two rows per warp
 // (spills, 0.42 ms) and packed fp32x2 row arithmetic (the pair packing moves cost more than the FFMA2s save: 0.41 ms
 // against 0.33 ms for this form at the cfg-2 shape).
-template <int NC, bool PF, bool FULL>
+// HB: the first LayerNorm has a bias (decoders' nn.LayerNorm); the zorro LayerNorms have none (beta is a zero buffer,
+// zorro_utils.py:103-110): without it the bias reads and adds of the second norm's recomputation drop out.
+template <int NC, bool PF, bool FULL, bool HB>
 __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) ln_bwd_kernel(const LnBwdParams p) {
   constexpr int LN_MAX_CHUNKS = NC;
   const int lane = threadIdx.x & 31;
@@ -257,10 +259,16 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
         if (FULL || lane + 32 * i < nchunk) {
-          const float4 G1 = g1[lane + 32 * i], B1 = b1[lane + 32 * i], G2 = g2[lane + 32 * i];
+          const float4 G1 = g1[lane + 32 * i], G2 = g2[lane + 32 * i];
+          const float4 B1 = HB ? b1[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 xh2;
-          xh2.x = (xh1[i].x * G1.x + B1.x - mean2) * rstd2; xh2.y = (xh1[i].y * G1.y + B1.y - mean2) * rstd2;
-          xh2.z = (xh1[i].z * G1.z + B1.z - mean2) * rstd2; xh2.w = (xh1[i].w * G1.w + B1.w - mean2) * rstd2;
+          if (HB) {
+            xh2.x = (xh1[i].x * G1.x + B1.x - mean2) * rstd2; xh2.y = (xh1[i].y * G1.y + B1.y - mean2) * rstd2;
+            xh2.z = (xh1[i].z * G1.z + B1.z - mean2) * rstd2; xh2.w = (xh1[i].w * G1.w + B1.w - mean2) * rstd2;
+          } else {
+            xh2.x = (xh1[i].x * G1.x - mean2) * rstd2; xh2.y = (xh1[i].y * G1.y - mean2) * rstd2;
+            xh2.z = (xh1[i].z * G1.z - mean2) * rstd2; xh2.w = (xh1[i].w * G1.w - mean2) * rstd2;
+          }
           float4 t = adg2[lane + 32 * i];
           t.x += d[i].x * xh2.x; t.y += d[i].y * xh2.y; t.z += d[i].z * xh2.z; t.w += d[i].w * xh2.w;
           adg2[lane + 32 * i] = t;
@@ -274,11 +282,19 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
         if (FULL || lane + 32 * i < nchunk) {
-          const float4 G1 = g1[lane + 32 * i], B1 = b1[lane + 32 * i];
-          d[i].x = rstd2 * (d[i].x - s1 - (xh1[i].x * G1.x + B1.x - mean2) * rstd2 * s2);
-          d[i].y = rstd2 * (d[i].y - s1 - (xh1[i].y * G1.y + B1.y - mean2) * rstd2 * s2);
-          d[i].z = rstd2 * (d[i].z - s1 - (xh1[i].z * G1.z + B1.z - mean2) * rstd2 * s2);
-          d[i].w = rstd2 * (d[i].w - s1 - (xh1[i].w * G1.w + B1.w - mean2) * rstd2 * s2);
+          const float4 G1 = g1[lane + 32 * i];
+          if (HB) {
+            const float4 B1 = b1[lane + 32 * i];
+            d[i].x = rstd2 * (d[i].x - s1 - (xh1[i].x * G1.x + B1.x - mean2) * rstd2 * s2);
+            d[i].y = rstd2 * (d[i].y - s1 - (xh1[i].y * G1.y + B1.y - mean2) * rstd2 * s2);
+            d[i].z = rstd2 * (d[i].z - s1 - (xh1[i].z * G1.z + B1.z - mean2) * rstd2 * s2);
+            d[i].w = rstd2 * (d[i].w - s1 - (xh1[i].w * G1.w + B1.w - mean2) * rstd2 * s2);
+          } else {
+            d[i].x = rstd2 * (d[i].x - s1 - (xh1[i].x * G1.x - mean2) * rstd2 * s2);
+            d[i].y = rstd2 * (d[i].y - s1 - (xh1[i].y * G1.y - mean2) * rstd2 * s2);
+            d[i].z = rstd2 * (d[i].z - s1 - (xh1[i].z * G1.z - mean2) * rstd2 * s2);
+            d[i].w = rstd2 * (d[i].w - s1 - (xh1[i].w * G1.w - mean2) * rstd2 * s2);
+          }
         }
       }
     }
@@ -416,27 +432,32 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
   // row prefetch: 0.382 -> 0.329 ms at the cfg-2 shape (D = 768); at D = 1024 its registers spill, so it stays off there
   static const int variant = getenv("MMF_LN_BWD_PF") ? atoi(getenv("MMF_LN_BWD_PF")) : 1;
   const bool early = variant != 0 && nc <= 6;
-#define MMF_LN_BWD_LAUNCH(NCV, E, F)                                                                                       \
+#define MMF_LN_BWD_LAUNCH(NCV, E, F, HBV)                                                                                       \
   do {                                                                                                                    \
     static bool attr_done = false;                                                                                        \
     if (!attr_done) {                                                                                                     \
-      cudaFuncSetAttribute(ln_bwd_kernel<NCV, E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * NCV * 32 * 16); \
-      cudaFuncSetAttribute(ln_bwd_kernel<NCV, E, F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+      cudaFuncSetAttribute(ln_bwd_kernel<NCV, E, F, HBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * NCV * 32 * 16); \
+      cudaFuncSetAttribute(ln_bwd_kernel<NCV, E, F, HBV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
       attr_done = true;                                                                                                   \
     }                                                                                                                     \
-    ln_bwd_kernel<NCV, E, F><<<ln_grid(ln_bwd_kernel<NCV, E, F>, smem, rows), LN_WARPS * 32, smem, st>>>(p);               \
+    ln_bwd_kernel<NCV, E, F, HBV><<<ln_grid(ln_bwd_kernel<NCV, E, F, HBV>, smem, rows), LN_WARPS * 32, smem, st>>>(p);               \
   } while (0)
-#define MMF_LN_BWD_DISPATCH(E, F)                       \
+#define MMF_LN_BWD_DISPATCH_B(E, F, HBV)                 \
   do {                                                  \
-    if (nc <= 2) MMF_LN_BWD_LAUNCH(2, E, F);            \
-    else if (nc <= 4) MMF_LN_BWD_LAUNCH(4, E, F);       \
-    else if (nc <= 6) MMF_LN_BWD_LAUNCH(6, E, F);       \
-    else MMF_LN_BWD_LAUNCH(8, E, F);                    \
+    if (nc <= 2) MMF_LN_BWD_LAUNCH(2, E, F, HBV);       \
+    else if (nc <= 4) MMF_LN_BWD_LAUNCH(4, E, F, HBV);  \
+    else if (nc <= 6) MMF_LN_BWD_LAUNCH(6, E, F, HBV);  \
+    else MMF_LN_BWD_LAUNCH(8, E, F, HBV);               \
+  } while (0)
+#define MMF_LN_BWD_DISPATCH(E, F)                                                           \
+  do {                                                                                      \
+    if (b1) MMF_LN_BWD_DISPATCH_B(E, F, true); else MMF_LN_BWD_DISPATCH_B(E, F, false);    \
   } while (0)
   const bool full = D == 256 || D == 512 || D == 768 || D == 1024;   // = NC * 128 of the kernel chosen below
   if (early) { if (full) MMF_LN_BWD_DISPATCH(true, true); else MMF_LN_BWD_DISPATCH(true, false); }
   else { if (full) MMF_LN_BWD_DISPATCH(false, true); else MMF_LN_BWD_DISPATCH(false, false); }
 #undef MMF_LN_BWD_DISPATCH
+#undef MMF_LN_BWD_DISPATCH_B
 #undef MMF_LN_BWD_LAUNCH
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();

@@ -6,7 +6,10 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from incomplete_multimodal_fusion_b200 import kernels as K  # noqa: E402
+from incomplete_multimodal_fusion_b200 import _lib, kernels as K  # noqa: E402
+
+if os.environ.get("MMF_LIB"):   # e.g. scratch/old_libmmf.so built from another revision, for A/B runs on the same box
+    _lib.LIB_PATH = os.path.abspath(os.environ["MMF_LIB"])
 
 bf16, f32 = torch.bfloat16, torch.float32
 B, nenc, Fn, D, H = 256, 294, 196, 768, 8
