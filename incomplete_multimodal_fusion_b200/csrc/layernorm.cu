@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
   for (int64_t row = row_first; row < p.rows; row += row_step) {
     const float4 st = PF ? nst : __ldg(reinterpret_cast<const float4*>(p.stats) + row);
     const float mean1 = st.x, rstd1 = st.y, mean2 = st.z, rstd2 = st.w;
+    const float nm1 = -mean1 * rstd1, nm2 = -mean2 * rstd2;   // xhat = fma(x, rstd, -mean * rstd): one instruction per value
     const float4* xr = reinterpret_cast<const float4*>(
         (p.x2 && row >= p.x_split) ? p.x2 + (row - p.x_split) * p.ldx : p.x + row * p.ldx);
     float4 xh1[LN_MAX_CHUNKS], d[LN_MAX_CHUNKS], rs[PF ? LN_MAX_CHUNKS : 1];
@@ -250,8 +251,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
       const bool in = FULL || lane + 32 * i < nchunk;
-      xh1[i].x = in ? (xh1[i].x - mean1) * rstd1 : 0.f; xh1[i].y = in ? (xh1[i].y - mean1) * rstd1 : 0.f;
-      xh1[i].z = in ? (xh1[i].z - mean1) * rstd1 : 0.f; xh1[i].w = in ? (xh1[i].w - mean1) * rstd1 : 0.f;
+      xh1[i].x = in ? fmaf(xh1[i].x, rstd1, nm1) : 0.f; xh1[i].y = in ? fmaf(xh1[i].y, rstd1, nm1) : 0.f;
+      xh1[i].z = in ? fmaf(xh1[i].z, rstd1, nm1) : 0.f; xh1[i].w = in ? fmaf(xh1[i].w, rstd1, nm1) : 0.f;
     }
     if (dbl) {
       // second LN: y = xh2 * g2, xh2 = (y1 - mean2) * rstd2, y1 = xh1 * g1 + b1
@@ -266,8 +267,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
             xh2.x = (xh1[i].x * G1.x + B1.x - mean2) * rstd2; xh2.y = (xh1[i].y * G1.y + B1.y - mean2) * rstd2;
             xh2.z = (xh1[i].z * G1.z + B1.z - mean2) * rstd2; xh2.w = (xh1[i].w * G1.w + B1.w - mean2) * rstd2;
           } else {
-            xh2.x = (xh1[i].x * G1.x - mean2) * rstd2; xh2.y = (xh1[i].y * G1.y - mean2) * rstd2;
-            xh2.z = (xh1[i].z * G1.z - mean2) * rstd2; xh2.w = (xh1[i].w * G1.w - mean2) * rstd2;
+            xh2.x = fmaf(xh1[i].x * G1.x, rstd2, nm2); xh2.y = fmaf(xh1[i].y * G1.y, rstd2, nm2);
+            xh2.z = fmaf(xh1[i].z * G1.z, rstd2, nm2); xh2.w = fmaf(xh1[i].w * G1.w, rstd2, nm2);
           }
           float4 t = adg2[lane + 32 * i];
           t.x += d[i].x * xh2.x; t.y += d[i].y * xh2.y; t.z += d[i].z * xh2.z; t.w += d[i].w * xh2.w;
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
       }
       s1 = warp_sum(s1) * invD;
       s2 = warp_sum(s2) * invD;
+      const float c2a = -rstd2 * s1, c2b = -rstd2 * s2;
 #pragma unroll
       for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
         if (FULL || lane + 32 * i < nchunk) {
@@ -290,10 +292,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
             d[i].z = rstd2 * (d[i].z - s1 - (xh1[i].z * G1.z + B1.z - mean2) * rstd2 * s2);
             d[i].w = rstd2 * (d[i].w - s1 - (xh1[i].w * G1.w + B1.w - mean2) * rstd2 * s2);
           } else {
-            d[i].x = rstd2 * (d[i].x - s1 - (xh1[i].x * G1.x - mean2) * rstd2 * s2);
-            d[i].y = rstd2 * (d[i].y - s1 - (xh1[i].y * G1.y - mean2) * rstd2 * s2);
-            d[i].z = rstd2 * (d[i].z - s1 - (xh1[i].z * G1.z - mean2) * rstd2 * s2);
-            d[i].w = rstd2 * (d[i].w - s1 - (xh1[i].w * G1.w - mean2) * rstd2 * s2);
+            // rstd2 * (d - s1 - xh2 * s2) as two dependent FMAs on top of xh2's two
+            d[i].x = fmaf(d[i].x, rstd2, fmaf(fmaf(xh1[i].x * G1.x, rstd2, nm2), c2b, c2a));
+            d[i].y = fmaf(d[i].y, rstd2, fmaf(fmaf(xh1[i].y * G1.y, rstd2, nm2), c2b, c2a));
+            d[i].z = fmaf(d[i].z, rstd2, fmaf(fmaf(xh1[i].z * G1.z, rstd2, nm2), c2b, c2a));
+            d[i].w = fmaf(d[i].w, rstd2, fmaf(fmaf(xh1[i].w * G1.w, rstd2, nm2), c2b, c2a));
           }
         }
       }
@@ -326,15 +329,16 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
     }
     s1 = warp_sum(s1) * invD;
     s2 = warp_sum(s2) * invD;
+    const float c1a = -rstd1 * s1, c1b = -rstd1 * s2;   // rstd1 * (d - s1 - xh1 * s2) = fma(d, rstd1, fma(xh1, c1b, c1a))
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
       const int c = lane + 32 * i;
       if (FULL || c < nchunk) {
         float4 o;
-        o.x = rstd1 * (d[i].x - s1 - xh1[i].x * s2);
-        o.y = rstd1 * (d[i].y - s1 - xh1[i].y * s2);
-        o.z = rstd1 * (d[i].z - s1 - xh1[i].z * s2);
-        o.w = rstd1 * (d[i].w - s1 - xh1[i].w * s2);
+        o.x = fmaf(d[i].x, rstd1, fmaf(xh1[i].x, c1b, c1a));
+        o.y = fmaf(d[i].y, rstd1, fmaf(xh1[i].y, c1b, c1a));
+        o.z = fmaf(d[i].z, rstd1, fmaf(xh1[i].z, c1b, c1a));
+        o.w = fmaf(d[i].w, rstd1, fmaf(xh1[i].w, c1b, c1a));
         if (PF) {
           o.x += rs[PF ? i : 0].x; o.y += rs[PF ? i : 0].y; o.z += rs[PF ? i : 0].z; o.w += rs[PF ? i : 0].w;
         } else if (p.dres) {
