@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmmf_b200.so")
+# MMF_LIB: another build of the same library (e.g. scratch/new_libmmf.so from a work-in-progress revision) for A/B runs of
+# tools/ and tests/ on one box; unset, the in-tree library is the only one ever loaded
+LIB_PATH = os.path.abspath(os.environ["MMF_LIB"]) if os.environ.get("MMF_LIB") else os.path.join(HERE, "libmmf_b200.so")
 
 _lib = None
 
