@@ -733,17 +733,27 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           coords(w + num_clusters, cbn, r0n, live_n);
           mbar_wait(&tmem_full[acc], acc_phase);
           tc_fence_after();
-          if (live) tmem_ld_32x64(taddr + part * 64, v0);
-          tmem_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          if (!live) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+          }
           if (live) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+              // 32 accumulator columns per half, read where they are used: the 64-register read of the whole share
+              // spilled under this kernel's 96-register cap (18 warps); the accumulator is released after the second read
+              uint32_t vh[32];
+              tmem_ld_32x32(taddr + part * 64 + 32 * h, vh);
+              tmem_wait_ld();
+              if (h == 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+              }
               mbar_wait(&box_bar[2 * ew + h], box_phase);
               uint8_t* hb = sbox + h * 4096;
-              geglu_bwd_box32(hb, hb + 2048, v0 + 32 * h, lane, p.alpha);
+              geglu_bwd_box32(hb, hb + 2048, vh, lane, p.alpha);
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
