@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-eager-on-this-GPU leg")
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "simple"])
     return ap.parse_args()
 
@@ -97,34 +98,96 @@ def synthetic_batch(batch, image, seed, pin=False):
     return out
 
 
+def _oracle_cfg(args):
+    import oracle
+    return oracle.OracleConfig(variant=args.variant, dim={"tiny": 192, "small": 384, "base": 768, "large": 1024}[args.size],
+                               depth=24 if args.size == "large" else 12, heads={"tiny": 3, "small": 6}.get(args.size, 8),
+                               image_size=args.image, patch=16)
+
+
 def cpu_reference_steps(args, steps, warmup, batch):
-    """the reference's arithmetic (oracle port, fp32, all host threads): fwd + losses + bwd + AdamW; returns samples/s"""
+    """The reference's CPU implementation of the step on all host threads, fp32: forward + losses + backward + AdamW.
+    kind "reference": the reference's OWN code (baseline/_ref, built from /root/reference by tools/make_ref.py -- it
+    travels with the tree); kind "port": the oracle restatement, only when baseline/_ref is absent.
+    Returns (samples/s, threads, s/step, kind)."""
     import torch
     import oracle
-    cfg = oracle.OracleConfig(variant=args.variant, dim={"tiny": 192, "small": 384, "base": 768, "large": 1024}[args.size],
-                              depth=24 if args.size == "large" else 12, heads={"tiny": 3, "small": 6}.get(args.size, 8),
-                              image_size=args.image, patch=16)
+    from baseline import harness as H
+    cfg = _oracle_cfg(args)
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = oracle.init_state_dict(cfg, seed=0)
-    params = []
-    for k, v in sd.items():
-        if not (k.endswith(".beta") or k.endswith("pos_emb")):
-            v.requires_grad_(True)
-            params.append(v)
-    opt = torch.optim.AdamW(params, lr=1e-4 * batch / 256, betas=(0.9, 0.95), weight_decay=0.05)
     x = synthetic_batch(batch, args.image, 1234)
     times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        torch.manual_seed(1 + i)
-        opt.zero_grad(set_to_none=True)
-        out = oracle.multimae_forward(sd, cfg, x, num_encoded_tokens=args.nenc, sample_tasks_uniformly=True)
-        loss, _ = oracle.pretrain_loss(out, x, cfg)
-        loss.backward()
-        opt.step()
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return batch * len(times) / sum(times), torch.get_num_threads(), sum(times) / len(times)
+    if H.available():
+        kind = "reference"
+        torch.manual_seed(0)
+        model = H.build_model(cfg, None, "cpu")
+        opt = H.make_optimizer(model, batch)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            H.train_step(model, opt, x, cfg, args.nenc, 1 + i)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        kind = "port"
+        sd = oracle.init_state_dict(cfg, seed=0)
+        params = []
+        for k, v in sd.items():
+            if not (k.endswith(".beta") or k.endswith("pos_emb")):
+                v.requires_grad_(True)
+                params.append(v)
+        opt = torch.optim.AdamW(params, lr=1e-4 * batch / 256, betas=(0.9, 0.95), weight_decay=0.05)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            torch.manual_seed(1 + i)
+            opt.zero_grad(set_to_none=True)
+            out = oracle.multimae_forward(sd, cfg, x, num_encoded_tokens=args.nenc, sample_tasks_uniformly=True)
+            loss, _ = oracle.pretrain_loss(out, x, cfg)
+            loss.backward()
+            opt.step()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return batch * len(times) / sum(times), torch.get_num_threads(), sum(times) / len(times), kind
+
+
+def gpu_eager_reference(args, dev, steps=4, warmup=2):
+    """The practical bar: the reference's own eager PyTorch step on THIS GPU under torch.autocast(bf16) --
+    what a user of the reference gets on the same box -- at the largest batch (<= the workload's) that fits."""
+    import torch
+    from baseline import harness as H
+    if not H.available():
+        return {"unavailable": "baseline/_ref not built"}
+    cfg = _oracle_cfg(args)
+    batch = args.batch
+    while batch >= 8:
+        model = opt = x = None
+        try:
+            torch.manual_seed(0)
+            model = H.build_model(cfg, None, dev)
+            opt = H.make_optimizer(model, batch)
+            x = {k: v.to(dev) for k, v in synthetic_batch(batch, args.image, 1234).items()}
+            for i in range(warmup):
+                H.train_step(model, opt, x, cfg, args.nenc, 1 + i, autocast_device="cuda")
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                loss = H.train_step(model, opt, x, cfg, args.nenc, 100 + i, autocast_device="cuda")
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            peak = torch.cuda.max_memory_allocated() / 2 ** 30
+            res = {"value": batch / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "per_step_batch": batch, "steps": steps,
+                   "warmup": warmup, "dtype": "bf16 autocast", "loss": float(loss), "peak_hbm_gb": round(peak, 1),
+                   "what": "the reference's own nn.Modules (baseline/_ref), eager PyTorch, fwd + losses + bwd + AdamW, same model / inputs / token budget"}
+            del model, opt, x, loss
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats()
+            return res
+        except torch.cuda.OutOfMemoryError:
+            del model, opt, x
+            torch.cuda.empty_cache()
+            batch //= 2
+    return {"unavailable": "out of memory down to batch 8"}
 
 
 def run_reference(args):
@@ -133,15 +196,16 @@ def run_reference(args):
         return
     # bounded sample: a few samples per step so that K + W steps end within minutes on the host cores
     batch = args.cpu_batch if args.steps + args.warmup <= 16 else max(1, args.cpu_batch // 2)
-    sps, cores, sec = cpu_reference_steps(args, args.steps, args.warmup, batch)
-    sample = f"batch {batch} per step (of the {args.batch}-sample workload), fp32, {args.warmup} warm-up + {args.steps} timed steps"
+    sps, cores, sec, kind = cpu_reference_steps(args, args.steps, args.warmup, batch)
+    sample = (f"{'the reference code itself (baseline/_ref)' if kind == 'reference' else 'oracle port'}, batch {batch} per step (of the "
+              f"{args.batch}-sample workload), fp32, {args.warmup} warm-up + {args.steps} timed steps")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "model": f"ViT-{args.size}/16 {args.variant}", "image": args.image,
                    "visible_tokens": args.nenc, "per_step_batch": batch},
-        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -234,6 +298,14 @@ def run_ours(args):
         kernels.set_gemm_reserved_sms(reserve)
     dev = torch.device("cuda", local)
 
+    eager_ref = None
+    if world == 1 and not args.no_gpu_reference:
+        try:
+            eager_ref = gpu_eager_reference(args, dev)
+        except Exception as e:   # the practical-bar leg must never take the measurement of our own path down with it
+            eager_ref = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        torch.cuda.empty_cache()
+
     torch.manual_seed(0)
     model = build_pretrain_model(args.size, args.variant, image_size=args.image).to(dev)
     if world > 1:
@@ -255,10 +327,9 @@ def run_ours(args):
     barrier()
     assert torch.isfinite(loss).item(), "non-finite loss"
 
-    # ---- timed region 1: inputs resident in HBM ----
+    # ---- timed region 1: inputs resident in HBM, nothing instrumented (no per-launch events inside the number) ----
     sampler = ClockSampler(local)
     sampler.start()
-    timing = kernels.enable_gemm_timing(True)
     kernels.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -270,8 +341,42 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = kernels.launch_count()
-    kernels.enable_gemm_timing(False)
     clocks = sampler.summary()
+    t_max = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms = float(t_max)
+    value = args.batch * world * args.steps / (ms / 1e3)
+    if world > 1:
+        # data-parallel correctness, proven inside the measured job: after K steps of all-reduced gradients every replica
+        # must hold the same parameters (a checksum per rank, compared across ranks; the run aborts on a mismatch)
+        ps = [p.detach().double() for p in model.parameters()]
+        chk = torch.stack([p.sum() for p in ps] + [p.abs().sum() for p in ps])      # per tensor: sum and abs-sum
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        n_t = len(ps)
+        spread = float(((hi - lo)[:n_t].abs() / hi[n_t:].clamp_min(1e-30)).max())   # worst tensor, relative to its abs-sum
+        dp_consistent = {"max_rel_spread_over_ranks": spread, "tensors": n_t, "identical": spread == 0.0}
+        assert spread <= 1e-6, "replicas diverged after %d all-reduced steps: %r" % (args.steps, dp_consistent)
+    else:
+        dp_consistent = None
+
+    # ---- instrumented pass (untimed): CUDA events on the launch stream around every GEMM launch and around the
+    # attention / LayerNorm launches of the same steps; per-kernel durations for `roofline` / `other_kernels` come from here ----
+    n_instr = min(args.steps, int(os.environ.get("MMF_BENCH_INSTR_STEPS", "4")))
+    timing = kernels.enable_gemm_timing(True)
+    ktiming = kernels.enable_kernel_timing(True)
+    ei0, ei1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ei0.record()
+    for i in range(n_instr):
+        torch.manual_seed(100 + i)
+        step(x)
+    ei1.record()
+    torch.cuda.synchronize()
+    kernels.enable_gemm_timing(False)
+    kernels.enable_kernel_timing(False)
+    ms_instr = ei0.elapsed_time(ei1)
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _, _ in timing)
     gemm_flops = sum(f for _, _, f, _, _ in timing)
     by_kind, by_shape = {}, {}
@@ -281,19 +386,6 @@ def run_ours(args):
         by_kind[kind] = (t + dt, fl + f, n + 1)
         t, fl, n = by_shape.get(shape, (0.0, 0.0, 0))
         by_shape[shape] = (t + dt, fl + f, n + 1)
-    t_max = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    ms = float(t_max)
-    value = args.batch * world * args.steps / (ms / 1e3)
-
-    # ---- untimed pass: CUDA events around the attention / LayerNorm launches of two more steps (other_kernels) ----
-    ktiming = kernels.enable_kernel_timing(True)
-    for i in range(2):
-        torch.manual_seed(200 + i)
-        step(x)
-    torch.cuda.synchronize()
-    kernels.enable_kernel_timing(False)
 
     # ---- timed region 2: end to end (pinned host -> device copy of the inputs and loss read-back every step) ----
     e2e = None
@@ -352,15 +444,15 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     pk = peaks()
-    other = other_kernels(ktiming, 2, pk)
+    other = other_kernels(ktiming, n_instr, pk)
     other["input_pipeline"] = raster_pipeline_figures(args.batch, args.image, dev, pk)
     gb = [(k, v) for k, v in by_shape.items() if k[0].endswith("_geglubwd")]
     if gb:   # dgrad GEMM + fused GEGLU backward: tensor flops AND the elementwise pass's algorithmic bytes (u read, du write, A read)
         t = sum(v[0] for _, v in gb)
         nb = sum(v[2] * k[1] * (8.0 * k[2] + 2.0 * k[3]) for k, v in gb)
         other["dgrad_geglu_bwd_fused"] = {"bound": "hbm", "gbs": round(nb / (t / 1e3) / 1e9, 1), "frac_of_hbm_peak": round(nb / (t / 1e3) / 1e9 / pk["hbm"], 3),
-                                          "tflops": round(sum(v[1] for _, v in gb) / (t / 1e3) / 1e12, 1), "ms_per_step": round(t / args.steps, 3),
-                                          "launches_per_step": sum(v[2] for _, v in gb) / args.steps}
+                                          "tflops": round(sum(v[1] for _, v in gb) / (t / 1e3) / 1e12, 1), "ms_per_step": round(t / n_instr, 3),
+                                          "launches_per_step": sum(v[2] for _, v in gb) / n_instr}
     achieved_all = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
     # the dominant kernel launch of the step: the FFN-1 GEGLU GEMM of the zorro blocks (largest single share of the time).
     # The dgrad GEMM with the fused GEGLU backward takes about as long, but its 2*M*N*K flops share the launch with an
@@ -382,20 +474,22 @@ def run_ours(args):
                    "image": args.image, "visible_tokens": args.nenc, "parallelism": f"dp{world}",
                    "optimizer": "AdamW(0.9,0.95) wd 0.05", "l2": "inputs (257 MB/step) and activations (GBs) exceed the 126 MB L2"},
         "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+        "dp_consistency": dp_consistent,
         "clocks": clocks,
         "roofline": {"bound": "tensor",
                      "kernel": "gemm2_tcgen05_kernel (cta_group::2 pair GEMM), launch %s M=%d N=%d K=%d" % dom_key if dom_key else None,
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_sustained"] if achieved else None, "traffic": traffic,
                      "flops_per_launch": dom_fl / dom_n if dom_n else None, "ms_per_launch": dom_t / dom_n if dom_n else None,
-                     "share_of_step": dom_t / ms if ms else None,
+                     "share_of_step": dom_t / ms_instr if ms_instr else None,
+                     "timed_in": "instrumented pass of %d steps right after the timed region (%.1f ms/step with the per-launch events, %.1f without)" % (n_instr, ms_instr / n_instr, ms / args.steps),
                      "peak_source": pk["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
                      "all_gemm_launches": {"achieved": achieved_all, "frac": achieved_all / pk["bf16_sustained"] if achieved_all else None},
-                     "gemm_share_of_step": gemm_ms / ms if ms else None,
-                     "by_kind": {k: {"tflops": fl / (t / 1e3) / 1e12, "ms_per_step": t / args.steps, "launches_per_step": n / args.steps}
+                     "gemm_share_of_step": gemm_ms / ms_instr if ms_instr else None,
+                     "by_kind": {k: {"tflops": fl / (t / 1e3) / 1e12, "ms_per_step": t / n_instr, "launches_per_step": n / n_instr}
                                  for k, (t, fl, n) in by_kind.items()},
                      "top_shapes": [{"gemm": "%s M=%d N=%d K=%d" % k, "tflops": round(fl / (t / 1e3) / 1e12, 1),
-                                     "ms_per_step": round(t / args.steps, 3), "launches_per_step": n / args.steps}
+                                     "ms_per_step": round(t / n_instr, 3), "launches_per_step": n / n_instr}
                                     for k, (t, fl, n) in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("MMF_BENCH_TOP_SHAPES", "14"))]]},
         "other_kernels": other,
         "loss": float(loss),
@@ -404,11 +498,13 @@ def run_ours(args):
     if e2e:
         result["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
-        sps, cores, sec = cpu_reference_steps(args, 10, 2, args.cpu_batch)
-        result["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                                  "sample": f"oracle port (fp32 restatement of the reference's step: fwd + losses + bwd + AdamW), same "
-                                            f"model, batch {args.cpu_batch} of the {args.batch}-sample workload per step, 2 warm-up + 10 timed "
-                                            f"steps ({sec:.2f} s/step)"}
+        sps, cores, sec, kind = cpu_reference_steps(args, 8, 2, args.cpu_batch)
+        what = "the reference's own code (baseline/_ref)" if kind == "reference" else "oracle port (fp32 restatement of the reference's step)"
+        result["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": kind,
+                                  "sample": f"{what}: fwd + losses + bwd + AdamW, fp32, same model, batch {args.cpu_batch} of the "
+                                            f"{args.batch}-sample workload per step, 2 warm-up + 8 timed steps ({sec:.2f} s/step)"}
+    if eager_ref is not None:
+        result["gpu_eager_reference"] = eager_ref
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()

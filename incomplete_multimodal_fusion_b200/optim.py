@@ -53,7 +53,8 @@ class FusedAdamW:
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("FusedAdamW needs contiguous fp32 CUDA parameters (no CPU fallback)")
         self.device = self.params[0].device
-        self.param_groups = [dict(params=self.params, lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)]
+        # `lr_scale` is read by the reference loop's schedule code (pretrain_mmae.py:441-445: lr_table[it] * group["lr_scale"])
+        self.param_groups = [dict(params=self.params, lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, lr_scale=1.0)]
         self.max_grad_norm = max_grad_norm
         self.track_grad_norm = track_grad_norm or bool(max_grad_norm)
         self.emit_bf16 = emit_bf16
@@ -76,6 +77,7 @@ class FusedAdamW:
         nbytes = C.sizeof(_lib.AdamWTensor) * len(self.params)
         self._host = [torch.zeros(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]   # alternate: the async copy of
         self._tables = [(_lib.AdamWTensor * len(self.params)).from_buffer(h.numpy()) for h in self._host]  # step k may still be queued
+        self._copied = [None, None]   # event recorded after each pinned table's H2D copy: waited for before the table is rewritten
         self._dev = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         self._scal = torch.zeros(3, dtype=torch.float32, device=self.device)   # sqnorm, norm, clip coefficient
         self._it = 0
@@ -131,9 +133,12 @@ class FusedAdamW:
         g = self.param_groups[0]
         lr, (b1, b2), eps, wd = float(g["lr"]), g["betas"], float(g["eps"]), float(g["weight_decay"])
         images, entries = self._images() if self.emit_bf16 else ({}, [])
-        tab = self._tables[self._it & 1]
-        host = self._host[self._it & 1]
+        slot = self._it & 1
+        tab = self._tables[slot]
+        host = self._host[slot]
         self._it += 1
+        if self._copied[slot] is not None:      # the copy queued two steps ago must have read this table before it is rewritten
+            self._copied[slot].synchronize()
         active = []
         for i, (e, p) in enumerate(zip(tab, self.params)):
             gr = p.grad
@@ -154,6 +159,9 @@ class FusedAdamW:
         if not active:
             return
         self._dev.copy_(host, non_blocking=True)
+        if self._copied[slot] is None:
+            self._copied[slot] = torch.cuda.Event()
+        self._copied[slot].record()
         st = _stream()
         L = _L()
         scale_ptr = None
@@ -169,6 +177,44 @@ class FusedAdamW:
         for p in active:
             torch.autograd.graph.increment_version(p)
         # ... and that the images refreshed in the same launch are current
+        # (only images whose sources were ALL updated by this launch: an image of a parameter without a gradient was not
+        # rewritten and keeps its old stamp)
+        act = {id(p) for p in active}
         for key, srcs in entries:
+            if not all(id(s) in act for s in srcs):
+                continue
             refs, _vers, img = functions.WEIGHTS._store[key]
             functions.WEIGHTS._store[key] = (refs, tuple((s.data_ptr(), s._version) for s in srcs), img)
+
+    # ---- checkpointing: torch.optim.AdamW's layout (the reference saves / restores optimizer.state_dict(),
+    # utils/checkpoint.py:83,128) ----
+    def state_dict(self):
+        state = {}
+        for i, p in enumerate(self.params):
+            if self.steps[i] > 0:
+                state[i] = {"step": torch.tensor(float(self.steps[i])), "exp_avg": self.exp_avg[i].detach().clone(),
+                            "exp_avg_sq": self.exp_avg_sq[i].detach().clone()}
+        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        groups[0]["params"] = list(range(len(self.params)))
+        return {"state": state, "param_groups": groups}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(self.params):
+            raise ValueError("loaded state dict has %d parameters, the optimiser %d" % (len(ids), len(self.params)))
+        pos = {pid: j for j, pid in enumerate(ids)}           # checkpoint parameter id -> our index (torch's order)
+        for k, v in groups[0].items():
+            if k != "params":
+                self.param_groups[0][k] = tuple(v) if k == "betas" else v
+        self._m.zero_()
+        self._v.zero_()
+        self.steps = [0] * len(self.params)
+        for pid, st in sd["state"].items():
+            j = pos[int(pid)]
+            if st["exp_avg"].shape != self.params[j].shape:
+                raise ValueError("state of parameter %d has shape %s, expected %s" % (j, tuple(st["exp_avg"].shape), tuple(self.params[j].shape)))
+            self.exp_avg[j].copy_(st["exp_avg"])
+            self.exp_avg_sq[j].copy_(st["exp_avg_sq"])
+            self.steps[j] = int(float(st["step"]))

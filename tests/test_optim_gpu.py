@@ -82,3 +82,40 @@ def test_optimizer_refreshes_bf16_weight_images():
             assert checked > 10
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) < 2e-3 * abs(b), (losses[False], losses[True])
+
+
+def test_fused_adamw_state_dict_round_trip_with_torch():
+    """checkpoint layout = torch.optim.AdamW's (the reference saves / restores optimizer.state_dict(),
+    utils/checkpoint.py:83,128): our state loads into torch's AdamW and torch's state loads into ours, and both
+    continue identically; the single param group carries `lr_scale` for the reference loop's schedule code"""
+    from incomplete_multimodal_fusion_b200.optim import FusedAdamW
+    ours = [torch.nn.Parameter(p.clone()) for p in _params()]
+    ref = [torch.nn.Parameter(p.clone()) for p in _params()]
+    opt = FusedAdamW(ours, lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    topt = torch.optim.AdamW(ref, lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    assert opt.param_groups[0]["lr_scale"] == 1.0
+    for step in range(2):
+        for a, b, g in zip(ours, ref, _params(seed=20 + step)):
+            a.grad, b.grad = g.clone(), g.clone()
+        opt.step()
+        topt.step()
+    sd = opt.state_dict()
+    assert set(sd) == {"state", "param_groups"} and sd["param_groups"][0]["params"] == list(range(len(ours)))
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 2.0
+    # ours -> a fresh torch AdamW, torch's -> a fresh FusedAdamW (on copies of the current parameters)
+    ours2 = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    ref2 = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    opt2 = FusedAdamW(ours2, lr=1.0)
+    opt2.load_state_dict(topt.state_dict())
+    topt2 = torch.optim.AdamW(ref2, lr=1.0)
+    topt2.load_state_dict(sd)
+    assert opt2.param_groups[0]["lr"] == 3e-3 and opt2.param_groups[0]["betas"] == (0.9, 0.95)
+    for a, b, g in zip(ours2, ref2, _params(seed=30)):
+        a.grad, b.grad = g.clone(), g.clone()
+    opt2.step()
+    topt2.step()
+    for a, b in zip(ours2, ref2):
+        assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), float((a - b).abs().max())
+    for i, b in enumerate(ref2):
+        assert torch.allclose(opt2.exp_avg[i], topt2.state[b]["exp_avg"], rtol=1e-5, atol=1e-7)
+        assert opt2.steps[i] == 3
