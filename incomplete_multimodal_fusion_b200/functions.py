@@ -157,12 +157,26 @@ def to_bf16(x: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # generic pieces used by the pooling head and the decoders
 # ------------------------------------------------------------------------------------------------
+def _split_bf16(x: torch.Tensor):
+    """fp32 -> (hi, lo) bf16 with hi + lo = x to ~16 mantissa bits: lets a bf16 tensor-core GEMM consume an fp32 operand
+    without the single 2^-9 rounding (used where one rounded row stands for a whole batch, see LinearFn.precise_grad)"""
+    hi = K.cast_bf16(x)
+    lo = K.cast_bf16((x - hi.float()).contiguous())
+    return hi, lo
+
+
 class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) [+ residual].  x: [M, K] bf16 or f32 (cast once to bf16); y bf16, or f32 when a
-    residual (f32) is given or out_f32.  act: 0 none, 1 exact GELU."""
+    residual (f32) is given or out_f32.  act: 0 none, 1 exact GELU.
+
+    precise_grad: the incoming gradient (fp32) enters the two backward GEMMs as a hi + lo pair of bf16 matrices instead of
+    one bf16 rounding.  For batch-INVARIANT rows (the pooling head's learned queries): the reference projects B copies of
+    them and rounds B per-sample gradients to bf16 before summing, so its rounding error averages out over the batch; here
+    the batch is summed first (fp32) and a single bf16 rounding of that sum would not average (measured 1.3-1.4x the
+    reference-autocast error on attn_pool.to_q / return_tokens gradients without this)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, act, out_f32):
+    def forward(ctx, x, weight, bias, residual, act, out_f32, precise_grad=False):
         xb = to_bf16(x)
         wb = w_bf16(weight)
         M, N = xb.shape[0], weight.shape[0]
@@ -180,12 +194,27 @@ class LinearFn(torch.autograd.Function):
         ctx.x_dtype = x.dtype
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
+        ctx.precise = bool(precise_grad)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         xb, weight, pre = ctx.saved_tensors
         dy = dy.contiguous()
+        if ctx.precise and dy.dtype == f32 and pre is None and not ctx.has_bias and xb.shape[0] > 0:
+            hi, lo = _split_bf16(dy)
+            wb = w_bf16(weight)
+            dx = dw = None
+            if ctx.needs_input_grad[0]:
+                acc = torch.empty(xb.shape, dtype=f32, device=dy.device)
+                K.gemm(hi, wb, acc, b_mn=True)
+                K.gemm(lo, wb, acc, b_mn=True, accumulate=True)
+                dx = acc if ctx.x_dtype == f32 else acc.to(ctx.x_dtype)
+            if ctx.needs_input_grad[1]:
+                dw = wgrad(hi, xb)
+                wgrad(lo, xb, out=dw, accumulate=True)
+                dw = dw.view(weight.shape)
+            return dx, dw, None, (dy if (ctx.has_res and ctx.needs_input_grad[3]) else None), None, None, None
         dyb = to_bf16(dy)
         if pre is not None:
             dyb = K.gelu_bwd(pre, dyb, torch.empty_like(dyb))
@@ -204,11 +233,11 @@ class LinearFn(torch.autograd.Function):
             if M > 0:
                 K.colsum(dyb, db)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None
-        return dx, dw, db, dres, None, None
+        return dx, dw, db, dres, None, None, None
 
 
-def linear(x, weight, bias=None, residual=None, act=0, out_f32=False):
-    return LinearFn.apply(x, weight, bias, residual, act, out_f32)
+def linear(x, weight, bias=None, residual=None, act=0, out_f32=False, precise_grad=False):
+    return LinearFn.apply(x, weight, bias, residual, act, out_f32, precise_grad)
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -350,6 +379,8 @@ class PoolAttnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, kv, mask_u8, mode, B, H, N, n_head, scale):
+        ctx.q_dtype = q.dtype
+        q = to_bf16(q)          # (an fp32 q keeps its GRADIENT in fp32; the forward value is the reference's bf16 Linear output)
         R = q.shape[0]
         out = torch.empty(B, R, H * 64, dtype=bf16, device=q.device)
         stat = torch.empty(B * R * H * 3, dtype=f32, device=q.device)
@@ -367,7 +398,7 @@ class PoolAttnFn(torch.autograd.Function):
         dkv = torch.empty_like(kv)
         K.pool_attn_bwd(q, kv, mask_u8, mode, out, stat, dout, dq, dkv, B=B, R=R, H=H, N=N, n_head=n_head, scale=scale,
                         q_batched=False)
-        return dq.to(bf16), dkv, None, None, None, None, None, None, None
+        return (dq if ctx.q_dtype == f32 else dq.to(bf16)), dkv, None, None, None, None, None, None, None
 
 
 class UnpatchifyFn(torch.autograd.Function):

@@ -344,8 +344,10 @@ class MultiMAEBase(nn.Module):
                 pmask[R + j, nenc + ix.long()] = 1  # visible positions (multimae_crossattn.py:529-543)
             mode[R:] = 1                            # empty context -> zeros, not the uniform fallback
         ap = self.attn_pool
-        qn = Fn.layer_norm(queries.float(), ap.norm.gamma, None, 1e-5, out_bf16=True)
-        q = Fn.linear(qn, ap.to_q.weight)
+        # the learned queries are batch-invariant rows: their normalised values and projection stay fp32 on the autograd
+        # tape so that the batch-summed gradient is not rounded to bf16 once for the whole batch (LinearFn.precise_grad)
+        qn = Fn.layer_norm(queries.float(), ap.norm.gamma, None, 1e-5, out_bf16=False)
+        q = Fn.linear(qn, ap.to_q.weight, out_f32=True, precise_grad=True)
         kv = Fn.linear(T, ap.to_kv.weight)
         pooled = Fn.PoolAttnFn.apply(q, kv, pmask, mode, B, Hh, N, nenc, ap.scale)
         r = Fn.linear(pooled.view(B * Rt, Hh * 64), ap.to_out.weight)

@@ -195,6 +195,10 @@ class FusedAdamW:
                 state[i] = {"step": torch.tensor(float(self.steps[i])), "exp_avg": self.exp_avg[i].detach().clone(),
                             "exp_avg_sq": self.exp_avg_sq[i].detach().clone()}
         groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        # the keys torch.optim.AdamW expects in a loaded group (its step() indexes them without defaults)
+        for k, v in (("amsgrad", False), ("maximize", False), ("foreach", None), ("capturable", False), ("differentiable", False),
+                     ("fused", None), ("decoupled_weight_decay", True)):
+            groups[0].setdefault(k, v)
         groups[0]["params"] = list(range(len(self.params)))
         return {"state": state, "param_groups": groups}
 
