@@ -65,6 +65,14 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -154,6 +162,8 @@ struct KeyBlocks {
 // TC_HSPLIT CTAs over the heads (measured: no further gain, so 1).  `tiles` = the host's upper bound of tiles per sample;
 // the grid is (tiles + (TC_HSPLIT - 1) * heavy_max) * B CTAs, surplus ones exit.
 constexpr int TC_HSPLIT = 1;
+constexpr int TC_FWD_DEFAULT = 1;
+constexpr int TC_DQ_DEFAULT = 1;    // MMF_ATTN_DQ default (see attn_bwd_tc_launch)   // MMF_ATTN_FWD default (see attn_fwd_tc_launch)
 __device__ __forceinline__ void lpt_tile(const int32_t* seg, int nseg, int tiles, int B, int H, int& tile, int& b, int& h0, int& h1) {
   const int L = blockIdx.x;
   h0 = 0; h1 = H;
@@ -441,6 +451,318 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 }
 
+
+// ================================================================================================
+// FORWARD, second generation (round 2): the same tile / TMEM / barrier skeleton, software-pipelined on HALF blocks.
+//
+// Round-1 measurements (ncu + clock instrumentation): tensor pipe 18 % active, MUFU 46 % busy, a
+// fusion-tile CTA spent 1030 of its 3370 clk per 64-key block WAITING for the next S: per CTA the chain
+//   S MMA -> commit -> tcgen05.ld -> max -> exp -> tcgen05.st -> arrive -> P.V MMA -> S MMA ...
+// is strictly serial, so the only overlap came from the three CTAs sharing an SM.  Here a 64-key block is two 32-key
+// halves A / B with their own S columns (A: 0..31, B: 32..63; P written in place) and their own s_full / p_full
+// barriers.  The MMA thread issues   P.V_A(g), S_A(g+1), P.V_B(g), S_B(g+1), ...   so while the softmax warps work on
+// half B of block g the tensor pipe accumulates half A and already computes half A of block g+1, and vice versa: in steady
+// state neither side waits for the other, and the per-thread register footprint halves (32 S values instead of 64), which
+// admits FOUR CTAs per SM (template CTAS; with a single Q buffer the shared memory fits too).
+// A fraction of the exponentials (POLY of every 4) runs on the FMA pipe as Cody-Waite range reduction + a degree-3 minimax
+// polynomial (max rel. error 7.5e-5, far below the bf16 rounding of P) to unload the 16-lane MUFU pipe that bounds the
+// kernel (tools/micro/pipes.cu); warps whose 32 query rows are all padding (rows >= r1) skip the arithmetic.
+// Every s_full / p_full barrier completes exactly once per block (a missing half B still commits / arrives), so all phase
+// parities are simply (g & 1).
+// ================================================================================================
+constexpr uint32_t F2_SA = 0, F2_SB = 32, F2_O = 64;
+
+// 2^x on the FMA / ALU pipes: x = n + f with n = round(x) (magic-number add), 2^f by a degree-3 minimax polynomial on
+// [-0.5, 0.5], scaled by 2^n through the exponent field.  x <= ~+120; x < -125 saturates at 2^-125 (~0).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;          // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.0551716685f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+__device__ __forceinline__ float row_max32(const uint32_t (&v)[32], int nv) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+  if (nv >= 32) {
+#pragma unroll
+    for (int t = 0; t < 16; ++t) { m0 = fmaxf(m0, __uint_as_float(v[2 * t])); m1 = fmaxf(m1, __uint_as_float(v[2 * t + 1])); }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 32; ++t)
+      if (t < nv) m0 = fmaxf(m0, __uint_as_float(v[t]));
+  }
+  return fmaxf(m0, m1);
+}
+
+template <int POLY>
+__device__ __forceinline__ float exp_pack32(const uint32_t (&v)[32], uint32_t (&pk)[16], int nv, float scale_log2, float m_ref) {
+  float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const float x0 = fmaf(__uint_as_float(v[2 * t]), scale_log2, -m_ref);
+    const float x1 = fmaf(__uint_as_float(v[2 * t + 1]), scale_log2, -m_ref);
+    float p0 = ((2 * t) & 3) < POLY ? exp2_poly(x0) : ex2_approx(x0);
+    float p1 = ((2 * t + 1) & 3) < POLY ? exp2_poly(x1) : ex2_approx(x1);
+    if (nv < 32) {
+      if (2 * t >= nv) p0 = 0.f;
+      if (2 * t + 1 >= nv) p1 = 0.f;
+    }
+    rs0 += p0; rs1 += p1;
+    pk[t] = pack_bf16(p0, p1);
+  }
+  return rs0 + rs1;
+}
+
+template <int CTAS, int QBUF, int POLY>
+__global__ void __launch_bounds__(TC_THREADS, CTAS)
+attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  int r0 = 0, r1 = 0, k0 = 0, k1 = 0, b = 0, h0 = 0, h1 = 0;
+  {
+    int tile;
+    lpt_tile(p.seg, p.nseg, p.tiles, p.B, p.H, tile, b, h0, h1);
+    bool found = false;
+    if (p.seg == nullptr) {
+      r0 = tile * TC_BM; r1 = min(r0 + TC_BM, p.N); k0 = 0; k1 = p.N; found = r0 < p.N;
+    } else {
+      for (int s = 0; s < p.nseg; ++s) {
+        const int a = p.seg[s], e = p.seg[s + 1];
+        const int nt = (e - a + TC_BM - 1) / TC_BM;
+        if (tile < nt) {
+          r0 = a + tile * TC_BM; r1 = min(r0 + TC_BM, e);
+          if (s == p.nseg - 1) { k0 = 0; k1 = p.N; } else { k0 = a; k1 = e; }
+          found = true;
+          break;
+        }
+        tile -= nt;
+      }
+    }
+    if (!found) return;
+  }
+  const int nh = h1 - h0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                            // QBUF buffers
+  uint8_t* sK = smem + QBUF * TC_TILE_BYTES;     // 2 stages of 64 keys
+  uint8_t* sV = sK + 2 * TC_KV_BYTES;            // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * TC_KV_BYTES);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* kv_full = bars + 4;    // [2]
+  uint64_t* kv_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;     // [2] per half
+  uint64_t* p_full = bars + 10;    // [2] per half
+  uint64_t* o_full = bars + 12;
+  uint64_t* o_empty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int64_t q_row0 = r0 < p.n_head ? (int64_t)b * p.n_head + r0 : p.head_rows + (int64_t)b * p.n_tail + (r0 - p.n_head);
+  KeyBlocks kb;
+  kb.init(k0, k1, p.n_head, p.n_tail, p.head_rows, b);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
+        mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+        mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4);
+      }
+      mbar_init(o_full, 1);
+      mbar_init(o_empty, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int total = kb.nb * nh;      // blocks this CTA processes, g = h * kb.nb + j
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int g = 0;
+      for (int h = 0; h < nh; ++h) {
+        const int qs = h % QBUF;
+        mbar_wait(&q_empty[qs], ((h / QBUF) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qs], TC_TILE_BYTES);
+        tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], (h0 + h) * 64, (int)q_row0);
+        for (int j = 0; j < kb.nb; ++j, ++g) {
+          const int st = g & 1;
+          mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+          int64_t row; int nvalid;
+          kb.get(j, row, nvalid);
+          mbar_expect_tx(&kv_full[st], 2 * TC_KV_BYTES);
+          tma_load_2d(sK + st * TC_KV_BYTES, &tmap_k, &kv_full[st], (h0 + h) * 64, (int)row);
+          tma_load_2d(sV + st * TC_KV_BYTES, &tmap_v, &kv_full[st], (h0 + h) * 64, (int)row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0 && total > 0) {
+      const uint32_t idesc_pv = umma_idesc_bf16(TC_BM, 64, false, true);   // A = P (TMEM, K-major), B = V (MN-major)
+      // S of half `hf` of block gg (head h, key block j): waits for the block's operands when it is the block's first MMA
+      auto issue_s = [&](int gg, int hf) {
+        const int h = gg / kb.nb, j = gg - h * kb.nb;
+        const int st = gg & 1;
+        int64_t row; int nvalid;
+        kb.get(j, row, nvalid);
+        if (hf == 0) {
+          if (j == 0) mbar_wait(&q_full[h % QBUF], (h / QBUF) & 1);
+          mbar_wait(&kv_full[st], (gg >> 1) & 1);
+          tc_fence_after();
+        }
+        const int nvh = min(32, nvalid - 32 * hf);
+        if (nvh > 0) {
+          const int n16 = (nvh + 15) & ~15;
+          const uint32_t idesc = umma_idesc_bf16(TC_BM, n16, false, false);
+          const uint32_t q_addr = smem_u32(sQ + (h % QBUF) * TC_TILE_BYTES);
+          const uint32_t k_addr = smem_u32(sK + st * TC_KV_BYTES) + hf * 4096;   // key rows 32.. of the stage
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // dh = 64 = 4 x 16
+            umma_bf16(tmem + (hf ? F2_SB : F2_SA), umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024), idesc, k > 0);
+        }
+        umma_commit(&s_full[hf]);     // completes once per block and half, whether or not the half has keys
+        // the head's Q tile has no reader after the last block's half-B S (with a single Q buffer the next head's Q can
+        // only be requested now, and the next head's first S -- issued before this block's last P.V -- waits for it)
+        if (hf == 1 && j + 1 == kb.nb) umma_commit(&q_empty[h % QBUF]);
+      };
+      issue_s(0, 0);
+      issue_s(0, 1);
+      for (int g = 0; g < total; ++g) {
+        const int h = g / kb.nb, j = g - h * kb.nb;
+        const int st = g & 1;
+        int64_t row; int nvalid;
+        kb.get(j, row, nvalid);
+        const uint32_t v_addr = smem_u32(sV + st * TC_KV_BYTES);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&p_full[hf], g & 1);      // the softmax warps wrote P of this half (and are done reading its S)
+          if (j == 0 && hf == 0 && h > 0) mbar_wait(o_empty, (h - 1) & 1);   // previous head's O has been read out
+          tc_fence_after();
+          const int nvh = min(32, nvalid - 32 * hf);
+          const int ksteps = nvh > 0 ? (nvh + 15) >> 4 : 0;
+          for (int k = 0; k < ksteps; ++k)   // 16 keys per step: P advances 8 packed columns, V 16 rows of 128 B
+            umma_bf16_ts(tmem + F2_O, tmem + (hf ? F2_SB : F2_SA) + k * 8, umma_smem_desc(v_addr + (2 * hf + k) * 2048, 8192, 1024),
+                         idesc_pv, (j > 0) || (hf > 0) || (k > 0));
+          if (hf == 1) {
+            umma_commit(&kv_empty[st]);        // every MMA reading this K/V stage has been issued
+            if (j + 1 == kb.nb) umma_commit(o_full);
+          }
+          // the half's S columns are free again (in-order tensor pipe: S(next) executes after this P.V)
+          if (g + 1 < total) issue_s(g + 1, hf);
+          else umma_commit(&s_full[hf]);       // final phase flip: lets a rescale at the last block wait for this P.V
+        }
+      }
+    }
+  } else {
+    // ------------------------------ softmax / output warps (2..5) ------------------------------
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int i = r0 + row_in_tile;
+    const bool warp_live = r0 + quarter * 32 < r1;     // any real query row in this warp?
+    uint32_t sreg[32];
+    int g = 0;
+    for (int h = 0; h < nh; ++h) {
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < kb.nb; ++j, ++g) {
+        int64_t row; int nvalid;
+        kb.get(j, row, nvalid);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int nvh = min(32, nvalid - 32 * hf);
+          mbar_wait(&s_full[hf], g & 1);
+          if (warp_live && nvh > 0) {
+            tc_fence_after();
+            tmem_ld_32x32(lane_addr + (hf ? F2_SB : F2_SA), sreg);
+            tmem_wait_ld();
+            const float m_new = row_max32(sreg, nvh) * p.scale_log2;
+            const bool grow = m_new > m_ref + 8.0f;
+            if (j == 0 && hf == 0) {
+              m_ref = m_new;
+            } else if (__any_sync(0xffffffffu, grow)) {
+              // lazy rescale of O.  The P.V of the PREVIOUS half may still be accumulating: it is complete once the
+              // other half's s_full has flipped for (hf == 0: this block; hf == 1: the next block / the final flip)
+              mbar_wait(&s_full[hf ^ 1], hf == 0 ? (g & 1) : ((g + 1) & 1));
+              tc_fence_after();
+              const float new_ref = grow ? m_new : m_ref;
+              const float alpha = exp2f(m_ref - new_ref);
+              m_ref = new_ref;
+              l *= alpha;
+              // (rare path; 16 columns at a time so that it does not push the S row out of the register file)
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                uint32_t raw[16];
+                tmem_ld_32x16(lane_addr + F2_O + c * 16, raw);
+                tmem_wait_ld();
+#pragma unroll
+                for (int t = 0; t < 16; ++t) raw[t] = __float_as_uint(__uint_as_float(raw[t]) * alpha);
+                tmem_st_32x16(lane_addr + F2_O + c * 16, raw);
+              }
+              tmem_wait_st();
+            }
+            uint32_t pk[16];
+            l += exp_pack32<POLY>(sreg, pk, nvh, p.scale_log2, m_ref);
+            tmem_st_32x16(lane_addr + (hf ? F2_SB : F2_SA), pk);
+            tmem_wait_st();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[hf]);
+        }
+      }
+      // ---- head epilogue: O / l -> bf16 row, log-sum-exp ----
+      mbar_wait(o_full, h & 1);
+      tc_fence_after();
+      if (warp_live) {
+        const float inv = 1.0f / l;
+        __nv_bfloat16* orow = p.o + (q_row0 + row_in_tile) * p.ldo + (h0 + h) * 64;
+        uint32_t raw[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_32x32(lane_addr + F2_O + c * 32, raw);
+          tmem_wait_ld();
+          if (i < r1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = make_uint4(
+                  pack_bf16(__uint_as_float(raw[8 * q]) * inv, __uint_as_float(raw[8 * q + 1]) * inv),
+                  pack_bf16(__uint_as_float(raw[8 * q + 2]) * inv, __uint_as_float(raw[8 * q + 3]) * inv),
+                  pack_bf16(__uint_as_float(raw[8 * q + 4]) * inv, __uint_as_float(raw[8 * q + 5]) * inv),
+                  pack_bf16(__uint_as_float(raw[8 * q + 6]) * inv, __uint_as_float(raw[8 * q + 7]) * inv));
+          }
+        }
+        if (p.lse && i < r1) p.lse[((int64_t)b * p.H + h0 + h) * p.N + i] = (m_ref + log2f(l)) * 0.6931471805599453f;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);   // the MMA warp may overwrite O for the next head
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -474,18 +796,49 @@ int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   p.head_rows = (int64_t)a->B * a->n_head_q;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.seg = a->seg; p.nseg = a->nseg;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    // the default carve-out is sized for fewer CTAs: ask for the whole shared memory so TC_CTAS_PER_SM CTAs fit
-    cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr = true;
-  }
   const int tiles = (a->Nq + TC_BM - 1) / TC_BM + (a->seg ? a->nseg : 0);
   p.tiles = tiles;
   const int heavy_max = a->seg ? (a->Nq + TC_BM - 1) / TC_BM : 0;
-  attn_fwd_tc_kernel<<<(tiles + (TC_HSPLIT - 1) * heavy_max) * a->B, TC_THREADS, TC_SMEM, stream>>>(tq, tk, tv, p);
+  const int grid = (tiles + (TC_HSPLIT - 1) * heavy_max) * a->B;
+  // MMF_ATTN_FWD selects the kernel generation / configuration for same-box A/B runs (default: the best measured):
+  //   0 = round-1 kernel (64-key blocks, 3 CTAs/SM);  v2 (half-block pipeline): 1 = 3 CTAs/SM, 2 = 4 CTAs/SM,
+  //   3 / 4 = the same with 1 of 4 exponentials on the FMA pipe, 5 / 6 = 2 of 4
+  const char* env = getenv("MMF_ATTN_FWD");      // read per call: a bench process may switch variants between launches
+  int variant = env ? atoi(env) : TC_FWD_DEFAULT;
+  if (variant < 0 || variant > 6) variant = TC_FWD_DEFAULT;
+  static std::atomic<unsigned> attr_done_v[8];   // per variant: bit d set = function attributes applied on device d
+  std::atomic<unsigned>& attr_done = attr_done_v[variant];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned bit = 1u << (dev & 31);
+  auto prep = [&](const void* fn, int smem) -> int {
+    if (attr_done.load(std::memory_order_acquire) & bit) return 0;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    // the default carve-out is sized for fewer CTAs: ask for the whole shared memory so that all resident CTAs fit
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return 0;
+  };
+#define MMF_FWD2(CT, QB, PL)                                                                                           \
+  do {                                                                                                                 \
+    constexpr int smem = QB * TC_TILE_BYTES + 4 * TC_KV_BYTES + 1024 + 128;                                            \
+    if ((rc = prep(reinterpret_cast<const void*>(attn_fwd_tc2_kernel<CT, QB, PL>), smem))) return rc;                  \
+    attn_fwd_tc2_kernel<CT, QB, PL><<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, p);                                \
+  } while (0)
+  switch (variant) {
+    case 0:
+      if ((rc = prep(reinterpret_cast<const void*>(attn_fwd_tc_kernel), TC_SMEM))) return rc;
+      attn_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tq, tk, tv, p);
+      break;
+    case 2: MMF_FWD2(4, 1, 0); break;
+    case 3: MMF_FWD2(3, 2, 1); break;
+    case 4: MMF_FWD2(4, 1, 1); break;
+    case 5: MMF_FWD2(3, 2, 2); break;
+    case 6: MMF_FWD2(4, 1, 2); break;
+    default: MMF_FWD2(3, 2, 0); break;
+  }
+#undef MMF_FWD2
+  attr_done.fetch_or(bit, std::memory_order_release);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
@@ -741,6 +1094,245 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 pack_bf16(__uint_as_float(rs[8 * q + 2]), __uint_as_float(rs[8 * q + 3])),
                 pack_bf16(__uint_as_float(rs[8 * q + 4]), __uint_as_float(rs[8 * q + 5])),
                 pack_bf16(__uint_as_float(rs[8 * q + 6]), __uint_as_float(rs[8 * q + 7])));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ---------------------------------------- dQ, second generation ----------------------------------------
+// The round-1 dQ kernel above is one serial chain per CTA (S, dP MMA -> elementwise -> dQ MMA -> next S ...; two CTAs per
+// SM).  Same restructuring as the forward (attn_fwd_tc2_kernel): a 64-key block is two 32-key halves with their own
+// S / dP columns and barriers, dS is written in place over the half's S columns, and the MMA thread issues
+//   dQ += dS_A(g).K_A,  S_A / dP_A (g+1),  dQ += dS_B(g).K_B,  S_B / dP_B (g+1), ...
+// so the tensor pipe works on one half while the elementwise warps work on the other.  Every barrier completes exactly
+// once per block (phase parity = g & 1).  TMEM: S_A | S_B | dP_A | dP_B | dQ = 192 of 256 allocated columns.
+constexpr uint32_t DQ2_S = 0, DQ2_DP = 64, DQ2_ACC = 128;
+
+template <int POLY>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                       const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                       const AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  int r0 = 0, r1 = 0, k0 = 0, k1 = 0, b = 0, h0 = 0, h1 = 0;
+  {
+    int tile;
+    lpt_tile(p.seg, p.nseg, p.tiles, p.B, p.H, tile, b, h0, h1);
+    bool found = false;
+    if (p.seg == nullptr) {
+      r0 = tile * TC_BM; r1 = min(r0 + TC_BM, p.N); k0 = 0; k1 = p.N; found = r0 < p.N;
+    } else {
+      for (int s = 0; s < p.nseg; ++s) {
+        const int a = p.seg[s], e = p.seg[s + 1];
+        const int nt = (e - a + TC_BM - 1) / TC_BM;
+        if (tile < nt) {
+          r0 = a + tile * TC_BM; r1 = min(r0 + TC_BM, e);
+          if (s == p.nseg - 1) { k0 = 0; k1 = p.N; } else { k0 = a; k1 = e; }
+          found = true;
+          break;
+        }
+        tile -= nt;
+      }
+    }
+    if (!found) return;
+  }
+  const int nh = h1 - h0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // 2 buffers of 128x64
+  uint8_t* sdO = smem + 2 * TC_TILE_BYTES;              // 2 buffers
+  uint8_t* sK = smem + 4 * TC_TILE_BYTES;               // 2 stages of 64x64
+  uint8_t* sV = sK + 2 * BW_BLK_BYTES;                  // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * BW_BLK_BYTES);
+  uint64_t* q_full = bars;         // [2] (Q and dO of a head)
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* kv_full = bars + 4;    // [2]
+  uint64_t* kv_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;     // [2] S and dP of a half ready
+  uint64_t* ds_full = bars + 10;   // [2] dS of a half written (its S / dP consumed)
+  uint64_t* acc_full = bars + 12;  // dQ of the head complete
+  uint64_t* acc_empty = bars + 13; // dQ read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int64_t q_row0 = r0 < p.n_head ? (int64_t)b * p.n_head + r0 : p.head_rows + (int64_t)b * p.n_tail + (r0 - p.n_head);
+  RowBlocks kb;   // key range split at the plane boundary
+  kb.init(k0, min(k1, p.n_head), max(k0, p.n_head), k1, p.n_head, p.n_tail, p.head_rows, b);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
+        mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
+        mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], 4);
+      }
+      mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int total = kb.nb * nh;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      for (int h = 0; h < nh; ++h) {
+        const int qs = h & 1;
+        mbar_wait(&q_empty[qs], ((h >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qs], 2 * TC_TILE_BYTES);
+        tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], (h0 + h) * 64, (int)q_row0);
+        tma_load_2d(sdO + qs * TC_TILE_BYTES, &tmap_do, &q_full[qs], (h0 + h) * 64, (int)q_row0);
+        for (int j = 0; j < kb.nb; ++j, ++g) {
+          const int st = g & 1;
+          mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+          int tok, nvalid; int64_t row;
+          kb.get(j, tok, row, nvalid);
+          mbar_expect_tx(&kv_full[st], 2 * BW_BLK_BYTES);
+          tma_load_2d(sK + st * BW_BLK_BYTES, &tmap_k, &kv_full[st], (h0 + h) * 64, (int)row);
+          tma_load_2d(sV + st * BW_BLK_BYTES, &tmap_v, &kv_full[st], (h0 + h) * 64, (int)row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && total > 0) {
+      const uint32_t idesc_acc = umma_idesc_bf16(TC_BM, 64, false, true);      // dQ[128 x 64dh] += dS[128 x keys] . K (MN-major)
+      auto issue_s = [&](int gg, int hf) {
+        const int h = gg / kb.nb, j = gg - h * kb.nb;
+        const int st = gg & 1;
+        int tok, nvalid; int64_t row;
+        kb.get(j, tok, row, nvalid);
+        if (hf == 0) {
+          if (j == 0) mbar_wait(&q_full[h & 1], (h >> 1) & 1);
+          mbar_wait(&kv_full[st], (gg >> 1) & 1);
+          tc_fence_after();
+        }
+        const int nvh = min(32, nvalid - 32 * hf);
+        if (nvh > 0) {
+          const uint32_t idesc_s = umma_idesc_bf16(TC_BM, (nvh + 15) & ~15, false, false);
+          const uint32_t q_addr = smem_u32(sQ + (h & 1) * TC_TILE_BYTES), do_addr = smem_u32(sdO + (h & 1) * TC_TILE_BYTES);
+          const uint32_t k_addr = smem_u32(sK + st * BW_BLK_BYTES) + hf * 4096, v_addr = smem_u32(sV + st * BW_BLK_BYTES) + hf * 4096;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + DQ2_S + hf * 32, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + DQ2_DP + hf * 32, umma_smem_desc(do_addr + k * 32, 16, 1024), umma_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k > 0);
+        }
+        umma_commit(&s_full[hf]);
+        if (hf == 1 && j + 1 == kb.nb) umma_commit(&q_empty[h & 1]);     // Q / dO of the head have no later reader
+      };
+      issue_s(0, 0);
+      issue_s(0, 1);
+      for (int g = 0; g < total; ++g) {
+        const int h = g / kb.nb, j = g - h * kb.nb;
+        const int st = g & 1;
+        int tok, nvalid; int64_t row;
+        kb.get(j, tok, row, nvalid);
+        const uint32_t k_addr = smem_u32(sK + st * BW_BLK_BYTES);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&ds_full[hf], g & 1);
+          if (j == 0 && hf == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);
+          tc_fence_after();
+          const int nvh = min(32, nvalid - 32 * hf);
+          const int ksteps = nvh > 0 ? (nvh + 15) >> 4 : 0;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_ts(tmem + DQ2_ACC, tmem + DQ2_S + hf * 32 + k * 8, umma_smem_desc(k_addr + (2 * hf + k) * 2048, 8192, 1024), idesc_acc,
+                         (j > 0) || (hf > 0) || (k > 0));
+          if (hf == 1) {
+            umma_commit(&kv_empty[st]);
+            if (j + 1 == kb.nb) umma_commit(acc_full);
+          }
+          if (g + 1 < total) issue_s(g + 1, hf);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int i = r0 + row_in_tile;
+    const bool row_ok = i < r1;
+    const bool warp_live = r0 + quarter * 32 < r1;
+    uint32_t rs[32], rd[32];
+    int g = 0;
+    const int64_t stat0 = ((int64_t)b * p.H + h0) * p.N + (row_ok ? i : r0);
+    float lse_raw = p.lse[stat0], dl_raw = p.delta[stat0];
+    for (int h = 0; h < nh; ++h) {
+      const float lse2 = row_ok ? lse_raw * 1.4426950408889634f : INFINITY;   // invalid rows -> P = 0
+      const float dl = row_ok ? dl_raw : 0.f;
+      if (h + 1 < nh) {
+        lse_raw = p.lse[stat0 + (int64_t)(h + 1) * p.N];
+        dl_raw = p.delta[stat0 + (int64_t)(h + 1) * p.N];
+      }
+      for (int j = 0; j < kb.nb; ++j, ++g) {
+        int tok, nvalid; int64_t row;
+        kb.get(j, tok, row, nvalid);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int nvh = min(32, nvalid - 32 * hf);
+          mbar_wait(&s_full[hf], g & 1);
+          if (warp_live && nvh > 0) {
+            tc_fence_after();
+            tmem_ld_32x32(lane_addr + DQ2_S + hf * 32, rs);
+            tmem_ld_32x32(lane_addr + DQ2_DP + hf * 32, rd);
+            tmem_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const float x0 = fmaf(__uint_as_float(rs[2 * t]), p.scale_log2, -lse2);
+              const float x1 = fmaf(__uint_as_float(rs[2 * t + 1]), p.scale_log2, -lse2);
+              float p0 = ((2 * t) & 3) < POLY ? exp2_poly(x0) : ex2(x0);
+              float p1 = ((2 * t + 1) & 3) < POLY ? exp2_poly(x1) : ex2(x1);
+              if (nvh < 32) {
+                if (2 * t >= nvh) p0 = 0.f;
+                if (2 * t + 1 >= nvh) p1 = 0.f;
+              }
+              pk[t] = pack_bf16(p0 * (__uint_as_float(rd[2 * t]) - dl) * p.scale, p1 * (__uint_as_float(rd[2 * t + 1]) - dl) * p.scale);
+            }
+            tmem_st_32x16(lane_addr + DQ2_S + hf * 32, pk);
+            tmem_wait_st();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ds_full[hf]);
+        }
+      }
+      mbar_wait(acc_full, h & 1);
+      tc_fence_after();
+      if (warp_live) {
+        __nv_bfloat16* orow = p.dq + (q_row0 + row_in_tile) * p.lddq + (h0 + h) * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_32x32(lane_addr + DQ2_ACC + c * 32, rs);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = make_uint4(
+                  pack_bf16(__uint_as_float(rs[8 * q]), __uint_as_float(rs[8 * q + 1])),
+                  pack_bf16(__uint_as_float(rs[8 * q + 2]), __uint_as_float(rs[8 * q + 3])),
+                  pack_bf16(__uint_as_float(rs[8 * q + 4]), __uint_as_float(rs[8 * q + 5])),
+                  pack_bf16(__uint_as_float(rs[8 * q + 6]), __uint_as_float(rs[8 * q + 7])));
+          }
         }
       }
       tc_fence_before();
@@ -1086,20 +1678,46 @@ int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   p.head_rows = (int64_t)a->B * a->n_head_q;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
   p.seg = a->seg; p.nseg = a->nseg;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr = true;
-  }
   const int tiles = (a->Nq + TC_BM - 1) / TC_BM + (a->seg ? a->nseg : 0);
   p.tiles = tiles;
   const int heavy_max = a->seg ? (a->Nq + TC_BM - 1) / TC_BM : 0;
-  attn_bwd_dq_tc_kernel<<<(tiles + (TC_HSPLIT - 1) * heavy_max) * a->B, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
+  const int grid_q = (tiles + (TC_HSPLIT - 1) * heavy_max) * a->B;
+  // MMF_ATTN_DQ: 0 = round-1 dQ kernel, 1 = half-block pipeline (attn_bwd_dq_tc2_kernel), 2 / 3 = the same with 1 / 2 of
+  // every 4 exponentials on the FMA pipe.  Read per call (A/B runs switch it between launches).
+  const char* env = getenv("MMF_ATTN_DQ");
+  int vq = env ? atoi(env) : TC_DQ_DEFAULT;
+  if (vq < 0 || vq > 3) vq = TC_DQ_DEFAULT;
+  static std::atomic<unsigned> attr_done_v[5];   // [0..3] dQ variants, [4] dK/dV: bit d set = attributes applied on device d
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned bit = 1u << (dev & 31);
+  auto prep = [&](std::atomic<unsigned>& done, const void* fn, int smem) -> int {
+    if (done.load(std::memory_order_acquire) & bit) return 0;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    done.fetch_or(bit, std::memory_order_release);
+    return 0;
+  };
+  switch (vq) {
+    case 0:
+      if ((rc = prep(attr_done_v[0], reinterpret_cast<const void*>(attn_bwd_dq_tc_kernel), DQ_SMEM))) return rc;
+      attn_bwd_dq_tc_kernel<<<grid_q, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
+      break;
+    case 2:
+      if ((rc = prep(attr_done_v[2], reinterpret_cast<const void*>(attn_bwd_dq_tc2_kernel<1>), DQ_SMEM))) return rc;
+      attn_bwd_dq_tc2_kernel<1><<<grid_q, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
+      break;
+    case 3:
+      if ((rc = prep(attr_done_v[3], reinterpret_cast<const void*>(attn_bwd_dq_tc2_kernel<2>), DQ_SMEM))) return rc;
+      attn_bwd_dq_tc2_kernel<2><<<grid_q, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
+      break;
+    default:
+      if ((rc = prep(attr_done_v[1], reinterpret_cast<const void*>(attn_bwd_dq_tc2_kernel<0>), DQ_SMEM))) return rc;
+      attn_bwd_dq_tc2_kernel<0><<<grid_q, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
+      break;
+  }
+  if ((rc = prep(attr_done_v[4], reinterpret_cast<const void*>(attn_bwd_dkv_tc_kernel), DKV_SMEM))) return rc;
   attn_bwd_dkv_tc_kernel<<<tiles * a->B, TC_THREADS, DKV_SMEM, stream>>>(k128, v128, q64, do64, p);
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
