@@ -275,6 +275,19 @@ int mmf_dino_loss(const void* student, int64_t lds, const void* teacher, int64_t
                   float student_temp, float teacher_temp, float* row_loss, float* dstudent, mmf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Debiased hard-negative contrastive loss, forward and both input gradients in one call (criterion.py:214-268
+ * HardNegtive_loss.forward incl. get_negative_mask :224-231; call sites pretrain_mmae_s2dsm.py:482-492).
+ * out1 / out2: [B, D] f32 rows (row pitches ld1 / ld2), B >= 2, D <= 2048.  easy = 0: estimator 'hard' (tau_plus, beta),
+ * 1: estimator 'easy'.  loss: f32 scalar = mean over the 2B rows; dout1 / dout2 [B, D] f32 contiguous = d loss / d out
+ * for an upstream gradient of 1.  work: f32 scratch of mmf_hardneg_workspace_floats(B, D) elements.
+ * The [2B, 2B] similarity takes bf16-rounded operands with fp32 accumulation (torch.mm under the reference's
+ * autocast); normalisation, exp / log and reductions are fp32.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t mmf_hardneg_workspace_floats(int32_t B, int32_t D);
+int mmf_hardneg_loss(const float* out1, int64_t ld1, const float* out2, int64_t ld2, int32_t B, int32_t D, float tau_plus, float beta,
+                     float temperature, int32_t easy, float* work, float* loss, float* dout1, float* dout2, mmf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Masked cross-entropy over class maps (criterion.py:24-58 MaskedCrossEntropyLoss with label_smoothing = 0; the loss of
  * the 4th, semantic, modality `dnw` in pretrain_mmae_my.py:68-75).  logits [B, C, H, W] (bf16 or f32),
  * target [B, H, W] int64 class ids, mask [B, (H/P)*(W/P)] int64 (1 = masked patch, counted) or NULL.  Per pixel

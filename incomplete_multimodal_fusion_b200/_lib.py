@@ -108,11 +108,13 @@ SIGNATURES = {
     "mmf_add_inplace_f32": [c_vp, c_vp, c_i64, c_vp],
     "mmf_add_bf16_f32": [c_vp, c_vp, c_vp, c_i64, c_vp],
     "mmf_dino_loss": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp],
+    "mmf_hardneg_workspace_floats": [c_i32, c_i32],
+    "mmf_hardneg_loss": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
     "mmf_adamw_step": [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp],
     "mmf_grad_norm": [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp],
     "mmf_mask_build": [c_vp, c_vp, c_vp, c_i32, C.POINTER(c_i32), c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
 }
-_RESTYPES = {"mmf_launch_count": c_i64, "mmf_reset_launch_count": None, "mmf_set_gemm_reserved_sms": None}
+_RESTYPES = {"mmf_hardneg_workspace_floats": c_i64, "mmf_launch_count": c_i64, "mmf_reset_launch_count": None, "mmf_set_gemm_reserved_sms": None}
 
 
 def lib_path() -> str:

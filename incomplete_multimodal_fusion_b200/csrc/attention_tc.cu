@@ -504,8 +504,13 @@ __device__ __forceinline__ float exp_pack32(const uint32_t (&v)[32], uint32_t (&
   for (int t = 0; t < 16; ++t) {
     const float x0 = fmaf(__uint_as_float(v[2 * t]), scale_log2, -m_ref);
     const float x1 = fmaf(__uint_as_float(v[2 * t + 1]), scale_log2, -m_ref);
-    float p0 = ((2 * t) & 3) < POLY ? exp2_poly(x0) : ex2_approx(x0);
-    float p1 = ((2 * t + 1) & 3) < POLY ? exp2_poly(x1) : ex2_approx(x1);
+    float p0, p1;
+    if (POLY == 8 || POLY == 10) {   // TIMING ABLATION ONLY (wrong results): no exponentials
+      p0 = x0; p1 = x1;
+    } else {
+      p0 = ((2 * t) & 3) < POLY ? exp2_poly(x0) : ex2_approx(x0);
+      p1 = ((2 * t + 1) & 3) < POLY ? exp2_poly(x1) : ex2_approx(x1);
+    }
     if (nv < 32) {
       if (2 * t >= nv) p0 = 0.f;
       if (2 * t + 1 >= nv) p1 = 0.f;
@@ -689,8 +694,13 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           mbar_wait(&s_full[hf], g & 1);
           if (warp_live && nvh > 0) {
             tc_fence_after();
-            tmem_ld_32x32(lane_addr + (hf ? F2_SB : F2_SA), sreg);
-            tmem_wait_ld();
+            if (POLY == 9 || POLY == 10) {   // TIMING ABLATION ONLY (wrong results): no TMEM read of S
+#pragma unroll
+              for (int t = 0; t < 32; ++t) sreg[t] = __float_as_uint((float)(t + lane) * 0.01f);
+            } else {
+              tmem_ld_32x32(lane_addr + (hf ? F2_SB : F2_SA), sreg);
+              tmem_wait_ld();
+            }
             const float m_new = row_max32(sreg, nvh) * p.scale_log2;
             const bool grow = m_new > m_ref + 8.0f;
             if (j == 0 && hf == 0) {
@@ -805,8 +815,8 @@ int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   //   3 / 4 = the same with 1 of 4 exponentials on the FMA pipe, 5 / 6 = 2 of 4
   const char* env = getenv("MMF_ATTN_FWD");      // read per call: a bench process may switch variants between launches
   int variant = env ? atoi(env) : TC_FWD_DEFAULT;
-  if (variant < 0 || variant > 6) variant = TC_FWD_DEFAULT;
-  static std::atomic<unsigned> attr_done_v[8];   // per variant: bit d set = function attributes applied on device d
+  if (variant < 0 || variant > 9) variant = TC_FWD_DEFAULT;
+  static std::atomic<unsigned> attr_done_v[10];   // per variant: bit d set = function attributes applied on device d
   std::atomic<unsigned>& attr_done = attr_done_v[variant];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -835,6 +845,9 @@ int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
     case 4: MMF_FWD2(4, 1, 1); break;
     case 5: MMF_FWD2(3, 2, 2); break;
     case 6: MMF_FWD2(4, 1, 2); break;
+    case 7: MMF_FWD2(3, 2, 8); break;     // 7 .. 9: timing ablations (WRONG RESULTS): no exp / no TMEM read of S / neither
+    case 8: MMF_FWD2(3, 2, 9); break;
+    case 9: MMF_FWD2(3, 2, 10); break;
     default: MMF_FWD2(3, 2, 0); break;
   }
 #undef MMF_FWD2

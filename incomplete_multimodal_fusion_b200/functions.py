@@ -487,6 +487,26 @@ class DinoLossFn(torch.autograd.Function):
         return (ds * dloss).to(ctx.in_dtype), None, None, None
 
 
+class HardNegLossFn(torch.autograd.Function):
+    """criterion.py:214-268 fused: forward + both input gradients in one call of three launches (kernels.hardneg_loss)"""
+
+    @staticmethod
+    def forward(ctx, out1, out2, tau_plus, beta, temperature, easy):
+        a = out1.float()
+        b = out2.float()
+        a = a if a.stride(-1) == 1 else a.contiguous()
+        b = b if b.stride(-1) == 1 else b.contiguous()
+        loss, d1, d2 = K.hardneg_loss(a, b, tau_plus, beta, temperature, easy)
+        ctx.save_for_backward(d1, d2)
+        ctx.dtypes = (out1.dtype, out2.dtype)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        d1, d2 = ctx.saved_tensors
+        return (d1 * dloss).to(ctx.dtypes[0]), (d2 * dloss).to(ctx.dtypes[1]), None, None, None, None
+
+
 class MatmulNTFn(torch.autograd.Function):
     """C = A . B^T with bf16 tensor-core operands and an fp32 result (what torch.mm does under the reference's
     autocast, e.g. the [2B, D] x [D, 2B] similarity of HardNegtive_loss, criterion.py:240).  A [M, K], B [N, K]."""

@@ -445,3 +445,18 @@ def dino_loss(student, teacher, student_temp, teacher_temp):
     check(_L().mmf_dino_loss(_p(student), student.stride(0), _p(teacher), teacher.stride(0), int(student.dtype == f32), B, D,
                              student_temp, teacher_temp, _p(row_loss), _p(dstudent), _stream()), "mmf_dino_loss")
     return row_loss, dstudent
+
+
+def hardneg_loss(out1, out2, tau_plus, beta, temperature, easy=False):
+    """-> (loss [1] f32, dout1, dout2 [B, D] f32 for an upstream gradient of 1); out1 / out2: [B, D] f32 rows"""
+    assert out1.dim() == 2 and out1.shape == out2.shape and out1.dtype == f32 and out2.dtype == f32
+    assert out1.stride(1) == 1 and out2.stride(1) == 1
+    B, D = out1.shape
+    L = _L()
+    work = torch.empty(int(L.mmf_hardneg_workspace_floats(B, D)), dtype=f32, device=out1.device)
+    loss = torch.empty(1, dtype=f32, device=out1.device)
+    d1 = torch.empty(B, D, dtype=f32, device=out1.device)
+    d2 = torch.empty(B, D, dtype=f32, device=out1.device)
+    check(L.mmf_hardneg_loss(_p(out1), out1.stride(0), _p(out2), out2.stride(0), B, D, float(tau_plus), float(beta), float(temperature),
+                             int(easy), _p(work), _p(loss), _p(d1), _p(d2), _stream()), "mmf_hardneg_loss")
+    return loss, d1, d2

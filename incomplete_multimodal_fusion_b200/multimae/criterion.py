@@ -65,53 +65,28 @@ class MaskedCrossEntropyLoss(nn.Module):
 
 
 class HardNegtive_loss(nn.Module):
-    """Debiased hard-negative contrastive loss (criterion.py:214-268).  The [2B, D] x [D, 2B] similarity runs on the
-    tcgen05 GEMM with bf16 operands (torch.mm under the reference's autocast, Appendix A #19); normalisation, exp / log
-    and the row reductions are fp32 device ops (no Python loop over the batch, no hard-coded .cuda())."""
+    """Debiased hard-negative contrastive loss (criterion.py:214-268), fused: normalisation, the [2B, 2B] similarity (bf16
+    operands, fp32 accumulation: torch.mm under the reference's autocast, Appendix A #19), the negative mask of
+    get_negative_mask (:224-231, a B-iteration Python loop + .cuda() in the reference), the debiased re-weighting, the
+    loss AND both input gradients come out of one call of three small launches (mmf_hardneg_loss); no autograd graph of
+    elementwise ops, no host synchronisation."""
 
     def __init__(self, tau_plus=0.1, beta=1.0, temperature=0.5, alpha=256, estimator='hard'):
         super().__init__()
         self.tau_plus, self.beta, self.temperature, self.alpha, self.estimator = tau_plus, beta, temperature, alpha, estimator
 
     def get_negative_mask(self, batch_size, device=None):
-        """[2B, 2B] bool, False on the diagonal and on the positive pair (criterion.py:224-231 without the loop)"""
+        """[2B, 2B] bool, False on the diagonal and on the positive pair (criterion.py:224-231 without the loop); kept for
+        API parity -- the kernel applies the same exclusion by index"""
         eye = torch.eye(batch_size, dtype=torch.bool, device=device)
         return ~torch.cat([torch.cat([eye, eye], 1), torch.cat([eye, eye], 1)], 0)
 
-    def _negative_index(self, batch_size, device):
-        """[2B, 2B - 2] int64: column of the j-th True of get_negative_mask's row r (what masked_select walks)"""
-        cache = self.__dict__.setdefault('_neg_index_cache', {})
-        key = (batch_size, str(device))
-        if key not in cache:
-            j = torch.arange(2 * batch_size - 2, device=device)[None, :]
-            b = (torch.arange(2 * batch_size, device=device) % batch_size)[:, None]
-            cache[key] = j + (j >= b).long() + (j >= b + batch_size - 1).long()
-        return cache[key]
-
     def forward(self, out_1, out_2):
-        B = out_1.shape[0]
         if not out_1.is_cuda:
             raise RuntimeError("HardNegtive_loss runs on CUDA only (no CPU fallback)")
-        o1 = F.normalize(out_1.float(), dim=1)
-        o2 = F.normalize(out_2.float(), dim=1)
-        out = torch.cat([o1, o2], dim=0)
-        neg = torch.exp(Fn.MatmulNTFn.apply(out, out) / self.temperature)
-        # the negatives of row r are all columns but r mod B and (r mod B) + B, in ascending order: a gather through a static
-        # index instead of masked_select (whose output size is read back: a host synchronisation per loss call)
-        neg = torch.gather(neg, 1, self._negative_index(B, out.device))
-        pos = torch.exp((o1 * o2).sum(-1) / self.temperature)
-        pos = torch.cat([pos, pos], 0)
-        if self.estimator == 'hard':
-            N = 2 * B - 2
-            imp = (self.beta * neg.log()).exp()
-            reweight = (imp * neg).sum(-1) / imp.mean(-1)
-            Ng = (-self.tau_plus * N * pos + reweight) / (1 - self.tau_plus)
-            Ng = torch.clamp(Ng, min=N * math.e ** (-1 / self.temperature))
-        elif self.estimator == 'easy':
-            Ng = neg.sum(-1)
-        else:
+        if self.estimator not in ('hard', 'easy'):
             raise Exception('Invalid estimator selected. Please use any of [hard, easy]')
-        return (-torch.log(pos / (pos + Ng))).mean()
+        return Fn.HardNegLossFn.apply(out_1, out_2, self.tau_plus, self.beta, self.temperature, self.estimator == 'easy')
 
 
 def dino_loss_func(student_output, teacher_output, teacher_temp=0.04, student_temp=0.1):

@@ -560,3 +560,51 @@ def test_hard_negative_loss_matches_golden_and_oracle(golden_dir):
     from incomplete_multimodal_fusion_b200.multimae.criterion import dino_loss_func
     d = dino_loss_func(fa.cuda(), fb.cuda())
     assert abs(float(d) - float(fx["dino"])) < 1e-5 * abs(float(fx["dino"]))
+
+
+@pytest.mark.parametrize("B,D,beta,tau_plus,temp", [(64, 384, 1.0, 0.1, 0.5), (100, 768, 0.5, 0.05, 0.2), (2, 40, 1.0, 0.1, 0.5)])
+def test_hard_negative_loss_fused_kernel(B, D, beta, tau_plus, temp):
+    """mmf_hardneg_loss (forward + both input gradients in one call) against the reference's arithmetic in fp32 autograd
+    (oracle restatement of criterion.py:233-268) at pre-training batch sizes; also the reference class itself when
+    baseline/_ref is available (its .cuda() call runs here), and the 'easy' estimator against autograd of its formula"""
+    import oracle
+    from incomplete_multimodal_fusion_b200.multimae.criterion import HardNegtive_loss
+    g = torch.Generator().manual_seed(5)
+    fa, fb = torch.randn(B, D, generator=g), torch.randn(B, D, generator=g) * 0.5 + 0.3 * torch.randn(B, D, generator=torch.Generator().manual_seed(5))
+    a, b = fa.cuda().requires_grad_(True), fb.cuda().requires_grad_(True)
+    loss = HardNegtive_loss(tau_plus=tau_plus, beta=beta, temperature=temp)(a, b)
+    (loss * 1.7).backward()
+    a2, b2 = fa.cuda().requires_grad_(True), fb.cuda().requires_grad_(True)
+    ref = oracle.hard_negative_loss(a2, b2, tau_plus=tau_plus, beta=beta, temperature=temp)
+    (ref * 1.7).backward()
+    # the similarity takes bf16-rounded operands (torch.mm under the reference's autocast): 1e-2 on the loss, 3e-2 on gradients
+    assert abs(float(loss) - float(ref)) < 1e-2 * abs(float(ref)), (float(loss), float(ref))
+    assert rel(a.grad, a2.grad) < 3e-2 and rel(b.grad, b2.grad) < 3e-2, (rel(a.grad, a2.grad), rel(b.grad, b2.grad))
+    try:
+        from baseline import harness as H
+        refmod = H.load().criterion.HardNegtive_loss(tau_plus=tau_plus, beta=beta, temperature=temp) if H.available() else None
+    except Exception:
+        refmod = None
+    if refmod is not None:
+        a3, b3 = fa.cuda().requires_grad_(True), fb.cuda().requires_grad_(True)
+        r3 = refmod(a3, b3)
+        r3.backward()
+        assert abs(float(loss) - float(r3)) < 1e-2 * abs(float(r3))
+        assert rel(a.grad / 1.7, a3.grad) < 3e-2
+    # 'easy' estimator: Ng = sum of the negatives
+    a4, b4 = fa.cuda().requires_grad_(True), fb.cuda().requires_grad_(True)
+    le = HardNegtive_loss(temperature=temp, estimator='easy')(a4, b4)
+    le.backward()
+    a5, b5 = fa.cuda().requires_grad_(True), fb.cuda().requires_grad_(True)
+    o1, o2 = torch.nn.functional.normalize(a5, dim=1), torch.nn.functional.normalize(b5, dim=1)
+    out = torch.cat([o1, o2], 0)
+    neg = torch.exp(out @ out.t() / temp)
+    eye = torch.eye(B, dtype=torch.bool, device="cuda")
+    keep = ~torch.cat([torch.cat([eye, eye], 1), torch.cat([eye, eye], 1)], 0)
+    Ng = (neg * keep).sum(-1)
+    pos = torch.exp((o1 * o2).sum(-1) / temp)
+    pos = torch.cat([pos, pos], 0)
+    lr = (-torch.log(pos / (pos + Ng))).mean()
+    lr.backward()
+    assert abs(float(le) - float(lr)) < 1e-2 * abs(float(lr))
+    assert rel(a4.grad, a5.grad) < 3e-2 and rel(b4.grad, b5.grad) < 3e-2
