@@ -48,6 +48,7 @@ struct AttnTcParams {
   const int32_t* seg;
   int nseg;
   int tiles;                  // query tiles per sample the grid was sized for (upper bound)
+  int pf;                     // L2 prefetch distance in key blocks (0 = off)
 };
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
@@ -163,6 +164,7 @@ struct KeyBlocks {
 // the grid is (tiles + (TC_HSPLIT - 1) * heavy_max) * B CTAs, surplus ones exit.
 constexpr int TC_HSPLIT = 1;
 constexpr int TC_FWD_DEFAULT = 1;
+constexpr int TC_PF_DEFAULT = 0;    // MMF_ATTN_PF default: L2 prefetch distance in blocks
 constexpr int TC_DQ_DEFAULT = 1;    // MMF_ATTN_DQ default (see attn_bwd_tc_launch)   // MMF_ATTN_FWD default (see attn_fwd_tc_launch)
 __device__ __forceinline__ void lpt_tile(const int32_t* seg, int nseg, int tiles, int B, int H, int& tile, int& b, int& h0, int& h1) {
   const int L = blockIdx.x;
@@ -521,7 +523,7 @@ __device__ __forceinline__ float exp_pack32(const uint32_t (&v)[32], uint32_t (&
   return rs0 + rs1;
 }
 
-template <int CTAS, int QBUF, int POLY>
+template <int CTAS, int QBUF, int KVST, int POLY>
 __global__ void __launch_bounds__(TC_THREADS, CTAS)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
@@ -553,18 +555,18 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                            // QBUF buffers
-  uint8_t* sK = smem + QBUF * TC_TILE_BYTES;     // 2 stages of 64 keys
-  uint8_t* sV = sK + 2 * TC_KV_BYTES;            // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * TC_KV_BYTES);
+  uint8_t* sK = smem + QBUF * TC_TILE_BYTES;     // KVST stages of 64 keys
+  uint8_t* sV = sK + KVST * TC_KV_BYTES;         // KVST stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KVST * TC_KV_BYTES);
   uint64_t* q_full = bars;         // [2]
   uint64_t* q_empty = bars + 2;    // [2]
-  uint64_t* kv_full = bars + 4;    // [2]
-  uint64_t* kv_empty = bars + 6;   // [2]
-  uint64_t* s_full = bars + 8;     // [2] per half
-  uint64_t* p_full = bars + 10;    // [2] per half
-  uint64_t* o_full = bars + 12;
-  uint64_t* o_empty = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* s_full = bars + 4;     // [2] per half
+  uint64_t* p_full = bars + 6;     // [2] per half
+  uint64_t* o_full = bars + 8;
+  uint64_t* o_empty = bars + 9;
+  uint64_t* kv_full = bars + 10;   // [KVST]
+  uint64_t* kv_empty = kv_full + KVST;   // [KVST]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + KVST);
 
   const int64_t q_row0 = r0 < p.n_head ? (int64_t)b * p.n_head + r0 : p.head_rows + (int64_t)b * p.n_tail + (r0 - p.n_head);
   KeyBlocks kb;
@@ -579,9 +581,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
         mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
-        mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
         mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4);
       }
+      for (int s = 0; s < KVST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
       mbar_init(o_full, 1);
       mbar_init(o_empty, 4);
       mbar_fence_init();
@@ -599,15 +601,31 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
+      // L2 prefetch of the operands p.pf blocks / heads ahead of the shared-memory loads (the ring holds only KVST key
+      // blocks, i.e. KVST - 1 loads in flight, against a global -> shared latency of a few thousand cycles)
+      auto prefetch_kv = [&](int gg) {
+        if (gg >= total) return;
+        const int hh = gg / kb.nb, jj = gg - hh * kb.nb;
+        int64_t row; int nvalid;
+        kb.get(jj, row, nvalid);
+        tma_prefetch_2d(&tmap_k, (h0 + hh) * 64, (int)row);
+        tma_prefetch_2d(&tmap_v, (h0 + hh) * 64, (int)row);
+      };
+      if (p.pf > 0) {
+        for (int gg = 0; gg < p.pf; ++gg) prefetch_kv(gg);
+        for (int hh = 1; hh < nh && hh <= 2; ++hh) tma_prefetch_2d(&tmap_q, (h0 + hh) * 64, (int)q_row0);
+      }
       int g = 0;
       for (int h = 0; h < nh; ++h) {
         const int qs = h % QBUF;
+        if (p.pf > 0 && h + 3 < nh) tma_prefetch_2d(&tmap_q, (h0 + h + 3) * 64, (int)q_row0);
         mbar_wait(&q_empty[qs], ((h / QBUF) & 1) ^ 1);
         mbar_expect_tx(&q_full[qs], TC_TILE_BYTES);
         tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], (h0 + h) * 64, (int)q_row0);
         for (int j = 0; j < kb.nb; ++j, ++g) {
-          const int st = g & 1;
-          mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+          const int st = g % KVST;
+          if (p.pf > 0) prefetch_kv(g + p.pf);
+          mbar_wait(&kv_empty[st], ((g / KVST) & 1) ^ 1);
           int64_t row; int nvalid;
           kb.get(j, row, nvalid);
           mbar_expect_tx(&kv_full[st], 2 * TC_KV_BYTES);
@@ -623,12 +641,12 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       // S of half `hf` of block gg (head h, key block j): waits for the block's operands when it is the block's first MMA
       auto issue_s = [&](int gg, int hf) {
         const int h = gg / kb.nb, j = gg - h * kb.nb;
-        const int st = gg & 1;
+        const int st = gg % KVST;
         int64_t row; int nvalid;
         kb.get(j, row, nvalid);
         if (hf == 0) {
           if (j == 0) mbar_wait(&q_full[h % QBUF], (h / QBUF) & 1);
-          mbar_wait(&kv_full[st], (gg >> 1) & 1);
+          mbar_wait(&kv_full[st], (gg / KVST) & 1);
           tc_fence_after();
         }
         const int nvh = min(32, nvalid - 32 * hf);
@@ -650,7 +668,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       issue_s(0, 1);
       for (int g = 0; g < total; ++g) {
         const int h = g / kb.nb, j = g - h * kb.nb;
-        const int st = g & 1;
+        const int st = g % KVST;
         int64_t row; int nvalid;
         kb.get(j, row, nvalid);
         const uint32_t v_addr = smem_u32(sV + st * TC_KV_BYTES);
@@ -806,6 +824,11 @@ int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   p.head_rows = (int64_t)a->B * a->n_head_q;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.seg = a->seg; p.nseg = a->nseg;
+  {
+    const char* pe = getenv("MMF_ATTN_PF");
+    p.pf = pe ? atoi(pe) : TC_PF_DEFAULT;
+    if (p.pf < 0 || p.pf > 64) p.pf = TC_PF_DEFAULT;
+  }
   const int tiles = (a->Nq + TC_BM - 1) / TC_BM + (a->seg ? a->nseg : 0);
   p.tiles = tiles;
   const int heavy_max = a->seg ? (a->Nq + TC_BM - 1) / TC_BM : 0;
@@ -829,26 +852,26 @@ int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
     cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return 0;
   };
-#define MMF_FWD2(CT, QB, PL)                                                                                           \
+#define MMF_FWD2(CT, QB, KS, PL)                                                                                       \
   do {                                                                                                                 \
-    constexpr int smem = QB * TC_TILE_BYTES + 4 * TC_KV_BYTES + 1024 + 128;                                            \
-    if ((rc = prep(reinterpret_cast<const void*>(attn_fwd_tc2_kernel<CT, QB, PL>), smem))) return rc;                  \
-    attn_fwd_tc2_kernel<CT, QB, PL><<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, p);                                \
+    constexpr int smem = QB * TC_TILE_BYTES + 2 * KS * TC_KV_BYTES + 1024 + 512;                                       \
+    if ((rc = prep(reinterpret_cast<const void*>(attn_fwd_tc2_kernel<CT, QB, KS, PL>), smem))) return rc;              \
+    attn_fwd_tc2_kernel<CT, QB, KS, PL><<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, p);                            \
   } while (0)
   switch (variant) {
     case 0:
       if ((rc = prep(reinterpret_cast<const void*>(attn_fwd_tc_kernel), TC_SMEM))) return rc;
       attn_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tq, tk, tv, p);
       break;
-    case 2: MMF_FWD2(4, 1, 0); break;
-    case 3: MMF_FWD2(3, 2, 1); break;
-    case 4: MMF_FWD2(4, 1, 1); break;
-    case 5: MMF_FWD2(3, 2, 2); break;
-    case 6: MMF_FWD2(4, 1, 2); break;
-    case 7: MMF_FWD2(3, 2, 8); break;     // 7 .. 9: timing ablations (WRONG RESULTS): no exp / no TMEM read of S / neither
-    case 8: MMF_FWD2(3, 2, 9); break;
-    case 9: MMF_FWD2(3, 2, 10); break;
-    default: MMF_FWD2(3, 2, 0); break;
+    case 2: MMF_FWD2(4, 1, 2, 0); break;
+    case 3: MMF_FWD2(3, 1, 3, 0); break;    // deeper K/V rings: 3 CTAs x 3 stages, 2 CTAs x 5 stages, 1 CTA x 12 stages
+    case 4: MMF_FWD2(2, 2, 5, 0); break;
+    case 5: MMF_FWD2(1, 2, 12, 0); break;
+    case 6: MMF_FWD2(2, 2, 5, 1); break;    // + 1 of 4 exponentials on the FMA pipe
+    case 7: MMF_FWD2(3, 2, 2, 8); break;    // 7 .. 9: timing ablations (WRONG RESULTS): no exp / no TMEM read of S / neither
+    case 8: MMF_FWD2(3, 2, 2, 9); break;
+    case 9: MMF_FWD2(3, 2, 2, 10); break;
+    default: MMF_FWD2(3, 2, 2, 0); break;
   }
 #undef MMF_FWD2
   attr_done.fetch_or(bit, std::memory_order_release);
@@ -902,6 +925,7 @@ struct AttnBwdTcParams {
   const int32_t* seg;
   int nseg;
   int tiles;             // tiles per sample the grids were sized for (upper bound)
+  int pf;                // L2 prefetch distance in streamed blocks (0 = off)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -1131,12 +1155,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 // once per block (phase parity = g & 1).  TMEM: S_A | S_B | dP_A | dP_B | dQ = 192 of 256 allocated columns.
 constexpr uint32_t DQ2_S = 0, DQ2_DP = 64, DQ2_ACC = 128;
 
-template <int POLY>
+template <int KVST, int POLY>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                        const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                        const AttnBwdTcParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned by declaration (the 128B-swizzle atoms need it): no alignment slack in the allocation, which is what
+  // lets 2 CTAs x (64 KB of Q / dO + three 16 KB K / V stages) share an SM
+  extern __shared__ __align__(1024) uint8_t smem_dq2[];
   int r0 = 0, r1 = 0, k0 = 0, k1 = 0, b = 0, h0 = 0, h1 = 0;
   {
     int tile;
@@ -1161,21 +1187,21 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   }
   const int nh = h1 - h0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_dq2;
   uint8_t* sQ = smem;                                   // 2 buffers of 128x64
   uint8_t* sdO = smem + 2 * TC_TILE_BYTES;              // 2 buffers
-  uint8_t* sK = smem + 4 * TC_TILE_BYTES;               // 2 stages of 64x64
-  uint8_t* sV = sK + 2 * BW_BLK_BYTES;                  // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * BW_BLK_BYTES);
+  uint8_t* sK = smem + 4 * TC_TILE_BYTES;               // KVST stages of 64x64
+  uint8_t* sV = sK + KVST * BW_BLK_BYTES;               // KVST stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KVST * BW_BLK_BYTES);
   uint64_t* q_full = bars;         // [2] (Q and dO of a head)
   uint64_t* q_empty = bars + 2;    // [2]
-  uint64_t* kv_full = bars + 4;    // [2]
-  uint64_t* kv_empty = bars + 6;   // [2]
-  uint64_t* s_full = bars + 8;     // [2] S and dP of a half ready
-  uint64_t* ds_full = bars + 10;   // [2] dS of a half written (its S / dP consumed)
-  uint64_t* acc_full = bars + 12;  // dQ of the head complete
-  uint64_t* acc_empty = bars + 13; // dQ read out
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* s_full = bars + 4;     // [2] S and dP of a half ready
+  uint64_t* ds_full = bars + 6;    // [2] dS of a half written (its S / dP consumed)
+  uint64_t* acc_full = bars + 8;   // dQ of the head complete
+  uint64_t* acc_empty = bars + 9;  // dQ read out
+  uint64_t* kv_full = bars + 10;   // [KVST]
+  uint64_t* kv_empty = kv_full + KVST;   // [KVST]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + KVST);
 
   const int64_t q_row0 = r0 < p.n_head ? (int64_t)b * p.n_head + r0 : p.head_rows + (int64_t)b * p.n_tail + (r0 - p.n_head);
   RowBlocks kb;   // key range split at the plane boundary
@@ -1188,9 +1214,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
         mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
-        mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1);
         mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], 4);
       }
+      for (int s = 0; s < KVST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
       mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
       mbar_fence_init();
     }
@@ -1206,16 +1232,36 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
+      auto prefetch_kv = [&](int gg) {     // L2 prefetch ahead of the shared-memory ring (see attn_fwd_tc2_kernel)
+        if (gg >= total) return;
+        const int hh = gg / kb.nb, jj = gg - hh * kb.nb;
+        int tok, nvalid; int64_t row;
+        kb.get(jj, tok, row, nvalid);
+        tma_prefetch_2d(&tmap_k, (h0 + hh) * 64, (int)row);
+        tma_prefetch_2d(&tmap_v, (h0 + hh) * 64, (int)row);
+      };
+      if (p.pf > 0) {
+        for (int gg = 0; gg < p.pf; ++gg) prefetch_kv(gg);
+        for (int hh = 1; hh < nh && hh <= 2; ++hh) {
+          tma_prefetch_2d(&tmap_q, (h0 + hh) * 64, (int)q_row0);
+          tma_prefetch_2d(&tmap_do, (h0 + hh) * 64, (int)q_row0);
+        }
+      }
       int g = 0;
       for (int h = 0; h < nh; ++h) {
         const int qs = h & 1;
+        if (p.pf > 0 && h + 3 < nh) {
+          tma_prefetch_2d(&tmap_q, (h0 + h + 3) * 64, (int)q_row0);
+          tma_prefetch_2d(&tmap_do, (h0 + h + 3) * 64, (int)q_row0);
+        }
         mbar_wait(&q_empty[qs], ((h >> 1) & 1) ^ 1);
         mbar_expect_tx(&q_full[qs], 2 * TC_TILE_BYTES);
         tma_load_2d(sQ + qs * TC_TILE_BYTES, &tmap_q, &q_full[qs], (h0 + h) * 64, (int)q_row0);
         tma_load_2d(sdO + qs * TC_TILE_BYTES, &tmap_do, &q_full[qs], (h0 + h) * 64, (int)q_row0);
         for (int j = 0; j < kb.nb; ++j, ++g) {
-          const int st = g & 1;
-          mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+          const int st = g % KVST;
+          if (p.pf > 0) prefetch_kv(g + p.pf);
+          mbar_wait(&kv_empty[st], ((g / KVST) & 1) ^ 1);
           int tok, nvalid; int64_t row;
           kb.get(j, tok, row, nvalid);
           mbar_expect_tx(&kv_full[st], 2 * BW_BLK_BYTES);
@@ -1229,12 +1275,12 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       const uint32_t idesc_acc = umma_idesc_bf16(TC_BM, 64, false, true);      // dQ[128 x 64dh] += dS[128 x keys] . K (MN-major)
       auto issue_s = [&](int gg, int hf) {
         const int h = gg / kb.nb, j = gg - h * kb.nb;
-        const int st = gg & 1;
+        const int st = gg % KVST;
         int tok, nvalid; int64_t row;
         kb.get(j, tok, row, nvalid);
         if (hf == 0) {
           if (j == 0) mbar_wait(&q_full[h & 1], (h >> 1) & 1);
-          mbar_wait(&kv_full[st], (gg >> 1) & 1);
+          mbar_wait(&kv_full[st], (gg / KVST) & 1);
           tc_fence_after();
         }
         const int nvh = min(32, nvalid - 32 * hf);
@@ -1256,7 +1302,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       issue_s(0, 1);
       for (int g = 0; g < total; ++g) {
         const int h = g / kb.nb, j = g - h * kb.nb;
-        const int st = g & 1;
+        const int st = g % KVST;
         int tok, nvalid; int64_t row;
         kb.get(j, tok, row, nvalid);
         const uint32_t k_addr = smem_u32(sK + st * BW_BLK_BYTES);
@@ -1441,15 +1487,36 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
+      const int total = qb.nb * p.H;
+      auto prefetch_q = [&](int gg) {      // L2 prefetch ahead of the two-stage Q / dO ring (see attn_fwd_tc2_kernel)
+        if (gg >= total) return;
+        const int hh = gg / qb.nb, jj = gg - hh * qb.nb;
+        int tok, nvalid; int64_t row;
+        qb.get(jj, tok, row, nvalid);
+        tma_prefetch_2d(&tmap_q, hh * 64, (int)row);
+        tma_prefetch_2d(&tmap_do, hh * 64, (int)row);
+      };
+      if (p.pf > 0) {
+        for (int gg = 0; gg < p.pf; ++gg) prefetch_q(gg);
+        for (int hh = 1; hh < p.H && hh <= 2; ++hh) {
+          tma_prefetch_2d(&tmap_k, hh * 64, (int)k_row0);
+          tma_prefetch_2d(&tmap_v, hh * 64, (int)k_row0);
+        }
+      }
       int g = 0;
       for (int h = 0; h < p.H; ++h) {
         const int ks = h & 1;
+        if (p.pf > 0 && h + 3 < p.H) {
+          tma_prefetch_2d(&tmap_k, (h + 3) * 64, (int)k_row0);
+          tma_prefetch_2d(&tmap_v, (h + 3) * 64, (int)k_row0);
+        }
         mbar_wait(&kvt_empty[ks], ((h >> 1) & 1) ^ 1);
         mbar_expect_tx(&kvt_full[ks], 2 * TC_TILE_BYTES);
         tma_load_2d(sK + ks * TC_TILE_BYTES, &tmap_k, &kvt_full[ks], h * 64, (int)k_row0);
         tma_load_2d(sV + ks * TC_TILE_BYTES, &tmap_v, &kvt_full[ks], h * 64, (int)k_row0);
         for (int j = 0; j < qb.nb; ++j, ++g) {
           const int st = g & 1;
+          if (p.pf > 0) prefetch_q(g + p.pf);
           mbar_wait(&qb_empty[st], ((g >> 1) & 1) ^ 1);
           int tok, nvalid; int64_t row;
           qb.get(j, tok, row, nvalid);
@@ -1691,6 +1758,11 @@ int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   p.head_rows = (int64_t)a->B * a->n_head_q;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
   p.seg = a->seg; p.nseg = a->nseg;
+  {
+    const char* pe = getenv("MMF_ATTN_PF");
+    p.pf = pe ? atoi(pe) : TC_PF_DEFAULT;
+    if (p.pf < 0 || p.pf > 64) p.pf = TC_PF_DEFAULT;
+  }
   const int tiles = (a->Nq + TC_BM - 1) / TC_BM + (a->seg ? a->nseg : 0);
   p.tiles = tiles;
   const int heavy_max = a->seg ? (a->Nq + TC_BM - 1) / TC_BM : 0;
@@ -1712,24 +1784,22 @@ int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
     done.fetch_or(bit, std::memory_order_release);
     return 0;
   };
+#define MMF_DQ2(IDX, KS, PL)                                                                                          \
+  do {                                                                                                                 \
+    constexpr int smem = 4 * TC_TILE_BYTES + 2 * KS * BW_BLK_BYTES + 256;                                              \
+    if ((rc = prep(attr_done_v[IDX], reinterpret_cast<const void*>(attn_bwd_dq_tc2_kernel<KS, PL>), smem))) return rc;  \
+    attn_bwd_dq_tc2_kernel<KS, PL><<<grid_q, TC_THREADS, smem, stream>>>(q128, do128, k64, v64, p);                    \
+  } while (0)
   switch (vq) {
     case 0:
       if ((rc = prep(attr_done_v[0], reinterpret_cast<const void*>(attn_bwd_dq_tc_kernel), DQ_SMEM))) return rc;
       attn_bwd_dq_tc_kernel<<<grid_q, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
       break;
-    case 2:
-      if ((rc = prep(attr_done_v[2], reinterpret_cast<const void*>(attn_bwd_dq_tc2_kernel<1>), DQ_SMEM))) return rc;
-      attn_bwd_dq_tc2_kernel<1><<<grid_q, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
-      break;
-    case 3:
-      if ((rc = prep(attr_done_v[3], reinterpret_cast<const void*>(attn_bwd_dq_tc2_kernel<2>), DQ_SMEM))) return rc;
-      attn_bwd_dq_tc2_kernel<2><<<grid_q, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
-      break;
-    default:
-      if ((rc = prep(attr_done_v[1], reinterpret_cast<const void*>(attn_bwd_dq_tc2_kernel<0>), DQ_SMEM))) return rc;
-      attn_bwd_dq_tc2_kernel<0><<<grid_q, TC_THREADS, DQ_SMEM, stream>>>(q128, do128, k64, v64, p);
-      break;
+    case 2: MMF_DQ2(2, 3, 0); break;      // three K/V stages (2 CTAs per SM still fit)
+    case 3: MMF_DQ2(3, 3, 1); break;      // + 1 of 4 exponentials on the FMA pipe
+    default: MMF_DQ2(1, 2, 0); break;
   }
+#undef MMF_DQ2
   if ((rc = prep(attr_done_v[4], reinterpret_cast<const void*>(attn_bwd_dkv_tc_kernel), DKV_SMEM))) return rc;
   attn_bwd_dkv_tc_kernel<<<tiles * a->B, TC_THREADS, DKV_SMEM, stream>>>(k128, v128, q64, do64, p);
   g_launch_count.fetch_add(2, std::memory_order_relaxed);

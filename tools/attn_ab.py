@@ -18,7 +18,7 @@ Mt = B * N
 HD = H * 64
 dev = "cuda"
 args = sys.argv[1:]
-sel = {"fwd": [0, 1, 2, 3, 4, 5, 6], "dq": [0, 1, 2, 3], "dkv": [0]}
+sel = {"fwd": [0, 1, 2, 3, 4, 5, 6], "dq": [0, 1, 2, 3], "dkv": [0], "pf": [0]}
 for i in range(0, len(args) - 1, 2):
     sel[args[i]] = [int(v) for v in args[i + 1].split(",")]
 
@@ -52,8 +52,8 @@ for counts in SPLITS:
     kw = dict(B=B, H=H, Nq=N, Nk=N, dh=64, scale=0.125, n_head_q=nenc, n_head_k=nenc, seg=seg, nseg=4)
     print("== split %s: %.1f GFLOP forward over allowed pairs" % (counts, gf))
     ref_o = ref_lse = None
-    for v in sel["fwd"]:
-        os.environ["MMF_ATTN_FWD"] = str(v)
+    for v, pf in [(v, pf) for v in sel["fwd"] for pf in sel["pf"]]:
+        os.environ["MMF_ATTN_FWD"], os.environ["MMF_ATTN_PF"] = str(v), str(pf)
         o = torch.full((Mt, HD), float("nan"), dtype=bf16, device=dev)
         lse = torch.full((B, H, N), float("nan"), device=dev)
         f = lambda: K.attn_fwd(qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, **kw)
@@ -64,16 +64,16 @@ for counts in SPLITS:
             raise
         if ref_o is None:
             ref_o, ref_lse = o.clone(), lse.clone()
-        print("  fwd v%d  %7.3f ms  %6.1f TFLOP/s   rel(o) %.2e  rel(lse) %.2e  finite %s" % (
-            v, ms, gf / ms, rel(o, ref_o), rel(lse, ref_lse), bool(torch.isfinite(o.float()).all())))
-    os.environ["MMF_ATTN_FWD"] = "0"
+        print("  fwd v%d pf%-2d %7.3f ms  %6.1f TFLOP/s   rel(o) %.2e  rel(lse) %.2e  finite %s" % (
+            v, pf, ms, gf / ms, rel(o, ref_o), rel(lse, ref_lse), bool(torch.isfinite(o.float()).all())))
+    os.environ["MMF_ATTN_FWD"], os.environ["MMF_ATTN_PF"] = "0", "0"
     o = torch.empty(Mt, HD, dtype=bf16, device=dev)
     lse = torch.empty(B, H, N, device=dev)
     K.attn_fwd(qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, **kw)
     ref_d = None
     for vq in sel["dq"]:
-        for vk in sel["dkv"]:
-            os.environ["MMF_ATTN_DQ"], os.environ["MMF_ATTN_DKV"] = str(vq), str(vk)
+        for vk, pf in [(vk, pf) for vk in sel["dkv"] for pf in sel["pf"]]:
+            os.environ["MMF_ATTN_DQ"], os.environ["MMF_ATTN_DKV"], os.environ["MMF_ATTN_PF"] = str(vq), str(vk), str(pf)
             dqkv = torch.full_like(qkv, float("nan"))
             delta = torch.empty(B, H, N, device=dev)
             f = lambda: K.attn_bwd(qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:], o, lse, do, dqkv[:, :HD], dqkv[:, HD:2 * HD],
@@ -81,6 +81,6 @@ for counts in SPLITS:
             ms = timed(f)
             if ref_d is None:
                 ref_d = dqkv.clone()
-            print("  bwd dq v%d dkv v%d  %7.3f ms  %6.1f TFLOP/s   rel(dq) %.2e rel(dk) %.2e rel(dv) %.2e  finite %s" % (
-                vq, vk, ms, 2.5 * gf / ms, rel(dqkv[:, :HD], ref_d[:, :HD]), rel(dqkv[:, HD:2 * HD], ref_d[:, HD:2 * HD]),
+            print("  bwd dq v%d dkv v%d pf%-2d %7.3f ms  %6.1f TFLOP/s   rel(dq) %.2e rel(dk) %.2e rel(dv) %.2e  finite %s" % (
+                vq, vk, pf, ms, 2.5 * gf / ms, rel(dqkv[:, :HD], ref_d[:, :HD]), rel(dqkv[:, HD:2 * HD], ref_d[:, HD:2 * HD]),
                 rel(dqkv[:, 2 * HD:], ref_d[:, 2 * HD:]), bool(torch.isfinite(dqkv.float()).all())))
