@@ -636,60 +636,80 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0 && total > 0) {
+    // The WHOLE warp runs this loop and one elected lane issues the tcgen05 instructions.  Round 1 wrapped the loop in
+    // `if (lane == 0)`: inside a divergent region nothing is provably warp-uniform, so ptxas moved every descriptor to
+    // the uniform datapath through an R2UR + vote loop (~17 SASS instructions per UTCHMMA, ~400 dependent
+    // single-thread instructions per key block) -- and THAT scalar stream, not MUFU / TMEM / TMA, paced the kernel: a
+    // lone CTA took ~3200 clk per 64-key block whatever the softmax did (tools/attn_ab.py ablations).
+    // Here every operand is computed in converged code from uniform sources (shuffle-broadcast where the compiler cannot
+    // see it), the descriptors are running sums, and (h, j) advance incrementally instead of through divisions.
+    if (total > 0) {
+      const bool leader = elect_one();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc_pv = umma_idesc_bf16(TC_BM, 64, false, true);   // A = P (TMEM, K-major), B = V (MN-major)
-      // S of half `hf` of block gg (head h, key block j): waits for the block's operands when it is the block's first MMA
-      auto issue_s = [&](int gg, int hf) {
-        const int h = gg / kb.nb, j = gg - h * kb.nb;
-        const int st = gg % KVST;
-        int64_t row; int nvalid;
-        kb.get(j, row, nvalid);
+      const uint32_t idesc_s0 = umma_idesc_bf16(TC_BM, 0, false, false);   // N is added per half
+      const uint64_t dq0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sQ), 0), 16, 1024);
+      const uint64_t dk0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sK), 0), 16, 1024);
+      const uint64_t dv0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sV), 0), 8192, 1024);
+      const int nb = __shfl_sync(0xffffffffu, kb.nb, 0);
+      // (h, j, stage, stage parity) of the NEXT S to issue
+      int sh = 0, sj = 0, sst = 0, sph = 0;
+      auto nvalid_of = [&](int j) { int64_t row; int nv; kb.get(j, row, nv); return nv; };
+      auto issue_s = [&](int hf) {      // half hf of block (sh, sj); hf == 1 also advances the cursor
         if (hf == 0) {
-          if (j == 0) mbar_wait(&q_full[h % QBUF], (h / QBUF) & 1);
-          mbar_wait(&kv_full[st], (gg / KVST) & 1);
+          if (sj == 0) mbar_wait(&q_full[sh % QBUF], (sh / QBUF) & 1);
+          mbar_wait(&kv_full[sst], sph);
           tc_fence_after();
         }
-        const int nvh = min(32, nvalid - 32 * hf);
-        if (nvh > 0) {
-          const int n16 = (nvh + 15) & ~15;
-          const uint32_t idesc = umma_idesc_bf16(TC_BM, n16, false, false);
-          const uint32_t q_addr = smem_u32(sQ + (h % QBUF) * TC_TILE_BYTES);
-          const uint32_t k_addr = smem_u32(sK + st * TC_KV_BYTES) + hf * 4096;   // key rows 32.. of the stage
+        const int nvh = min(32, nvalid_of(sj) - 32 * hf);
+        if (nvh > 0 && leader) {
+          const uint32_t idesc = idesc_s0 | ((uint32_t)((nvh + 15) >> 4) << 18);     // n_dim = n16 >> 3 at bit 17
+          const uint64_t dq = dq0 + (uint64_t)((sh % QBUF) * (TC_TILE_BYTES >> 4));
+          const uint64_t dk = dk0 + (uint64_t)(sst * (TC_KV_BYTES >> 4) + hf * (4096 >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // dh = 64 = 4 x 16
-            umma_bf16(tmem + (hf ? F2_SB : F2_SA), umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024), idesc, k > 0);
+          for (int k = 0; k < 4; ++k)   // dh = 64 = 4 x 16: 32 bytes per step
+            umma_bf16(tm + (hf ? F2_SB : F2_SA), dq + 2 * k, dk + 2 * k, idesc, k > 0);
         }
-        umma_commit(&s_full[hf]);     // completes once per block and half, whether or not the half has keys
-        // the head's Q tile has no reader after the last block's half-B S (with a single Q buffer the next head's Q can
-        // only be requested now, and the next head's first S -- issued before this block's last P.V -- waits for it)
-        if (hf == 1 && j + 1 == kb.nb) umma_commit(&q_empty[h % QBUF]);
+        if (leader) {
+          umma_commit(&s_full[hf]);     // completes once per block and half, whether or not the half has keys
+          // the head's Q tile has no reader after the last block's half-B S
+          if (hf == 1 && sj + 1 == nb) umma_commit(&q_empty[sh % QBUF]);
+        }
+        __syncwarp();
+        if (hf == 1) {
+          if (++sj == nb) { sj = 0; ++sh; }
+          if (++sst == KVST) { sst = 0; sph ^= 1; }
+        }
       };
-      issue_s(0, 0);
-      issue_s(0, 1);
+      issue_s(0);
+      issue_s(1);
+      int h = 0, j = 0, st = 0;
       for (int g = 0; g < total; ++g) {
-        const int h = g / kb.nb, j = g - h * kb.nb;
-        const int st = g % KVST;
-        int64_t row; int nvalid;
-        kb.get(j, row, nvalid);
-        const uint32_t v_addr = smem_u32(sV + st * TC_KV_BYTES);
+        const int nvalid = nvalid_of(j);
+        const uint64_t dv = dv0 + (uint64_t)(st * (TC_KV_BYTES >> 4));
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           mbar_wait(&p_full[hf], g & 1);      // the softmax warps wrote P of this half (and are done reading its S)
           if (j == 0 && hf == 0 && h > 0) mbar_wait(o_empty, (h - 1) & 1);   // previous head's O has been read out
           tc_fence_after();
           const int nvh = min(32, nvalid - 32 * hf);
-          const int ksteps = nvh > 0 ? (nvh + 15) >> 4 : 0;
-          for (int k = 0; k < ksteps; ++k)   // 16 keys per step: P advances 8 packed columns, V 16 rows of 128 B
-            umma_bf16_ts(tmem + F2_O, tmem + (hf ? F2_SB : F2_SA) + k * 8, umma_smem_desc(v_addr + (2 * hf + k) * 2048, 8192, 1024),
-                         idesc_pv, (j > 0) || (hf > 0) || (k > 0));
-          if (hf == 1) {
-            umma_commit(&kv_empty[st]);        // every MMA reading this K/V stage has been issued
-            if (j + 1 == kb.nb) umma_commit(o_full);
+          if (leader) {
+            const int ksteps = nvh > 0 ? (nvh + 15) >> 4 : 0;
+            for (int k = 0; k < ksteps; ++k)   // 16 keys per step: P advances 8 packed columns, V 16 rows of 128 B
+              umma_bf16_ts(tm + F2_O, tm + (hf ? F2_SB : F2_SA) + k * 8, dv + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_pv,
+                           (j > 0) || (hf > 0) || (k > 0));
+            if (hf == 1) {
+              umma_commit(&kv_empty[st]);        // every MMA reading this K/V stage has been issued
+              if (j + 1 == nb) umma_commit(o_full);
+            }
           }
+          __syncwarp();
           // the half's S columns are free again (in-order tensor pipe: S(next) executes after this P.V)
-          if (g + 1 < total) issue_s(g + 1, hf);
-          else umma_commit(&s_full[hf]);       // final phase flip: lets a rescale at the last block wait for this P.V
+          if (g + 1 < total) issue_s(hf);
+          else if (leader) umma_commit(&s_full[hf]);       // final phase flip: lets a rescale at the last block wait for this P.V
         }
+        if (++j == nb) { j = 0; ++h; }
+        if (++st == KVST) st = 0;
       }
     }
   } else {
