@@ -204,8 +204,10 @@ __device__ __forceinline__ void lpt_key_tile(const int32_t* seg, int nseg, int t
 #ifdef MMF_ATTN_CLOCKS
 __device__ unsigned long long g_attn_clk[16];
 #define CLK(i, expr) do { if (dbg_on) { const long long t__ = clock64(); g_attn_clk[i] += (unsigned long long)(t__ - t_last); t_last = t__; } } while (0)
+#define CLK2(i, expr) do { if (dbg_on) { const unsigned t__ = clock(); acc_clk[i] += t__ - t_last; t_last = t__; } } while (0)
 #else
 #define CLK(i, expr) do { } while (0)
+#define CLK2(i, expr) do { } while (0)
 #endif
 
 __global__ void __launch_bounds__(TC_THREADS, TC_CTAS_PER_SM)
@@ -681,6 +683,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           if (++sst == KVST) { sst = 0; sph ^= 1; }
         }
       };
+#ifdef MMF_ATTN_CLOCKS
+      const bool dbg_on = (b == 3) && (r0 == p.n_head) && lane == 0;   // first fusion tile of sample 3
+      unsigned t_last = clock();
+      unsigned acc_clk[16] = {0};
+#endif
       issue_s(0);
       issue_s(1);
       int h = 0, j = 0, st = 0;
@@ -689,9 +696,12 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint64_t dv = dv0 + (uint64_t)(st * (TC_KV_BYTES >> 4));
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
+          CLK2(8, 0);
           mbar_wait(&p_full[hf], g & 1);      // the softmax warps wrote P of this half (and are done reading its S)
+          CLK2(9 + hf, 0);
           if (j == 0 && hf == 0 && h > 0) mbar_wait(o_empty, (h - 1) & 1);   // previous head's O has been read out
           tc_fence_after();
+          CLK2(11, 0);
           const int nvh = min(32, nvalid - 32 * hf);
           if (leader) {
             const int ksteps = nvh > 0 ? (nvh + 15) >> 4 : 0;
@@ -704,6 +714,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
           }
           __syncwarp();
+          CLK2(12, 0);
           // the half's S columns are free again (in-order tensor pipe: S(next) executes after this P.V)
           if (g + 1 < total) issue_s(hf);
           else if (leader) umma_commit(&s_full[hf]);       // final phase flip: lets a rescale at the last block wait for this P.V
@@ -711,6 +722,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (++j == nb) { j = 0; ++h; }
         if (++st == KVST) st = 0;
       }
+#ifdef MMF_ATTN_CLOCKS
+      if (dbg_on) for (int i = 8; i < 13; ++i) g_attn_clk[i] = acc_clk[i];
+#endif
     }
   } else {
     // ------------------------------ softmax / output warps (2..5) ------------------------------
@@ -721,6 +735,12 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const bool warp_live = r0 + quarter * 32 < r1;     // any real query row in this warp?
     uint32_t sreg[32];
     int g = 0;
+#ifdef MMF_ATTN_CLOCKS
+    const bool dbg_on = (b == 3) && (r0 == p.n_head) && warp == 2 && lane == 0;   // first fusion tile of sample 3
+    if (dbg_on) g_attn_clk[15] = (unsigned long long)kb.nb * nh;
+    unsigned t_last = clock();
+    unsigned acc_clk[16] = {0};
+#endif
     for (int h = 0; h < nh; ++h) {
       float m_ref = -INFINITY, l = 0.f;
       for (int j = 0; j < kb.nb; ++j, ++g) {
@@ -729,7 +749,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int nvh = min(32, nvalid - 32 * hf);
+          CLK2(4, 0);
           mbar_wait(&s_full[hf], g & 1);
+          CLK2(0, 0);
           if (warp_live && nvh > 0) {
             tc_fence_after();
             if (POLY == 9 || POLY == 10) {   // TIMING ABLATION ONLY (wrong results): no TMEM read of S
@@ -740,6 +762,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               tmem_wait_ld();
             }
             const float m_new = row_max32(sreg, nvh) * p.scale_log2;
+            CLK2(1, 0);
             const bool grow = m_new > m_ref + 8.0f;
             if (j == 0 && hf == 0) {
               m_ref = m_new;
@@ -767,16 +790,19 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             uint32_t pk[16];
             l += exp_pack32<POLY>(sreg, pk, nvh, p.scale_log2, m_ref);
             tmem_st_32x16(lane_addr + (hf ? F2_SB : F2_SA), pk);
+            CLK2(2, 0);
             tmem_wait_st();
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[hf]);
+          CLK2(3, 0);
         }
       }
       // ---- head epilogue: O / l -> bf16 row, log-sum-exp ----
       mbar_wait(o_full, h & 1);
       tc_fence_after();
+      CLK2(5, 0);
       if (warp_live) {
         const float inv = 1.0f / l;
         __nv_bfloat16* orow = p.o + (q_row0 + row_in_tile) * p.ldo + (h0 + h) * 64;
@@ -800,7 +826,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);   // the MMA warp may overwrite O for the next head
+      CLK2(6, 0);
     }
+#ifdef MMF_ATTN_CLOCKS
+    if (dbg_on) for (int i = 0; i < 7; ++i) g_attn_clk[i] = acc_clk[i];
+#endif
   }
 
   tc_fence_before();
@@ -1291,57 +1321,74 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && total > 0) {
+    // whole warp, one elected issuing lane, running-sum descriptors (see attn_fwd_tc2_kernel)
+    if (total > 0) {
+      const bool leader = elect_one();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc_acc = umma_idesc_bf16(TC_BM, 64, false, true);      // dQ[128 x 64dh] += dS[128 x keys] . K (MN-major)
-      auto issue_s = [&](int gg, int hf) {
-        const int h = gg / kb.nb, j = gg - h * kb.nb;
-        const int st = gg % KVST;
-        int tok, nvalid; int64_t row;
-        kb.get(j, tok, row, nvalid);
+      const uint32_t idesc_s0 = umma_idesc_bf16(TC_BM, 0, false, false);
+      const uint64_t dq0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sQ), 0), 16, 1024);
+      const uint64_t ddo0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sdO), 0), 16, 1024);
+      const uint64_t dk0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sK), 0), 16, 1024);
+      const uint64_t dv0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sV), 0), 16, 1024);
+      const uint64_t dkm0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sK), 0), 8192, 1024);   // K read MN-major for dQ
+      const int nb = __shfl_sync(0xffffffffu, kb.nb, 0);
+      int sh = 0, sj = 0, sst = 0, sph = 0;   // (h, j, stage, stage parity) of the NEXT S / dP to issue
+      auto nvalid_of = [&](int j) { int tok, nv; int64_t row; kb.get(j, tok, row, nv); return nv; };
+      auto issue_s = [&](int hf) {
         if (hf == 0) {
-          if (j == 0) mbar_wait(&q_full[h & 1], (h >> 1) & 1);
-          mbar_wait(&kv_full[st], (gg / KVST) & 1);
+          if (sj == 0) mbar_wait(&q_full[sh & 1], (sh >> 1) & 1);
+          mbar_wait(&kv_full[sst], sph);
           tc_fence_after();
         }
-        const int nvh = min(32, nvalid - 32 * hf);
-        if (nvh > 0) {
-          const uint32_t idesc_s = umma_idesc_bf16(TC_BM, (nvh + 15) & ~15, false, false);
-          const uint32_t q_addr = smem_u32(sQ + (h & 1) * TC_TILE_BYTES), do_addr = smem_u32(sdO + (h & 1) * TC_TILE_BYTES);
-          const uint32_t k_addr = smem_u32(sK + st * BW_BLK_BYTES) + hf * 4096, v_addr = smem_u32(sV + st * BW_BLK_BYTES) + hf * 4096;
+        const int nvh = min(32, nvalid_of(sj) - 32 * hf);
+        if (nvh > 0 && leader) {
+          const uint32_t idesc = idesc_s0 | ((uint32_t)((nvh + 15) >> 4) << 18);
+          const uint64_t qd = dq0 + (uint64_t)((sh & 1) * (TC_TILE_BYTES >> 4)), od = ddo0 + (uint64_t)((sh & 1) * (TC_TILE_BYTES >> 4));
+          const uint64_t kd = dk0 + (uint64_t)(sst * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
+          const uint64_t vd = dv0 + (uint64_t)(sst * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + DQ2_S + hf * 32, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k_addr + k * 32, 16, 1024), idesc_s, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16(tm + DQ2_S + hf * 32, qd + 2 * k, kd + 2 * k, idesc, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + DQ2_DP + hf * 32, umma_smem_desc(do_addr + k * 32, 16, 1024), umma_smem_desc(v_addr + k * 32, 16, 1024), idesc_s, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16(tm + DQ2_DP + hf * 32, od + 2 * k, vd + 2 * k, idesc, k > 0);
         }
-        umma_commit(&s_full[hf]);
-        if (hf == 1 && j + 1 == kb.nb) umma_commit(&q_empty[h & 1]);     // Q / dO of the head have no later reader
+        if (leader) {
+          umma_commit(&s_full[hf]);
+          if (hf == 1 && sj + 1 == nb) umma_commit(&q_empty[sh & 1]);     // Q / dO of the head have no later reader
+        }
+        __syncwarp();
+        if (hf == 1) {
+          if (++sj == nb) { sj = 0; ++sh; }
+          if (++sst == KVST) { sst = 0; sph ^= 1; }
+        }
       };
-      issue_s(0, 0);
-      issue_s(0, 1);
+      issue_s(0);
+      issue_s(1);
+      int h = 0, j = 0, st = 0;
       for (int g = 0; g < total; ++g) {
-        const int h = g / kb.nb, j = g - h * kb.nb;
-        const int st = g % KVST;
-        int tok, nvalid; int64_t row;
-        kb.get(j, tok, row, nvalid);
-        const uint32_t k_addr = smem_u32(sK + st * BW_BLK_BYTES);
+        const int nvalid = nvalid_of(j);
+        const uint64_t kd = dkm0 + (uint64_t)(st * (BW_BLK_BYTES >> 4));
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           mbar_wait(&ds_full[hf], g & 1);
           if (j == 0 && hf == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);
           tc_fence_after();
           const int nvh = min(32, nvalid - 32 * hf);
-          const int ksteps = nvh > 0 ? (nvh + 15) >> 4 : 0;
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16_ts(tmem + DQ2_ACC, tmem + DQ2_S + hf * 32 + k * 8, umma_smem_desc(k_addr + (2 * hf + k) * 2048, 8192, 1024), idesc_acc,
-                         (j > 0) || (hf > 0) || (k > 0));
-          if (hf == 1) {
-            umma_commit(&kv_empty[st]);
-            if (j + 1 == kb.nb) umma_commit(acc_full);
+          if (leader) {
+            const int ksteps = nvh > 0 ? (nvh + 15) >> 4 : 0;
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16_ts(tm + DQ2_ACC, tm + DQ2_S + hf * 32 + k * 8, kd + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
+                           (j > 0) || (hf > 0) || (k > 0));
+            if (hf == 1) {
+              umma_commit(&kv_empty[st]);
+              if (j + 1 == nb) umma_commit(acc_full);
+            }
           }
-          if (g + 1 < total) issue_s(g + 1, hf);
+          __syncwarp();
+          if (g + 1 < total) issue_s(hf);
         }
+        if (++j == nb) { j = 0; ++h; }
+        if (++st == KVST) st = 0;
       }
     }
   } else {
@@ -1547,70 +1594,89 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // A block of 64 queries is handled as two 32-query halves with their own S^T / dP^T columns and barriers: while
-      // the elementwise warps turn half B into P^T / dS^T, the tensor pipe accumulates half A into dV / dK and computes
-      // half A of the NEXT block (and vice versa), so neither side waits for the other in steady state.  (With one
-      // 64-query unit per block the elementwise warps spent 27 % of their time waiting for S: tools/attn_clocks_bwd.py.)
-      const uint32_t idesc_s = umma_idesc_bf16(TC_BM, 32, false, false);       // S^T[128 keys x 32 q] = K . Q^T (one half)
-      const uint32_t idesc_acc = umma_idesc_bf16(TC_BM, 64, false, true);      // dV/dK[128 x 64dh] += A(TMEM)[128 x q] . B (MN-major)
-      int g = 0;
-      auto issue_s = [&](int h, int j, int gg, int hf) {
-        const int st = gg & 1;
+    // A block of 64 queries is handled as two 32-query halves with their own S^T / dP^T columns and barriers: while
+    // the elementwise warps turn half B into P^T / dS^T, the tensor pipe accumulates half A into dV / dK and computes
+    // half A of the NEXT block (and vice versa), so neither side waits for the other in steady state.  (With one
+    // 64-query unit per block the elementwise warps spent 27 % of their time waiting for S: tools/attn_clocks_bwd.py.)
+    // Round 2: the whole warp runs the loop and an elected lane issues (see attn_fwd_tc2_kernel: inside `if (lane == 0)`
+    // every one of the 24 UTCHMMAs of a block cost an R2UR vote loop, and that scalar stream paced the kernel).
+    const int total = qb.nb * p.H;
+    if (total > 0) {
+      const bool leader = elect_one();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t idesc_s0 = umma_idesc_bf16(TC_BM, 0, false, false);      // S^T[128 keys x nq] = K . Q^T (one half): N added per half
+      const uint32_t idesc_acc = umma_idesc_bf16(TC_BM, 64, false, true);     // dV/dK[128 x 64dh] += A(TMEM)[128 x q] . B (MN-major)
+      const uint64_t dk0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sK), 0), 16, 1024);
+      const uint64_t dv0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sV), 0), 16, 1024);
+      const uint64_t dq0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sQ), 0), 16, 1024);
+      const uint64_t ddo0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sdO), 0), 16, 1024);
+      const uint64_t dqm0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sQ), 0), 8192, 1024);    // Q / dO read MN-major
+      const uint64_t ddom0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sdO), 0), 8192, 1024);
+      const int nb = __shfl_sync(0xffffffffu, qb.nb, 0);
+      auto nvalid_of = [&](int j) { int tok, nv; int64_t row; qb.get(j, tok, row, nv); return nv; };
+      int sh = 0, sj = 0, sg = 0;              // (head, query block, running block) of the NEXT S^T / dP^T to issue
+      auto issue_s = [&](int hf) {            // half hf of block (sh, sj); only issued when the half has queries
+        const int st = sg & 1;
         if (hf == 0) {   // half A exists in every block: it carries the waits for the block's operands
-          if (j == 0) mbar_wait(&kvt_full[h & 1], (h >> 1) & 1);
-          mbar_wait(&qb_full[st], (gg >> 1) & 1);
+          if (sj == 0) mbar_wait(&kvt_full[sh & 1], (sh >> 1) & 1);
+          mbar_wait(&qb_full[st], (sg >> 1) & 1);
+          tc_fence_after();
         }
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + (h & 1) * TC_TILE_BYTES), v_addr = smem_u32(sV + (h & 1) * TC_TILE_BYTES);
-        const uint32_t q_addr = smem_u32(sQ + st * BW_BLK_BYTES) + hf * 4096, do_addr = smem_u32(sdO + st * BW_BLK_BYTES) + hf * 4096;
+        if (leader) {
+          // N = 32 whatever the number of valid queries: the columns past them hold finite values of other rows (or TMA
+          // zero fill) and are zeroed through lse = +inf by the elementwise warps
+          const uint32_t idesc = idesc_s0 | ((uint32_t)(32 >> 3) << 17);
+          const uint64_t kd = dk0 + (uint64_t)((sh & 1) * (TC_TILE_BYTES >> 4)), vd = dv0 + (uint64_t)((sh & 1) * (TC_TILE_BYTES >> 4));
+          const uint64_t qd = dq0 + (uint64_t)(st * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
+          const uint64_t od = ddo0 + (uint64_t)(st * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + KV_ST + hf * 32, umma_smem_desc(k_addr + k * 32, 16, 1024), umma_smem_desc(q_addr + k * 32, 16, 1024), idesc_s, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16(tm + KV_ST + hf * 32, kd + 2 * k, qd + 2 * k, idesc, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + KV_DPT + hf * 32, umma_smem_desc(v_addr + k * 32, 16, 1024), umma_smem_desc(do_addr + k * 32, 16, 1024), idesc_s, k > 0);
-        umma_commit(&s_full[hf]);
+          for (int k = 0; k < 4; ++k) umma_bf16(tm + KV_DPT + hf * 32, vd + 2 * k, od + 2 * k, idesc, k > 0);
+          umma_commit(&s_full[hf]);
+        }
+        __syncwarp();
       };
+      auto advance_s = [&]() { ++sg; if (++sj == nb) { sj = 0; ++sh; } };
       int used0 = 0, used1 = 0;   // completed waits on ds_full[0] / ds_full[1]
-      if (qb.nb > 0) {
-        int tok, nvalid; int64_t row;
-        qb.get(0, tok, row, nvalid);
-        issue_s(0, 0, 0, 0);
-        if (nvalid > 32) issue_s(0, 0, 0, 1);
-      }
-      for (int h = 0; h < p.H; ++h) {
-        for (int j = 0; j < qb.nb; ++j, ++g) {
-          const int st = g & 1;
-          int tok, nvalid, nvalid_next = 0; int64_t row;
-          qb.get(j, tok, row, nvalid);
-          const int hn = (j + 1 < qb.nb) ? h : h + 1, jn = (j + 1 < qb.nb) ? j + 1 : 0;
-          const bool has_next = hn < p.H;
-          if (has_next) qb.get(jn, tok, row, nvalid_next);
-          const uint32_t q_addr = smem_u32(sQ + st * BW_BLK_BYTES), do_addr = smem_u32(sdO + st * BW_BLK_BYTES);
+      issue_s(0);
+      if (nvalid_of(0) > 32) issue_s(1);
+      advance_s();                // the cursor now points at block 1
+      int h = 0, j = 0;
+      for (int g = 0; g < total; ++g) {
+        const int st = g & 1;
+        const int nvalid = nvalid_of(j);
+        const bool has_next = g + 1 < total;
+        const int nvalid_next = has_next ? nvalid_of(sj) : 0;
+        const uint64_t qd = dqm0 + (uint64_t)(st * (BW_BLK_BYTES >> 4)), od = ddom0 + (uint64_t)(st * (BW_BLK_BYTES >> 4));
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int nvh = min(32, nvalid - 32 * hf);
-            if (nvh > 0) {
-              if (hf == 0) { mbar_wait(&ds_full[0], used0 & 1); ++used0; } else { mbar_wait(&ds_full[1], used1 & 1); ++used1; }
-              if (j == 0 && hf == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);   // previous head's dV / dK have been read out
-              tc_fence_after();
+        for (int hf = 0; hf < 2; ++hf) {
+          const int nvh = min(32, nvalid - 32 * hf);
+          if (nvh > 0) {
+            if (hf == 0) { mbar_wait(&ds_full[0], used0 & 1); ++used0; } else { mbar_wait(&ds_full[1], used1 & 1); ++used1; }
+            if (j == 0 && hf == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);   // previous head's dV / dK have been read out
+            tc_fence_after();
+            if (leader) {
               const int ksteps = (nvh + 15) >> 4;
               for (int k = 0; k < ksteps; ++k)   // dV += P^T . dO
-                umma_bf16_ts(tmem + KV_DV, tmem + KV_ST + hf * 32 + k * 8, umma_smem_desc(do_addr + (2 * hf + k) * 2048, 8192, 1024),
-                             idesc_acc, (j > 0) || (hf > 0) || (k > 0));
+                umma_bf16_ts(tm + KV_DV, tm + KV_ST + hf * 32 + k * 8, od + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
+                             (j > 0) || (hf > 0) || (k > 0));
               for (int k = 0; k < ksteps; ++k)   // dK += dS^T . Q
-                umma_bf16_ts(tmem + KV_DK, tmem + KV_DPT + hf * 32 + k * 8, umma_smem_desc(q_addr + (2 * hf + k) * 2048, 8192, 1024),
-                             idesc_acc, (j > 0) || (hf > 0) || (k > 0));
+                umma_bf16_ts(tm + KV_DK, tm + KV_DPT + hf * 32 + k * 8, qd + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
+                             (j > 0) || (hf > 0) || (k > 0));
             }
-            if (hf == 1) umma_commit(&qb_empty[st]);   // every MMA reading this Q / dO stage has been issued
-            if (has_next && nvalid_next > 32 * hf) issue_s(hn, jn, g + 1, hf);   // its columns are free: in-order tensor pipe
           }
-          if (j + 1 == qb.nb) {
-            umma_commit(acc_full);
-            umma_commit(&kvt_empty[h & 1]);
-          }
+          if (hf == 1 && leader) umma_commit(&qb_empty[st]);   // every MMA reading this Q / dO stage has been issued
+          __syncwarp();
+          if (has_next && nvalid_next > 32 * hf) issue_s(hf);   // its columns are free: in-order tensor pipe
         }
+        if (has_next) advance_s();
+        if (j + 1 == nb && leader) {
+          umma_commit(acc_full);
+          umma_commit(&kvt_empty[h & 1]);
+        }
+        __syncwarp();
+        if (++j == nb) { j = 0; ++h; }
       }
     }
   } else {
