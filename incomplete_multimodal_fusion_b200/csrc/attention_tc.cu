@@ -163,9 +163,9 @@ struct KeyBlocks {
 // TC_HSPLIT CTAs over the heads (measured: no further gain, so 1).  `tiles` = the host's upper bound of tiles per sample;
 // the grid is (tiles + (TC_HSPLIT - 1) * heavy_max) * B CTAs, surplus ones exit.
 constexpr int TC_HSPLIT = 1;
-constexpr int TC_FWD_DEFAULT = 1;
+constexpr int TC_FWD_DEFAULT = 2;
 constexpr int TC_PF_DEFAULT = 0;    // MMF_ATTN_PF default: L2 prefetch distance in blocks
-constexpr int TC_DQ_DEFAULT = 1;    // MMF_ATTN_DQ default (see attn_bwd_tc_launch)   // MMF_ATTN_FWD default (see attn_fwd_tc_launch)
+constexpr int TC_DQ_DEFAULT = 2;    // MMF_ATTN_DQ default (see attn_bwd_tc_launch)   // MMF_ATTN_FWD default (see attn_fwd_tc_launch)
 __device__ __forceinline__ void lpt_tile(const int32_t* seg, int nseg, int tiles, int B, int H, int& tile, int& b, int& h0, int& h1) {
   const int L = blockIdx.x;
   h0 = 0; h1 = H;

@@ -657,10 +657,18 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
-    if (leader && lane == 0) {
+    // The whole warp runs the loop in converged code and ONE elected lane issues: inside an `if (lane == 0)` region
+    // nothing is provably warp-uniform and ptxas feeds every UTCHMMA's descriptors to the uniform datapath through an
+    // R2UR + vote loop (~19 SASS instructions per MMA; found on the attention kernels).  Descriptors are
+    // a per-stage base plus a constant step.
+    if (leader) {
+      const bool issuer = elect_one();
       const uint32_t idesc = umma_idesc_bf16(256, G2_BN, a_mn, b_mn);
-      const uint32_t a_step = a_mn ? 2048 : 32, a_lbo = a_mn ? 8192 : 16;
-      const uint32_t b_step = b_mn ? 2048 : 32, b_lbo = b_mn ? 8192 : 16;
+      const uint32_t a_step = (a_mn ? 2048 : 32) >> 4, a_lbo = a_mn ? 8192 : 16;
+      const uint32_t b_step = (b_mn ? 2048 : 32) >> 4, b_lbo = b_mn ? 8192 : 16;
+      const uint64_t da0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(smem_a), 0), a_lbo, 1024);
+      const uint64_t db0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(smem_b), 0), b_lbo, 1024);
+      const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -671,22 +679,23 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * G2_BN;
+        const uint32_t tmem_d = tmem0 + acc * G2_BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + stage * G2_A_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * G2_B_BYTES);
+          if (issuer) {
+            const uint64_t da = da0 + (uint64_t)(stage * (G2_A_BYTES >> 4));
+            const uint64_t db = db0 + (uint64_t)(stage * (G2_B_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * a_step, a_lbo, 1024);
-            const uint64_t db = umma_smem_desc(sb + k * b_step, b_lbo, 1024);
-            umma_bf16_cg2(tmem_d, da, db, idesc, (kb > kb0) || (k > 0));
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16_cg2(tmem_d, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc, (kb > kb0) || (k > 0));
+            umma_commit_cg2(&empty_bar[stage]);   // frees this smem slot in both CTAs
           }
-          umma_commit_cg2(&empty_bar[stage]);   // frees this smem slot in both CTAs
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_cg2(&tmem_full[acc]);       // accumulator ready, both CTAs' epilogues
+        if (issuer) umma_commit_cg2(&tmem_full[acc]);       // accumulator ready, both CTAs' epilogues
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
