@@ -197,6 +197,19 @@ int mmf_masked_loss_bwd(const void* pred, int32_t pred_f32, const float* target,
                         const float* dloss, void* dpred, mmf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Patch im2col of ALL modalities through a device token table (input_adapters.py:110 for every adapter + the token
+ * selection of multimae.py:378-383, with no per-modality count on the host): row b * nenc + i of `out` [B * nenc, ld_out]
+ * bf16 belongs to token tok[i] = global id; with m the modality that id falls into (tok_off[m] <= id < tok_off[m+1]) and
+ * patch = id - tok_off[m], columns [col_off[m], col_off[m] + C_m * P * P) hold that patch of imgs[m] ([B, C_m, H, W] f32,
+ * (c, ph, pw) order), column ind_col + m holds 1.0 and every other column 0.  One GEMM of `out` against the column-wise
+ * concatenation of the modalities' projection weights then embeds all visible tokens at once, and the weight-gradient
+ * GEMM's columns ind_col + m are the bias gradients.  M <= 4 modalities; all arrays below are HOST arrays.
+ * ---------------------------------------------------------------------------------------------- */
+int mmf_im2col_tokens(const float* const* imgs, const int32_t* chans, const int32_t* col_off, const int32_t* tok_off, int32_t M,
+                      const int32_t* tok, int32_t nenc, void* out, int64_t ld_out, int32_t ind_col, int64_t batch, int32_t H,
+                      int32_t W, int32_t P, mmf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Elementwise / data movement (all HBM-bound)
  * ---------------------------------------------------------------------------------------------- */
 /* f32 [rows, cols] -> bf16 [rows_pad, cols_pad] with zero padding and a scale: the per-step bf16
@@ -258,13 +271,22 @@ int mmf_add_bf16_f32(float* out, const float* x, const void* d, int64_t n, mmf_s
  *   rand_like draw of :241; share [T]: the Dirichlet sample; want_t = round_half_even(share_t * nenc) (:210).
  * Outputs (device): mask [sum sizes] int64 (0 = visible), ids_restore [sum sizes] / ids_keep [nenc] int64,
  *   idx: task t's ascending visible positions (int32) at offset sum(sizes[:t]), counts [T], seg [T+2] =
- *   [0, c0, c0+c1, .., nenc, nenc + n_fusion], slotmap [T, n_fusion] (rank of a position in idx_t or -1; nullable).
+ *   [0, c0, c0+c1, .., nenc, nenc + n_fusion], slotmap [T, n_fusion] (rank of a position in idx_t or -1; nullable),
+ *   tok [nenc] int32 (nullable): the visible tokens in encoder order (task-major, ascending position) as global ids
+ *   sum(sizes[:t]) + position -- the table the token-gather kernels read, so that no count has to reach the host.
  * argsort is stable (rank counting); the reference's CUDA argsort leaves the order of equal keys unspecified.
  * sizes is a HOST array.  sum sizes <= 4096, T <= 8.
+ * mmf_mask_explicit: the same bookkeeping for caller-provided masks (multimae.py:372-376: argsort of the 0 / 1 row,
+ *   ids_restore, ids_keep, the per-task selections of :378-383) from ONE mask row `given` [sum sizes] int64 (0 = visible),
+ *   without the reference's host synchronisations ((mask_all == 0).sum(), three nonzero()).  *err is set to 1 when the row
+ *   keeps a number of tokens different from nenc (the reference would silently use that other sequence length).
  * ---------------------------------------------------------------------------------------------- */
 int mmf_mask_build(const float* noise1, const float* noise2, const float* share, int32_t T, const int32_t* sizes,
                    int32_t nenc, int32_t n_fusion, int64_t* mask, int64_t* ids_restore, int64_t* ids_keep, int32_t* idx,
-                   int32_t* counts, int32_t* seg, int32_t* slotmap, mmf_stream_t stream);
+                   int32_t* counts, int32_t* seg, int32_t* slotmap, int32_t* tok, mmf_stream_t stream);
+int mmf_mask_explicit(const int64_t* given, int32_t T, const int32_t* sizes, int32_t nenc, int32_t n_fusion, int64_t* ids_restore,
+                      int64_t* ids_keep, int32_t* idx, int32_t* counts, int32_t* seg, int32_t* slotmap, int32_t* tok, int32_t* err,
+                      mmf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DINO-style distillation loss, forward and student gradient in one launch (criterion.py:328-335 dino_loss_func;

@@ -112,7 +112,10 @@ SIGNATURES = {
     "mmf_hardneg_loss": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
     "mmf_adamw_step": [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp],
     "mmf_grad_norm": [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp],
-    "mmf_mask_build": [c_vp, c_vp, c_vp, c_i32, C.POINTER(c_i32), c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "mmf_mask_build": [c_vp, c_vp, c_vp, c_i32, C.POINTER(c_i32), c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "mmf_mask_explicit": [c_vp, c_i32, C.POINTER(c_i32), c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "mmf_im2col_tokens": [C.POINTER(c_vp), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), c_i32, c_vp, c_i32, c_vp, c_i64, c_i32,
+                          c_i64, c_i32, c_i32, c_i32, c_vp],
 }
 _RESTYPES = {"mmf_hardneg_workspace_floats": c_i64, "mmf_launch_count": c_i64, "mmf_reset_launch_count": None, "mmf_set_gemm_reserved_sms": None}
 

@@ -186,6 +186,49 @@ __global__ void im2col_gather_kernel(const float* __restrict__ img, const int32_
   }
 }
 
+// Token-table im2col over all modalities (see mmf_im2col_tokens in the header): a row is written in 4-column (8-byte)
+// chunks; a chunk inside the token's own modality block converts one float4 of the patch line, the indicator chunk holds
+// the one-hot modality flag, every other chunk is zero.
+struct TokIm2colParams {
+  const float* img[4];
+  int C[4], col_off[4], tok_off[5];
+  int M, nenc, H, W, P, ind_col;
+  const int32_t* tok;
+  __nv_bfloat16* out;
+  int64_t ld_out, batch;
+};
+__global__ void im2col_tokens_kernel(const TokIm2colParams p) {
+  const int chunks = (int)(p.ld_out >> 2);
+  const int nw = p.W / p.P, PP = p.P * p.P;
+  const int64_t total = p.batch * p.nenc * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(t % chunks);
+    const int64_t row = t / chunks;
+    const int i = (int)(row % p.nenc);
+    const int64_t b = row / p.nenc;
+    const int id = p.tok[i];
+    int m = 0;
+    while (m + 1 < p.M && id >= p.tok_off[m + 1]) ++m;
+    const int col = ch * 4;
+    uint2 v = make_uint2(0u, 0u);
+    const int rel = col - p.col_off[m];
+    if (rel >= 0 && rel < p.C[m] * PP) {
+      const int patch = id - p.tok_off[m];
+      const int py = patch / nw, px = patch % nw;
+      const int c = rel / PP, r2 = rel % PP;
+      const int ph = r2 / p.P, pw = r2 % p.P;
+      const float4 f = *reinterpret_cast<const float4*>(p.img[m] + (((b * p.C[m] + c) * p.H + (py * p.P + ph)) * (int64_t)p.W + px * p.P + pw));
+      v = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+    } else if (col == p.ind_col) {   // (ind_col is a multiple of 4 and M <= 4: the flags live in this one chunk)
+      float o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = (col + q == p.ind_col + m) ? 1.0f : 0.0f;
+      v = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+    }
+    *reinterpret_cast<uint2*>(p.out + row * p.ld_out + col) = v;
+  }
+}
+
 // One-hot im2col of a class map (SemSegInputAdapter, input_adapters.py:209-328): row b*n_keep + i of `out`
 // ([.., num_classes*P*P] bf16, ZEROED by the caller) gets a 1 at column cls*P*P + ph*P + pw for every pixel of visible
 // patch idx[i].  With it the adapter's embedding lookup + Conv2d(k = s = P) becomes one GEMM against the
@@ -381,6 +424,29 @@ extern "C" int mmf_im2col_gather(const float* img, const int32_t* idx, void* out
   const int64_t total = batch * n_keep * C * P * (P / 4);
   im2col_gather_kernel<<<ew_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       img, idx, reinterpret_cast<__nv_bfloat16*>(out), batch, C, H, W, P, n_keep, ld_out);
+  MMF_COUNT_LAUNCH();
+  MMF_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmf_im2col_tokens(const float* const* imgs, const int32_t* chans, const int32_t* col_off, const int32_t* tok_off,
+                                 int32_t M, const int32_t* tok, int32_t nenc, void* out, int64_t ld_out, int32_t ind_col, int64_t batch,
+                                 int32_t H, int32_t W, int32_t P, mmf_stream_t stream) {
+  if (!imgs || !chans || !col_off || !tok_off || !tok || !out) MMF_BAD_ARG(1);
+  if (M <= 0 || M > 4 || P <= 0 || (P & 3) || H % P || W % P || (W & 3) || (ld_out & 3) || ind_col < 0 || (ind_col & 3) || ind_col + 4 > ld_out) MMF_BAD_ARG(2);
+  if (batch * nenc == 0) return 0;
+  TokIm2colParams p;
+  for (int m = 0; m < 4; ++m) { p.img[m] = nullptr; p.C[m] = 0; p.col_off[m] = 0; }
+  for (int m = 0; m < M; ++m) {
+    if (!imgs[m] || chans[m] <= 0 || (col_off[m] & 3) || col_off[m] + chans[m] * P * P > ind_col) MMF_BAD_ARG(3);
+    p.img[m] = imgs[m]; p.C[m] = chans[m]; p.col_off[m] = col_off[m];
+  }
+  for (int m = 0; m <= M; ++m) p.tok_off[m] = tok_off[m];
+  for (int m = M + 1; m < 5; ++m) p.tok_off[m] = tok_off[M];
+  p.M = M; p.nenc = nenc; p.H = H; p.W = W; p.P = P; p.ind_col = ind_col; p.tok = tok;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ld_out = ld_out; p.batch = batch;
+  const int64_t total = batch * nenc * (ld_out >> 2);
+  im2col_tokens_kernel<<<ew_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   MMF_COUNT_LAUNCH();
   MMF_LAUNCH_CHECK();
   return 0;

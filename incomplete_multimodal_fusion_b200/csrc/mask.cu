@@ -35,6 +35,9 @@ struct MaskParams {
   int32_t* counts;       // [T]
   int32_t* seg;          // [T + 2]
   int32_t* slotmap;      // [T, n_fusion] or null
+  int32_t* tok;          // [nenc] or null: global ids (off[t] + position) of the visible tokens in encoder order
+  const int64_t* given;  // explicit mode: [n_total] caller's mask row (0 = visible); null = sampled mode
+  int32_t* err;          // explicit mode: set to 1 when the mask keeps a number of tokens different from nenc
 };
 
 __global__ void __launch_bounds__(MASK_THREADS) mask_build_kernel(const MaskParams p) {
@@ -43,9 +46,35 @@ __global__ void __launch_bounds__(MASK_THREADS) mask_build_kernel(const MaskPara
   __shared__ uint8_t keep[MASK_MAX_N];
   __shared__ int32_t s_counts[MASK_MAX_TASKS];
   const int n = p.n_total;
+  if (threadIdx.x < MASK_MAX_TASKS) s_counts[threadIdx.x] = 0;
+  if (p.given != nullptr) {
+    // ---- explicit masks (multimae.py:372-376): ids_shuffle = STABLE argsort of the 0 / 1 row, i.e. a stable partition;
+    // the reference's CUDA argsort leaves the order among equal keys unspecified (documented difference) ----
+    __shared__ int s_nzero;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) keep[i] = p.given[i] == 0;
+    if (threadIdx.x == 0) s_nzero = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_nzero, (int)keep[i]);
+    __syncthreads();
+    const int nzero = s_nzero;
+    if (threadIdx.x == 0 && p.err) *p.err = nzero != p.nenc;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int before = 0;                       // equal keys before i
+      for (int j = 0; j < i; ++j) before += keep[j] == keep[i];
+      const int r = keep[i] ? before : nzero + before;
+      p.ids_restore[i] = r;
+      if (r < p.nenc) p.ids_keep[r] = i;
+      if (p.mask) p.mask[i] = keep[i] ? 0 : 1;
+      order[i] = r;
+    }
+    __syncthreads();
+    // the tables below always describe exactly nenc tokens (the first nenc of the partition order = ids_keep), so that a
+    // wrong num_encoded_tokens -- reported through *err -- can never make a consumer run past its buffers
+    for (int i = threadIdx.x; i < n; i += blockDim.x) keep[i] = order[i] < p.nenc;
+    __syncthreads();
+  } else {
   // ---- per-task argsort of noise1 ----
   for (int i = threadIdx.x; i < n; i += blockDim.x) key[i] = p.noise1[i];
-  if (threadIdx.x < MASK_MAX_TASKS) s_counts[threadIdx.x] = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     int t = 0;
@@ -83,6 +112,7 @@ __global__ void __launch_bounds__(MASK_THREADS) mask_build_kernel(const MaskPara
     p.mask[i] = r < p.nenc ? 0 : 1;
   }
   __syncthreads();
+  }
   // ---- per-task ascending index lists, counts, slot map ----
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     int t = 0;
@@ -107,32 +137,58 @@ __global__ void __launch_bounds__(MASK_THREADS) mask_build_kernel(const MaskPara
     }
     p.seg[p.T + 1] = acc + p.n_fusion;
   }
+  if (p.tok) {   // encoder order = modality-major, ascending position = ascending global id: rank among the kept ids
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      if (!keep[i]) continue;
+      int before = 0;
+      for (int j = 0; j < i; ++j) before += keep[j];
+      if (before < p.nenc) p.tok[before] = i;
+    }
+  }
 }
 
 }  // namespace mmf
 
-extern "C" int mmf_mask_build(const float* noise1, const float* noise2, const float* share, int32_t T, const int32_t* sizes,
-                              int32_t nenc, int32_t n_fusion, int64_t* mask, int64_t* ids_restore, int64_t* ids_keep,
-                              int32_t* idx, int32_t* counts, int32_t* seg, int32_t* slotmap, mmf_stream_t stream) {
+static int mask_launch(mmf::MaskParams& p, int32_t T, const int32_t* sizes, int32_t nenc, int32_t n_fusion, bool slot, mmf_stream_t stream) {
   using namespace mmf;
-  if (!noise1 || !noise2 || !share || !sizes || !mask || !ids_restore || !ids_keep || !idx || !counts || !seg) MMF_BAD_ARG(1);
   if (T <= 0 || T > MASK_MAX_TASKS) MMF_BAD_ARG(2);
-  MaskParams p;
-  p.noise1 = noise1; p.noise2 = noise2; p.share = share;
   p.T = T; p.nenc = nenc; p.n_fusion = n_fusion;
   p.off[0] = 0;
   for (int t = 0; t < T; ++t) {
     if (sizes[t] < 0) MMF_BAD_ARG(3);
-    if (slotmap && sizes[t] != n_fusion) MMF_BAD_ARG(6);   // the slot map is per fusion-token position
+    if (slot && sizes[t] != n_fusion) MMF_BAD_ARG(6);   // the slot map is per fusion-token position
     p.off[t + 1] = p.off[t] + sizes[t];
   }
   for (int t = T; t < MASK_MAX_TASKS; ++t) p.off[t + 1] = p.off[T];
   p.n_total = p.off[T];
   if (p.n_total <= 0 || p.n_total > MASK_MAX_N) MMF_BAD_ARG(4);
   if (nenc < 0 || nenc > p.n_total) MMF_BAD_ARG(5);
-  p.mask = mask; p.ids_restore = ids_restore; p.ids_keep = ids_keep; p.idx = idx; p.counts = counts; p.seg = seg; p.slotmap = slotmap;
   mask_build_kernel<<<1, MASK_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mmf_mask_build(const float* noise1, const float* noise2, const float* share, int32_t T, const int32_t* sizes,
+                              int32_t nenc, int32_t n_fusion, int64_t* mask, int64_t* ids_restore, int64_t* ids_keep,
+                              int32_t* idx, int32_t* counts, int32_t* seg, int32_t* slotmap, int32_t* tok, mmf_stream_t stream) {
+  using namespace mmf;
+  if (!noise1 || !noise2 || !share || !sizes || !mask || !ids_restore || !ids_keep || !idx || !counts || !seg) MMF_BAD_ARG(1);
+  MaskParams p;
+  p.noise1 = noise1; p.noise2 = noise2; p.share = share;
+  p.mask = mask; p.ids_restore = ids_restore; p.ids_keep = ids_keep; p.idx = idx; p.counts = counts; p.seg = seg; p.slotmap = slotmap;
+  p.tok = tok; p.given = nullptr; p.err = nullptr;
+  return mask_launch(p, T, sizes, nenc, n_fusion, slotmap != nullptr, stream);
+}
+
+extern "C" int mmf_mask_explicit(const int64_t* given, int32_t T, const int32_t* sizes, int32_t nenc, int32_t n_fusion,
+                                 int64_t* ids_restore, int64_t* ids_keep, int32_t* idx, int32_t* counts, int32_t* seg,
+                                 int32_t* slotmap, int32_t* tok, int32_t* err, mmf_stream_t stream) {
+  using namespace mmf;
+  if (!given || !sizes || !ids_restore || !ids_keep || !idx || !counts || !seg || !err) MMF_BAD_ARG(1);
+  MaskParams p;
+  p.noise1 = nullptr; p.noise2 = nullptr; p.share = nullptr;
+  p.mask = nullptr; p.ids_restore = ids_restore; p.ids_keep = ids_keep; p.idx = idx; p.counts = counts; p.seg = seg; p.slotmap = slotmap;
+  p.tok = tok; p.given = given; p.err = err;
+  return mask_launch(p, T, sizes, nenc, n_fusion, slotmap != nullptr, stream);
 }

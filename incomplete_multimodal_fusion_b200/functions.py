@@ -83,6 +83,20 @@ def w_cat_bf16(ws: Sequence[torch.Tensor]) -> torch.Tensor:
     return WEIGHTS.get(("cat",) + tuple(id(w) for w in ws), list(ws), build)
 
 
+def w_hcat_bf16(ws: Sequence[torch.Tensor], cols_pad: int) -> torch.Tensor:
+    """column-concatenation of several [D, K_i] (conv weights flattened) as one bf16 matrix [D, cols_pad], zero padded:
+    the B operand of the one-GEMM patch embedding of all modalities (EmbedFn)"""
+    def build():
+        out = torch.zeros(ws[0].shape[0], cols_pad, dtype=bf16, device=ws[0].device)
+        c = 0
+        for w in ws:
+            w2 = w.detach().reshape(w.shape[0], -1)
+            K.cast_bf16(w2, out[:, c:c + w2.shape[1]])
+            c += w2.shape[1]
+        return out
+    return WEIGHTS.get(("hcat", cols_pad) + tuple(id(w) for w in ws), list(ws), build)
+
+
 def w_geglu_bf16(w1: torch.Tensor, ipad: int) -> torch.Tensor:
     """[2I, D] GEGLU weight -> bf16 [2*ipad, D]: value rows at [0, I), gate rows at [ipad, ipad+I), zero padding."""
     def build():
@@ -560,7 +574,65 @@ class EmbedFn(torch.autograd.Function):
         return 4 if kind == "semseg" else 3
 
     @staticmethod
+    def _forward_tokens(ctx, meta, fusion_tokens, mod_args):
+        """All modalities through ONE im2col + ONE GEMM driven by the device token table meta["tok"] (global ids of the
+        visible tokens in encoder order): no per-modality count ever reaches the host.  A [B*nenc, Kpad] holds each token's
+        patch in its modality's column block (zeros elsewhere) and a one-hot modality flag; B = [W_0 | W_1 | .. | 0]; the
+        epilogue adds (bias_m + pos_m)[patch] through the row map.  Zero columns add exact zeros to the fp32 accumulators,
+        so every token's value equals the per-modality GEMM's."""
+        B, D, P, Fn, nenc = meta["B"], meta["D"], meta["P"], meta["F"], meta["nenc"]
+        dev = fusion_tokens.device
+        Mh = B * nenc
+        imgs = [mod_args[3 * m].contiguous() for m in range(len(meta["pos"]))]
+        ws = [mod_args[3 * m + 1] for m in range(len(imgs))]
+        bs = [mod_args[3 * m + 2] for m in range(len(imgs))]
+        ks = [int(im.shape[1]) * P * P for im in imgs]
+        col_off = [sum(ks[:m]) for m in range(len(ks))]
+        ktot = sum(ks)
+        kpad = ktot + 8                      # flag columns ktot .. ktot + M - 1 (16-byte row pitch kept)
+        tok_off = [0]
+        for pos in meta["pos"]:
+            tok_off.append(tok_off[-1] + pos.shape[0])
+        X = torch.empty(Mh + B * Fn, D, dtype=f32, device=dev)
+        A = torch.empty(Mh, kpad, dtype=bf16, device=dev)
+        if Mh > 0:
+            K.im2col_tokens(imgs, meta["tok"], A, P, col_off, tok_off, ktot)
+            table = torch.cat([pos + b.detach()[None, :] for pos, b in zip(meta["pos"], bs)], 0)     # [sum F_m, D] fp32
+            K.gemm(A, w_hcat_bf16(ws, kpad), X, residual=table, res_row_map=meta["tok"], res_period=nenc)
+        if Fn > 0:
+            fus = (fusion_tokens.detach()[0] + meta["pos_fusion"]).contiguous()
+            K.bcast_rows(fus, X[Mh:], B, Fn, D, Fn * D)
+        ctx.meta = meta
+        ctx.tokens_path = (A, ks, col_off, ktot, [w.shape for w in ws])
+        return X
+
+    @staticmethod
+    def _backward_tokens(ctx, dX):
+        meta = ctx.meta
+        B, D, Fn, nenc = meta["B"], meta["D"], meta["F"], meta["nenc"]
+        A, ks, col_off, ktot, wshapes = ctx.tokens_path
+        Mh = B * nenc
+        dX = dX.contiguous()
+        grads: List[Optional[torch.Tensor]] = []
+        if Mh > 0:
+            dY = K.cast_bf16(dX[:Mh])
+            dW = wgrad(dY, A)                                              # [D, kpad] fp32: weight blocks, then bias columns
+            for m, (kk, c0, shp) in enumerate(zip(ks, col_off, wshapes)):
+                grads += [None, dW[:, c0:c0 + kk].contiguous().view(shp), dW[:, ktot + m].contiguous()]
+        else:
+            for shp in wshapes:
+                grads += [None, torch.zeros(shp, dtype=f32, device=dX.device), torch.zeros(D, dtype=f32, device=dX.device)]
+        dfus = None
+        if Fn > 0:
+            dfus = torch.empty(1, Fn, D, dtype=f32, device=dX.device)
+            K.reduce_batch(dX[Mh:], dfus, B, Fn, D, Fn * D)
+        return (None, dfus) + tuple(grads)
+
+    @staticmethod
     def forward(ctx, meta, fusion_tokens, *mod_args):
+        ctx.tokens_path = None
+        if meta.get("tok") is not None:
+            return EmbedFn._forward_tokens(ctx, meta, fusion_tokens, mod_args)
         B, D, P, Fn, nenc = meta["B"], meta["D"], meta["P"], meta["F"], meta["nenc"]
         kinds = meta.get("kinds") or ["patch"] * len(meta["idx"])
         dev = fusion_tokens.device
@@ -608,6 +680,8 @@ class EmbedFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dX):
+        if ctx.tokens_path is not None:
+            return EmbedFn._backward_tokens(ctx, dX)
         meta = ctx.meta
         B, D, P, Fn, nenc = meta["B"], meta["D"], meta["P"], meta["F"], meta["nenc"]
         Mh = B * nenc

@@ -417,7 +417,7 @@ def add_bf16(x, d, out=None):
 def mask_build(noise1, noise2, share, sizes, nenc, n_fusion, want_slotmap):
     """Everything of generate_random_masks / token selection after the random draws (see include/mmf_b200.h).
     Returns (mask [n] int64, ids_restore [n] int64, ids_keep [nenc] int64, idx [n] int32, counts [T] int32,
-    seg [T+2] int32, slotmap [T, n_fusion] int32 or None), all on the device, no host sync."""
+    seg [T+2] int32, slotmap [T, n_fusion] int32 or None, tok [nenc] int32), all on the device, no host sync."""
     dev = noise1.device
     T, n = len(sizes), int(sum(sizes))
     assert noise1.dtype == f32 and noise2.dtype == f32 and share.dtype == f32
@@ -429,10 +429,47 @@ def mask_build(noise1, noise2, share, sizes, nenc, n_fusion, want_slotmap):
     counts = torch.empty(T, dtype=torch.int32, device=dev)
     seg = torch.empty(T + 2, dtype=torch.int32, device=dev)
     slotmap = torch.empty(T, n_fusion, dtype=torch.int32, device=dev) if want_slotmap else None
+    tok = torch.empty(nenc, dtype=torch.int32, device=dev)
     csizes = (C.c_int32 * T)(*[int(v) for v in sizes])
     check(_L().mmf_mask_build(_p(noise1), _p(noise2), _p(share), T, csizes, nenc, n_fusion, _p(mask), _p(ids_restore),
-                              _p(ids_keep), _p(idx), _p(counts), _p(seg), _p(slotmap), _stream()), "mmf_mask_build")
-    return mask, ids_restore, ids_keep, idx, counts, seg, slotmap
+                              _p(ids_keep), _p(idx), _p(counts), _p(seg), _p(slotmap), _p(tok), _stream()), "mmf_mask_build")
+    return mask, ids_restore, ids_keep, idx, counts, seg, slotmap, tok
+
+
+def mask_explicit(given, sizes, nenc, n_fusion, want_slotmap):
+    """the same bookkeeping for a caller-provided mask row `given` [sum sizes] int64 (0 = visible): returns (ids_restore,
+    ids_keep, idx, counts, seg, slotmap, tok, err [1] int32), all on the device, no host sync"""
+    dev = given.device
+    T, n = len(sizes), int(sum(sizes))
+    assert given.dtype == torch.int64 and given.is_contiguous() and given.numel() == n
+    ids_restore = torch.empty(n, dtype=torch.int64, device=dev)
+    ids_keep = torch.zeros(nenc, dtype=torch.int64, device=dev)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    counts = torch.empty(T, dtype=torch.int32, device=dev)
+    seg = torch.empty(T + 2, dtype=torch.int32, device=dev)
+    slotmap = torch.empty(T, n_fusion, dtype=torch.int32, device=dev) if want_slotmap else None
+    tok = torch.zeros(nenc, dtype=torch.int32, device=dev)
+    err = torch.empty(1, dtype=torch.int32, device=dev)
+    csizes = (C.c_int32 * T)(*[int(v) for v in sizes])
+    check(_L().mmf_mask_explicit(_p(given), T, csizes, nenc, n_fusion, _p(ids_restore), _p(ids_keep), _p(idx), _p(counts), _p(seg),
+                                 _p(slotmap), _p(tok), _p(err), _stream()), "mmf_mask_explicit")
+    return ids_restore, ids_keep, idx, counts, seg, slotmap, tok, err
+
+
+def im2col_tokens(imgs, tok, out, P, col_off, tok_off, ind_col):
+    """token-table im2col over all modalities (see mmf_im2col_tokens): imgs = list of [B, C_m, H, W] f32, tok [nenc] int32"""
+    M = len(imgs)
+    B, _, H, W = imgs[0].shape
+    for im in imgs:
+        assert im.is_contiguous() and im.dtype == f32 and im.shape[0] == B and tuple(im.shape[2:]) == (H, W)
+    assert tok.dtype == torch.int32 and out.dtype == bf16 and out.shape[0] == B * tok.numel()
+    ptrs = (C.c_void_p * M)(*[_p(im) for im in imgs])
+    chans = (C.c_int32 * M)(*[int(im.shape[1]) for im in imgs])
+    coff = (C.c_int32 * M)(*[int(v) for v in col_off])
+    toff = (C.c_int32 * (M + 1))(*[int(v) for v in tok_off])
+    check(_L().mmf_im2col_tokens(ptrs, chans, coff, toff, M, _p(tok), tok.numel(), _p(out), _ld(out), int(ind_col), B, H, W, P, _stream()),
+          "mmf_im2col_tokens")
+    return out
 
 
 def dino_loss(student, teacher, student_temp, teacher_temp):

@@ -29,6 +29,38 @@ from .zorro_utils import Attention, AttentionBiLSTM, Block, Block_Fusion, LayerN
 
 MODALITIES = ('s1', 's2', 'dem')   # hard-coded token order of the reference (multimae.py:378-407)
 _MASK_STREAMS = {}                 # device index -> the mask sampler's side stream (see _sample_masks)
+_VALIDATED_MASKS = {}              # explicit task_masks already checked against num_encoded_tokens (see _explicit_masks)
+
+
+class MaskTables(dict):
+    """What the mask builder leaves on the DEVICE for one step (one mask row for the whole batch): `mask`, `ids_restore`,
+    `ids_keep`, `idx` (per-task ascending visible positions at the task offsets), `counts`, `seg` (zorro segment table),
+    `slotmap`, `tok` (visible tokens in encoder order as global ids).  The fused path reads only these; nothing here
+    needs the per-modality counts on the host.  `counts_host` / `idx_list()` are the legacy accessors (one host read-back)
+    for callers that size tensors by the counts (the 4-modality semantic adapter, ViTBaseline)."""
+
+    @property
+    def counts_host(self):
+        if "_counts_host" not in self:
+            if self["nenc"] == sum(self["sizes"]):          # nothing masked: the counts are the sizes, no read-back
+                self["_counts_host"] = list(self["sizes"])
+            else:
+                side = self.get("stream")            # read on the builder's own stream: no wait for the main stream's queue
+                if side is not None:
+                    with torch.cuda.stream(side):
+                        self["_counts_host"] = self["counts"].tolist()
+                else:
+                    self["_counts_host"] = self["counts"].tolist()
+        return self["_counts_host"]
+
+    def idx_list(self, order=None):
+        cnt = self.counts_host
+        off = [0]
+        for n in self["sizes"]:
+            off.append(off[-1] + n)
+        where = {t: i for i, t in enumerate(self["tasks"])}
+        order = order or self["tasks"]
+        return [self["idx"][off[where[t]]: off[where[t]] + cnt[where[t]]] for t in order]
 
 
 class MultiMAEBase(nn.Module):
@@ -137,12 +169,11 @@ class MultiMAEBase(nn.Module):
         else:
             share_cpu = Dirichlet(torch.Tensor(alphas)).sample((1,))
         Fn_tok = self.fusion_tokens.shape[1]
-        want_slot = self.FUSION_BLOCKS and all(n == Fn_tok for n in sizes)
-        # The draws and the mask builder run on their own (high-priority) stream: the per-modality token counts are the
-        # one thing the host has to read back per step, and read on the main stream that copy would wait for everything
-        # still queued there -- the whole previous step -- and leave the GPU idle until the host has queued new work.
-        # The mask depends on the random draws only (whose Philox offsets are assigned in host call order, whatever the
-        # stream), so the values are unchanged.
+        want_slot = (self.FUSION_BLOCKS or self.LSTM_FUSION) and all(n == Fn_tok for n in sizes)
+        # The draws and the mask builder run on their own (high-priority) stream: they depend on nothing of the step, so
+        # they can run ahead of whatever the main stream still holds.  The mask depends on the random draws only (whose
+        # Philox offsets are assigned in host call order, whatever the stream), so the values are unchanged.  Nothing is
+        # read back: every consumer takes the device tables (MaskTables).
         main = torch.cuda.current_stream(device)
         side = _MASK_STREAMS.get(device.index)
         if side is None:
@@ -151,15 +182,39 @@ class MultiMAEBase(nn.Module):
             share = share_cpu.to(device)
             noise1 = torch.cat([torch.rand(1, n, device=device) for n in sizes], dim=1)
             noise2 = torch.rand_like(noise1)
-            mask, ids_restore, ids_keep, idx, counts, seg, slotmap = K.mask_build(
+            mask, ids_restore, ids_keep, idx, counts, seg, slotmap, tok = K.mask_build(
                 noise1.view(-1), noise2.view(-1), share.float().view(-1).contiguous(), sizes, num_encoded_tokens, Fn_tok, want_slot)
-            counts_host = counts.tolist()          # synchronises the side stream only
         main.wait_stream(side)
-        for t in (mask, ids_restore, ids_keep, idx, counts, seg, slotmap):
+        for t in (mask, ids_restore, ids_keep, idx, counts, seg, slotmap, tok):
             if t is not None:
                 t.record_stream(main)
-        return dict(tasks=list(input_tokens.keys()), sizes=sizes, B=B, mask=mask, ids_restore=ids_restore, ids_keep=ids_keep,
-                    idx=idx, counts=counts, counts_host=counts_host, seg=seg, slotmap=slotmap)
+        return MaskTables(tasks=list(input_tokens.keys()), sizes=sizes, B=B, nenc=num_encoded_tokens, mask=mask, ids_restore=ids_restore,
+                          ids_keep=ids_keep, idx=idx, counts=counts, seg=seg, slotmap=slotmap, tok=tok, stream=side)
+
+    def _explicit_masks(self, task_masks: Dict[str, torch.Tensor], tasks: List[str], sizes: List[int], B: int, nenc: int, device):
+        """Caller-provided masks (multimae.py:372-376 + the selections of :378-383) through the same single-CTA builder: a
+        stable partition of row 0 of the masks (the reference selects tokens from row 0 as well, :378-382) gives
+        ids_shuffle / ids_restore / ids_keep and every table of the sampled branch, on the device.  The reference reads
+        (mask_all == 0).sum() and three nonzero() results back; here the kept-token count is checked against
+        num_encoded_tokens ONCE per mask object (keyed on storage, version and shape -- inference loops pass the same
+        masks for every batch), so repeated calls have no host round-trip at all."""
+        Fn_tok = self.fusion_tokens.shape[1]
+        want_slot = (self.FUSION_BLOCKS or self.LSTM_FUSION) and all(n == Fn_tok for n in sizes)
+        rows = [task_masks[t][0].to(device=device, dtype=torch.int64) for t in tasks]
+        given = torch.cat(rows).contiguous()
+        ids_restore, ids_keep, idx, counts, seg, slotmap, tok, err = K.mask_explicit(given, sizes, nenc, Fn_tok, want_slot)
+        key = tuple((task_masks[t].data_ptr(), task_masks[t]._version, tuple(task_masks[t].shape)) for t in tasks) + (nenc,)
+        if key not in _VALIDATED_MASKS:
+            if int(err.item()):
+                kept = int((given == 0).sum())
+                raise ValueError(f"num_encoded_tokens={nenc} but the masks keep {kept} tokens; pass the true count "
+                                 "(the reference mis-slices silently in this case)")
+            if len(_VALIDATED_MASKS) > 256:
+                _VALIDATED_MASKS.clear()
+            _VALIDATED_MASKS[key] = True
+        Bm = next(iter(task_masks.values())).shape[0]
+        return MaskTables(tasks=tasks, sizes=sizes, B=B, nenc=nenc, mask=given, ids_restore=ids_restore.unsqueeze(0).expand(Bm, -1),
+                          ids_keep=ids_keep.unsqueeze(0).expand(Bm, -1), idx=idx, counts=counts, seg=seg, slotmap=slotmap, tok=tok)
 
     def generate_random_masks(self, input_tokens: Dict[str, torch.Tensor], num_encoded_tokens: int,
                               alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False):
@@ -236,39 +291,42 @@ class MultiMAEBase(nn.Module):
         input_info = self.generate_input_info(carriers, image_size=(H, W))
         nenc = num_encoded_tokens if mask_inputs else sum(c.shape[1] for c in carriers.values())
 
-        slotmap = None
         if task_masks is None:
             r = self._sample_masks(carriers, nenc, alphas=alphas, sample_tasks_uniformly=sample_tasks_uniformly)
             task_masks, ids_keep, ids_restore = self._public_masks(r)
-            cnt = r["counts_host"]                                      # the one host read-back of the step: token counts
-            off = [0]
-            for n in r["sizes"]:
-                off.append(off[-1] + n)
-            where = {t: i for i, t in enumerate(r["tasks"])}
-            idx = [r["idx"][off[where[t]]: off[where[t]] + cnt[where[t]]] for t in MODALITIES]
-            counts = [cnt[where[t]] for t in MODALITIES]
-            if r["slotmap"] is not None:
-                slotmap = r["slotmap"] if r["tasks"][:len(MODALITIES)] == list(MODALITIES) else \
-                    torch.stack([r["slotmap"][where[t]] for t in MODALITIES]).contiguous()
         else:
-            flat = torch.cat([task_masks[t] for t in tasks], dim=1)
-            ids_shuffle = torch.argsort(flat, dim=1, stable=True)
-            ids_restore = torch.argsort(ids_shuffle, dim=1, stable=True)
-            ids_keep = ids_shuffle[:, :int((flat == 0).sum())]
-            idx = [(task_masks[t][0] == 0).nonzero(as_tuple=True)[0].to(torch.int32) for t in MODALITIES]
-            counts = [int(i.numel()) for i in idx]
-        if sum(counts) != nenc:
-            raise ValueError(f"num_encoded_tokens={nenc} but the masks keep {sum(counts)} tokens; pass the true count "
-                             "(the reference mis-slices silently in this case)")
+            r = self._explicit_masks(task_masks, tasks, [c.shape[1] for c in carriers.values()], B, nenc, device)
+            ids_keep, ids_restore = r["ids_keep"], r["ids_restore"]
+        in_order = r["tasks"][:len(MODALITIES)] == list(MODALITIES)       # the input dict lists the modalities in encoder order
+        kinds = [getattr(self.input_adapters[t], 'KIND', 'patch') for t in MODALITIES]
+        # device-table path: all modalities are plain patch adapters in encoder order (every reference script); otherwise
+        # the legacy path sizes per-modality tensors by the counts (one host read-back)
+        fused_tables = in_order and len(r["tasks"]) == len(MODALITIES) and all(k == 'patch' for k in kinds) and \
+            all(sz == Fn_tok for sz in r["sizes"])
         n_tail = nenc if self.LSTM_FUSION else Fn_tok          # fusion tokens in the encoder sequence
-        zmask = ZorroMask(counts, n_tail, device)
+        nseg = len(MODALITIES) + 1
+        slotmap = r["slotmap"]
+        if fused_tables:
+            idx = counts = None
+            seg = r["seg"]
+            if n_tail != Fn_tok:                               # (LSTM variant: one fusion token per visible token)
+                seg = torch.cat([seg[:-1], seg[-2:-1] + n_tail])
+        else:
+            idx = r.idx_list(MODALITIES)
+            where = {t: i for i, t in enumerate(r["tasks"])}
+            counts = [r.counts_host[where[t]] for t in MODALITIES]
+            if sum(counts) != nenc:
+                raise ValueError(f"num_encoded_tokens={nenc} but the masks keep {sum(counts)} tokens; pass the true count "
+                                 "(the reference mis-slices silently in this case)")
+            seg = ZorroMask(counts, n_tail, device).seg
+            if slotmap is not None and not in_order:
+                slotmap = torch.stack([slotmap[where[t]] for t in MODALITIES]).contiguous()
 
         # ---- tokens: visible-patch embedding + fusion tokens, planar layout ----
-        mod_args, kinds, pads = [], [], {}
+        mod_args, pads = [], {}
         for m, t in enumerate(MODALITIES):
             ad = self.input_adapters[t]
-            kinds.append(getattr(ad, 'KIND', 'patch'))
-            if kinds[-1] == 'semseg':          # class map [B, H, W] (SemSegInputAdapter): embedded through a one-hot GEMM
+            if kinds[m] == 'semseg':          # class map [B, H, W] (SemSegInputAdapter): embedded through a one-hot GEMM
                 mod_args += ad.embed_args(x[t])
                 pads[m] = ad.emb_padding_idx
             else:
@@ -276,6 +334,7 @@ class MultiMAEBase(nn.Module):
         fus_ad = self.input_adapters['fusion']
         pos_fusion = fus_ad.pos_table(H // fus_ad.P_H, W // fus_ad.P_W)
         meta_e = dict(B=B, D=D, P=self.input_adapters[first].P_H, F=0 if self.LSTM_FUSION else Fn_tok, nenc=nenc, idx=idx,
+                      tok=r["tok"] if fused_tables else None,
                       pos=[self.input_adapters[t].pos_table(*grids[t]) for t in MODALITIES], pos_fusion=pos_fusion, kinds=kinds,
                       padding_idx=pads)
         X = Fn.EmbedFn.apply(meta_e, self.fusion_tokens, *mod_args)
@@ -284,19 +343,19 @@ class MultiMAEBase(nn.Module):
             # multimae_lstm_s2dsm.py:384-434: the fusion token of every visible position, merged with that position's
             # modality token by the BiLSTM (cuDNN under bf16 autocast, like the reference's AMP step)
             complete_fusion = self.fusion_tokens[0] + pos_fusion                      # [F, D]
-            sel = torch.cat([i.long() for i in idx])
+            sel = (r["tok"].long() % Fn_tok) if fused_tables else torch.cat([i.long() for i in idx])   # patch of every visible token
             pairs = torch.stack([X.view(B, nenc, D), complete_fusion[sel].unsqueeze(0).expand(B, -1, -1)], dim=2)
             with torch.autocast('cuda', dtype=torch.bfloat16):
                 fus0 = self.attn_lstm(pairs.reshape(B * nenc, 2, D))
             X = torch.cat([X, fus0.float()], dim=0)                                   # planar: modality rows, then fusion rows
 
         # ---- encoder stack ----
-        if self.FUSION_BLOCKS and slotmap is None:
+        if self.FUSION_BLOCKS and slotmap is None:            # (legacy path with grids that differ from the fusion grid)
             slotmap = torch.full((len(MODALITIES), Fn_tok), -1, dtype=torch.int32, device=device)
             for m, ix in enumerate(idx):
                 slotmap[m, ix.long()] = torch.arange(ix.numel(), dtype=torch.int32, device=device)
         meta = dict(B=B, D=D, H=Hh, F=n_tail, nenc=nenc, fusion=self.FUSION_BLOCKS, depth=self.depth,
-                    I=int(D * self.ff_mult * 2 / 3), seg=zmask.seg, nseg=zmask.nseg, slotmap=slotmap,
+                    I=int(D * self.ff_mult * 2 / 3), seg=seg, nseg=nseg, slotmap=slotmap,
                     grad_hook=getattr(self, 'grad_hook', None),
                     grad_hook_inplace=getattr(self, 'grad_hook_inplace', None))
         params = []
@@ -335,13 +394,15 @@ class MultiMAEBase(nn.Module):
         type_ids = self._device_const(('type_ids', tuple(MODALITIES)), device,
                                       lambda: torch.tensor([self.TYPE_IDS[t] for t in MODALITIES] + [self.FUSION_TYPE_ID]))
         pos = self._device_const(('arange', N), device, lambda: torch.arange(N, dtype=torch.int32))
-        types = type_ids[(pos[:, None] >= zmask.seg[None, 1:-1]).sum(1)]
+        types = type_ids[(pos[:, None] >= seg[None, 1:-1]).sum(1)]
         pmask = torch.zeros(Rt, N, dtype=torch.uint8, device=device)
         pmask[:R] = ((rtypes[:, None] == types[None, :]) | (rtypes[:, None] == self.FUSION_TYPE_ID)).to(torch.uint8)
         mode = torch.zeros(Rt, dtype=torch.int32, device=device)
         if self.FUSION_BLOCKS:
-            for j, ix in enumerate(idx):           # per-modality pools over the fusion tokens at that modality's
-                pmask[R + j, nenc + ix.long()] = 1  # visible positions (multimae_crossattn.py:529-543)
+            # per-modality pools over the fusion tokens at that modality's visible positions (multimae_crossattn.py:529-543):
+            # straight from the mask rows (0 = visible), no index lists
+            vis = torch.stack([(task_masks[t][0] == 0) for t in MODALITIES]).to(device=device, dtype=torch.uint8)    # [M, F]
+            pmask[R:R + len(MODALITIES), nenc:nenc + vis.shape[1]] = vis
             mode[R:] = 1                            # empty context -> zeros, not the uniform fallback
         ap = self.attn_pool
         # the learned queries are batch-invariant rows: their normalised values and projection stay fp32 on the autograd
@@ -364,11 +425,21 @@ class MultiMAEBase(nn.Module):
             # decoders read the whole fusion grid with the encoded tokens scattered back (multimae_lstm_s2dsm.py:470-477;
             # the reference writes position by position in order, so a position visible in both modalities keeps the
             # later, dem, copy: one index_copy per modality in order reproduces that deterministically)
-            dec_in = complete_fusion.unsqueeze(0).expand(B, -1, -1).clone()
-            o = 0
-            for ix in idx:
-                dec_in = dec_in.index_copy(1, ix.long(), enc_fusion[:, o:o + ix.numel()])
-                o += ix.numel()
+            if fused_tables:
+                # slotmap[m][p] = rank of position p among modality m's visible tokens (or -1); the LAST modality that sees
+                # p wins, as in the reference's in-order writes: one gather instead of per-modality index_copy
+                src = torch.full((Fn_tok,), -1, dtype=torch.int64, device=device)
+                for m in range(len(MODALITIES)):
+                    sm = slotmap[m].long()
+                    src = torch.where(sm >= 0, sm + seg[m].long(), src)
+                picked = enc_fusion[:, src.clamp_min(0)]
+                dec_in = torch.where((src >= 0)[None, :, None], picked, complete_fusion.unsqueeze(0).expand(B, -1, -1))
+            else:
+                dec_in = complete_fusion.unsqueeze(0).expand(B, -1, -1).clone()
+                o = 0
+                for ix in idx:
+                    dec_in = dec_in.index_copy(1, ix.long(), enc_fusion[:, o:o + ix.numel()])
+                    o += ix.numel()
         preds = {}
         for domain, adapter in self.output_adapters.items():
             p = adapter(encoder_tokens=dec_in, input_info=input_info, ids_keep=ids_keep, ids_restore=ids_restore)

@@ -88,16 +88,16 @@ class ViTBaseline(MultiMAE):
             nenc = num_encoded_tokens if num_encoded_tokens is not None else total
         else:
             nenc = int(total * 0.9) if self.training else total          # (:576-580)
+        sizes = [c.shape[1] for c in carriers.values()]
         if task_masks is None:
             r = self._sample_masks(carriers, nenc, alphas=alphas, sample_tasks_uniformly=sample_tasks_uniformly)
-            cnt = r["counts_host"]
-            off = [0]
-            for n in r["sizes"]:
-                off.append(off[-1] + n)
-            idx = [r["idx"][off[i]: off[i] + cnt[i]] for i in range(len(present))]
-            slotmap = r["slotmap"]
         else:
-            idx = [(task_masks[t][0] == 0).nonzero(as_tuple=True)[0].to(torch.int32) for t in present]
+            r = self._explicit_masks(task_masks, present, sizes, B, nenc, device)
+        # eval encodes every token of the present modalities (nenc == total): the counts are the grid sizes and nothing is
+        # read back; training's 0.9-of-the-tokens masking reads the counts once (counts_host) to size the patch-embed GEMMs
+        idx = r.idx_list(present)
+        slotmap = r["slotmap"]
+        if slotmap is None:
             slotmap = torch.full((len(present), Fn_tok), -1, dtype=torch.int32, device=device)
             for m, ix in enumerate(idx):
                 slotmap[m, ix.long()] = torch.arange(ix.numel(), dtype=torch.int32, device=device)

@@ -111,11 +111,18 @@ class FusedAdamW:
                 w = srcs[0]
                 if img.shape[0] != w.shape[0]:          # padded value | gate halves: leave to the lazy rebuild
                     continue
-            elif kind not in ("w", "cat"):
+            elif kind not in ("w", "cat", "hcat"):
                 continue
-            row, ok, slots = 0, True, []
+            row, col, ok, slots = 0, 0, True, []
             for s in srcs:
                 cols = s.numel() // s.shape[0]
+                if kind == "hcat":                       # column-wise concatenation: same rows, a column offset per source
+                    if col + cols > img.shape[1] or s.shape[0] != img.shape[0]:
+                        ok = False
+                        break
+                    slots.append((index[id(s)], img.data_ptr() + col * 2, img.stride(0)))
+                    col += cols
+                    continue
                 if cols > img.shape[1] or row + s.shape[0] > img.shape[0]:
                     ok = False
                     break

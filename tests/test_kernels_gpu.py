@@ -487,7 +487,7 @@ def test_mask_build_matches_torch_ops(sizes, nenc):
         noise2 = torch.rand(n, device="cuda", generator=g)
         share = torch.distributions.Dirichlet(torch.ones(T)).sample().cuda() if seed else torch.tensor([1.0] + [0.0] * (T - 1)).cuda()
         same = len(set(sizes)) == 1
-        mask, ids_restore, ids_keep, idx, counts, seg, slotmap = K().mask_build(noise1, noise2, share, sizes, nenc, sizes[0], same)
+        mask, ids_restore, ids_keep, idx, counts, seg, slotmap, tok = K().mask_build(noise1, noise2, share, sizes, nenc, sizes[0], same)
         # reference op sequence
         want = (share * nenc).round().long()
         pre = []
@@ -518,6 +518,8 @@ def test_mask_build_matches_torch_ops(sizes, nenc):
                 sm[ix] = torch.arange(ix.numel(), dtype=torch.int32, device="cuda")
                 assert torch.equal(slotmap[t], sm)
             off += nt
+        # token table: the visible tokens in encoder order = the kept global ids in ascending order
+        assert torch.equal(tok.long(), (m[0] == 0).nonzero(as_tuple=True)[0])
         assert acc == nenc and int(seg[T + 1]) == nenc + sizes[0]
 
 
@@ -608,3 +610,68 @@ def test_hard_negative_loss_fused_kernel(B, D, beta, tau_plus, temp):
     lr.backward()
     assert abs(float(le) - float(lr)) < 1e-2 * abs(float(lr))
     assert rel(a4.grad, a5.grad) < 3e-2 and rel(b4.grad, b5.grad) < 3e-2
+
+
+@pytest.mark.parametrize("sizes,keep", [((49, 49, 49), (10, 0, 49)), ((196, 196, 196), (196, 0, 0)), ((64, 64), (1, 63))])
+def test_mask_explicit_matches_torch_ops(sizes, keep):
+    """caller-provided masks (multimae.py:372-376, 378-383): stable argsort of the 0 / 1 row, ids_restore, ids_keep, the
+    per-task nonzero() lists, counts, segment table, slot map and token table, all in one launch with no host sync; a wrong
+    num_encoded_tokens sets the error flag and still yields tables that describe exactly nenc tokens"""
+    g = torch.Generator().manual_seed(3)
+    rows = []
+    for nt, k in zip(sizes, keep):
+        m = torch.ones(nt, dtype=torch.int64)
+        m[torch.randperm(nt, generator=g)[:k]] = 0
+        rows.append(m)
+    given = torch.cat(rows).cuda()
+    nenc = sum(keep)
+    same = len(set(sizes)) == 1
+    ids_restore, ids_keep, idx, counts, seg, slotmap, tok, err = K().mask_explicit(given, sizes, nenc, sizes[0], same)
+    assert int(err) == 0
+    shuf = torch.argsort(given.unsqueeze(0), dim=1, stable=True)
+    assert torch.equal(ids_restore, torch.argsort(shuf, dim=1)[0]) and torch.equal(ids_keep, shuf[0, :nenc])
+    assert torch.equal(tok.long(), (given == 0).nonzero(as_tuple=True)[0])
+    off, acc = 0, 0
+    for t, nt in enumerate(sizes):
+        ix = (given[off:off + nt] == 0).nonzero(as_tuple=True)[0]
+        assert int(counts[t]) == ix.numel() and torch.equal(idx[off:off + ix.numel()].long(), ix)
+        acc += ix.numel()
+        assert int(seg[t + 1]) == acc
+        if same:
+            sm = torch.full((nt,), -1, dtype=torch.int32, device="cuda")
+            sm[ix] = torch.arange(ix.numel(), dtype=torch.int32, device="cuda")
+            assert torch.equal(slotmap[t], sm)
+        off += nt
+    assert int(seg[len(sizes) + 1]) == nenc + sizes[0]
+    for wrong in (nenc - 1, nenc + 3):
+        if 0 < wrong <= sum(sizes):
+            r = K().mask_explicit(given, sizes, wrong, sizes[0], same)
+            assert int(r[-1]) == 1 and int(r[3].sum()) == wrong and int(r[4][len(sizes)]) == wrong
+
+
+def test_im2col_tokens_matches_per_modality_gather():
+    """the token-table im2col over all modalities against the per-modality visible-patch gather it replaces: each row holds
+    its token's patch in its modality's column block, the one-hot modality flag, and zeros elsewhere"""
+    B, P, H = 3, 8, 32
+    chans = (1, 3, 1)
+    g = torch.Generator().manual_seed(0)
+    imgs = [torch.randn(B, c, H, H, generator=g).cuda() for c in chans]
+    F_ = (H // P) ** 2
+    keep = [torch.tensor(sorted(torch.randperm(F_, generator=g)[:k].tolist()), dtype=torch.int32) for k in (5, 0, 9)]
+    tok = torch.cat([k + m * F_ for m, k in enumerate(keep)]).to(torch.int32).cuda()
+    nenc = tok.numel()
+    ks = [c * P * P for c in chans]
+    col_off = [0, ks[0], ks[0] + ks[1]]
+    ktot = sum(ks)
+    A = torch.full((B * nenc, ktot + 8), float("nan"), dtype=bf16, device="cuda")
+    K().im2col_tokens(imgs, tok, A, P, col_off, [0, F_, 2 * F_, 3 * F_], ktot)
+    want = torch.zeros(B, nenc, ktot + 8, dtype=bf16, device="cuda")
+    o = 0
+    for m, k in enumerate(keep):
+        if k.numel():
+            ref = torch.empty(B * k.numel(), ks[m], dtype=bf16, device="cuda")
+            K().im2col_gather(imgs[m], k.cuda(), ref, P)
+            want[:, o:o + k.numel(), col_off[m]:col_off[m] + ks[m]] = ref.view(B, k.numel(), ks[m])
+            want[:, o:o + k.numel(), ktot + m] = 1
+        o += k.numel()
+    assert torch.equal(A.view(B, nenc, -1), want)
