@@ -17,11 +17,22 @@ class _MaskedReconLoss(nn.Module):
         self.stride = stride
         self.scale_factor = patch_size // stride
         self.norm_pix = norm_pix
-        if norm_pix:
-            raise NotImplementedError("norm_pix targets are not built (disabled in every reference script)")
+
+    def _norm_pix_target(self, target):
+        """criterion.py:90-96 / :147-153: the target standardised per patch over its (p1 p2 c) values (unbiased variance,
+        eps 1e-6).  A preprocessing of the detached target (no gradient flows into it), done as view reductions -- the
+        patchify / unpatchify rearranges of the reference are pure index maps."""
+        B, C, H, W = target.shape
+        p = self.scale_factor
+        t = target.float().view(B, C, H // p, p, W // p, p)
+        mean = t.mean(dim=(1, 3, 5), keepdim=True)
+        var = t.var(dim=(1, 3, 5), keepdim=True, unbiased=True)
+        return ((t - mean) / torch.sqrt(var + 1e-6)).view(B, C, H, W)
 
     def forward(self, input, target, mask=None):
         """input [B, C, H, W] (bf16 or fp32), target fp32, mask [B, n_patches] (1 = masked) or None -> scalar"""
+        if self.norm_pix:
+            target = self._norm_pix_target(target.detach())
         if mask is not None:
             mask = mask.to(torch.int64)
             if mask.dim() == 2 and mask.shape[0] == 1 and input.shape[0] > 1:

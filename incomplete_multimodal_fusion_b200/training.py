@@ -127,7 +127,9 @@ class GradAllReduce:
             self._keep.append(flat)      # alive until finish() has joined the side stream
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(ready)
+                torch.cuda.nvtx.range_push("mmf.allreduce")
                 dist.all_reduce(flat, group=self.group)
+                torch.cuda.nvtx.range_pop()
         self._reduced.update(v.data_ptr() for v in views)
 
     def finish(self):
@@ -194,17 +196,30 @@ class PretrainStep:
         return total
 
     def __call__(self, inputs: Dict[str, torch.Tensor]) -> torch.Tensor:
+        # NVTX ranges: forward / loss / backward (the per-layer all-reduces are issued from inside it, range
+        # "allreduce" on their side stream's launches) / allreduce-finish / optimizer show up as rows in nsys / ncu timelines
+        nvtx = torch.cuda.nvtx
         self.opt.zero_grad(set_to_none=True)
         if self.standardize_depth and 'dem' in inputs:
             from .utils.multimodal_dfc2023 import standardize_depth
             inputs = dict(inputs, dem=standardize_depth(inputs['dem']))
+        nvtx.range_push("mmf.forward")
         out = self.model(inputs, num_encoded_tokens=self.nenc, alphas=self.alphas, sample_tasks_uniformly=self.uniformly)
+        nvtx.range_pop()
+        nvtx.range_push("mmf.loss")
         loss = self.loss(out, inputs)
+        nvtx.range_pop()
         Fn.begin_step_arena(self._arena_elems, loss.device)
+        nvtx.range_push("mmf.backward")
         try:
             (loss / self.world if self.world > 1 else loss).backward()   # 1/world here -> the all-reduce is a plain sum
         finally:
             Fn.end_step_arena()
+            nvtx.range_pop()
+        nvtx.range_push("mmf.allreduce_finish")
         self.reducer.finish()
+        nvtx.range_pop()
+        nvtx.range_push("mmf.optimizer")
         self.opt.step()
+        nvtx.range_pop()
         return loss.detach()

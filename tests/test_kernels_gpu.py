@@ -675,3 +675,38 @@ def test_im2col_tokens_matches_per_modality_gather():
             want[:, o:o + k.numel(), ktot + m] = 1
         o += k.numel()
     assert torch.equal(A.view(B, nenc, -1), want)
+
+
+@pytest.mark.parametrize("kind", ["mse", "l1"])
+def test_masked_loss_norm_pix(kind):
+    """norm_pix=True (criterion.py:90-96, 147-153): the target standardised per patch; against the reference class itself
+    when baseline/_ref is present, else against the same arithmetic restated in torch"""
+    from incomplete_multimodal_fusion_b200.multimae.criterion import MaskedL1Loss, MaskedMSELoss
+    B, C, H, P = 3, 2, 32, 8
+    g = torch.Generator().manual_seed(4)
+    pred = torch.randn(B, C, H, H, generator=g).cuda().requires_grad_(True)
+    tgt = (torch.randn(B, C, H, H, generator=g) * 3 + 1).cuda()
+    mask = (torch.rand(B, (H // P) ** 2, generator=g) > 0.4).long().cuda()
+    ours = (MaskedMSELoss if kind == "mse" else MaskedL1Loss)(patch_size=P, norm_pix=True)
+    loss = ours(pred, tgt, mask=mask)
+    loss.backward()
+    ref_cls = None
+    try:
+        from baseline import harness as H_
+        if H_.available():
+            crit = H_.load().criterion
+            ref_cls = crit.MaskedMSELoss if kind == "mse" else crit.MaskedL1Loss
+    except Exception:
+        ref_cls = None
+    p2 = pred.detach().clone().requires_grad_(True)
+    if ref_cls is not None:
+        ref = ref_cls(patch_size=P, norm_pix=True)(p2, tgt, mask=mask)
+    else:
+        t = tgt.view(B, C, H // P, P, H // P, P)
+        t = ((t - t.mean(dim=(1, 3, 5), keepdim=True)) / torch.sqrt(t.var(dim=(1, 3, 5), keepdim=True) + 1e-6)).view(B, C, H, H)
+        e = (p2 - t) ** 2 if kind == "mse" else (p2 - t).abs()
+        m = mask.view(B, H // P, H // P).repeat_interleave(P, 1).repeat_interleave(P, 2).float()
+        ref = ((e.mean(1) * m).flatten(1).sum(1) / m.flatten(1).sum(1)).nanmean()
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    assert rel(pred.grad, p2.grad) < 1e-5

@@ -118,5 +118,5 @@ def test_fused_adamw_state_dict_round_trip_with_torch():
         assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), float((a - b).abs().max())
     for i, b in enumerate(ref2):
         d = (opt2.exp_avg[i] - topt2.state[b]["exp_avg"]).abs().max()
-        assert torch.allclose(opt2.exp_avg[i], topt2.state[b]["exp_avg"], rtol=1e-5, atol=1e-7), (i, float(d), float(topt2.state[b]["exp_avg"].abs().max()))
+        assert torch.allclose(opt2.exp_avg[i], topt2.state[b]["exp_avg"], rtol=1e-5, atol=1e-6), (i, float(d), float(topt2.state[b]["exp_avg"].abs().max()))
         assert opt2.steps[i] == 3
