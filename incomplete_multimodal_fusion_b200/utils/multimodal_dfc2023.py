@@ -118,3 +118,142 @@ def standardize_depth(dem):
     if not dem.is_cuda:
         raise RuntimeError("standardize_depth: CUDA tensors only (no CPU fallback)")
     return K.trunc_standardize(dem.float().contiguous())
+
+
+# ------------------------------------------------------------------------------------------------
+# Host half: decode -> Dataset -> loader.  Reference: DFC2023 (multimodal_dfc2023.py:180-238) and the
+# DataLoader of pretrain_mmae.py:317-323.  The reference's __getitem__ decodes AND transforms each sample on the host
+# (5.4 ms of numpy / cv2 per sample); here __getitem__ only decodes and returns the RAW rasters (uint8 optical bands,
+# float32 backscatter / heights, at native size) plus the crop origin drawn by the reference's RandomCrop calls; the
+# loader stacks them into pinned host buffers, copies them to the GPU on a copy stream while the previous batch trains,
+# and one mmf_raster_prep launch per modality produces the fp32 {'s1', 's2', 'dem'} tensors the model reads.
+# ------------------------------------------------------------------------------------------------
+import glob
+import os
+
+
+def decode_tiff(path, first_band_only=False):
+    """(Geo)TIFF -> numpy [C, H, W] in the file's own dtype (what `rasterio.open(path).read()` returns).  rasterio is used
+    when it is installed; otherwise OpenCV's libtiff reader (uint8 / uint16 / float32, strips or tiles, LZW / deflate),
+    whose 3- and 4-channel results come back in BGR(A) order and are put back into file order."""
+    try:
+        import rasterio   # noqa: F401  (not in this image; the reference's decoder)
+        with rasterio.open(path) as data:
+            return data.read(1)[None] if first_band_only else data.read()
+    except ImportError:
+        pass
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise IOError("cannot decode %s" % path)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    elif img.shape[2] == 3:
+        img = img[:, :, ::-1]
+    elif img.shape[2] == 4:
+        img = img[:, :, [2, 1, 0, 3]]
+    img = np.ascontiguousarray(img.transpose(2, 0, 1))
+    return img[:1] if first_band_only else img
+
+
+class DFC2023(torch.utils.data.Dataset):
+    """The reference's dataset class (same constructor, same directory layout <path>/{rgb,sar,dsm,lc}/*.tiff, same sample
+    list order) returning RAW decoded rasters: {'rgb': uint8 [3, H, W], 'sar': float32 [1, H, W], 'dsm': float32
+    [1, H, W], 'id': name[, 'label': [H, W]][, 'crop': int32 [2] = (top, left)]}.  With transform=True the crop origin is
+    drawn here, per sample and in the reference's order (RandomCrop.__call__: top, then left, :66-73), so a single-process
+    loader consumes numpy's global RNG exactly like the reference's; the window itself is cut on the device."""
+
+    def __init__(self, path, use_rgb=True, use_sar=True, use_dsm=True, unlabeled=True, transform=False, crop_size=32):
+        super().__init__()
+        self.use_rgb, self.use_sar, self.use_dsm, self.unlabeled = use_rgb, use_sar, use_dsm, unlabeled
+        self.transform = RandomCrop(crop_size) if transform else None
+        assert os.path.exists(path)
+        self.samples = []
+        for rgb_loc in glob.glob(os.path.join(path, "rgb/*.tiff"), recursive=True):
+            s = {"rgb": rgb_loc, "sar": rgb_loc.replace("rgb", "sar"), "dsm": rgb_loc.replace("rgb", "dsm"), "id": os.path.basename(rgb_loc)}
+            if not unlabeled:
+                s["lc"] = rgb_loc.replace("rgb", "lc")
+            self.samples.append(s)
+
+    def __len__(self):
+        return len(self.samples)
+
+    def __getitem__(self, index):
+        s = self.samples[index]
+        out = {"id": s["id"]}
+        if self.use_rgb:
+            out["rgb"] = decode_tiff(s["rgb"])
+        if self.use_sar:
+            out["sar"] = decode_tiff(s["sar"]).astype(np.float32, copy=False)
+        if self.use_dsm:
+            out["dsm"] = decode_tiff(s["dsm"], first_band_only=True)
+        if not self.unlabeled:
+            out["label"] = decode_tiff(s["lc"], first_band_only=True)[0]
+        if self.transform is not None:
+            top, left = self.transform.draw(1)
+            out["crop"] = np.array([top[0], left[0]], np.int32)
+        return out
+
+
+class DeviceBatchLoader:
+    """pretrain_mmae.py:317-323 + :447-450 for raw batches: wraps a torch DataLoader over `DFC2023` (default collate, pinned
+    memory) and yields the reference's per-step dict {'s1', 's2', 'dem'[, 'label'], 'id'} of normalised fp32 CUDA tensors.
+    Batch i + 1 is copied host -> device on a copy stream into the other of two device buffer sets while batch i is in
+    use; the three mmf_raster_prep launches run on the consumer's stream."""
+
+    def __init__(self, dataset, batch_size, device="cuda", sampler=None, shuffle=False, num_workers=0, drop_last=True,
+                 use_rgb=True, use_sar=True, use_dsm=True):
+        self.dataset, self.device = dataset, torch.device(device)
+        self.use = dict(rgb=use_rgb, sar=use_sar, dsm=use_dsm)
+        self.crop_hw = dataset.transform.output_size if getattr(dataset, "transform", None) is not None else None
+        self.loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, sampler=sampler, shuffle=shuffle and sampler is None,
+                                                  num_workers=num_workers, pin_memory=True, drop_last=drop_last)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _upload(self, batch):
+        """pinned host batch -> device, asynchronously on the copy stream; returns (device tensors, ready event)"""
+        dev = {}
+        with torch.cuda.stream(self.copy_stream):
+            for k in ("rgb", "sar", "dsm", "label", "crop"):
+                if k in batch:
+                    dev[k] = batch[k].to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        dev["id"] = batch["id"]
+        return dev, ev
+
+    def _prepare(self, dev):
+        B = next(v for k, v in dev.items() if k in ("rgb", "sar", "dsm")).shape[0]
+        crop = None
+        if "crop" in dev and self.crop_hw is not None:
+            c = dev["crop"].to(torch.int32)
+            crop = (c[:, 0].contiguous(), c[:, 1].contiguous(), self.crop_hw)
+        out = prepare_rgb_sar_dsm({"rgb": dev.get("rgb"), "sar": dev.get("sar"), "dsm": dev.get("dsm")},
+                                  use_rgb="rgb" in dev, use_sar="sar" in dev, use_dsm="dsm" in dev, crop=crop)
+        out = {k: v for k, v in out.items() if v is not None}
+        if "label" in dev:
+            out["label"] = dev["label"]
+        out["id"] = dev["id"]
+        assert all(v.shape[0] == B for k, v in out.items() if torch.is_tensor(v))
+        return out
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._upload(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            dev, ev = nxt
+            try:
+                nxt = self._upload(next(it))       # the next batch's copy overlaps this batch's use
+            except StopIteration:
+                nxt = None
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            for v in dev.values():
+                if torch.is_tensor(v):
+                    v.record_stream(torch.cuda.current_stream(self.device))
+            yield self._prepare(dev)

@@ -148,3 +148,68 @@ def test_standardize_depth_matches_reference_expression(kind):
     assert float((got - want).abs().max()) <= 2e-5 * scale, (kind, float((got - want).abs().max()))
     ref32 = O.standardize_depth(dem)            # the reference's own fp32 arithmetic sits at the same distance
     assert float((got - ref32).abs().max()) <= 2e-4 * scale
+
+
+# ------------------------------------------------------------------------------------------------
+# host half: decode -> Dataset -> device loader (multimodal_dfc2023.py:180-238, pretrain_mmae.py:317-323)
+# ------------------------------------------------------------------------------------------------
+def _write_dataset(root, n, size, seed=0):
+    import cv2
+    rng = np.random.default_rng(seed)
+    raws = []
+    for sub in ("rgb", "sar", "dsm"):
+        os.makedirs(os.path.join(root, sub), exist_ok=True)
+    for i in range(n):
+        rgb = rng.integers(0, 256, (3, size, size), dtype=np.uint8)
+        sar = (rng.random((1, size, size), dtype=np.float32) * 2 + 1e-3).astype(np.float32)
+        dsm = (rng.random((1, size, size), dtype=np.float32) * 40).astype(np.float32)
+        name = "tile_%03d.tiff" % i
+        cv2.imwrite(os.path.join(root, "rgb", name), np.ascontiguousarray(rgb.transpose(1, 2, 0)[:, :, ::-1]))   # cv2 writes BGR
+        cv2.imwrite(os.path.join(root, "sar", name), sar[0])
+        cv2.imwrite(os.path.join(root, "dsm", name), dsm[0])
+        raws.append({"id": name, "rgb": rgb, "sar": sar, "dsm": dsm})
+    return {r["id"]: r for r in raws}
+
+
+def test_dataset_decodes_raw_rasters(tmp_path):
+    """DFC2023.__getitem__ returns the files' own values (uint8 optical bands in file order, float32 SAR / DSM) and the crop
+    origins the reference's RandomCrop would draw, in its order"""
+    from incomplete_multimodal_fusion_b200.utils import multimodal_dfc2023 as D
+    raws = _write_dataset(str(tmp_path), 3, 64)
+    ds = D.DFC2023(str(tmp_path), transform=True, crop_size=224)
+    assert len(ds) == 3
+    np.random.seed(5)
+    got = [ds[i] for i in range(3)]
+    np.random.seed(5)
+    for s in got:
+        r = raws[s["id"]]
+        assert s["rgb"].dtype == np.uint8 and np.array_equal(s["rgb"], r["rgb"])
+        assert s["sar"].dtype == np.float32 and np.array_equal(s["sar"], r["sar"])
+        assert s["dsm"].dtype == np.float32 and np.array_equal(s["dsm"], r["dsm"])
+        top, left = np.random.randint(0, 256 - 224), np.random.randint(0, 256 - 224)     # RandomCrop.__call__ :66-73
+        assert tuple(s["crop"]) == (top, left)
+
+
+@pytest.mark.gpu
+def test_device_loader_matches_reference_pipeline(tmp_path):
+    """decode -> pinned batch -> copy stream -> mmf_raster_prep, against the (golden-pinned) restatement of the reference's
+    load_rgb / load_sar / load_dsm + RandomCrop on the same files"""
+    from incomplete_multimodal_fusion_b200.utils import multimodal_dfc2023 as D
+    size, crop = 512, 224
+    raws = _write_dataset(str(tmp_path), 5, size, seed=3)
+    ds = D.DFC2023(str(tmp_path), transform=True, crop_size=crop)
+    loader = D.DeviceBatchLoader(ds, batch_size=2, drop_last=True)
+    np.random.seed(11)
+    batches = list(loader)
+    assert len(batches) == 2
+    np.random.seed(11)
+    for b in batches:
+        assert set(b) == {"s1", "s2", "dem", "id"} and b["s2"].shape == (2, 3, crop, crop) and b["s2"].dtype == torch.float32
+        for i, name in enumerate(b["id"]):
+            r = raws[name]
+            top, left = np.random.randint(0, 256 - crop), np.random.randint(0, 256 - crop)
+            want = {"s2": O.crop(O.load_rgb(r["rgb"]), top, left, (crop, crop)), "s1": O.crop(O.load_sar(r["sar"]), top, left, (crop, crop)),
+                    "dem": O.crop(O.load_dsm(r["dsm"]), top, left, (crop, crop))}
+            assert torch.equal(b["s2"][i].cpu(), torch.as_tensor(want["s2"]))                       # integer raster: bit-exact
+            assert float((b["s1"][i].cpu() - torch.as_tensor(want["s1"])).abs().max()) <= 2e-5
+            assert float((b["dem"][i].cpu() - torch.as_tensor(want["dem"])).abs().max()) <= 2e-5
