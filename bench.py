@@ -461,10 +461,18 @@ def run_ours(args):
     dom_key = max(pure, key=lambda k: pure[k][0]) if pure else None
     dom_t, dom_fl, dom_n = by_shape[dom_key] if dom_key else (0.0, 0.0, 0)
     achieved = dom_fl / (dom_t / 1e3) / 1e12 if dom_t > 0 else None
-    traffic = None
+    traffic = traffic_src = None
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tpath) and dom_key and dom_key[0] == "fwd_geglu":
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        # the ncu --set full capture of this launch is stamped with the sha256 of csrc/gemm.cu it was taken from: a capture
+        # of another kernel source is reported as stale instead of being passed off as this build's traffic
+        import hashlib
+        tj = json.load(open(tpath))
+        sha = hashlib.sha256(open(os.path.join(ROOT, "incomplete_multimodal_fusion_b200", "csrc", "gemm.cu"), "rb").read()).hexdigest()
+        fresh = tj.get("gemm_cu_sha256") == sha
+        traffic = tj.get("dram_bytes_per_launch") if fresh else None
+        traffic_src = {"file": "profiles/gemm_traffic.json", "captured_at_commit": tj.get("captured_at_commit"), "stale": not fresh,
+                       "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch")}
     result = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -479,7 +487,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor",
                      "kernel": "gemm2_tcgen05_kernel (cta_group::2 pair GEMM), launch %s M=%d N=%d K=%d" % dom_key if dom_key else None,
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["bf16_sustained"] if achieved else None, "traffic": traffic,
+                     "frac": achieved / pk["bf16_sustained"] if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                      "flops_per_launch": dom_fl / dom_n if dom_n else None, "ms_per_launch": dom_t / dom_n if dom_n else None,
                      "share_of_step": dom_t / ms_instr if ms_instr else None,
                      "timed_in": "instrumented pass of %d steps right after the timed region (%.1f ms/step with the per-launch events, %.1f without)" % (n_instr, ms_instr / n_instr, ms / args.steps),

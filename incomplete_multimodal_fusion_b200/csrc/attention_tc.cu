@@ -1639,6 +1639,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       };
       auto advance_s = [&]() { ++sg; if (++sj == nb) { sj = 0; ++sh; } };
       int used0 = 0, used1 = 0;   // completed waits on ds_full[0] / ds_full[1]
+#ifdef MMF_ATTN_CLOCKS
+      const bool dbg_on = (b == 3) && (c0 == 0) && lane == 0;
+      unsigned t_last = clock();
+      unsigned acc_clk[16] = {0};
+#endif
       issue_s(0);
       if (nvalid_of(0) > 32) issue_s(1);
       advance_s();                // the cursor now points at block 1
@@ -1653,9 +1658,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         for (int hf = 0; hf < 2; ++hf) {
           const int nvh = min(32, nvalid - 32 * hf);
           if (nvh > 0) {
+            CLK2(8, 0);
             if (hf == 0) { mbar_wait(&ds_full[0], used0 & 1); ++used0; } else { mbar_wait(&ds_full[1], used1 & 1); ++used1; }
+            CLK2(9, 0);
             if (j == 0 && hf == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);   // previous head's dV / dK have been read out
             tc_fence_after();
+            CLK2(10, 0);
             if (leader) {
               const int ksteps = (nvh + 15) >> 4;
               for (int k = 0; k < ksteps; ++k)   // dV += P^T . dO
@@ -1668,7 +1676,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
           }
           if (hf == 1 && leader) umma_commit(&qb_empty[st]);   // every MMA reading this Q / dO stage has been issued
           __syncwarp();
+          CLK2(11, 0);
           if (has_next && nvalid_next > 32 * hf) issue_s(hf);   // its columns are free: in-order tensor pipe
+          CLK2(12, 0);
         }
         if (has_next) advance_s();
         if (j + 1 == nb && leader) {
@@ -1678,6 +1688,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         __syncwarp();
         if (++j == nb) { j = 0; ++h; }
       }
+#ifdef MMF_ATTN_CLOCKS
+      if (dbg_on) for (int i = 8; i < 13; ++i) g_attn_clk[i] = acc_clk[i];
+#endif
     }
   } else {
     const int quarter = warp & 3;
@@ -1690,7 +1703,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
 #ifdef MMF_ATTN_CLOCKS
     const bool dbg_on = (b == 3) && (c0 == 0) && warp == 2 && lane == 0;   // first modality key tile of sample 3
     if (dbg_on) g_attn_clk[15] = (unsigned long long)qb.nb * p.H;
-    long long t_last = clock64();
+    unsigned t_last = clock();
+    unsigned acc_clk[16] = {0};
 #endif
     // lse*log2e and delta of a block's 64 query rows are staged in shared memory PER WARP (each warp keeps its own two
     // stages; lane l fetches rows l and l + 32), so the four elementwise warps never meet at a barrier.  The values of
@@ -1724,12 +1738,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         const int st = g & 1;
         int tok, nvalid; int64_t row;
         qb.get(j, tok, row, nvalid);
-        CLK(4, 0);
+        CLK2(4, 0);
         __syncwarp();   // this warp's stage st is complete (written at the end of the previous block), st^1 is free
         const int hn = (j + 1 < qb.nb) ? h : h + 1, jn = (j + 1 < qb.nb) ? j + 1 : 0;
         const bool stage_next = hn < p.H;
         if (stage_next) fetch(hn, jn);
-        CLK(5, 0);
+        CLK2(5, 0);
         const float* ls = w_lse + st * BW_BLK;
         const float* dl = w_dl + st * BW_BLK;
 #pragma unroll
@@ -1737,7 +1751,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
           if (nvalid <= 32 * c) continue;
           if (c == 0) { mbar_wait(&s_full[0], used0 & 1); ++used0; } else { mbar_wait(&s_full[1], used1 & 1); ++used1; }
           tc_fence_after();
-          CLK(0, 0);
+          CLK2(0, 0);
           tmem_ld_32x32(lane_addr + KV_ST + c * 32, rs);
           tmem_ld_32x32(lane_addr + KV_DPT + c * 32, rd);
           tmem_wait_ld();
@@ -1760,11 +1774,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ds_full[c]);
-          CLK(1, 0);
+          CLK2(1, 0);
         }
-        CLK(2, 0);
+        CLK2(2, 0);
         if (stage_next) stage(st ^ 1);
-        CLK(3, 0);
+        CLK2(3, 0);
       }
       if (qb.nb == 0) continue;
       mbar_wait(acc_full, h & 1);
@@ -1796,8 +1810,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
-      CLK(6, 0);
+      CLK2(6, 0);
     }
+#ifdef MMF_ATTN_CLOCKS
+    if (dbg_on) for (int i = 0; i < 7; ++i) g_attn_clk[i] = acc_clk[i];
+#endif
   }
   tc_fence_before();
   __syncthreads();

@@ -23,8 +23,10 @@ buf = (C.c_ulonglong * 16)()
 raw.mmf_debug_attn_clocks(buf, 1)
 f(); torch.cuda.synchronize()
 raw.mmf_debug_attn_clocks(buf, 0)
-names = ["wait s_full (both halves)", "ld + exp + pack + st + arrive (both halves)", "-", "stage next lse/delta", "loop top", "bar.sync + issue next lse/delta loads", "head epilogue (+wait acc)"]
+names = ["wait s_full (both halves)", "ld + exp + pack + st + arrive (both halves)", "-", "stage next lse/delta", "loop top", "bar.sync + issue next lse/delta loads", "head epilogue (+wait acc)",
+         "-", "mma: loop top / between halves", "mma: wait ds_full", "mma: acc_empty + fence", "mma: issue dV, dK (+commit)", "mma: issue next S^T, dP^T (+waits)"]
 tot = sum(buf[i] for i in range(7))
+print("mma warp instrumented total", sum(buf[i] for i in range(8, 13)))
 its = max(int(buf[15]), 1)
 print("one modality key-tile CTA of dK/dV, heads x query blocks = %d iterations; total cycles" % its, tot)
 for i, n in enumerate(names):
