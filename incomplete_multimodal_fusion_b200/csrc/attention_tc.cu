@@ -66,11 +66,6 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -1403,36 +1398,8 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     const int i = r0 + row_in_tile;
     const bool row_ok = i < r1;
     const bool warp_live = r0 + quarter * 32 < r1;
-    uint32_t rs[32];                           // (head epilogue)
-    uint32_t sa[16], da[16], sb[16], db[16];   // S / dP of the even / odd 16-key chunk in flight
+    uint32_t rs[32], rd[32];
     int g = 0;
-    bool pref = false;                         // the next chunk to process has already been requested
-    auto ld_chunk = [&](int q, uint32_t (&ss)[16], uint32_t (&dd)[16]) {
-      tmem_ld_32x16(lane_addr + DQ2_S + q * 16, ss);
-      tmem_ld_32x16(lane_addr + DQ2_DP + q * 16, dd);
-    };
-    auto try_half = [&](int c, int parity) -> bool {   // has s_full[c] completed that phase already?  (warp-uniform)
-      const bool ok = __shfl_sync(0xffffffffu, (int)mbar_try_wait(&s_full[c], parity), 0) != 0;
-      if (ok) tc_fence_after();
-      return ok;
-    };
-    auto compute_chunk = [&](int q, const uint32_t (&ss)[16], const uint32_t (&dd)[16], int nvalid, float lse2, float dl) {
-      uint32_t pk[8];
-      const int nvc = nvalid - 16 * q;     // valid keys in this chunk (>= 1 when called)
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float x0 = fmaf(__uint_as_float(ss[2 * t]), p.scale_log2, -lse2);
-        const float x1 = fmaf(__uint_as_float(ss[2 * t + 1]), p.scale_log2, -lse2);
-        float p0 = ((2 * t) & 3) < POLY ? exp2_poly(x0) : ex2(x0);
-        float p1 = ((2 * t + 1) & 3) < POLY ? exp2_poly(x1) : ex2(x1);
-        if (nvc < 16) {
-          if (2 * t >= nvc) p0 = 0.f;
-          if (2 * t + 1 >= nvc) p1 = 0.f;
-        }
-        pk[t] = pack_bf16(p0 * (__uint_as_float(dd[2 * t]) - dl) * p.scale, p1 * (__uint_as_float(dd[2 * t + 1]) - dl) * p.scale);
-      }
-      tmem_st_32x8(lane_addr + DQ2_S + (q >> 1) * 32 + (q & 1) * 8, pk);   // dS in place: 16 keys = 8 packed columns
-    };
     const int64_t stat0 = ((int64_t)b * p.H + h0) * p.N + (row_ok ? i : r0);
     float lse_raw = p.lse[stat0], dl_raw = p.delta[stat0];
     for (int h = 0; h < nh; ++h) {
@@ -1445,60 +1412,35 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       for (int j = 0; j < kb.nb; ++j, ++g) {
         int tok, nvalid; int64_t row;
         kb.get(j, tok, row, nvalid);
-        // four 16-key chunks through a two-deep register pipeline (see attn_bwd_dkv_tc_kernel): the tcgen05.ld of the next
-        // chunk is in flight during the arithmetic of the current one
-        if (!warp_live) {
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            mbar_wait(&s_full[hf], g & 1);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ds_full[hf]);
+        for (int hf = 0; hf < 2; ++hf) {
+          const int nvh = min(32, nvalid - 32 * hf);
+          mbar_wait(&s_full[hf], g & 1);
+          if (warp_live && nvh > 0) {
+            tc_fence_after();
+            tmem_ld_32x32(lane_addr + DQ2_S + hf * 32, rs);
+            tmem_ld_32x32(lane_addr + DQ2_DP + hf * 32, rd);
+            tmem_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const float x0 = fmaf(__uint_as_float(rs[2 * t]), p.scale_log2, -lse2);
+              const float x1 = fmaf(__uint_as_float(rs[2 * t + 1]), p.scale_log2, -lse2);
+              float p0 = ((2 * t) & 3) < POLY ? exp2_poly(x0) : ex2(x0);
+              float p1 = ((2 * t + 1) & 3) < POLY ? exp2_poly(x1) : ex2(x1);
+              if (nvh < 32) {
+                if (2 * t >= nvh) p0 = 0.f;
+                if (2 * t + 1 >= nvh) p1 = 0.f;
+              }
+              pk[t] = pack_bf16(p0 * (__uint_as_float(rd[2 * t]) - dl) * p.scale, p1 * (__uint_as_float(rd[2 * t + 1]) - dl) * p.scale);
+            }
+            tmem_st_32x16(lane_addr + DQ2_S + hf * 32, pk);
+            tmem_wait_st();
           }
-          continue;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ds_full[hf]);
         }
-        if (!pref) {
-          mbar_wait(&s_full[0], g & 1);
-          tc_fence_after();
-          ld_chunk(0, sa, da);
-        }
-        tmem_wait_ld();
-        if (nvalid > 16) ld_chunk(1, sb, db);
-        compute_chunk(0, sa, da, nvalid, lse2, dl);
-        if (nvalid > 16) {
-          tmem_wait_ld();
-          pref = nvalid > 32 && try_half(1, g & 1);
-          if (pref) ld_chunk(2, sa, da);
-          compute_chunk(1, sb, db, nvalid, lse2, dl);
-        } else {
-          pref = false;
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ds_full[0]);
-        // half B: its barriers complete once per block whether or not it holds keys
-        if (!pref) {
-          mbar_wait(&s_full[1], g & 1);
-          tc_fence_after();
-          if (nvalid > 32) ld_chunk(2, sa, da);
-        }
-        if (nvalid > 32) {
-          tmem_wait_ld();
-          if (nvalid > 48) ld_chunk(3, sb, db);
-          compute_chunk(2, sa, da, nvalid, lse2, dl);
-        }
-        pref = false;
-        if (nvalid > 48) {
-          tmem_wait_ld();
-          pref = g + 1 < total && try_half(0, (g + 1) & 1);
-          if (pref) ld_chunk(0, sa, da);
-          compute_chunk(3, sb, db, nvalid, lse2, dl);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ds_full[1]);
       }
       mbar_wait(acc_full, h & 1);
       tc_fence_after();
@@ -1732,19 +1674,18 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
                              (j > 0) || (hf > 0) || (k > 0));
             }
           }
-          if (hf == 1 && leader) {
-            umma_commit(&qb_empty[st]);   // every MMA reading this Q / dO stage has been issued
-            if (j + 1 == nb) {             // head complete: committed BEFORE the next head's S^T / dP^T are issued, so that
-              umma_commit(acc_full);       // the epilogue waits for this head's MMAs only
-              umma_commit(&kvt_empty[h & 1]);
-            }
-          }
+          if (hf == 1 && leader) umma_commit(&qb_empty[st]);   // every MMA reading this Q / dO stage has been issued
           __syncwarp();
           CLK2(11, 0);
           if (has_next && nvalid_next > 32 * hf) issue_s(hf);   // its columns are free: in-order tensor pipe
           CLK2(12, 0);
         }
         if (has_next) advance_s();
+        if (j + 1 == nb && leader) {
+          umma_commit(acc_full);
+          umma_commit(&kvt_empty[h & 1]);
+        }
+        __syncwarp();
         if (++j == nb) { j = 0; ++h; }
       }
 #ifdef MMF_ATTN_CLOCKS
@@ -1756,8 +1697,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
     const int row_in_tile = quarter * 32 + lane;      // key row of this thread
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const bool key_ok = c0 + row_in_tile < c1;
-    uint32_t rs[32], rd[32];      // (head epilogue)
-    uint32_t sa[16], da[16], sb[16], db[16];   // S^T / dP^T of the even / odd 16-query chunk in flight
+    uint32_t rs[32], rd[32];
     int g = 0;
     int used0 = 0, used1 = 0;   // completed waits on s_full[0] / s_full[1]
 #ifdef MMF_ATTN_CLOCKS
@@ -1778,10 +1718,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
     auto fetch = [&](int hh, int jj) {
       int tok, nvalid; int64_t row;
       qb.get(jj, tok, row, nvalid);
-      const int64_t sb_ = ((int64_t)b * p.H + hh) * p.N + tok;
+      const int64_t sb = ((int64_t)b * p.H + hh) * p.N + tok;
       nok0 = lane < nvalid; nok1 = lane + 32 < nvalid;
-      nl0 = p.lse[sb_ + (nok0 ? lane : 0)]; nd0 = p.delta[sb_ + (nok0 ? lane : 0)];
-      nl1 = p.lse[sb_ + (nok1 ? lane + 32 : 0)]; nd1 = p.delta[sb_ + (nok1 ? lane + 32 : 0)];
+      nl0 = p.lse[sb + (nok0 ? lane : 0)]; nd0 = p.delta[sb + (nok0 ? lane : 0)];
+      nl1 = p.lse[sb + (nok1 ? lane + 32 : 0)]; nd1 = p.delta[sb + (nok1 ? lane + 32 : 0)];
     };
     auto stage = [&](int stg) {
       w_lse[stg * BW_BLK + lane] = nok0 ? nl0 * 1.4426950408889634f : INFINITY;        // +inf beyond nvalid -> P = 0
@@ -1793,38 +1733,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       fetch(0, 0);
       stage(0);
     }
-    // Round 2: the block is processed as four 16-query CHUNKS through a two-deep register pipeline: the tcgen05.ld of chunk
-    // q+1 is issued before the arithmetic of chunk q, so the TMEM read latency (the ld -> wait::ld -> use round trip was
-    // ~45 % of the 1555 clk a block cost these warps, profiles/r02_attn_dkv_phase_clocks.txt) overlaps the exponentials.
-    // A chunk of the next half / next block is prefetched only if its s_full phase has already completed (non-blocking
-    // test, made warp-uniform: tcgen05.ld is warp-wide); otherwise it is loaded after the blocking wait as before.
-    bool pref = false;   // the next chunk to process has already been requested
-    auto ld_chunk = [&](int q, uint32_t (&ss)[16], uint32_t (&dd)[16]) {
-      tmem_ld_32x16(lane_addr + KV_ST + q * 16, ss);
-      tmem_ld_32x16(lane_addr + KV_DPT + q * 16, dd);
-    };
-    auto try_half = [&](int c) -> bool {   // has s_full[c]'s next phase completed?  (consumes it if so)
-      const bool ok = __shfl_sync(0xffffffffu, (int)mbar_try_wait(&s_full[c], (c == 0 ? used0 : used1) & 1), 0) != 0;
-      if (ok) { if (c == 0) ++used0; else ++used1; tc_fence_after(); }
-      return ok;
-    };
-    auto compute_chunk = [&](int q, const uint32_t (&ss)[16], const uint32_t (&dd)[16], const float* ls, const float* dl) {
-      uint32_t pk[8], dk_[8];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {   // four query columns per step: one 16-byte broadcast read of lse and of delta
-        const float4 l4 = reinterpret_cast<const float4*>(ls)[q * 4 + t], d4 = reinterpret_cast<const float4*>(dl)[q * 4 + t];
-        const float p0 = ex2(fmaf(__uint_as_float(ss[4 * t]), p.scale_log2, -l4.x));        // lse = +inf beyond nvalid -> 0
-        const float p1 = ex2(fmaf(__uint_as_float(ss[4 * t + 1]), p.scale_log2, -l4.y));
-        const float p2 = ex2(fmaf(__uint_as_float(ss[4 * t + 2]), p.scale_log2, -l4.z));
-        const float p3 = ex2(fmaf(__uint_as_float(ss[4 * t + 3]), p.scale_log2, -l4.w));
-        pk[2 * t] = pack_bf16(p0, p1);
-        pk[2 * t + 1] = pack_bf16(p2, p3);
-        dk_[2 * t] = pack_bf16(p0 * (__uint_as_float(dd[4 * t]) - d4.x), p1 * (__uint_as_float(dd[4 * t + 1]) - d4.y));
-        dk_[2 * t + 1] = pack_bf16(p2 * (__uint_as_float(dd[4 * t + 2]) - d4.z), p3 * (__uint_as_float(dd[4 * t + 3]) - d4.w));
-      }
-      tmem_st_32x8(lane_addr + KV_ST + (q >> 1) * 32 + (q & 1) * 8, pk);     // P^T in place: 16 queries = 8 packed columns
-      tmem_st_32x8(lane_addr + KV_DPT + (q >> 1) * 32 + (q & 1) * 8, dk_);   // dS^T in place over its dP^T columns
-    };
     for (int h = 0; h < p.H; ++h) {
       for (int j = 0; j < qb.nb; ++j, ++g) {
         const int st = g & 1;
@@ -1838,48 +1746,35 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         CLK2(5, 0);
         const float* ls = w_lse + st * BW_BLK;
         const float* dl = w_dl + st * BW_BLK;
-        // ---- chunk 0 (half A; always present) ----
-        if (!pref) {
-          mbar_wait(&s_full[0], used0 & 1); ++used0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {   // the block's two 32-query halves (see the MMA warp)
+          if (nvalid <= 32 * c) continue;
+          if (c == 0) { mbar_wait(&s_full[0], used0 & 1); ++used0; } else { mbar_wait(&s_full[1], used1 & 1); ++used1; }
           tc_fence_after();
-          ld_chunk(0, sa, da);
-        }
-        CLK2(0, 0);
-        tmem_wait_ld();
-        ld_chunk(1, sb, db);                       // same half: its S^T / dP^T are complete too (N = 32 whatever nvalid)
-        compute_chunk(0, sa, da, ls, dl);
-        // ---- chunk 1 ----
-        tmem_wait_ld();
-        pref = nvalid > 32 && try_half(1);
-        if (pref) ld_chunk(2, sa, da);
-        compute_chunk(1, sb, db, ls, dl);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ds_full[0]);
-        CLK2(1, 0);
-        if (nvalid > 32) {
-          // ---- chunk 2 (half B) ----
-          if (!pref) {
-            mbar_wait(&s_full[1], used1 & 1); ++used1;
-            tc_fence_after();
-            ld_chunk(2, sa, da);
+          CLK2(0, 0);
+          tmem_ld_32x32(lane_addr + KV_ST + c * 32, rs);
+          tmem_ld_32x32(lane_addr + KV_DPT + c * 32, rd);
+          tmem_wait_ld();
+          uint32_t pk[16], dk_[16];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {   // four query columns per step: one 16-byte broadcast read of lse and of delta
+            const float4 l4 = reinterpret_cast<const float4*>(ls)[c * 8 + t], d4 = reinterpret_cast<const float4*>(dl)[c * 8 + t];
+            const float p0 = ex2(fmaf(__uint_as_float(rs[4 * t]), p.scale_log2, -l4.x));        // lse = +inf beyond nvalid -> 0
+            const float p1 = ex2(fmaf(__uint_as_float(rs[4 * t + 1]), p.scale_log2, -l4.y));
+            const float p2 = ex2(fmaf(__uint_as_float(rs[4 * t + 2]), p.scale_log2, -l4.z));
+            const float p3 = ex2(fmaf(__uint_as_float(rs[4 * t + 3]), p.scale_log2, -l4.w));
+            pk[2 * t] = pack_bf16(p0, p1);
+            pk[2 * t + 1] = pack_bf16(p2, p3);
+            dk_[2 * t] = pack_bf16(p0 * (__uint_as_float(rd[4 * t]) - d4.x), p1 * (__uint_as_float(rd[4 * t + 1]) - d4.y));
+            dk_[2 * t + 1] = pack_bf16(p2 * (__uint_as_float(rd[4 * t + 2]) - d4.z), p3 * (__uint_as_float(rd[4 * t + 3]) - d4.w));
           }
-          tmem_wait_ld();
-          ld_chunk(3, sb, db);
-          compute_chunk(2, sa, da, ls, dl);
-          // ---- chunk 3 ----
-          tmem_wait_ld();
-          pref = (j + 1 < qb.nb || h + 1 < p.H) && try_half(0);     // first chunk of the next block
-          if (pref) ld_chunk(0, sa, da);
-          compute_chunk(3, sb, db, ls, dl);
+          tmem_st_32x16(lane_addr + KV_ST + c * 32, pk);     // P^T in place over the half's consumed S^T columns
+          tmem_st_32x16(lane_addr + KV_DPT + c * 32, dk_);   // dS^T in place over its dP^T columns
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ds_full[1]);
+          if (lane == 0) mbar_arrive(&ds_full[c]);
           CLK2(1, 0);
-        } else {
-          pref = false;
         }
         CLK2(2, 0);
         if (stage_next) stage(st ^ 1);
