@@ -1203,7 +1203,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 //   dQ += dS_A(g).K_A,  S_A / dP_A (g+1),  dQ += dS_B(g).K_B,  S_B / dP_B (g+1), ...
 // so the tensor pipe works on one half while the elementwise warps work on the other.  Every barrier completes exactly
 // once per block (phase parity = g & 1).  TMEM: S_A | S_B | dP_A | dP_B | dQ = 192 of 256 allocated columns.
-constexpr uint32_t DQ2_S = 0, DQ2_DP = 64, DQ2_ACC = 128;
+constexpr uint32_t DQ2_HALF = 64, DQ2_DP_OFF = 32, DQ2_ACC = 128;   // half hf: S at 64 hf, dP at 64 hf + 32 (one 64-column TMEM read)
 
 template <int KVST, int POLY>
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -1348,9 +1348,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           const uint64_t kd = dk0 + (uint64_t)(sst * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
           const uint64_t vd = dv0 + (uint64_t)(sst * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tm + DQ2_S + hf * 32, qd + 2 * k, kd + 2 * k, idesc, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16(tm + hf * DQ2_HALF, qd + 2 * k, kd + 2 * k, idesc, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tm + DQ2_DP + hf * 32, od + 2 * k, vd + 2 * k, idesc, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16(tm + hf * DQ2_HALF + DQ2_DP_OFF, od + 2 * k, vd + 2 * k, idesc, k > 0);
         }
         if (leader) {
           umma_commit(&s_full[hf]);
@@ -1377,7 +1377,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           if (leader) {
             const int ksteps = nvh > 0 ? (nvh + 15) >> 4 : 0;
             for (int k = 0; k < ksteps; ++k)
-              umma_bf16_ts(tm + DQ2_ACC, tm + DQ2_S + hf * 32 + k * 8, kd + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
+              umma_bf16_ts(tm + DQ2_ACC, tm + hf * DQ2_HALF + k * 8, kd + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
                            (j > 0) || (hf > 0) || (k > 0));
             if (hf == 1) {
               umma_commit(&kv_empty[st]);
@@ -1418,23 +1418,23 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
           mbar_wait(&s_full[hf], g & 1);
           if (warp_live && nvh > 0) {
             tc_fence_after();
-            tmem_ld_32x32(lane_addr + DQ2_S + hf * 32, rs);
-            tmem_ld_32x32(lane_addr + DQ2_DP + hf * 32, rd);
+            uint32_t sd[64];                             // S (0..31) | dP (32..63) of the half, one TMEM read
+            tmem_ld_32x64(lane_addr + hf * DQ2_HALF, sd);
             tmem_wait_ld();
             uint32_t pk[16];
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
-              const float x0 = fmaf(__uint_as_float(rs[2 * t]), p.scale_log2, -lse2);
-              const float x1 = fmaf(__uint_as_float(rs[2 * t + 1]), p.scale_log2, -lse2);
+              const float x0 = fmaf(__uint_as_float(sd[2 * t]), p.scale_log2, -lse2);
+              const float x1 = fmaf(__uint_as_float(sd[2 * t + 1]), p.scale_log2, -lse2);
               float p0 = ((2 * t) & 3) < POLY ? exp2_poly(x0) : ex2(x0);
               float p1 = ((2 * t + 1) & 3) < POLY ? exp2_poly(x1) : ex2(x1);
               if (nvh < 32) {
                 if (2 * t >= nvh) p0 = 0.f;
                 if (2 * t + 1 >= nvh) p1 = 0.f;
               }
-              pk[t] = pack_bf16(p0 * (__uint_as_float(rd[2 * t]) - dl) * p.scale, p1 * (__uint_as_float(rd[2 * t + 1]) - dl) * p.scale);
+              pk[t] = pack_bf16(p0 * (__uint_as_float(sd[32 + 2 * t]) - dl) * p.scale, p1 * (__uint_as_float(sd[32 + 2 * t + 1]) - dl) * p.scale);
             }
-            tmem_st_32x16(lane_addr + DQ2_S + hf * 32, pk);
+            tmem_st_32x16(lane_addr + hf * DQ2_HALF, pk);
             tmem_wait_st();
           }
           tc_fence_before();
@@ -1475,7 +1475,10 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 }
 
 // ---------------------------------------- dK, dV ----------------------------------------
-constexpr uint32_t KV_ST = 0, KV_DPT = 64, KV_DV = 128, KV_DK = 192;   // P^T aliases S^T, dS^T aliases dP^T
+// Round 2: a half's S^T and dP^T are ADJACENT (half c: S^T at 64c, dP^T at 64c + 32), so the elementwise warps fetch both with
+// one 64-column tcgen05.ld and return P^T (64c .. +15) and dS^T (64c + 16 .. +31) with one 32-column tcgen05.st: the TMEM
+// instructions carry a large fixed cost (splitting them further was measured 1.75x SLOWER, profiles/r02_attn_*chunked16*).
+constexpr uint32_t KV_HALF = 64, KV_DPT_OFF = 32, KV_DS_OFF = 16, KV_DV = 128, KV_DK = 192;
 constexpr int DKV_SMEM = 4 * TC_TILE_BYTES + 4 * BW_BLK_BYTES + 4 * 2 * 2 * BW_BLK * 4 + 1024 + 256;   // + per-warp lse / delta stages
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -1630,9 +1633,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
           const uint64_t qd = dq0 + (uint64_t)(st * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
           const uint64_t od = ddo0 + (uint64_t)(st * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tm + KV_ST + hf * 32, kd + 2 * k, qd + 2 * k, idesc, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16(tm + hf * KV_HALF, kd + 2 * k, qd + 2 * k, idesc, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tm + KV_DPT + hf * 32, vd + 2 * k, od + 2 * k, idesc, k > 0);
+          for (int k = 0; k < 4; ++k) umma_bf16(tm + hf * KV_HALF + KV_DPT_OFF, vd + 2 * k, od + 2 * k, idesc, k > 0);
           umma_commit(&s_full[hf]);
         }
         __syncwarp();
@@ -1667,10 +1670,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
             if (leader) {
               const int ksteps = (nvh + 15) >> 4;
               for (int k = 0; k < ksteps; ++k)   // dV += P^T . dO
-                umma_bf16_ts(tm + KV_DV, tm + KV_ST + hf * 32 + k * 8, od + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
+                umma_bf16_ts(tm + KV_DV, tm + hf * KV_HALF + k * 8, od + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
                              (j > 0) || (hf > 0) || (k > 0));
               for (int k = 0; k < ksteps; ++k)   // dK += dS^T . Q
-                umma_bf16_ts(tm + KV_DK, tm + KV_DPT + hf * 32 + k * 8, qd + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
+                umma_bf16_ts(tm + KV_DK, tm + hf * KV_HALF + KV_DS_OFF + k * 8, qd + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
                              (j > 0) || (hf > 0) || (k > 0));
             }
           }
@@ -1752,24 +1755,23 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
           if (c == 0) { mbar_wait(&s_full[0], used0 & 1); ++used0; } else { mbar_wait(&s_full[1], used1 & 1); ++used1; }
           tc_fence_after();
           CLK2(0, 0);
-          tmem_ld_32x32(lane_addr + KV_ST + c * 32, rs);
-          tmem_ld_32x32(lane_addr + KV_DPT + c * 32, rd);
+          uint32_t sd[64];                               // S^T (0..31) | dP^T (32..63) of the half, one TMEM read
+          tmem_ld_32x64(lane_addr + c * KV_HALF, sd);
           tmem_wait_ld();
-          uint32_t pk[16], dk_[16];
+          uint32_t pd[32];                               // P^T (0..15) | dS^T (16..31), one TMEM write
 #pragma unroll
           for (int t = 0; t < 8; ++t) {   // four query columns per step: one 16-byte broadcast read of lse and of delta
             const float4 l4 = reinterpret_cast<const float4*>(ls)[c * 8 + t], d4 = reinterpret_cast<const float4*>(dl)[c * 8 + t];
-            const float p0 = ex2(fmaf(__uint_as_float(rs[4 * t]), p.scale_log2, -l4.x));        // lse = +inf beyond nvalid -> 0
-            const float p1 = ex2(fmaf(__uint_as_float(rs[4 * t + 1]), p.scale_log2, -l4.y));
-            const float p2 = ex2(fmaf(__uint_as_float(rs[4 * t + 2]), p.scale_log2, -l4.z));
-            const float p3 = ex2(fmaf(__uint_as_float(rs[4 * t + 3]), p.scale_log2, -l4.w));
-            pk[2 * t] = pack_bf16(p0, p1);
-            pk[2 * t + 1] = pack_bf16(p2, p3);
-            dk_[2 * t] = pack_bf16(p0 * (__uint_as_float(rd[4 * t]) - d4.x), p1 * (__uint_as_float(rd[4 * t + 1]) - d4.y));
-            dk_[2 * t + 1] = pack_bf16(p2 * (__uint_as_float(rd[4 * t + 2]) - d4.z), p3 * (__uint_as_float(rd[4 * t + 3]) - d4.w));
+            const float p0 = ex2(fmaf(__uint_as_float(sd[4 * t]), p.scale_log2, -l4.x));        // lse = +inf beyond nvalid -> 0
+            const float p1 = ex2(fmaf(__uint_as_float(sd[4 * t + 1]), p.scale_log2, -l4.y));
+            const float p2 = ex2(fmaf(__uint_as_float(sd[4 * t + 2]), p.scale_log2, -l4.z));
+            const float p3 = ex2(fmaf(__uint_as_float(sd[4 * t + 3]), p.scale_log2, -l4.w));
+            pd[2 * t] = pack_bf16(p0, p1);
+            pd[2 * t + 1] = pack_bf16(p2, p3);
+            pd[16 + 2 * t] = pack_bf16(p0 * (__uint_as_float(sd[32 + 4 * t]) - d4.x), p1 * (__uint_as_float(sd[32 + 4 * t + 1]) - d4.y));
+            pd[16 + 2 * t + 1] = pack_bf16(p2 * (__uint_as_float(sd[32 + 4 * t + 2]) - d4.z), p3 * (__uint_as_float(sd[32 + 4 * t + 3]) - d4.w));
           }
-          tmem_st_32x16(lane_addr + KV_ST + c * 32, pk);     // P^T in place over the half's consumed S^T columns
-          tmem_st_32x16(lane_addr + KV_DPT + c * 32, dk_);   // dS^T in place over its dP^T columns
+          tmem_st_32x32(lane_addr + c * KV_HALF, pd);    // in place over the half's consumed S^T columns
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
