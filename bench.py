@@ -311,6 +311,8 @@ def run_ours(args):
     if world > 1:
         for p in model.parameters():
             dist.broadcast(p.data, 0)
+        from incomplete_multimodal_fusion_b200 import functions as _fn
+        _fn.invalidate_weight_cache()          # (writes through .data bypass the version counters the cache is stamped on)
     step = PretrainStep(model, num_encoded_tokens=args.nenc, patch_size=16, global_batch=args.batch * world)
     host = synthetic_batch(args.batch, args.image, 1234 + rank, pin=True)
     x = {k: v.to(dev) for k, v in host.items()}

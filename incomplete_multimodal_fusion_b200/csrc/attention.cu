@@ -599,11 +599,12 @@ extern "C" int mmf_attn_bwd(const MmfAttnArgs* a, mmf_stream_t stream) {
   }
   const int smem_dq = 6 * 64 * a->dh * 2, smem_dkv = 6 * 64 * a->dh * 2 + 4 * 64 * 4;
   if (a->dh == 64) {
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    const int attr_dev = current_device();
+    if (!attr.done(attr_dev)) {
       cudaFuncSetAttribute(attn_bwd_dq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
       cudaFuncSetAttribute(attn_bwd_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
-      attr = true;
+      attr.set(attr_dev);
     }
     attn_delta_kernel<64><<<dgrid, 256, 0, st>>>(p);
     attn_bwd_dq_kernel<64><<<dim3(qtiles, a->H, a->B), ATT_THREADS, smem_dq, st>>>(p);

@@ -20,6 +20,20 @@ namespace mmf {
     if (e__ != cudaSuccess) return (int)e__;     \
   } while (0)
 
+// Function attributes (dynamic shared-memory limit, carve-out) and the SM count belong to a DEVICE, not to the process:
+// a `static bool done` guard would leave a second GPU used by the same process with the default 48 KB limit.  One bit
+// per device ordinal, set after the attributes have been applied on that device (thread-safe: atomic or / acquire load).
+struct DeviceOnce {
+  unsigned long long bits_ = 0;
+  bool done(int dev) const { return (__atomic_load_n(&bits_, __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull; }
+  void set(int dev) { __atomic_fetch_or(&bits_, 1ull << (dev & 63), __ATOMIC_RELEASE); }
+};
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+
 __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -1005,14 +1005,15 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t c
   return r == CUDA_SUCCESS ? 0 : 2000 + (int)r;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+static int num_sms() {     // per device (a process may drive more than one GPU)
+  static int n[64] = {0};
+  const int dev = current_device() & 63;
+  int v = __atomic_load_n(&n[dev], __ATOMIC_RELAXED);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    __atomic_store_n(&n[dev], v, __ATOMIC_RELAXED);
   }
-  return n;
+  return v;
 }
 
 template <int BLOCK_N, int EPI>
@@ -1051,12 +1052,13 @@ static int launch_gemm(const MmfGemmArgs& a, cudaStream_t stream) {
               (!a.residual2 || al16(a.residual2)) && (!a.bias || al16(a.bias)) && (!a.out2 || (a.ldo2 % 4 == 0 && al16(a.out2))) &&
               (a.act != 2 || a.N % 4 == 0);
 
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
+  const int attr_dev = current_device();
   auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI>;
-  if (!attr_set) {
+  if (!attr_once.done(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_once.set(attr_dev);
   }
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.split_k;
   const int grid = (int)(total < num_sms() ? total : num_sms());
@@ -1111,13 +1113,14 @@ static int launch_gemm2(const MmfGemmArgs& a, cudaStream_t stream) {
     }
   }
 
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
+  const int attr_dev = current_device();
   auto kern = gemm2_tcgen05_kernel<EPI, TS>;
   constexpr int SMEM = G2Cfg<EPI, TS>::SMEM_BYTES;
-  if (!attr_set) {
+  if (!attr_once.done(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_once.set(attr_dev);
   }
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.split_k;
   int max_clusters = (num_sms() - g_reserved_sms.load(std::memory_order_relaxed)) / 2;

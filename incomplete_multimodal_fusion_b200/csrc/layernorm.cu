@@ -438,11 +438,12 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
   const bool early = variant != 0 && nc <= 6;
 #define MMF_LN_BWD_LAUNCH(NCV, E, F, HBV)                                                                                       \
   do {                                                                                                                    \
-    static bool attr_done = false;                                                                                        \
-    if (!attr_done) {                                                                                                     \
+    static DeviceOnce attr_done;                                                                                          \
+    const int attr_dev = current_device();                                                                                \
+    if (!attr_done.done(attr_dev)) {                                                                                      \
       cudaFuncSetAttribute(ln_bwd_kernel<NCV, E, F, HBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_WARPS * NCV * 32 * 16); \
       cudaFuncSetAttribute(ln_bwd_kernel<NCV, E, F, HBV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-      attr_done = true;                                                                                                   \
+      attr_done.set(attr_dev);                                                                                            \
     }                                                                                                                     \
     ln_bwd_kernel<NCV, E, F, HBV><<<ln_grid(ln_bwd_kernel<NCV, E, F, HBV>, smem, rows), LN_WARPS * 32, smem, st>>>(p);               \
   } while (0)

@@ -378,11 +378,12 @@ extern "C" int mmf_trunc_standardize(const float* x, float* out, int64_t batch, 
   const size_t smem = (size_t)n * sizeof(float);
   if (n <= 1 || smem > 220 * 1024) MMF_BAD_ARG(2);      // the sample lives in shared memory
   if (k_lo < 0 || k_hi > n || k_hi - k_lo < 2) MMF_BAD_ARG(3);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;
+  const int attr_dev = current_device();
+  if (!attr_done.done(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(trunc_standardize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done.set(attr_dev);
   }
   trunc_standardize_kernel<<<(unsigned)batch, TRUNC_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, n, k_lo, k_hi);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);

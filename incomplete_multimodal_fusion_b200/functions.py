@@ -54,6 +54,14 @@ class _WeightCache:
 
 WEIGHTS = _WeightCache()
 
+
+def invalidate_weight_cache():
+    """Drop every cached bf16 weight image.  The cache is stamped on (data_ptr, Tensor._version): writes that bypass the
+    version counter -- `p.data.copy_()`, `dist.broadcast(p.data, ..)`, EMA / weight surgery through `.data`, a foreign fused
+    optimiser -- must be followed by this call (torch optimisers do it through a step hook, `load_state_dict` through the
+    model's post hook, see MultiMAEBase.__init__), or the GEMMs keep reading the old images."""
+    WEIGHTS.clear()
+
 # torch's fused optimisers (observed: AdamW(fused=True), torch 2.11) update parameters WITHOUT bumping their version
 # counters, so version stamps alone would keep serving the pre-update images.  Any torch optimiser step therefore drops
 # the cache; `optim.FusedAdamW` (not a torch Optimizer) refreshes the images itself and re-stamps them instead.
@@ -894,6 +902,9 @@ class EncoderStackFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dX, *dtaps):
+        if ctx.saved is None:
+            raise RuntimeError("EncoderStackFn.backward ran twice: the encoder stack frees each layer's activations as its "
+                               "backward consumes them (retain_graph is not supported through this node)")
         meta, saved, params = ctx.meta, ctx.saved, ctx.params
         tap_grad = {i: g for i, g in zip(ctx.taps, dtaps) if g is not None}
         B, D, H, Fn, nenc, fusion = meta["B"], meta["D"], meta["H"], meta["F"], meta["nenc"], meta["fusion"]

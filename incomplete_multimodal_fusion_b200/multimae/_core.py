@@ -114,6 +114,8 @@ class MultiMAEBase(nn.Module):
                                            norm_layer=norm_layer) for _ in range(depth)])
         self.norm = LayerNorm(dim_tokens)
         self._init_parameters()
+        # loading a checkpoint writes the parameters in place: drop the bf16 weight images cached from the old values
+        self.register_load_state_dict_post_hook(lambda module, incompatible: Fn.invalidate_weight_cache())
 
     # ---- initialisation: multimae.py:116-142 ----
     def _init_parameters(self):
