@@ -730,6 +730,36 @@ class EmbedFn(torch.autograd.Function):
         return (None, dfus) + tuple(grads)
 
 
+class PosEmbGradFn(torch.autograd.Function):
+    """Gradient path of LEARNABLE positional embeddings (input_adapters.py:41-48, 76-87 with learnable_pos_emb=True or
+    sincos_pos_emb=False).  EmbedFn adds the (detached) tables in its GEMM epilogue; this node is the identity on the token
+    stream X and, in backward, returns d table[g] = sum over the batch of dX at the token whose global id is g (a batch
+    reduction + an index_add through the token table) and d pos_fusion = the batch sum of the fusion rows' gradients.
+    args: X [B*nenc + B*F, D], tok [nenc] int32, meta (B, nenc, F, sizes), table_all [sum F_m, D] or None, pos_fusion [F, D] or None"""
+
+    @staticmethod
+    def forward(ctx, X, tok, meta, table_all, pos_fusion):
+        ctx.tok, ctx.meta = tok, meta
+        ctx.rows = None if table_all is None else table_all.shape[0]
+        return X.view_as(X)
+
+    @staticmethod
+    def backward(ctx, dX):
+        B, nenc, Fn, D = ctx.meta["B"], ctx.meta["nenc"], ctx.meta["F"], dX.shape[1]
+        dX = dX.contiguous()
+        Mh = B * nenc
+        dtab = dfus = None
+        if ctx.needs_input_grad[3] and Mh > 0:
+            dsum = torch.empty(1, nenc, D, dtype=f32, device=dX.device)
+            K.reduce_batch(dX[:Mh], dsum, B, nenc, D, nenc * D)
+            dtab = torch.zeros(ctx.rows, D, dtype=f32, device=dX.device).index_add_(0, ctx.tok.long(), dsum[0])
+        if ctx.needs_input_grad[4] and Fn > 0:
+            dfus = torch.empty(1, Fn, D, dtype=f32, device=dX.device)
+            K.reduce_batch(dX[Mh:], dfus, B, Fn, D, Fn * D)
+            dfus = dfus[0]
+        return dX, None, None, dtab, dfus
+
+
 # ------------------------------------------------------------------------------------------------
 # the encoder stack
 # ------------------------------------------------------------------------------------------------

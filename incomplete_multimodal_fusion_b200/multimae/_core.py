@@ -340,11 +340,22 @@ class MultiMAEBase(nn.Module):
                       pos=[self.input_adapters[t].pos_table(*grids[t]) for t in MODALITIES], pos_fusion=pos_fusion, kinds=kinds,
                       padding_idx=pads)
         X = Fn.EmbedFn.apply(meta_e, self.fusion_tokens, *mod_args)
+        # learnable positional embeddings (off in every reference script): their gradient rides a pass-through node
+        pos_g = [self.input_adapters[t].pos_table_grad(*grids[t]) for t in MODALITIES]
+        fus_g = None if self.LSTM_FUSION else fus_ad.pos_table_grad(H // fus_ad.P_H, W // fus_ad.P_W)
+        if any(g is not None for g in pos_g) or fus_g is not None:
+            if not fused_tables:
+                raise NotImplementedError("learnable positional embeddings need the device-table path (patch adapters in encoder order)")
+            tab = None
+            if any(g is not None for g in pos_g):
+                tab = torch.cat([g if g is not None else p_.detach() for g, p_ in zip(pos_g, meta_e["pos"])], 0)
+            X = Fn.PosEmbGradFn.apply(X, r["tok"], dict(B=B, nenc=nenc, F=meta_e["F"]), tab, fus_g)
         complete_fusion = None
         if self.LSTM_FUSION:
             # multimae_lstm_s2dsm.py:384-434: the fusion token of every visible position, merged with that position's
             # modality token by the BiLSTM (cuDNN under bf16 autocast, like the reference's AMP step)
-            complete_fusion = self.fusion_tokens[0] + pos_fusion                      # [F, D]
+            pos_fusion_t = fus_ad.pos_table_grad(H // fus_ad.P_H, W // fus_ad.P_W)     # on the tape when learnable
+            complete_fusion = self.fusion_tokens[0] + (pos_fusion if pos_fusion_t is None else pos_fusion_t)   # [F, D]
             sel = (r["tok"].long() % Fn_tok) if fused_tables else torch.cat([i.long() for i in idx])   # patch of every visible token
             pairs = torch.stack([X.view(B, nenc, D), complete_fusion[sel].unsqueeze(0).expand(B, -1, -1)], dim=2)
             with torch.autocast('cuda', dtype=torch.bfloat16):

@@ -38,8 +38,6 @@ class _SpatialAdapterBase(nn.Module):
         else:
             self.pos_emb = nn.Parameter(torch.zeros(1, dim_tokens, h, w))
             trunc_normal_(self.pos_emb, std=0.02)
-        if self.pos_emb.requires_grad:
-            raise NotImplementedError("learnable positional embeddings are not built (never enabled by the reference scripts)")
 
     POS_RESIZE_MODE = 'bicubic'
 
@@ -53,6 +51,18 @@ class _SpatialAdapterBase(nn.Module):
                 pe = torch.nn.functional.interpolate(pe, size=(n_h, n_w), mode=self.POS_RESIZE_MODE, align_corners=False)
             self._pos_cache = (key, pe.flatten(2).transpose(1, 2)[0].contiguous())
         return self._pos_cache[1]
+
+    def pos_table_grad(self, n_h: int, n_w: int) -> Optional[torch.Tensor]:
+        """the same table ON THE AUTOGRAD TAPE when the positional embedding is learnable (learnable_pos_emb=True, or
+        sincos_pos_emb=False whose trunc-normal table is a trained parameter, input_adapters.py:76-87); None otherwise.  The
+        fused embedding adds the detached table in its GEMM epilogue; functions.PosEmbGradFn routes the token gradients back
+        into this tensor (and through the resize to `pos_emb`)."""
+        if not self.pos_emb.requires_grad:
+            return None
+        pe = self.pos_emb
+        if pe.shape[-2:] != (n_h, n_w):
+            pe = torch.nn.functional.interpolate(pe, size=(n_h, n_w), mode=self.POS_RESIZE_MODE, align_corners=False)
+        return pe.flatten(2).transpose(1, 2)[0]
 
     @torch.jit.ignore
     def no_weight_decay(self):

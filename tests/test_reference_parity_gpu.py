@@ -306,3 +306,60 @@ def test_cfg3_vitb_modality_subsets_through_vit_baseline(present):
     bad = _report("cfg3_vitbaseline_" + "+".join(present), acts, {}, None)
     assert not bad, bad
     assert fo[3].shape == f32[3].shape and err(fo[3], f32[3]) <= max(ACT_TOL, NOISE_FACTOR * err(fac[3], f32[3]))
+
+
+@pytest.mark.parametrize("variant,sincos", [("crossattn", True), ("plain", False)])
+def test_learnable_pos_emb_gradients_against_reference(variant, sincos):
+    """learnable_pos_emb=True / sincos_pos_emb=False (input_adapters.py:41-48, 76-87): the positional tables are trained
+    parameters; their gradients (token gradients summed over the batch, scattered through the token table) against the
+    reference's own modules in fp32, every other output / gradient as in the other cases"""
+    H = _harness()
+    ref = H.load()
+    cfg = OracleConfig(variant=variant, dim=128, depth=2, heads=2, image_size=64, patch=8, dec_dim=64, dec_depth=1, dec_heads=2)
+    from incomplete_multimodal_fusion_b200.multimae import multimae as m_plain, multimae_crossattn as m_cross
+    from incomplete_multimodal_fusion_b200.multimae import input_adapters as ours_ia, output_adapters_simple as ours_oa
+
+    def build(IA, OA, Model, TT, LN=None):
+        kw = dict(stride_level=1, patch_size_full=cfg.patch, image_size=cfg.image_size, sincos_pos_emb=sincos, learnable_pos_emb=True)
+        ia = OrderedDict((t, IA.PatchedInputAdapter(num_channels=C, **kw)) for t, C in cfg.channels.items())
+        ia["fusion"] = IA.FusionInputAdapter(num_channels=1, **kw)
+        oa = OrderedDict((t, OA.SpatialOutputAdapter(num_channels=cfg.channels[t], stride_level=1, patch_size_full=cfg.patch,
+                                                     dim_tokens=cfg.dec_dim, depth=cfg.dec_depth, num_heads=cfg.dec_heads, use_task_queries=True,
+                                                     task=t, context_tasks=list(cfg.channels), image_size=cfg.image_size, use_xattn=True))
+                         for t in cfg.out_tasks)
+        extra = {} if LN is None else {"norm_layer": LN}
+        return Model(input_adapters=ia, output_adapters=oa, dim_tokens=cfg.dim, depth=cfg.depth, dim_head=cfg.dim_head, heads=cfg.heads,
+                     ff_mult=cfg.ff_mult, num_fusion_tokens=cfg.num_patches, return_token_types=tuple(TT(v) for v in cfg.return_token_types), **extra)
+
+    with H.quiet():
+        rmod = build(ref.input_adapters, ref.output_adapters_simple, (ref.multimae_crossattn if variant == "crossattn" else ref.multimae).MultiMAE,
+                     ref.zorro_utils.TokenTypes, ref.zorro_utils.LayerNorm).cuda()
+    from incomplete_multimodal_fusion_b200.multimae.zorro_utils import TokenTypes
+    omod = build(ours_ia, ours_oa, (m_cross if variant == "crossattn" else m_plain).MultiMAE, TokenTypes).cuda()
+    sd = {k: v.detach().clone() for k, v in rmod.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    for k in sd:                      # move the tables / zero-initialised tensors off their init values
+        if k.endswith("pos_emb") or k == "mask_embedding":
+            sd[k] = sd[k] + 0.05 * torch.randn(sd[k].shape, generator=g).cuda()
+    rmod.load_state_dict(sd, strict=True)
+    omod.load_state_dict(sd, strict=True)
+    assert all(p.requires_grad for n, p in omod.named_parameters() if n.endswith("pos_emb"))
+    x = make_inputs(cfg, 4, 8, "cuda")
+    with _fp32_math():
+        torch.manual_seed(2)
+        with H.quiet():
+            ro = rmod(x, mask_inputs=True, num_encoded_tokens=70, alphas=1.0, sample_tasks_uniformly=True)
+            H.pretrain_loss(ro, x, cfg).backward()
+    torch.manual_seed(2)
+    oo = omod(x, num_encoded_tokens=70, sample_tasks_uniformly=True)
+    pretrain_loss_ours(oo, x, cfg.patch).backward()
+    for t in ro[1]:
+        assert torch.equal(oo[1][t], ro[1][t])
+    rg = {k: p.grad for k, p in rmod.named_parameters() if p.grad is not None}
+    og = {k: p.grad for k, p in omod.named_parameters() if p.grad is not None}
+    names = [k for k in rg if k.endswith("pos_emb")]
+    assert len(names) == 4, names
+    for k in names:
+        assert k in og and err(og[k], rg[k]) < 2e-2, (k, err(og[k], rg[k]) if k in og else None)
+    worst = max(err(og[k], v) for k, v in rg.items() if float(v.norm()) > 1e-9 and not k.startswith("output_adapters.dem."))
+    assert worst < 3e-2, worst
