@@ -343,7 +343,7 @@ def test_learnable_pos_emb_gradients_against_reference(variant, sincos):
             sd[k] = sd[k] + 0.05 * torch.randn(sd[k].shape, generator=g).cuda()
     rmod.load_state_dict(sd, strict=True)
     omod.load_state_dict(sd, strict=True)
-    assert all(p.requires_grad for n, p in omod.named_parameters() if n.endswith("pos_emb"))
+    assert all(p.requires_grad for n, p in omod.named_parameters() if n.startswith("input_adapters.") and n.endswith("pos_emb"))
     x = make_inputs(cfg, 4, 8, "cuda")
     with _fp32_math():
         torch.manual_seed(2)
@@ -357,7 +357,7 @@ def test_learnable_pos_emb_gradients_against_reference(variant, sincos):
         assert torch.equal(oo[1][t], ro[1][t])
     rg = {k: p.grad for k, p in rmod.named_parameters() if p.grad is not None}
     og = {k: p.grad for k, p in omod.named_parameters() if p.grad is not None}
-    names = [k for k in rg if k.endswith("pos_emb")]
+    names = [k for k in rg if k.startswith("input_adapters.") and k.endswith("pos_emb")]
     assert len(names) == 4, names
     for k in names:
         assert k in og and err(og[k], rg[k]) < 2e-2, (k, err(og[k], rg[k]) if k in og else None)
