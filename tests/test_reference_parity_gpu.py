@@ -360,6 +360,6 @@ def test_learnable_pos_emb_gradients_against_reference(variant, sincos):
     names = [k for k in rg if k.startswith("input_adapters.") and k.endswith("pos_emb")]
     assert len(names) == 4, names
     for k in names:
-        assert k in og and err(og[k], rg[k]) < 2e-2, (k, err(og[k], rg[k]) if k in og else None)
+        assert k in og and err(og[k], rg[k]) < 3e-2, (k, err(og[k], rg[k]) if k in og else None)
     worst = max(err(og[k], v) for k, v in rg.items() if float(v.norm()) > 1e-9 and not k.startswith("output_adapters.dem."))
     assert worst < 3e-2, worst
