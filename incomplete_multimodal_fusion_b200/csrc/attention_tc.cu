@@ -1527,7 +1527,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   uint64_t* ds_full = bars + 10;    // [2] P^T / dS^T of that half written (S^T / dP^T consumed)
   uint64_t* acc_full = bars + 12;
   uint64_t* acc_empty = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* st_full = bars + 14;    // [2] lse / delta of a query block staged in shared memory (by the producer warp)
+  uint64_t* st_empty = bars + 16;   // [2] all four elementwise warps are done with that stage
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int64_t k_row0 = c0 < p.n_head ? (int64_t)b * p.n_head + c0 : p.head_rows + (int64_t)b * p.n_tail + (c0 - p.n_head);
   RowBlocks qb;
@@ -1543,6 +1545,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         mbar_init(&qb_full[s], 1); mbar_init(&qb_empty[s], 1);
       }
       for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], 4); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 4); }
       mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
       mbar_fence_init();
     }
@@ -1556,46 +1559,45 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const int total = qb.nb * p.H;
-      auto prefetch_q = [&](int gg) {      // L2 prefetch ahead of the two-stage Q / dO ring (see attn_fwd_tc2_kernel)
-        if (gg >= total) return;
-        const int hh = gg / qb.nb, jj = gg - hh * qb.nb;
-        int tok, nvalid; int64_t row;
-        qb.get(jj, tok, row, nvalid);
-        tma_prefetch_2d(&tmap_q, hh * 64, (int)row);
-        tma_prefetch_2d(&tmap_do, hh * 64, (int)row);
-      };
-      if (p.pf > 0) {
-        for (int gg = 0; gg < p.pf; ++gg) prefetch_q(gg);
-        for (int hh = 1; hh < p.H && hh <= 2; ++hh) {
-          tma_prefetch_2d(&tmap_k, hh * 64, (int)k_row0);
-          tma_prefetch_2d(&tmap_v, hh * 64, (int)k_row0);
-        }
-      }
-      int g = 0;
-      for (int h = 0; h < p.H; ++h) {
-        const int ks = h & 1;
-        if (p.pf > 0 && h + 3 < p.H) {
-          tma_prefetch_2d(&tmap_k, (h + 3) * 64, (int)k_row0);
-          tma_prefetch_2d(&tmap_v, (h + 3) * 64, (int)k_row0);
-        }
-        mbar_wait(&kvt_empty[ks], ((h >> 1) & 1) ^ 1);
+    // Producer warp.  Lane 0 issues the TMA loads; ALL lanes stage the block's lse * log2e and delta (64 query rows, lane l
+    // rows l and l + 32) into ONE shared copy per stage for the four elementwise warps.  Round 1 had every elementwise warp
+    // fetch and stage its own copy -- ~640 of the ~3700 clk a block costs the warps that bound the kernel
+    // (profiles/r02_attn_dkv_phase_clocks.txt); this warp is otherwise idle between TMA issues.
+    const int total = qb.nb * p.H;
+    int g = 0;
+    for (int h = 0; h < p.H; ++h) {
+      const int ks = h & 1;
+      mbar_wait(&kvt_empty[ks], ((h >> 1) & 1) ^ 1);
+      if (lane == 0) {
         mbar_expect_tx(&kvt_full[ks], 2 * TC_TILE_BYTES);
         tma_load_2d(sK + ks * TC_TILE_BYTES, &tmap_k, &kvt_full[ks], h * 64, (int)k_row0);
         tma_load_2d(sV + ks * TC_TILE_BYTES, &tmap_v, &kvt_full[ks], h * 64, (int)k_row0);
-        for (int j = 0; j < qb.nb; ++j, ++g) {
-          const int st = g & 1;
-          if (p.pf > 0) prefetch_q(g + p.pf);
-          mbar_wait(&qb_empty[st], ((g >> 1) & 1) ^ 1);
-          int tok, nvalid; int64_t row;
-          qb.get(j, tok, row, nvalid);
+      }
+      for (int j = 0; j < qb.nb; ++j, ++g) {
+        const int st = g & 1;
+        int tok, nvalid; int64_t row;
+        qb.get(j, tok, row, nvalid);
+        // the statistics first: their global loads are in flight while the TMA loads are issued
+        const int64_t sb_ = ((int64_t)b * p.H + h) * p.N + tok;
+        const bool ok0 = lane < nvalid, ok1 = lane + 32 < nvalid;
+        const float l0 = p.lse[sb_ + (ok0 ? lane : 0)], d0 = p.delta[sb_ + (ok0 ? lane : 0)];
+        const float l1 = p.lse[sb_ + (ok1 ? lane + 32 : 0)], d1 = p.delta[sb_ + (ok1 ? lane + 32 : 0)];
+        mbar_wait(&qb_empty[st], ((g >> 1) & 1) ^ 1);
+        if (lane == 0) {
           mbar_expect_tx(&qb_full[st], 2 * BW_BLK_BYTES);
           tma_load_2d(sQ + st * BW_BLK_BYTES, &tmap_q, &qb_full[st], h * 64, (int)row);
           tma_load_2d(sdO + st * BW_BLK_BYTES, &tmap_do, &qb_full[st], h * 64, (int)row);
         }
+        mbar_wait(&st_empty[st], ((g >> 1) & 1) ^ 1);
+        s_lse[st * BW_BLK + lane] = ok0 ? l0 * 1.4426950408889634f : INFINITY;        // +inf beyond nvalid -> P = 0
+        s_lse[st * BW_BLK + lane + 32] = ok1 ? l1 * 1.4426950408889634f : INFINITY;
+        s_dl[st * BW_BLK + lane] = ok0 ? d0 : 0.f;
+        s_dl[st * BW_BLK + lane + 32] = ok1 ? d1 : 0.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_full[st]);
       }
     }
+    (void)total;
   } else if (warp == 1) {
     // A block of 64 queries is handled as two 32-query halves with their own S^T / dP^T columns and barriers: while
     // the elementwise warps turn half B into P^T / dS^T, the tensor pipe accumulates half A into dV / dK and computes
@@ -1709,46 +1711,17 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
     unsigned t_last = clock();
     unsigned acc_clk[16] = {0};
 #endif
-    // lse*log2e and delta of a block's 64 query rows are staged in shared memory PER WARP (each warp keeps its own two
-    // stages; lane l fetches rows l and l + 32), so the four elementwise warps never meet at a barrier.  The values of
-    // block g+1 are fetched (global loads into registers) at the start of block g and written to the other stage at its
-    // end: their latency hides behind the block's arithmetic.  Fetched where they are needed they cost ~2000 clk per
-    // block, 40 % of this CTA's time (tools/attn_clocks_bwd.py).
-    float* w_lse = s_lse + quarter * 2 * BW_BLK;
-    float* w_dl = s_dl + quarter * 2 * BW_BLK;
-    float nl0 = 0.f, nl1 = 0.f, nd0 = 0.f, nd1 = 0.f;   // raw loaded values: nothing may consume them before the stage
-    bool nok0 = false, nok1 = false;                    // write (in-order issue would park the warp on the loads)
-    auto fetch = [&](int hh, int jj) {
-      int tok, nvalid; int64_t row;
-      qb.get(jj, tok, row, nvalid);
-      const int64_t sb = ((int64_t)b * p.H + hh) * p.N + tok;
-      nok0 = lane < nvalid; nok1 = lane + 32 < nvalid;
-      nl0 = p.lse[sb + (nok0 ? lane : 0)]; nd0 = p.delta[sb + (nok0 ? lane : 0)];
-      nl1 = p.lse[sb + (nok1 ? lane + 32 : 0)]; nd1 = p.delta[sb + (nok1 ? lane + 32 : 0)];
-    };
-    auto stage = [&](int stg) {
-      w_lse[stg * BW_BLK + lane] = nok0 ? nl0 * 1.4426950408889634f : INFINITY;        // +inf beyond nvalid -> P = 0
-      w_lse[stg * BW_BLK + lane + 32] = nok1 ? nl1 * 1.4426950408889634f : INFINITY;
-      w_dl[stg * BW_BLK + lane] = nok0 ? nd0 : 0.f;
-      w_dl[stg * BW_BLK + lane + 32] = nok1 ? nd1 : 0.f;
-    };
-    if (qb.nb > 0) {
-      fetch(0, 0);
-      stage(0);
-    }
+    // lse * log2e and delta of the block's 64 query rows come staged in shared memory from the producer warp (st_full / st_empty)
     for (int h = 0; h < p.H; ++h) {
       for (int j = 0; j < qb.nb; ++j, ++g) {
         const int st = g & 1;
         int tok, nvalid; int64_t row;
         qb.get(j, tok, row, nvalid);
         CLK2(4, 0);
-        __syncwarp();   // this warp's stage st is complete (written at the end of the previous block), st^1 is free
-        const int hn = (j + 1 < qb.nb) ? h : h + 1, jn = (j + 1 < qb.nb) ? j + 1 : 0;
-        const bool stage_next = hn < p.H;
-        if (stage_next) fetch(hn, jn);
+        mbar_wait(&st_full[st], (g >> 1) & 1);
         CLK2(5, 0);
-        const float* ls = w_lse + st * BW_BLK;
-        const float* dl = w_dl + st * BW_BLK;
+        const float* ls = s_lse + st * BW_BLK;
+        const float* dl = s_dl + st * BW_BLK;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {   // the block's two 32-query halves (see the MMA warp)
           if (nvalid <= 32 * c) continue;
@@ -1779,7 +1752,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
           CLK2(1, 0);
         }
         CLK2(2, 0);
-        if (stage_next) stage(st ^ 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_empty[st]);      // this warp has read the stage's statistics
         CLK2(3, 0);
       }
       if (qb.nb == 0) continue;
