@@ -1527,9 +1527,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   uint64_t* ds_full = bars + 10;    // [2] P^T / dS^T of that half written (S^T / dP^T consumed)
   uint64_t* acc_full = bars + 12;
   uint64_t* acc_empty = bars + 13;
-  uint64_t* st_full = bars + 14;    // [2] lse / delta of a query block staged in shared memory (by the producer warp)
+  uint64_t* st_full = bars + 14;    // [2] lse / delta of a query block staged in shared memory
   uint64_t* st_empty = bars + 16;   // [2] all four elementwise warps are done with that stage
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* acc_done = bars + 18;   // [2] the dV / dK MMAs that read a half's P^T / dS^T have completed: its columns are free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int64_t k_row0 = c0 < p.n_head ? (int64_t)b * p.n_head + c0 : p.head_rows + (int64_t)b * p.n_tail + (c0 - p.n_head);
   RowBlocks qb;
@@ -1545,7 +1546,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         mbar_init(&qb_full[s], 1); mbar_init(&qb_empty[s], 1);
       }
       for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&ds_full[s], 4); }
-      for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 4); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&st_empty[s], 4); mbar_init(&acc_done[s], 1); }
       mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
       mbar_fence_init();
     }
@@ -1558,139 +1559,158 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // Two issuing warps (round 2).  One warp issuing everything spent ~2400 of the ~3600 clk a block takes on the 24 MMAs, the
+  // commits and the waits of a block (~90 clk each, profiles/r02_attn_dkv_phase_clocks.txt), in series with the elementwise
+  // warps it feeds.  Now warp 0 loads (TMA) and issues S^T / dP^T, warp 1 issues the dV / dK accumulations and stages the
+  // lse / delta statistics; each half's chain  S -> elementwise -> accumulate -> S(next)  crosses the two warps through
+  // completion barriers (s_full, ds_full, acc_done: tcgen05.commit only orders the issuing thread's own MMAs, so "its columns
+  // are free" is the COMPLETION of the accumulate MMAs, not their issue).
+  const int total = qb.nb * p.H;
   if (warp == 0) {
-    // Producer warp.  Lane 0 issues the TMA loads; ALL lanes stage the block's lse * log2e and delta (64 query rows, lane l
-    // rows l and l + 32) into ONE shared copy per stage for the four elementwise warps.  Round 1 had every elementwise warp
-    // fetch and stage its own copy -- ~640 of the ~3700 clk a block costs the warps that bound the kernel
-    // (profiles/r02_attn_dkv_phase_clocks.txt); this warp is otherwise idle between TMA issues.
-    const int total = qb.nb * p.H;
-    int g = 0;
-    for (int h = 0; h < p.H; ++h) {
-      const int ks = h & 1;
-      mbar_wait(&kvt_empty[ks], ((h >> 1) & 1) ^ 1);
-      if (lane == 0) {
-        mbar_expect_tx(&kvt_full[ks], 2 * TC_TILE_BYTES);
-        tma_load_2d(sK + ks * TC_TILE_BYTES, &tmap_k, &kvt_full[ks], h * 64, (int)k_row0);
-        tma_load_2d(sV + ks * TC_TILE_BYTES, &tmap_v, &kvt_full[ks], h * 64, (int)k_row0);
-      }
-      for (int j = 0; j < qb.nb; ++j, ++g) {
-        const int st = g & 1;
-        int tok, nvalid; int64_t row;
-        qb.get(j, tok, row, nvalid);
-        // the statistics first: their global loads are in flight while the TMA loads are issued
-        const int64_t sb_ = ((int64_t)b * p.H + h) * p.N + tok;
-        const bool ok0 = lane < nvalid, ok1 = lane + 32 < nvalid;
-        const float l0 = p.lse[sb_ + (ok0 ? lane : 0)], d0 = p.delta[sb_ + (ok0 ? lane : 0)];
-        const float l1 = p.lse[sb_ + (ok1 ? lane + 32 : 0)], d1 = p.delta[sb_ + (ok1 ? lane + 32 : 0)];
-        mbar_wait(&qb_empty[st], ((g >> 1) & 1) ^ 1);
-        if (lane == 0) {
-          mbar_expect_tx(&qb_full[st], 2 * BW_BLK_BYTES);
-          tma_load_2d(sQ + st * BW_BLK_BYTES, &tmap_q, &qb_full[st], h * 64, (int)row);
-          tma_load_2d(sdO + st * BW_BLK_BYTES, &tmap_do, &qb_full[st], h * 64, (int)row);
-        }
-        mbar_wait(&st_empty[st], ((g >> 1) & 1) ^ 1);
-        s_lse[st * BW_BLK + lane] = ok0 ? l0 * 1.4426950408889634f : INFINITY;        // +inf beyond nvalid -> P = 0
-        s_lse[st * BW_BLK + lane + 32] = ok1 ? l1 * 1.4426950408889634f : INFINITY;
-        s_dl[st * BW_BLK + lane] = ok0 ? d0 : 0.f;
-        s_dl[st * BW_BLK + lane + 32] = ok1 ? d1 : 0.f;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&st_full[st]);
-      }
-    }
-    (void)total;
-  } else if (warp == 1) {
-    // A block of 64 queries is handled as two 32-query halves with their own S^T / dP^T columns and barriers: while
-    // the elementwise warps turn half B into P^T / dS^T, the tensor pipe accumulates half A into dV / dK and computes
-    // half A of the NEXT block (and vice versa), so neither side waits for the other in steady state.  (With one
-    // 64-query unit per block the elementwise warps spent 27 % of their time waiting for S: tools/attn_clocks_bwd.py.)
-    // Round 2: the whole warp runs the loop and an elected lane issues (see attn_fwd_tc2_kernel: inside `if (lane == 0)`
-    // every one of the 24 UTCHMMAs of a block cost an R2UR vote loop, and that scalar stream paced the kernel).
-    const int total = qb.nb * p.H;
+    // ------------------------------ TMA producer + S^T / dP^T issuer ------------------------------
     if (total > 0) {
       const bool leader = elect_one();
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-      const uint32_t idesc_s0 = umma_idesc_bf16(TC_BM, 0, false, false);      // S^T[128 keys x nq] = K . Q^T (one half): N added per half
-      const uint32_t idesc_acc = umma_idesc_bf16(TC_BM, 64, false, true);     // dV/dK[128 x 64dh] += A(TMEM)[128 x q] . B (MN-major)
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, 32, false, false);    // S^T[128 keys x 32 q] = K . Q^T (one half); N = 32
+      // whatever the number of valid queries: columns past them hold finite values and are zeroed through lse = +inf
       const uint64_t dk0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sK), 0), 16, 1024);
       const uint64_t dv0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sV), 0), 16, 1024);
       const uint64_t dq0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sQ), 0), 16, 1024);
       const uint64_t ddo0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sdO), 0), 16, 1024);
+      const int nb = __shfl_sync(0xffffffffu, qb.nb, 0);
+      int cnt0 = 0, cnt1 = 0;       // S^T halves issued so far: the n-th issue of a half waits for acc_done completion n - 1
+      int h = 0, j = 0;             // block being loaded / issued
+      for (int g = 0; g < total; ++g) {
+        const int st = g & 1, ks = h & 1;
+        int tok, nvalid; int64_t row;
+        qb.get(j, tok, row, nvalid);
+        if (j == 0) {               // K / V tile of the head
+          mbar_wait(&kvt_empty[ks], ((h >> 1) & 1) ^ 1);
+          if (leader) {
+            mbar_expect_tx(&kvt_full[ks], 2 * TC_TILE_BYTES);
+            tma_load_2d(sK + ks * TC_TILE_BYTES, &tmap_k, &kvt_full[ks], h * 64, (int)k_row0);
+            tma_load_2d(sV + ks * TC_TILE_BYTES, &tmap_v, &kvt_full[ks], h * 64, (int)k_row0);
+          }
+        }
+        mbar_wait(&qb_empty[st], ((g >> 1) & 1) ^ 1);
+        if (leader) {
+          mbar_expect_tx(&qb_full[st], 2 * BW_BLK_BYTES);
+          tma_load_2d(sQ + st * BW_BLK_BYTES, &tmap_q, &qb_full[st], h * 64, (int)row);
+          tma_load_2d(sdO + st * BW_BLK_BYTES, &tmap_do, &qb_full[st], h * 64, (int)row);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (nvalid <= 32 * hf) continue;
+          const int n_prev = hf == 0 ? cnt0 : cnt1;
+          if (n_prev > 0) mbar_wait(&acc_done[hf], (n_prev - 1) & 1);     // the half's previous P^T / dS^T have been consumed
+          if (hf == 0) {
+            if (j == 0) mbar_wait(&kvt_full[ks], (h >> 1) & 1);
+            mbar_wait(&qb_full[st], (g >> 1) & 1);
+          }
+          tc_fence_after();
+          if (leader) {
+            const uint64_t kd = dk0 + (uint64_t)(ks * (TC_TILE_BYTES >> 4)), vd = dv0 + (uint64_t)(ks * (TC_TILE_BYTES >> 4));
+            const uint64_t qd = dq0 + (uint64_t)(st * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
+            const uint64_t od = ddo0 + (uint64_t)(st * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) umma_bf16(tm + hf * KV_HALF, kd + 2 * k2, qd + 2 * k2, idesc, k2 > 0);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) umma_bf16(tm + hf * KV_HALF + KV_DPT_OFF, vd + 2 * k2, od + 2 * k2, idesc, k2 > 0);
+            umma_commit(&s_full[hf]);
+          }
+          __syncwarp();
+          if (hf == 0) ++cnt0; else ++cnt1;
+        }
+        if (++j == nb) { j = 0; ++h; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ dV / dK issuer + statistics stager ------------------------------
+    if (total > 0) {
+      const bool leader = elect_one();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t idesc_acc = umma_idesc_bf16(TC_BM, 64, false, true);     // dV/dK[128 x 64dh] += A(TMEM)[128 x q] . B (MN-major)
       const uint64_t dqm0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sQ), 0), 8192, 1024);    // Q / dO read MN-major
       const uint64_t ddom0 = umma_smem_desc(__shfl_sync(0xffffffffu, smem_u32(sdO), 0), 8192, 1024);
       const int nb = __shfl_sync(0xffffffffu, qb.nb, 0);
-      auto nvalid_of = [&](int j) { int tok, nv; int64_t row; qb.get(j, tok, row, nv); return nv; };
-      int sh = 0, sj = 0, sg = 0;              // (head, query block, running block) of the NEXT S^T / dP^T to issue
-      auto issue_s = [&](int hf) {            // half hf of block (sh, sj); only issued when the half has queries
-        const int st = sg & 1;
-        if (hf == 0) {   // half A exists in every block: it carries the waits for the block's operands
-          if (sj == 0) mbar_wait(&kvt_full[sh & 1], (sh >> 1) & 1);
-          mbar_wait(&qb_full[st], (sg >> 1) & 1);
-          tc_fence_after();
-        }
-        if (leader) {
-          // N = 32 whatever the number of valid queries: the columns past them hold finite values of other rows (or TMA
-          // zero fill) and are zeroed through lse = +inf by the elementwise warps
-          const uint32_t idesc = idesc_s0 | ((uint32_t)(32 >> 3) << 17);
-          const uint64_t kd = dk0 + (uint64_t)((sh & 1) * (TC_TILE_BYTES >> 4)), vd = dv0 + (uint64_t)((sh & 1) * (TC_TILE_BYTES >> 4));
-          const uint64_t qd = dq0 + (uint64_t)(st * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
-          const uint64_t od = ddo0 + (uint64_t)(st * (BW_BLK_BYTES >> 4) + hf * (4096 >> 4));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tm + hf * KV_HALF, kd + 2 * k, qd + 2 * k, idesc, k > 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tm + hf * KV_HALF + KV_DPT_OFF, vd + 2 * k, od + 2 * k, idesc, k > 0);
-          umma_commit(&s_full[hf]);
-        }
-        __syncwarp();
+      // lse * log2e and delta of a block's 64 query rows (lane l: rows l and l + 32), staged ONE block ahead for the four
+      // elementwise warps: the global loads of block g + 1 are issued during block g and consumed at its end
+      float l0 = 0.f, l1 = 0.f, d0 = 0.f, d1 = 0.f;
+      bool ok0 = false, ok1 = false;
+      auto load_stats = [&](int hh, int jj) {
+        int tok, nvalid; int64_t row;
+        qb.get(jj, tok, row, nvalid);
+        const int64_t sb_ = ((int64_t)b * p.H + hh) * p.N + tok;
+        ok0 = lane < nvalid; ok1 = lane + 32 < nvalid;
+        l0 = p.lse[sb_ + (ok0 ? lane : 0)]; d0 = p.delta[sb_ + (ok0 ? lane : 0)];
+        l1 = p.lse[sb_ + (ok1 ? lane + 32 : 0)]; d1 = p.delta[sb_ + (ok1 ? lane + 32 : 0)];
       };
-      auto advance_s = [&]() { ++sg; if (++sj == nb) { sj = 0; ++sh; } };
+      auto store_stats = [&](int gg) {
+        const int stg = gg & 1;
+        mbar_wait(&st_empty[stg], ((gg >> 1) & 1) ^ 1);
+        s_lse[stg * BW_BLK + lane] = ok0 ? l0 * 1.4426950408889634f : INFINITY;        // +inf beyond nvalid -> P = 0
+        s_lse[stg * BW_BLK + lane + 32] = ok1 ? l1 * 1.4426950408889634f : INFINITY;
+        s_dl[stg * BW_BLK + lane] = ok0 ? d0 : 0.f;
+        s_dl[stg * BW_BLK + lane + 32] = ok1 ? d1 : 0.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_full[stg]);
+      };
+      load_stats(0, 0);
+      store_stats(0);
+      if (total > 1) load_stats(nb > 1 ? 0 : 1, nb > 1 ? 1 : 0);     // block 1, stored at the top of iteration 0
       int used0 = 0, used1 = 0;   // completed waits on ds_full[0] / ds_full[1]
 #ifdef MMF_ATTN_CLOCKS
       const bool dbg_on = (b == 3) && (c0 == 0) && lane == 0;
       unsigned t_last = clock();
       unsigned acc_clk[16] = {0};
 #endif
-      issue_s(0);
-      if (nvalid_of(0) > 32) issue_s(1);
-      advance_s();                // the cursor now points at block 1
       int h = 0, j = 0;
       for (int g = 0; g < total; ++g) {
         const int st = g & 1;
-        const int nvalid = nvalid_of(j);
-        const bool has_next = g + 1 < total;
-        const int nvalid_next = has_next ? nvalid_of(sj) : 0;
+        int tok, nvalid; int64_t row;
+        qb.get(j, tok, row, nvalid);
+        // statistics run TWO blocks ahead of the accumulation this warp issues: block g + 1 is published now (the
+        // elementwise warps reach it while this warp still waits for block g's ds_full), block g + 2 is requested
+        if (g + 1 < total) store_stats(g + 1);
+        if (g + 2 < total) {
+          int h2 = h, j2 = j + 2;
+          while (j2 >= nb) { j2 -= nb; ++h2; }
+          load_stats(h2, j2);
+        }
         const uint64_t qd = dqm0 + (uint64_t)(st * (BW_BLK_BYTES >> 4)), od = ddom0 + (uint64_t)(st * (BW_BLK_BYTES >> 4));
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int nvh = min(32, nvalid - 32 * hf);
-          if (nvh > 0) {
-            CLK2(8, 0);
-            if (hf == 0) { mbar_wait(&ds_full[0], used0 & 1); ++used0; } else { mbar_wait(&ds_full[1], used1 & 1); ++used1; }
-            CLK2(9, 0);
-            if (j == 0 && hf == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);   // previous head's dV / dK have been read out
-            tc_fence_after();
-            CLK2(10, 0);
-            if (leader) {
-              const int ksteps = (nvh + 15) >> 4;
-              for (int k = 0; k < ksteps; ++k)   // dV += P^T . dO
-                umma_bf16_ts(tm + KV_DV, tm + hf * KV_HALF + k * 8, od + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
-                             (j > 0) || (hf > 0) || (k > 0));
-              for (int k = 0; k < ksteps; ++k)   // dK += dS^T . Q
-                umma_bf16_ts(tm + KV_DK, tm + hf * KV_HALF + KV_DS_OFF + k * 8, qd + (uint64_t)((2 * hf + k) * (2048 >> 4)), idesc_acc,
-                             (j > 0) || (hf > 0) || (k > 0));
-            }
+          if (nvh <= 0) continue;
+          CLK2(8, 0);
+          if (hf == 0) { mbar_wait(&ds_full[0], used0 & 1); ++used0; } else { mbar_wait(&ds_full[1], used1 & 1); ++used1; }
+          CLK2(9, 0);
+          if (j == 0 && hf == 0 && h > 0) mbar_wait(acc_empty, (h - 1) & 1);   // previous head's dV / dK have been read out
+          tc_fence_after();
+          CLK2(10, 0);
+          if (leader) {
+            const int ksteps = (nvh + 15) >> 4;
+            for (int k2 = 0; k2 < ksteps; ++k2)   // dV += P^T . dO
+              umma_bf16_ts(tm + KV_DV, tm + hf * KV_HALF + k2 * 8, od + (uint64_t)((2 * hf + k2) * (2048 >> 4)), idesc_acc,
+                           (j > 0) || (hf > 0) || (k2 > 0));
+            for (int k2 = 0; k2 < ksteps; ++k2)   // dK += dS^T . Q
+              umma_bf16_ts(tm + KV_DK, tm + hf * KV_HALF + KV_DS_OFF + k2 * 8, qd + (uint64_t)((2 * hf + k2) * (2048 >> 4)), idesc_acc,
+                           (j > 0) || (hf > 0) || (k2 > 0));
+            umma_commit(&acc_done[hf]);           // the half's columns are free once these have completed
           }
-          if (hf == 1 && leader) umma_commit(&qb_empty[st]);   // every MMA reading this Q / dO stage has been issued
           __syncwarp();
           CLK2(11, 0);
-          if (has_next && nvalid_next > 32 * hf) issue_s(hf);   // its columns are free: in-order tensor pipe
-          CLK2(12, 0);
         }
-        if (has_next) advance_s();
-        if (j + 1 == nb && leader) {
-          umma_commit(acc_full);
-          umma_commit(&kvt_empty[h & 1]);
+        if (leader) {
+          umma_commit(&qb_empty[st]);             // every MMA reading this Q / dO stage has completed by then
+          if (j + 1 == nb) {
+            umma_commit(acc_full);
+            umma_commit(&kvt_empty[h & 1]);
+          }
         }
         __syncwarp();
+        CLK2(12, 0);
         if (++j == nb) { j = 0; ++h; }
       }
 #ifdef MMF_ATTN_CLOCKS

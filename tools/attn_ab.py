@@ -9,7 +9,10 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from incomplete_multimodal_fusion_b200 import kernels as K  # noqa: E402
+from incomplete_multimodal_fusion_b200 import _lib, kernels as K  # noqa: E402
+
+if os.environ.get("MMF_LIB"):   # another build of the library (e.g. scratch/prev_libmmf.so) for same-box A/B runs
+    _lib.LIB_PATH = os.path.abspath(os.environ["MMF_LIB"])
 
 bf16 = torch.bfloat16
 B, nenc, Fn, H = int(os.environ.get("AB_BATCH", "256")), 294, 196, 8
