@@ -170,6 +170,7 @@ struct LnBwdParams {
   float* dg1;         // f32 [D] accumulated with atomics (must be zeroed by the caller)
   float* db1;         // optional
   float* dg2;         // optional (double LN)
+  int l2_prefetch;    // issue L2 prefetches two rows ahead (MMF_LN_BWD_L2PF, default on)
 };
 
 // PF (software pipelining across rows): ncu shows the plain row loop stalled on its own loads (long-scoreboard 9.7 per
@@ -248,6 +249,31 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
       }
     }
     if (PF && row + row_step < p.rows) fetch_row(row + row_step);   // in flight during this row's arithmetic
+    if (PF && p.l2_prefetch) {
+      // L2 prefetch two rows ahead (x, dy) and of the next row's residual-branch gradient: a warp has only ONE row of loads
+      // in flight for ~1/4 of the time a row takes it (ncu: DRAM 58 %, issue 30 %: latency-bound, too few bytes in flight);
+      // with the lines already in L2 the register prefetch above completes in a third of the time
+      const int64_t r2 = row + 2 * row_step, r1 = row + row_step;
+      if (r2 < p.rows) {
+        const float* xr2 = (p.x2 && r2 >= p.x_split) ? p.x2 + (r2 - p.x_split) * p.ldx : p.x + r2 * p.ldx;
+        const __nv_bfloat16* dr2 = reinterpret_cast<const __nv_bfloat16*>(p.dy) + r2 * p.lddy;
+#pragma unroll
+        for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+          const int c = lane + 32 * i;
+          if (FULL || c < nchunk) {
+            if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr2 + 4 * c));
+            if (pf_dy && (lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(dr2 + 4 * c));
+          }
+        }
+      }
+      if (p.dres && r1 < p.rows) {
+#pragma unroll
+        for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+          const int c = lane + 32 * i;
+          if ((FULL || c < nchunk) && (lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dres + r1 * p.lddres + 4 * c));
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
       const bool in = FULL || lane + 32 * i < nchunk;
@@ -424,8 +450,9 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
   if (D <= 0 || (D & 3) || D > LN_MAX_D) MMF_BAD_ARG(2);
   if ((ldx & 3) || (lddy & 3) || (lddx & 3) || (dres && (lddres & 3)) || (dx_bf16 && (lddxb & 3))) MMF_BAD_ARG(3);
   if (g2 && !dg2) MMF_BAD_ARG(4);
+  const char* l2e = getenv("MMF_LN_BWD_L2PF");      // read per call (A/B runs switch it between launches)
   LnBwdParams p{dy, lddy, dy_f32, x, x2, x_split, rows, ldx, D, g1, b1, g2, stats, dres, lddres, dx, lddx, dx_bf16, lddxb, dg1, db1,
-                g2 ? dg2 : nullptr};
+                g2 ? dg2 : nullptr, l2e ? atoi(l2e) : 1};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nc = ceil_div(D, 128);
   const int ncp = nc <= 2 ? 2 : (nc <= 4 ? 4 : (nc <= 6 ? 6 : 8));
