@@ -38,6 +38,7 @@ struct LnParams {
   int64_t delta_row0, lddelta;
   float* xout;
   int64_t ldxout;
+  int l2_prefetch;  // L2-prefetch x (and delta) this many row steps ahead, 0 = off (MMF_LN_FWD_L2PF)
 };
 
 // gamma1 / bias1 / gamma2 staged once per CTA in shared memory (index = float4 chunk)
@@ -72,6 +73,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_fwd_kerne
       const int c = lane + 32 * i;
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (FULL || c < nchunk) v[i] = xr[c];
+    }
+    if (p.l2_prefetch) {  // same reasoning as the backward kernel: one row of loads per warp is too few bytes in flight
+      const int64_t r2 = row + (int64_t)p.l2_prefetch * gridDim.x * LN_WARPS;
+      if (r2 < p.rows) {
+        const float* xr2 = (p.x2 && r2 >= p.x_split) ? p.x2 + (r2 - p.x_split) * p.ldx : p.x + r2 * p.ldx;
+        const bool pd = p.delta && r2 >= p.delta_row0;
+#pragma unroll
+        for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+          const int c = lane + 32 * i;
+          if (FULL || c < nchunk) {
+            if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr2 + 4 * c));
+            if (pd && (lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.delta + (r2 - p.delta_row0) * p.lddelta + 4 * c));
+          }
+        }
+      }
     }
     if (p.delta && row >= p.delta_row0) {
       const uint2* dr = reinterpret_cast<const uint2*>(p.delta + (row - p.delta_row0) * p.lddelta);
@@ -170,7 +186,7 @@ struct LnBwdParams {
   float* dg1;         // f32 [D] accumulated with atomics (must be zeroed by the caller)
   float* db1;         // optional
   float* dg2;         // optional (double LN)
-  int l2_prefetch;    // issue L2 prefetches two rows ahead (MMF_LN_BWD_L2PF, default on)
+  int l2_prefetch;    // issue L2 prefetches this many row steps ahead, 0 = off (MMF_LN_BWD_L2PF, default 2)
 };
 
 // PF (software pipelining across rows): ncu shows the plain row loop stalled on its own loads (long-scoreboard 9.7 per
@@ -253,7 +269,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
       // L2 prefetch two rows ahead (x, dy) and of the next row's residual-branch gradient: a warp has only ONE row of loads
       // in flight for ~1/4 of the time a row takes it (ncu: DRAM 58 %, issue 30 %: latency-bound, too few bytes in flight);
       // with the lines already in L2 the register prefetch above completes in a third of the time
-      const int64_t r2 = row + 2 * row_step, r1 = row + row_step;
+      const int64_t r2 = row + p.l2_prefetch * row_step, r1 = row + (p.l2_prefetch - 1) * row_step;
       if (r2 < p.rows) {
         const float* xr2 = (p.x2 && r2 >= p.x_split) ? p.x2 + (r2 - p.x_split) * p.ldx : p.x + r2 * p.ldx;
         const __nv_bfloat16* dr2 = reinterpret_cast<const __nv_bfloat16*>(p.dy) + r2 * p.lddy;
@@ -397,6 +413,224 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (PF ? 2 : (NC <= 6 ? 3 : 2))) l
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Ring variant of the backward kernel (D = NC * 128, bf16 upstream gradient, 16-byte aligned rows): the rows travel
+// global -> shared memory as 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), issued by each warp's lane 0 into the
+// warp's PRIVATE two-deep ring two rows ahead of the row being worked on, so nothing in the row loop waits on HBM and no
+// register holds prefetched data.  Why: the register-prefetch kernel above is latency bound (ncu: 16 warps / SM, one
+// instruction per ~11 clocks per warp, 5.6 of them long-scoreboard); inside a training step the SM clock sits at the power
+// cap (~1.46 GHz against 1.9 GHz for the kernel run alone) and its rate falls with the clock (0.87 of the HBM peak alone,
+// 0.69 in the step).  Here ~160 KB per SM are in flight whatever the clock.  One CTA per SM, 12 warps (10 at D = 1024),
+// up to 168 registers: the parameter-gradient accumulators move from shared memory into registers, which also removes
+// four LDS/STS per chunk.  (x, dy, stats) and the residual-branch gradient have separate barriers: the first group is
+// copied to registers and re-armed at once, the second is read where it is added at the end of the row.
+// ------------------------------------------------------------------------------------------------
+template <int NC>
+struct LnRing {
+  static constexpr int WARPS = NC <= 6 ? 12 : 10;
+  static constexpr int XB = NC * 512, DYB = NC * 256;
+  static constexpr int STAGE_A = XB + DYB + 16;   // x row, dy row, the row's (mean1, rstd1, mean2, rstd2)
+  static constexpr int STAGE_R = XB;              // dres row
+  static constexpr int WARP_BYTES = 2 * STAGE_A + 2 * STAGE_R;
+  static constexpr int PARAM_BYTES = 3 * NC * 512;
+  static constexpr int BAR_BYTES = ((WARPS * 4 * 8 + 127) / 128) * 128;
+  static constexpr int SMEM = PARAM_BYTES + BAR_BYTES + WARPS * WARP_BYTES;
+  static_assert(WARP_BYTES >= 3 * NC * 512, "the ring doubles as the staging area of the final parameter-gradient reduction");
+};
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int NC, bool HB>
+__global__ void __launch_bounds__(LnRing<NC>::WARPS * 32, 1) ln_bwd_ring_kernel(const LnBwdParams p) {
+  using R = LnRing<NC>;
+  constexpr int W = R::WARPS;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const float invD = 1.0f / (float)p.D;
+  const bool dbl = p.g2 != nullptr;
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  float4* g1 = reinterpret_cast<float4*>(ring_smem);
+  float4* b1 = g1 + NC * 32;
+  float4* g2 = b1 + NC * 32;
+  uint64_t* bar_a = reinterpret_cast<uint64_t*>(ring_smem + R::PARAM_BYTES) + warp * 4;
+  uint64_t* bar_r = bar_a + 2;
+  uint8_t* wbase = ring_smem + R::PARAM_BYTES + R::BAR_BYTES + (size_t)warp * R::WARP_BYTES;
+  if (lane == 0) {
+    for (int s = 0; s < 4; ++s) mbar_init(&bar_a[s], 1);
+    mbar_fence_init();
+  }
+  ln_stage_params(g1, b1, g2, p.g1, p.b1, p.g2, NC * 32);   // ends with __syncthreads()
+  const int64_t row_first = (int64_t)blockIdx.x * W + warp, row_step = (int64_t)gridDim.x * W;
+  const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(p.dy);
+  auto issue_a = [&](int64_t r, int s) {
+    uint8_t* sa = wbase + s * R::STAGE_A;
+    mbar_expect_tx(&bar_a[s], R::STAGE_A);
+    bulk_load_1d(sa, (p.x2 && r >= p.x_split) ? p.x2 + (r - p.x_split) * p.ldx : p.x + r * p.ldx, R::XB, &bar_a[s]);
+    bulk_load_1d(sa + R::XB, dyp + r * p.lddy, R::DYB, &bar_a[s]);
+    bulk_load_1d(sa + R::XB + R::DYB, p.stats + 4 * r, 16, &bar_a[s]);
+  };
+  auto issue_r = [&](int64_t r, int s) {
+    mbar_expect_tx(&bar_r[s], R::STAGE_R);
+    bulk_load_1d(wbase + 2 * R::STAGE_A + s * R::STAGE_R, p.dres + r * p.lddres, R::STAGE_R, &bar_r[s]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int64_t r = row_first + s * row_step;
+      if (r < p.rows) {
+        issue_a(r, s);
+        if (p.dres) issue_r(r, s);
+      }
+    }
+  }
+  float4 adg1[NC], adg2[NC], adb1[HB ? NC : 1];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    adg1[i] = adg2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (HB) adb1[HB ? i : 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t row = row_first; row < p.rows; row += row_step) {
+    const uint8_t* sa = wbase + s * R::STAGE_A;
+    mbar_wait(&bar_a[s], ph);
+    float4 xh1[NC], d[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      xh1[i] = reinterpret_cast<const float4*>(sa)[lane + 32 * i];
+      const uint2 u = reinterpret_cast<const uint2*>(sa + R::XB)[lane + 32 * i];
+      const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
+      d[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    const float4 st = *reinterpret_cast<const float4*>(sa + R::XB + R::DYB);
+    __syncwarp();   // every lane's reads of the stage are done: lane 0 re-arms it for the row after next
+    if (lane == 0 && row + 2 * row_step < p.rows) {
+      fence_proxy_async_smem();
+      issue_a(row + 2 * row_step, s);
+    }
+    const float rstd1 = st.y, mean2 = st.z, rstd2 = st.w;
+    const float nm1 = -st.x * rstd1, nm2 = -mean2 * rstd2;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      xh1[i].x = fmaf(xh1[i].x, rstd1, nm1); xh1[i].y = fmaf(xh1[i].y, rstd1, nm1);
+      xh1[i].z = fmaf(xh1[i].z, rstd1, nm1); xh1[i].w = fmaf(xh1[i].w, rstd1, nm1);
+    }
+    if (dbl) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const float4 G1 = g1[lane + 32 * i], G2 = g2[lane + 32 * i];
+        float4 xh2;
+        if (HB) {
+          const float4 B1 = b1[lane + 32 * i];
+          xh2.x = (xh1[i].x * G1.x + B1.x - mean2) * rstd2; xh2.y = (xh1[i].y * G1.y + B1.y - mean2) * rstd2;
+          xh2.z = (xh1[i].z * G1.z + B1.z - mean2) * rstd2; xh2.w = (xh1[i].w * G1.w + B1.w - mean2) * rstd2;
+        } else {
+          xh2.x = fmaf(xh1[i].x * G1.x, rstd2, nm2); xh2.y = fmaf(xh1[i].y * G1.y, rstd2, nm2);
+          xh2.z = fmaf(xh1[i].z * G1.z, rstd2, nm2); xh2.w = fmaf(xh1[i].w * G1.w, rstd2, nm2);
+        }
+        adg2[i].x += d[i].x * xh2.x; adg2[i].y += d[i].y * xh2.y; adg2[i].z += d[i].z * xh2.z; adg2[i].w += d[i].w * xh2.w;
+        d[i].x *= G2.x; d[i].y *= G2.y; d[i].z *= G2.z; d[i].w *= G2.w;
+        s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+        s2 += d[i].x * xh2.x + d[i].y * xh2.y + d[i].z * xh2.z + d[i].w * xh2.w;
+      }
+      s1 = warp_sum(s1) * invD;
+      s2 = warp_sum(s2) * invD;
+      const float c2a = -rstd2 * s1, c2b = -rstd2 * s2;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const float4 G1 = g1[lane + 32 * i];
+        if (HB) {
+          const float4 B1 = b1[lane + 32 * i];
+          d[i].x = rstd2 * (d[i].x - s1 - (xh1[i].x * G1.x + B1.x - mean2) * rstd2 * s2);
+          d[i].y = rstd2 * (d[i].y - s1 - (xh1[i].y * G1.y + B1.y - mean2) * rstd2 * s2);
+          d[i].z = rstd2 * (d[i].z - s1 - (xh1[i].z * G1.z + B1.z - mean2) * rstd2 * s2);
+          d[i].w = rstd2 * (d[i].w - s1 - (xh1[i].w * G1.w + B1.w - mean2) * rstd2 * s2);
+        } else {
+          d[i].x = fmaf(d[i].x, rstd2, fmaf(fmaf(xh1[i].x * G1.x, rstd2, nm2), c2b, c2a));
+          d[i].y = fmaf(d[i].y, rstd2, fmaf(fmaf(xh1[i].y * G1.y, rstd2, nm2), c2b, c2a));
+          d[i].z = fmaf(d[i].z, rstd2, fmaf(fmaf(xh1[i].z * G1.z, rstd2, nm2), c2b, c2a));
+          d[i].w = fmaf(d[i].w, rstd2, fmaf(fmaf(xh1[i].w * G1.w, rstd2, nm2), c2b, c2a));
+        }
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      adg1[i].x += d[i].x * xh1[i].x; adg1[i].y += d[i].y * xh1[i].y; adg1[i].z += d[i].z * xh1[i].z; adg1[i].w += d[i].w * xh1[i].w;
+      if (HB) {
+        adb1[HB ? i : 0].x += d[i].x; adb1[HB ? i : 0].y += d[i].y; adb1[HB ? i : 0].z += d[i].z; adb1[HB ? i : 0].w += d[i].w;
+      }
+      const float4 G1 = g1[lane + 32 * i];
+      d[i].x *= G1.x; d[i].y *= G1.y; d[i].z *= G1.z; d[i].w *= G1.w;
+      s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+      s2 += d[i].x * xh1[i].x + d[i].y * xh1[i].y + d[i].z * xh1[i].z + d[i].w * xh1[i].w;
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    const float c1a = -rstd1 * s1, c1b = -rstd1 * s2;
+    const float4* sr = reinterpret_cast<const float4*>(wbase + 2 * R::STAGE_A + s * R::STAGE_R);
+    if (p.dres) mbar_wait(&bar_r[s], ph);
+    float* dxr = p.dx + row * p.lddx;
+    __nv_bfloat16* dxb = p.dx_bf16 ? reinterpret_cast<__nv_bfloat16*>(p.dx_bf16) + row * p.lddxb : nullptr;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int c = lane + 32 * i;
+      float4 o;
+      o.x = fmaf(d[i].x, rstd1, fmaf(xh1[i].x, c1b, c1a));
+      o.y = fmaf(d[i].y, rstd1, fmaf(xh1[i].y, c1b, c1a));
+      o.z = fmaf(d[i].z, rstd1, fmaf(xh1[i].z, c1b, c1a));
+      o.w = fmaf(d[i].w, rstd1, fmaf(xh1[i].w, c1b, c1a));
+      if (p.dres) {
+        const float4 r = sr[c];
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      reinterpret_cast<float4*>(dxr)[c] = o;
+      if (dxb) reinterpret_cast<uint2*>(dxb)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+    if (p.dres) {
+      __syncwarp();
+      if (lane == 0 && row + 2 * row_step < p.rows) {
+        fence_proxy_async_smem();
+        issue_r(row + 2 * row_step, s);
+      }
+    }
+    s ^= 1;
+    if (s == 0) ph ^= 1;
+  }
+  // parameter gradients: every copy this warp issued has been waited for, so its ring is free: park the accumulators there,
+  // sum the warps' slices, then one atomic per column
+  __syncwarp();
+  {
+    float4* acc = reinterpret_cast<float4*>(wbase);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      acc[lane + 32 * i] = adg1[i];
+      acc[NC * 32 + lane + 32 * i] = adg2[i];
+      if (HB) acc[2 * NC * 32 + lane + 32 * i] = adb1[HB ? i : 0];
+    }
+  }
+  __syncthreads();
+  for (int a = 0; a < 3; ++a) {
+    float* dst = a == 0 ? p.dg1 : (a == 1 ? (dbl ? p.dg2 : nullptr) : (HB ? p.db1 : nullptr));
+    if (!dst) continue;
+    const uint8_t* base = ring_smem + R::PARAM_BYTES + R::BAR_BYTES + (size_t)a * NC * 512;
+    for (int c = threadIdx.x; c < NC * 32; c += blockDim.x) {
+      float4 t = reinterpret_cast<const float4*>(base)[c];
+#pragma unroll
+      for (int w = 1; w < W; ++w) {
+        const float4 u = reinterpret_cast<const float4*>(base + (size_t)w * R::WARP_BYTES)[c];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      atomicAdd(dst + 4 * c, t.x); atomicAdd(dst + 4 * c + 1, t.y);
+      atomicAdd(dst + 4 * c + 2, t.z); atomicAdd(dst + 4 * c + 3, t.w);
+    }
+  }
+}
+
 // Persistent grid = exactly the CTAs that are co-resident (occupancy x SMs): the row loop is grid-strided, so a grid
 // that is not a whole number of resident waves leaves SMs idle during the last wave.
 template <typename Kern>
@@ -426,7 +660,11 @@ extern "C" int mmf_layernorm_fwd(const float* x, const float* x2, int64_t x_spli
                 (reinterpret_cast<uintptr_t>(delta) & 7) || (reinterpret_cast<uintptr_t>(xout) & 15)))
     MMF_BAD_ARG(5);
   LnParams p{x, x2, x_split, rows, ldx, D, g1, b1, g2, eps1, eps2, y, ldy, y_f32, stats,
-             reinterpret_cast<const __nv_bfloat16*>(delta), delta_row0, lddelta, xout, ldxout};
+             reinterpret_cast<const __nv_bfloat16*>(delta), delta_row0, lddelta, xout, ldxout, 0};
+  const char* l2e = getenv("MMF_LN_FWD_L2PF");      // read per call (A/B runs switch it between launches)
+  // isolated, cfg-2 shape: the plain kernel gains 7 % one row step ahead (5.73 -> 6.15 TB/s), the residual-add variant is at
+  // 6.1 TB/s without it and loses with it
+  p.l2_prefetch = l2e ? atoi(l2e) : (delta ? 0 : 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nc = ceil_div(D, 128);
 #define MMF_LN_FWD_LAUNCH(NCV, F) ln_fwd_kernel<NCV, F><<<ln_grid(ln_fwd_kernel<NCV, F>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p)
@@ -452,7 +690,7 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
   if (g2 && !dg2) MMF_BAD_ARG(4);
   const char* l2e = getenv("MMF_LN_BWD_L2PF");      // read per call (A/B runs switch it between launches)
   LnBwdParams p{dy, lddy, dy_f32, x, x2, x_split, rows, ldx, D, g1, b1, g2, stats, dres, lddres, dx, lddx, dx_bf16, lddxb, dg1, db1,
-                g2 ? dg2 : nullptr, l2e ? atoi(l2e) : 1};
+                g2 ? dg2 : nullptr, l2e ? atoi(l2e) : 2};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nc = ceil_div(D, 128);
   const int ncp = nc <= 2 ? 2 : (nc <= 4 ? 4 : (nc <= 6 ? 6 : 8));
@@ -461,6 +699,39 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
   // ~58 KB per CTA at D = 768: ask for the full shared-memory carve-out so that three CTAs fit (the default carve-out
   // stops at two and shared memory, not registers, would set the occupancy)
   // row prefetch: 0.382 -> 0.329 ms at the cfg-2 shape (D = 768); at D = 1024 its registers spill, so it stays off there
+  // ring variant (bulk copies into per-warp shared-memory rings): MMF_LN_BWD_RING=0 falls back to the register-prefetch kernel
+  const char* ring_e = getenv("MMF_LN_BWD_RING");   // read per call (A/B runs switch it between launches)
+  const bool ring_ok = (ring_e ? atoi(ring_e) : 1) != 0 && D == ncp * 128 && !dy_f32 && (!b1 || db1) && !(lddy & 7) &&
+                       !(reinterpret_cast<uintptr_t>(dy) & 15) && !(reinterpret_cast<uintptr_t>(x) & 15) &&
+                       !(x2 && (reinterpret_cast<uintptr_t>(x2) & 15)) && !(reinterpret_cast<uintptr_t>(stats) & 15) &&
+                       !(dres && (reinterpret_cast<uintptr_t>(dres) & 15)) && !(reinterpret_cast<uintptr_t>(dx) & 15) &&
+                       !(dx_bf16 && (reinterpret_cast<uintptr_t>(dx_bf16) & 7));
+  if (ring_ok) {
+#define MMF_LN_RING_LAUNCH(NCV, HBV)                                                                                          \
+  do {                                                                                                                      \
+    static DeviceOnce attr_done;                                                                                            \
+    const int attr_dev = current_device();                                                                                  \
+    if (!attr_done.done(attr_dev)) {                                                                                        \
+      cudaFuncSetAttribute(ln_bwd_ring_kernel<NCV, HBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnRing<NCV>::SMEM);   \
+      attr_done.set(attr_dev);                                                                                              \
+    }                                                                                                                       \
+    int sms = 148;                                                                                                          \
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, attr_dev);                                                 \
+    const int64_t need = ceil_div64(rows, LnRing<NCV>::WARPS);                                                              \
+    ln_bwd_ring_kernel<NCV, HBV><<<(int)(need < sms ? need : sms), LnRing<NCV>::WARPS * 32, LnRing<NCV>::SMEM, st>>>(p);     \
+  } while (0)
+    if (b1) {
+      if (ncp == 2) MMF_LN_RING_LAUNCH(2, true); else if (ncp == 4) MMF_LN_RING_LAUNCH(4, true);
+      else if (ncp == 6) MMF_LN_RING_LAUNCH(6, true); else MMF_LN_RING_LAUNCH(8, true);
+    } else {
+      if (ncp == 2) MMF_LN_RING_LAUNCH(2, false); else if (ncp == 4) MMF_LN_RING_LAUNCH(4, false);
+      else if (ncp == 6) MMF_LN_RING_LAUNCH(6, false); else MMF_LN_RING_LAUNCH(8, false);
+    }
+#undef MMF_LN_RING_LAUNCH
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    MMF_LAUNCH_CHECK();
+    return 0;
+  }
   static const int variant = getenv("MMF_LN_BWD_PF") ? atoi(getenv("MMF_LN_BWD_PF")) : 1;
   const bool early = variant != 0 && nc <= 6;
 #define MMF_LN_BWD_LAUNCH(NCV, E, F, HBV)                                                                                       \

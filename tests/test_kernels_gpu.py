@@ -181,6 +181,53 @@ def test_layernorm_fwd_bwd(D, double):
         assert rel(dg2, g2.grad) < 2e-5
 
 
+@pytest.mark.parametrize("D", [256, 512, 768, 1024])
+@pytest.mark.parametrize("double", [False, True])
+@pytest.mark.parametrize("rows", [300, 9001])
+def test_layernorm_bwd_ring(D, double, rows, monkeypatch):
+    """the bulk-copy ring kernel (bf16 upstream gradient, D a multiple of 128): against torch autograd, and bit-identical dx to
+    the register-prefetch kernel it replaces (MMF_LN_BWD_RING=0); 9001 rows = up to five rows per warp, so both stages of the
+    ring wrap and the barrier phase flips; with and without the residual-branch gradient, with the input in two buffers"""
+    x = rnd(rows, D, seed=1, scale=2.0).requires_grad_(True)
+    g1 = (1 + 0.1 * rnd(D, seed=2)).requires_grad_(True)
+    b1 = None if double else (0.1 * rnd(D, seed=3)).requires_grad_(True)
+    g2 = (1 + 0.1 * rnd(D, seed=4)).requires_grad_(True) if double else None
+    eps1, eps2 = (1e-5, 1e-5) if double else (1e-6, 0.0)
+    y_ref = F.layer_norm(x, (D,), g1, b1, eps1)
+    if double:
+        y_ref = F.layer_norm(y_ref, (D,), g2, None, eps2)
+    dy = rnd(rows, D, seed=5).to(bf16)
+    dres = rnd(rows, D, seed=6)
+    y_ref.backward(dy.float())
+    y = torch.empty(rows, D, dtype=bf16, device="cuda")
+    stats = torch.empty(rows, 4, device="cuda")
+    kw = dict(b1=None if b1 is None else b1.detach(), g2=None if g2 is None else g2.detach())
+    K().layernorm_fwd(x.detach(), g1.detach(), y, eps1=eps1, eps2=eps2, stats=stats, **kw)
+    split = rows // 3
+    xa, xb = x.detach()[:split].clone(), x.detach()[split:].clone()
+    outs = {}
+    for ring in ("1", "0"):
+        monkeypatch.setenv("MMF_LN_BWD_RING", ring)
+        for case in ("dres", "plain", "two_sources"):
+            dx = torch.full((rows, D), float("nan"), device="cuda")
+            dxb = torch.full((rows, D), float("nan"), dtype=bf16, device="cuda")
+            dg1 = torch.zeros(D, device="cuda"); db1 = torch.zeros(D, device="cuda"); dg2 = torch.zeros(D, device="cuda")
+            src = dict(x2=xb, x_split=split, rows=rows) if case == "two_sources" else {}
+            K().layernorm_bwd(dy, xa if case == "two_sources" else x.detach(), g1.detach(), stats, dx, dg1,
+                              dres=dres if case == "dres" else None, dx_bf16=dxb, db1=None if b1 is None else db1,
+                              dg2=dg2 if double else None, **kw, **src)
+            want = x.grad + dres if case == "dres" else x.grad
+            assert rel(dx, want) < 2e-5 and rel(dxb, want) < 5e-3, (ring, case)
+            assert rel(dg1, g1.grad) < 2e-5, (ring, case)
+            if b1 is not None:
+                assert rel(db1, b1.grad) < 2e-5, (ring, case)
+            if double:
+                assert rel(dg2, g2.grad) < 2e-5, (ring, case)
+            outs[ring, case] = (dx, dxb)
+    for case in ("dres", "plain", "two_sources"):
+        assert torch.equal(outs["1", case][0], outs["0", case][0]) and torch.equal(outs["1", case][1], outs["0", case][1]), case
+
+
 def test_layernorm_two_sources():
     D = 256
     xa, xb = rnd(100, D, seed=1), rnd(60, D, seed=2)
