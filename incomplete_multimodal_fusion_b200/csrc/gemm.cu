@@ -52,6 +52,7 @@ struct GemmParams {
   float alpha;
   int32_t fast_ok;  // all pitches / pointers allow the vectorised epilogue
   int32_t one;      // always 1, but opaque to the compiler: pins basic-block boundaries in the epilogues (see GEGLU)
+  int32_t epi_flags;  // debug builds (-DMMF_GEMM_CLOCKS) only: epilogue ablation bits, see GABL
 };
 
 __device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
@@ -71,6 +72,20 @@ enum : int {
   EPI_BF16_ACC = 5, // out bf16 += alpha*acc
   EPI_GEGLU_BWD = 6 // acc = dg (gradient of the GEGLU output); out2 = saved [value | gate] (INPUT), out = [dvalue | dgate] bf16
 };
+
+#ifdef MMF_GEMM_CLOCKS
+// timing experiments only (tools/gemm_clocks.py, debug build): per-phase clock totals of one cluster's warps
+__device__ unsigned long long g_gemm_clk[32];
+#define GCLK(i) do { if (dbg_on) { const unsigned t__ = clock(); acc_clk[i] += t__ - t_last; t_last = t__; } } while (0)
+#define GCLK_DECL(cond) const bool dbg_on = (cond); unsigned acc_clk[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; unsigned t_last = clock()
+#define GCLK_FLUSH(base, n) do { if (dbg_on) for (int i__ = 0; i__ < (n); ++i__) g_gemm_clk[(base) + i__] = acc_clk[i__]; } while (0)
+#define GABL(bit) ((p.epi_flags & (bit)) != 0)   // ablations of the GEGLU-backward epilogue (MMF_GEGLU_BWD_ABL): 2 math, 4 stores, 8 loads
+#else
+#define GABL(bit) false
+#define GCLK(i) do { } while (0)
+#define GCLK_DECL(cond) do { } while (0)
+#define GCLK_FLUSH(base, n) do { } while (0)
+#endif
 
 // Per-warp 32x32 fp32 staging block, 128-byte rows, 16-byte groups XOR-swizzled with (row & 7): the row-per-lane
 // 128-bit writes and the row-contiguous 128-bit reads both run at one 128-byte wavefront per 8 lanes.
@@ -624,6 +639,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      GCLK_DECL(cluster_id == 5 && leader);
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         const int tile = w % tiles_mn;
         const int split = w / tiles_mn;
@@ -632,7 +648,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         for (int kb = kb0; kb < kb1; ++kb) {
+          GCLK(0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          GCLK(1);
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
           uint8_t* sa = smem_a + stage * G2_A_BYTES;
           uint8_t* sb = smem_b + stage * G2_B_BYTES;
@@ -654,6 +672,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      GCLK_FLUSH(20, 2);
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
@@ -673,16 +692,21 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      GCLK_DECL(cluster_id == 5 && lane == 0);
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         const int split = w / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        GCLK(0);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        GCLK(1);
         const uint32_t tmem_d = tmem0 + acc * G2_BN;
         for (int kb = kb0; kb < kb1; ++kb) {
+          GCLK(0);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          GCLK(2);
           if (issuer) {
             const uint64_t da = da0 + (uint64_t)(stage * (G2_A_BYTES >> 4));
             const uint64_t db = db0 + (uint64_t)(stage * (G2_B_BYTES >> 4));
@@ -697,7 +721,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         if (issuer) umma_commit_cg2(&tmem_full[acc]);       // accumulator ready, both CTAs' epilogues
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef MMF_GEMM_CLOCKS
+        if (dbg_on) g_gemm_clk[31] += 1;
+#endif
       }
+      GCLK_FLUSH(16, 3);
     }
   } else {
     // ------------------------------ epilogue (warps 2..9, both CTAs) ------------------------------
@@ -731,17 +759,27 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             lv = ww < total_work && cb < p.N && r0 < p.M;   // warp-uniform
           };
           auto load_half = [&](int h, int cb, int r0) {
+            if (GABL(8)) return;
             mbar_expect_tx(&box_bar[2 * ew + h], 4096);
             tma_load_2d(sbox + h * 4096, &tmap_o2, &box_bar[2 * ew + h], cb + 32 * h, r0);
             tma_load_2d(sbox + h * 4096 + 2048, &tmap_o2, &box_bar[2 * ew + h], ipad + cb + 32 * h, r0);
           };
           int cb, r0, cbn, r0n;
           bool live, live_n;
+#ifdef MMF_GEMM_CLOCKS
+          const bool dbg_on = cluster_id == 5 && rank == 0 && ew == 5 && lane == 0;
+          static __shared__ unsigned acc_clk_s[10];
+          unsigned* acc_clk = acc_clk_s;
+          if (dbg_on && w == cluster_id) for (int i = 0; i < 10; ++i) acc_clk[i] = 0;
+          unsigned t_last = clock();
+#endif
           coords(w, cb, r0, live);
           if (w == cluster_id && live && lane == 0) { load_half(0, cb, r0); load_half(1, cb, r0); }
           coords(w + num_clusters, cbn, r0n, live_n);
+          GCLK(0);
           mbar_wait(&tmem_full[acc], acc_phase);
           tc_fence_after();
+          GCLK(1);
           if (!live) {
             tc_fence_before();
             __syncwarp();
@@ -760,17 +798,24 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
               }
-              mbar_wait(&box_bar[2 * ew + h], box_phase);
+              GCLK(2);
+              if (!GABL(8)) mbar_wait(&box_bar[2 * ew + h], box_phase);
+              GCLK(3 + h);
               uint8_t* hb = sbox + h * 4096;
-              geglu_bwd_box32(hb, hb + 2048, vh, lane, p.alpha);
+              if (!GABL(2)) geglu_bwd_box32(hb, hb + 2048, vh, lane, p.alpha);
               fence_proxy_async_smem();
               __syncwarp();
+              GCLK(5);
               if (lane == 0) {
-                tma_store_2d(&tmap_o, hb, cb + 32 * h, r0);
-                tma_store_2d(&tmap_o, hb + 2048, ipad + cb + 32 * h, r0);
+                if (!GABL(4)) {
+                  tma_store_2d(&tmap_o, hb, cb + 32 * h, r0);
+                  tma_store_2d(&tmap_o, hb + 2048, ipad + cb + 32 * h, r0);
+                }
                 tma_store_commit();
+                GCLK(6);
                 if (live_n) {
                   tma_store_wait_read<0>();   // this half's boxes have left shared memory
+                  GCLK(7);
                   load_half(h, cbn, r0n);
                 }
               }
@@ -780,6 +825,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             load_half(0, cbn, r0n); load_half(1, cbn, r0n);
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          GCLK(8);
+          GCLK_FLUSH(0, 9);
           continue;
         }
         mbar_wait(&tmem_full[acc], acc_phase);
@@ -1097,6 +1144,11 @@ static int launch_gemm2(const MmfGemmArgs& a, cudaStream_t stream) {
   p.split_k = ceil_div(p.num_kb, p.kb_per_split);
   p.geglu_ipad = a.N;
   p.alpha = a.alpha;
+#ifdef MMF_GEMM_CLOCKS
+  { const char* e = getenv("MMF_GEGLU_BWD_ABL"); p.epi_flags = e ? atoi(e) : 0; }
+#else
+  p.epi_flags = 0;
+#endif
   p.one = 1;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.fast_ok = (a.ldo % 4 == 0) && al16(a.out) && (!a.residual || (a.ldr % 4 == 0 && al16(a.residual))) &&
@@ -1233,3 +1285,13 @@ extern "C" int mmf_abi_version(void) { return 1; }
 extern "C" void mmf_set_gemm_reserved_sms(int32_t n) { mmf::g_reserved_sms.store(n < 0 ? 0 : n); }
 extern "C" int64_t mmf_launch_count(void) { return mmf::g_launch_count.load(); }
 extern "C" void mmf_reset_launch_count(void) { mmf::g_launch_count.store(0); }
+
+#ifdef MMF_GEMM_CLOCKS
+extern "C" int mmf_debug_gemm_clocks(unsigned long long* out32, int reset) {
+  if (reset) {
+    unsigned long long z[32] = {0};
+    return (int)cudaMemcpyToSymbol(mmf::g_gemm_clk, z, sizeof(z));
+  }
+  return (int)cudaMemcpyFromSymbol(out32, mmf::g_gemm_clk, 32 * sizeof(unsigned long long));
+}
+#endif
