@@ -528,23 +528,34 @@ __device__ __forceinline__ void geglu_bwd_pair(uint32_t vraw, uint32_t graw, flo
   og = pack_bf16(o0, o1);
 }
 
+// explicit shared-window accesses: through uint8_t* the box pointers are generic to ptxas (ST.E.128 / LD.E.128 in the SASS)
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // 32 columns of the fused GEGLU backward, in place on this lane's row of a (value, gate) box pair (32 rows x 64 bytes,
 // CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index XOR address bits 7-8)
 __device__ __forceinline__ void geglu_bwd_box32(uint8_t* vbox, uint8_t* gbox, const uint32_t* acc, int lane, float alpha) {
   const uint64_t alpha2 = f2_pack(alpha, alpha);
+  const uint32_t vb = smem_u32(vbox), gb = smem_u32(gbox);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
-    const uint4 uv = *reinterpret_cast<const uint4*>(vbox + off);
-    const uint4 ug = *reinterpret_cast<const uint4*>(gbox + off);
+    const uint4 uv = lds128(vb + off);
+    const uint4 ug = lds128(gb + off);
     const uint32_t* pv = &uv.x; const uint32_t* pg = &ug.x;
     uint4 ov, og;
     uint32_t* qv = &ov.x; uint32_t* qg = &og.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       geglu_bwd_pair(pv[k], pg[k], __uint_as_float(acc[8 * j + 2 * k]), __uint_as_float(acc[8 * j + 2 * k + 1]), alpha2, qv[k], qg[k]);
-    *reinterpret_cast<uint4*>(vbox + off) = ov;
-    *reinterpret_cast<uint4*>(gbox + off) = og;
+    sts128(vb + off, ov);
+    sts128(gb + off, og);
   }
 }
 
@@ -559,8 +570,8 @@ __device__ __forceinline__ void pack_box(uint8_t* box, const uint32_t (&v)[64], 
       x[t] = __uint_as_float(v[8 * j + t]) * alpha;
       if (bias != nullptr) x[t] += __ldg(bias + 8 * j + t);
     }
-    *reinterpret_cast<uint4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-        make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    sts128(smem_u32(box) + lane * 128 + ((j ^ (lane & 7)) << 4),
+           make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7])));
   }
 }
 
@@ -829,8 +840,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           GCLK_FLUSH(0, 9);
           continue;
         }
+#ifdef MMF_GEMM_CLOCKS
+        const bool dbg_on = cluster_id == 5 && rank == 0 && ew == 5 && lane == 0;
+        static __shared__ unsigned acc_clk_t[10];
+        unsigned* acc_clk = acc_clk_t;
+        if (dbg_on && w == cluster_id) for (int i = 0; i < 10; ++i) acc_clk[i] = 0;
+        unsigned t_last = clock();
+#endif
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
+        GCLK(1);
         if constexpr (!geglu) {
           const int col_base = n0 + half * 128;
           const bool live0 = col_base < p.N && row0 < p.M, live1 = col_base + 64 < p.N && row0 < p.M;   // warp-uniform
@@ -840,9 +859,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);   // accumulator released before any store work
+          GCLK(2);
           if (live0) {
             if (lane == 0) tma_store_wait_read<0>();   // the previous tile's stores have drained this warp's boxes
             __syncwarp();
+            GCLK(3);
             if constexpr (EPI == EPI_GELU) {
               // x = alpha * acc + bias; out2 (optional) = x, out = gelu(x): both leave through the same two boxes
               bias_scale64(v0, p.bias ? p.bias + col_base : nullptr, p.alpha);
@@ -872,16 +893,22 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               if (live1) pack_box(sbox + 4096, v1, lane, nullptr, 1.0f);
             } else {
               pack_box(sbox, v0, lane, p.bias ? p.bias + col_base : nullptr, p.alpha);
+              GCLK(6);
               if (live1) pack_box(sbox + 4096, v1, lane, p.bias ? p.bias + col_base + 64 : nullptr, p.alpha);
+              GCLK(7);
             }
             fence_proxy_async_smem();
+            GCLK(8);
             __syncwarp();
+            GCLK(4);
             if (lane == 0) {
               tma_store_2d(&tmap_o, sbox, col_base, row0);
               if (live1) tma_store_2d(&tmap_o, sbox + 4096, col_base + 64, row0);
               tma_store_commit();
             }
+            GCLK(5);
           }
+          GCLK_FLUSH(0, 9);
         } else {
           // value columns [half*64, +64) and the gate columns of the same 64 features
           const int col_base = n0 + half * 64;

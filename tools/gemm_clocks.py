@@ -13,7 +13,7 @@ _lib.LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__f
 from incomplete_multimodal_fusion_b200 import kernels as K
 lib = _lib.load()
 raw = C.CDLL(_lib.LIB_PATH)
-M, D, I = 125440, 768, 2048
+M, D, I = int(os.environ.get("AB_M", "125440")), 768, 2048
 bf16 = torch.bfloat16
 dY = (torch.randn(M, D, device="cuda") * 0.5).to(bf16); W2 = (torch.randn(D, I, device="cuda") * 0.1).to(bf16)
 u = torch.randn(M, 2 * I, device="cuda").to(bf16); du = torch.empty(M, 2 * I, dtype=bf16, device="cuda")
@@ -37,6 +37,9 @@ for v in sys.argv[1:] or ["0"]:
     names = {0: "epi: loop top / coords", 1: "epi: wait tmem_full (accumulator)", 2: "epi: tcgen05.ld (+ release on h=1)", 3: "epi: wait boxes h=0",
              4: "epi: wait boxes h=1", 5: "epi: GEGLU-backward math + fence", 6: "epi: issue stores", 7: "epi: wait store read", 8: "epi: issue next loads",
              16: "mma: issue + loop", 17: "mma: wait tmem_empty", 18: "mma: wait full_bar (operands)", 20: "tma: issue", 21: "tma: wait empty_bar (slot free)"}
+    if os.environ.get("PLAIN"):
+        names = {1: "epi: wait tmem_full (accumulator)", 2: "epi: tcgen05.ld 2 x 64 columns + release", 3: "epi: wait previous stores read",
+                 6: "epi: pack box 0", 7: "epi: pack box 1", 8: "epi: fence.proxy.async", 4: "epi: syncwarp", 5: "epi: issue stores (+ loop)", **{k: v for k, v in names.items() if k >= 16}}
     print("flags %s: %.3f ms, %d tiles on this pair, %.0f clk per tile (clock() domain)" % (v, e0.elapsed_time(e1), tiles, sum(buf[i] for i in range(9)) / tiles))
     for i, n in names.items():
         print(f"  {n:44s} {buf[i]:10d} clk   per tile {buf[i]/tiles:8.0f}")
