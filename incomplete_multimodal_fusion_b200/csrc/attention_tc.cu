@@ -1649,10 +1649,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
       auto store_stats = [&](int gg) {
         const int stg = gg & 1;
         mbar_wait(&st_empty[stg], ((gg >> 1) & 1) ^ 1);
-        s_lse[stg * BW_BLK + lane] = ok0 ? l0 * 1.4426950408889634f : INFINITY;        // +inf beyond nvalid -> P = 0
-        s_lse[stg * BW_BLK + lane + 32] = ok1 ? l1 * 1.4426950408889634f : INFINITY;
-        s_dl[stg * BW_BLK + lane] = ok0 ? d0 : 0.f;
-        s_dl[stg * BW_BLK + lane + 32] = ok1 ? d1 : 0.f;
+        sts_f1(smem_u32(s_lse + stg * BW_BLK + lane), ok0 ? l0 * 1.4426950408889634f : INFINITY);        // +inf beyond nvalid -> P = 0
+        sts_f1(smem_u32(s_lse + stg * BW_BLK + lane + 32), ok1 ? l1 * 1.4426950408889634f : INFINITY);
+        sts_f1(smem_u32(s_dl + stg * BW_BLK + lane), ok0 ? d0 : 0.f);
+        sts_f1(smem_u32(s_dl + stg * BW_BLK + lane + 32), ok1 ? d1 : 0.f);
         __syncwarp();
         if (lane == 0) mbar_arrive(&st_full[stg]);
       };
@@ -1740,8 +1740,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
         CLK2(4, 0);
         mbar_wait(&st_full[st], (g >> 1) & 1);
         CLK2(5, 0);
-        const float* ls = s_lse + st * BW_BLK;
-        const float* dl = s_dl + st * BW_BLK;
+        const uint32_t ls = smem_u32(s_lse + st * BW_BLK), dl = smem_u32(s_dl + st * BW_BLK);   // explicit ld.shared below: as float* these were generic LD.E.128
 #pragma unroll
         for (int c = 0; c < 2; ++c) {   // the block's two 32-query halves (see the MMA warp)
           if (nvalid <= 32 * c) continue;
@@ -1754,7 +1753,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_
           uint32_t pd[32];                               // P^T (0..15) | dS^T (16..31), one TMEM write
 #pragma unroll
           for (int t = 0; t < 8; ++t) {   // four query columns per step: one 16-byte broadcast read of lse and of delta
-            const float4 l4 = reinterpret_cast<const float4*>(ls)[c * 8 + t], d4 = reinterpret_cast<const float4*>(dl)[c * 8 + t];
+            const float4 l4 = lds_f4(ls + (c * 8 + t) * 16), d4 = lds_f4(dl + (c * 8 + t) * 16);
             const float p0 = ex2(fmaf(__uint_as_float(sd[4 * t]), p.scale_log2, -l4.x));        // lse = +inf beyond nvalid -> 0
             const float p1 = ex2(fmaf(__uint_as_float(sd[4 * t + 1]), p.scale_log2, -l4.y));
             const float p2 = ex2(fmaf(__uint_as_float(sd[4 * t + 2]), p.scale_log2, -l4.z));
