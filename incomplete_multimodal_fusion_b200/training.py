@@ -8,6 +8,8 @@ NCCL all-reduce (mean) on a side stream while the rest of the step proceeds."""
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -75,6 +77,13 @@ class GradAllReduce:
         self._call = 0
         self._reduced = set()    # data_ptr of gradients already reduced this step
         self._keep = []          # source tensors kept alive until the side stream has consumed them
+        # MMF_ALLREDUCE=end (default): the buckets are filled during backward as usual but all-reduced back to back on the
+        # main stream in finish(), after the last backward kernel; MMF_ALLREDUCE=overlap launches each bucket's all-reduce
+        # on a side stream as soon as it is full.  Overlapped NCCL kernels cannot share an SM with the persistent GEMM
+        # CTAs (registers), so they start at kernel boundaries and delay whole GEMM clusters: measured 135.2 ms (overlap)
+        # against 133.0 ms (end) per step at 8 GPUs, 130.6 against 129.2 ms at 2 (profiles/r02_allreduce_modes.json).
+        self.deferred = os.environ.get("MMF_ALLREDUCE", "end") == "end"
+        self._pending = []       # deferred mode: flat buffers awaiting their all-reduce
 
     def enabled(self) -> bool:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
@@ -99,6 +108,9 @@ class GradAllReduce:
         if dev.type != "cuda":                      # gloo / CPU (tests): same bucketing, no streams
             torch._foreach_copy_(views, [t.reshape(v.shape) for t, v in zip(tensors, views)])
             dist.all_reduce(flat, group=self.group)
+        elif self.deferred:
+            torch._foreach_copy_(views, list(tensors))
+            self._pending.append(flat)
         else:
             if self.stream is None:
                 self.stream = torch.cuda.Stream()
@@ -119,6 +131,8 @@ class GradAllReduce:
             return
         if flat.device.type != "cuda":
             dist.all_reduce(flat, group=self.group)
+        elif self.deferred:
+            self._pending.append(flat)
         else:
             if self.stream is None:
                 self.stream = torch.cuda.Stream()
@@ -140,6 +154,18 @@ class GradAllReduce:
                 views = self.reduce_now([p.grad for p in rest])
                 for p, v in zip(rest, views):
                     p.grad = v
+            if self._pending:
+                torch.cuda.nvtx.range_push("mmf.allreduce")
+                cm = getattr(dist, "_coalescing_manager", None) if os.environ.get("MMF_ALLREDUCE_COALESCE", "1") != "0" else None
+                if cm is not None and self._pending[0].is_cuda:
+                    with cm(group=self.group, device=self._pending[0].device):   # one ncclGroup: a single fused launch
+                        for flat in self._pending:
+                            dist.all_reduce(flat, group=self.group)
+                else:
+                    for flat in self._pending:
+                        dist.all_reduce(flat, group=self.group)
+                torch.cuda.nvtx.range_pop()
+                self._pending.clear()
             if self.stream is not None:
                 torch.cuda.current_stream().wait_stream(self.stream)
         self._call = 0
