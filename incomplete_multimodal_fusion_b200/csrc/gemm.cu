@@ -797,18 +797,17 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
           }
           if (live) {
+            // the whole 64-column share in ONE tcgen05.ld (a TMEM read costs ~1.5-3 k clk here whatever its width while the
+            // other accumulator's MMAs run: two 32-column reads were 5.8 k of the 15.3 k clk per tile), accumulator released at once
+            uint32_t v64[64];
+            tmem_ld_32x64(taddr + part * 64, v64);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              // 32 accumulator columns per half, read where they are used: the 64-register read of the whole share
-              // spilled under this kernel's 96-register cap (18 warps); the accumulator is released after the second read
-              uint32_t vh[32];
-              tmem_ld_32x32(taddr + part * 64 + 32 * h, vh);
-              tmem_wait_ld();
-              if (h == 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
-              }
+              const uint32_t* vh = v64 + 32 * h;
               GCLK(2);
               if (!GABL(8)) mbar_wait(&box_bar[2 * ew + h], box_phase);
               GCLK(3 + h);
