@@ -291,6 +291,51 @@ def test_attention_fwd_bwd(dh, H, counts, nf):
     assert rel(got, qkv.grad) < 1.5e-2
 
 
+@pytest.mark.parametrize("counts", [(98, 98, 98), (150, 0, 144), (37, 196, 61), (0, 196, 98), (148, 148, 148), (196, 196, 196),
+                                    (1, 196, 97), (294, 0, 0)])
+def test_attention_encoder_shapes(counts):
+    """the tcgen05 kernels at the encoder's own shapes: H = 8 heads of 64, 196 fusion tokens behind nenc = 294 / 444 / 588
+    visible tokens (N = 490 / 640 / 784) in ragged modality segments, including an absent modality, a one-token segment
+    and a single-modality sample; per-row errors next to the L2 ratio (a few wrong rows would hide in the latter)"""
+    B, H, dh, nf = 2, 8, 64, 196
+    nenc = sum(counts)
+    N, n_head = nenc + nf, nenc
+    seg = torch.tensor([0, counts[0], counts[0] + counts[1], nenc, N], dtype=torch.int32, device="cuda")
+    types = torch.cat([torch.full((c,), i) for i, c in enumerate(list(counts) + [nf])]).cuda()
+    allowed = (types[:, None] == types[None, :]) | (types[:, None] == 3)
+    scale = dh ** -0.5
+    qkv = rnd(B, N, 3 * H * dh, dtype=bf16, seed=11).requires_grad_(True)
+    q, k, v = [t.view(B, N, H, dh).transpose(1, 2).float() for t in qkv.chunk(3, -1)]
+    s = ((q @ k.transpose(-1, -2)) * scale).masked_fill(~allowed, float("-inf"))
+    o_ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, N, H * dh)
+    do = rnd(B, N, H * dh, dtype=bf16, seed=12)
+    o_ref.backward(do.float())
+    qkv_p = _planar(qkv.detach(), B, n_head)
+    HD = H * dh
+    o = torch.full((B * N, HD), float("nan"), dtype=bf16, device="cuda")
+    lse = torch.empty(B, H, N, device="cuda")
+    kw = dict(B=B, H=H, Nq=N, Nk=N, dh=dh, scale=scale, n_head_q=n_head, n_head_k=n_head, seg=seg, nseg=4)
+    K().attn_fwd(qkv_p[:, :HD], qkv_p[:, HD:2 * HD], qkv_p[:, 2 * HD:], o, lse, **kw)
+    got_o = _unplanar(o, B, N, n_head).float()
+    assert torch.isfinite(got_o).all()
+    assert rel(got_o, o_ref) < 8e-3
+    lse_ref = torch.logsumexp(s, -1)                                     # [B, H, N] in token order
+    assert (lse - lse_ref).abs().max() < 2e-2
+    row = lambda a, b: ((a - b).norm(dim=-1) / b.norm(dim=-1).mean()).max()
+    assert row(got_o, o_ref.detach()) < 4e-2
+    dqkv = torch.full_like(qkv_p, float("nan"))
+    delta = torch.empty(B, H, N, device="cuda")
+    K().attn_bwd(qkv_p[:, :HD], qkv_p[:, HD:2 * HD], qkv_p[:, 2 * HD:], o, lse, _planar(do, B, n_head),
+                 dqkv[:, :HD], dqkv[:, HD:2 * HD], dqkv[:, 2 * HD:], delta, **kw)
+    got = _unplanar(dqkv, B, N, n_head).float()
+    assert torch.isfinite(got).all()
+    assert rel(got, qkv.grad) < 1.5e-2
+    for part, name in zip(range(3), "qkv"):
+        a, b = got[..., part * HD:(part + 1) * HD], qkv.grad[..., part * HD:(part + 1) * HD]
+        assert rel(a, b) < 1.5e-2, name
+        assert row(a, b) < 8e-2, name
+
+
 def test_slot_attention_fwd_bwd():
     B, Fn, H, S = 3, 16, 2, 4
     counts = (9, 0, 5)
