@@ -18,12 +18,21 @@ bf16 = torch.bfloat16
 dY = (torch.randn(M, D, device="cuda") * 0.5).to(bf16); W2 = (torch.randn(D, I, device="cuda") * 0.1).to(bf16)
 u = torch.randn(M, 2 * I, device="cuda").to(bf16); du = torch.empty(M, 2 * I, dtype=bf16, device="cuda")
 f = lambda: K.gemm(dY, W2, du, b_mn=True, act=3, out2=u)
-if os.environ.get("PLAIN"):   # a plain bf16 GEMM instead: PLAIN=N,K[,geglu] (fwd layout), only the mma / tma rows are meaningful
+if os.environ.get("PLAIN") and not os.environ.get("WGRAD"):   # a plain bf16 GEMM instead: PLAIN=N,K[,geglu] (fwd layout), only the mma / tma rows are meaningful
     sp = os.environ["PLAIN"].split(",")
     N_, K_ = int(sp[0]), int(sp[1]); act = 2 if len(sp) > 2 else 0
     a_ = (torch.randn(M, K_, device="cuda") * .1).to(bf16); w_ = (torch.randn(N_, K_, device="cuda") * .1).to(bf16)
     o_ = torch.empty(M, N_ // 2 if act == 2 else N_, dtype=bf16, device="cuda")
     f = lambda: K.gemm(a_, w_, o_, act=act)
+if os.environ.get("WGRAD"):   # WGRAD=NO,KI: dW[NO, KI] = dY[M, NO]^T . X[M, KI] (both operands MN-major, split-K, fp32 atomics)
+    from incomplete_multimodal_fusion_b200.functions import _wgrad_split
+    NO, KI = [int(t) for t in os.environ["WGRAD"].split(",")]
+    dy_ = (torch.randn(M, NO, device="cuda") * .1).to(bf16); x_ = (torch.randn(M, KI, device="cuda") * .1).to(bf16)
+    dw_ = torch.zeros(NO, KI, dtype=torch.float32, device="cuda")
+    sk = int(os.environ.get("SPLITK", _wgrad_split(M, NO * KI)))
+    print("wgrad %dx%d K=%d split_k=%d" % (NO, KI, M, sk))
+    f = lambda: K.gemm(dy_, x_, dw_, a_mn=True, b_mn=True, split_k=sk)
+    os.environ["PLAIN"] = "1"
 for v in sys.argv[1:] or ["0"]:
     os.environ["MMF_GEGLU_BWD_ABL"] = v
     for _ in range(3): f()
