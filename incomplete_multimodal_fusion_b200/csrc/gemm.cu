@@ -77,8 +77,8 @@ enum : int {
 // timing experiments only (tools/gemm_clocks.py, debug build): per-phase clock totals of one cluster's warps
 __device__ unsigned long long g_gemm_clk[32];
 #define GCLK(i) do { if (dbg_on) { const unsigned t__ = clock(); acc_clk[i] += t__ - t_last; t_last = t__; } } while (0)
-#define GCLK_DECL(cond) const bool dbg_on = (cond); unsigned acc_clk[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; unsigned t_last = clock()
-#define GCLK_FLUSH(base, n) do { if (dbg_on) for (int i__ = 0; i__ < (n); ++i__) g_gemm_clk[(base) + i__] = acc_clk[i__]; } while (0)
+#define GCLK_DECL(cond) const bool dbg_on = (cond); unsigned acc_clk[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; unsigned t_last = clock(); (void)t_last
+#define GCLK_FLUSH(base, n) do { if (dbg_on && (threadIdx.x & 31) == 0) for (int i__ = 0; i__ < (n); ++i__) g_gemm_clk[(base) + i__] = acc_clk[i__]; } while (0)
 #define GABL(bit) ((p.epi_flags & (bit)) != 0)   // ablations of the GEGLU-backward epilogue (MMF_GEGLU_BWD_ABL): 2 math, 4 stores, 8 loads
 #else
 #define GABL(bit) false
@@ -469,11 +469,19 @@ struct G2Cfg {
   static constexpr bool GB = (EPI == EPI_GEGLU_BWD);
   // epilogue warps per CTA: 2 per TMEM lane quarter (128 columns each); the GEGLU backward does ~30 FMA-pipe
   // instructions + 2 MUFU per accumulator element, so it runs 4 per quarter (64 columns each) to have the issue slots
-  static constexpr int EPI_WARPS = GB ? 16 : 8;
+  // GELU TMA-store epilogue (two outputs through the same boxes): 4 warps per quarter as well, 64 columns and ONE box each:
+  // 83 -> 68 us on the decoders' fc1 (M = 50176, N = 1024, K = 256).  The plain bf16 kind measured no faster that way
+  // (44.5 vs 46.2 us on the same shape, 37.9 vs 40.6 us at N = 768, K = 512: the chain is not per-warp pack latency) and
+  // keeps 2 warps per quarter; -DMMF_TS_EPI16=1 builds it with 4 for A/B runs.
+#ifndef MMF_TS_EPI16
+#define MMF_TS_EPI16 0
+#endif
+  static constexpr bool WIDE16 = TS && (EPI == EPI_GELU || (EPI == EPI_BF16 && (MMF_TS_EPI16 != 0)));
+  static constexpr int EPI_WARPS = (GB || WIDE16) ? 16 : 8;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int STAGES = GB ? 3 : (TS ? 5 : 6);
   // per epilogue warp: two 4 KB boxes / one 32x32 fp32 block
-  static constexpr int STG_WARP = (TS || GB) ? 8192 : STG_FLOATS * 4;
+  static constexpr int STG_WARP = WIDE16 ? 4096 : ((TS || GB) ? 8192 : STG_FLOATS * 4);
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;
   static constexpr int SMEM_BYTES = STAGES * G2_STAGE_BYTES + STG_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
@@ -749,6 +757,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if constexpr (TS) {
       uint8_t* sbox = stage_bytes + ew * G2Cfg<EPI, TS>::STG_WARP;   // two 4 KB boxes
       uint32_t box_phase = 0;
+      GCLK_DECL(cluster_id == 5 && rank == 0 && ew == 5);   // the whole warp takes the clocks (a lane-0 condition would diverge the measured code)
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         const int tile = w % tiles_mn;
         const int m0 = (tile / p.n_tiles) * 256 + (int)rank * 128;
@@ -778,11 +787,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           int cb, r0, cbn, r0n;
           bool live, live_n;
 #ifdef MMF_GEMM_CLOCKS
-          const bool dbg_on = cluster_id == 5 && rank == 0 && ew == 5 && lane == 0;
-          static __shared__ unsigned acc_clk_s[10];
-          unsigned* acc_clk = acc_clk_s;
-          if (dbg_on && w == cluster_id) for (int i = 0; i < 10; ++i) acc_clk[i] = 0;
-          unsigned t_last = clock();
+          t_last = clock();
 #endif
           coords(w, cb, r0, live);
           if (w == cluster_id && live && lane == 0) { load_half(0, cb, r0); load_half(1, cb, r0); }
@@ -840,20 +845,18 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           continue;
         }
 #ifdef MMF_GEMM_CLOCKS
-        const bool dbg_on = cluster_id == 5 && rank == 0 && ew == 5 && lane == 0;
-        static __shared__ unsigned acc_clk_t[10];
-        unsigned* acc_clk = acc_clk_t;
-        if (dbg_on && w == cluster_id) for (int i = 0; i < 10; ++i) acc_clk[i] = 0;
-        unsigned t_last = clock();
+        t_last = clock();
 #endif
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         GCLK(1);
         if constexpr (!geglu) {
-          const int col_base = n0 + half * 128;
-          const bool live0 = col_base < p.N && row0 < p.M, live1 = col_base + 64 < p.N && row0 < p.M;   // warp-uniform
-          if (live0) tmem_ld_32x64(taddr + half * 128, v0);
-          if (live1) tmem_ld_32x64(taddr + half * 128 + 64, v1);
+          constexpr bool W16 = G2Cfg<EPI, TS>::WIDE16;   // 16 epilogue warps: `half` is 0..3 and selects 64 columns, one box per warp
+          constexpr int EW_COLS = W16 ? 64 : 128;
+          const int col_base = n0 + half * EW_COLS;
+          const bool live0 = col_base < p.N && row0 < p.M, live1 = !W16 && col_base + 64 < p.N && row0 < p.M;   // warp-uniform
+          if (live0) tmem_ld_32x64(taddr + half * EW_COLS, v0);
+          if (live1) tmem_ld_32x64(taddr + half * EW_COLS + 64, v1);
           tmem_wait_ld();
           tc_fence_before();
           __syncwarp();
