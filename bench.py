@@ -287,8 +287,9 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"     # NCCL prints its version banner on STDOUT; rank 0 prints one JSON line only
+    # NCCL writes its version banner (NCCL_DEBUG >= VERSION, which includes WARN) to STDOUT; rank 0's stdout is ONE JSON line,
+    # so its log goes to stderr unless the caller chose a file
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local)
     reserve = int(os.environ.get("MMF_RESERVE_SMS", "0"))
     if world > 1:
