@@ -50,7 +50,7 @@ for name, N, Kd in [("dh1", 768, 1536), ("do", 512, 768), ("dg", 2048, 768), ("d
     ms = t(lambda: K.gemm(a, w, out, b_mn=True)); rows.append(("dgrad " + name, ms, 2 * M * N * Kd))
 for name, NO, KI in [("dWqkv", 1536, 768), ("dWo", 768, 512), ("dW1", 4096, 768), ("dW2", 768, 2048)]:
     dy = rnd(M, NO); x = rnd(M, KI); out = torch.zeros(NO, KI, dtype=f32, device=dev)
-    sk = _wgrad_split(M, NO * KI)
+    sk = _wgrad_split(M, NO * KI, NO, KI)
     ms = t(lambda: K.gemm(dy, x, out, a_mn=True, b_mn=True, split_k=sk)); rows.append((f"wgrad {name} split{sk}", ms, 2 * M * NO * KI))
 # cuBLAS reference points
 a = rnd(M, 768); w = rnd(1536, 768)

@@ -29,7 +29,7 @@ if os.environ.get("WGRAD"):   # WGRAD=NO,KI: dW[NO, KI] = dY[M, NO]^T . X[M, KI]
     NO, KI = [int(t) for t in os.environ["WGRAD"].split(",")]
     dy_ = (torch.randn(M, NO, device="cuda") * .1).to(bf16); x_ = (torch.randn(M, KI, device="cuda") * .1).to(bf16)
     dw_ = torch.zeros(NO, KI, dtype=torch.float32, device="cuda")
-    sk = int(os.environ.get("SPLITK", _wgrad_split(M, NO * KI)))
+    sk = int(os.environ.get("SPLITK", _wgrad_split(M, NO * KI, NO, KI)))
     print("wgrad %dx%d K=%d split_k=%d" % (NO, KI, M, sk))
     f = lambda: K.gemm(dy_, x_, dw_, a_mn=True, b_mn=True, split_k=sk)
     os.environ["PLAIN"] = "1"

@@ -47,7 +47,7 @@ for name, N, Kd in [("dgrad 1024->256", 256, 1024), ("dgrad 256->1024", 1024, 25
     rows.append((name, N, Kd, ms, 2 * M * N * Kd, M * Kd * 2 + N * Kd * 2 + M * N * 2, cub))
 for name, NO, KI in [("wgrad 1024x256", 1024, 256), ("wgrad 256x1024", 256, 1024), ("wgrad 256x256", 256, 256), ("wgrad 768x256", 768, 256)]:
     dy = rnd(M, NO); x = rnd(M, KI); out = torch.zeros(NO, KI, dtype=f32, device=dev)
-    sk = _wgrad_split(M, NO * KI)
+    sk = _wgrad_split(M, NO * KI, NO, KI)
     ms = t(lambda: K.gemm(dy, x, out, a_mn=True, b_mn=True, split_k=sk)); cub = t(lambda: dy.t() @ x)
     rows.append((f"{name} split{sk}", NO, KI, ms, 2 * M * NO * KI, M * (NO + KI) * 2 + NO * KI * 4, cub))
 for name, N, Kd, ms, fl, nb, cub in rows:
