@@ -12,6 +12,8 @@
 // Token (b, i) lives at row  i < n_head ? b*n_head + i : head_rows + b*n_tail + (i - n_head)
 // ("planar" layout: all modality tokens of the batch, then all fusion tokens).
 #include "common.cuh"
+
+#include <type_traits>
 #include "mmf_b200.h"
 
 #include <atomic>
@@ -98,14 +100,19 @@ __device__ __forceinline__ void load_a_frags(uint32_t tile, int row0, uint32_t (
 }
 
 // acc[16 x 64] += A[16 x DH] . T[64 x DH]^T   (T rows are the "n" index, DH contiguous: non-transposed ldmatrix)
-template <int DH>
-__device__ __forceinline__ void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)[DH / 16][4], uint32_t tile) {
+// RAGGED (the last block of a ragged range, e.g. 196 tokens = 3 x 64 + 4): only the first 16 * npairs rows of T are live
+// and the other accumulator columns stay zero.  A template flag, not a runtime test on the full blocks: with the test inside
+// the unrolled loops the full-block path lost its ldmatrix / mma interleaving (0.121 -> 0.149 ms forward at N = 256).  Used by
+// the two backward kernels (0.404 -> 0.368 ms at the decoders' shape); the forward kernel measured no faster with it.
+template <int DH, bool RAGGED = false>
+__device__ __forceinline__ void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)[DH / 16][4], uint32_t tile, int npairs = 4) {
   const int lane = threadIdx.x & 31;
   const int mi = lane >> 3, r = lane & 7;
 #pragma unroll
   for (int ks = 0; ks < DH / 16; ++ks) {
 #pragma unroll
     for (int np = 0; np < 4; ++np) {  // pairs of n-tiles
+      if (RAGGED && np >= npairs) continue;
       uint32_t b0, b1, b2, b3;
       ldsm_x4(tile + tile_off<DH>(np * 16 + (mi >> 1) * 8 + r, ks * 2 + (mi & 1)), b0, b1, b2, b3);
       mma16816(acc[2 * np], a[ks], b0, b1);
@@ -115,12 +122,13 @@ __device__ __forceinline__ void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)
 }
 
 // acc[16 x DH] += P[16 x 64] . T[64 x DH]   (T rows are the "k" index: transposed ldmatrix); P given as accumulators
-template <int DH>
-__device__ __forceinline__ void mma_p_t(float (&acc)[DH / 8][4], const float (&p)[8][4], uint32_t tile) {
+template <int DH, bool RAGGED = false>
+__device__ __forceinline__ void mma_p_t(float (&acc)[DH / 8][4], const float (&p)[8][4], uint32_t tile, int nks = 4) {
   const int lane = threadIdx.x & 31;
   const int mi = lane >> 3, r = lane & 7;
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {  // 16 keys per step
+    if (RAGGED && ks >= nks) continue;
     uint32_t a[4];
     a[0] = pack_bf16(p[2 * ks][0], p[2 * ks][1]);
     a[1] = pack_bf16(p[2 * ks][2], p[2 * ks][3]);
@@ -307,7 +315,7 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 //   P = exp(scale*S - lse);  dP = dO.V^T;  dS = P*(dP - delta);  dQ = scale * dS.K
 // ------------------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, (DH == 32 ? 4 : 3)) attn_bwd_dq_kernel(const AttnParams p) {   // register caps of 4 / 3 CTAs per SM (128 / 168)
   extern __shared__ __align__(128) uint8_t smem[];
   int r0, r1, k0, k1;
   if (!map_tile(p, blockIdx.x, r0, r1, k0, k1)) return;
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
   const float L2E = 1.4426950408889634f;
 
   const int nblk = (k1 - k0 + ATT_BN - 1) / ATT_BN;
-  for (int blk = 0; blk < nblk; ++blk) {
+  auto stage_in = [&](int blk) {   // every thread: prefetch the next key block, wait for this one
     const int st = blk & 1;
     if (blk + 1 < nblk) {
       const int kn = k0 + (blk + 1) * ATT_BN;
@@ -349,23 +357,25 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (blk == 0) {
-      load_a_frags<DH>(sQ, warp * 16, qf);
-      load_a_frags<DH>(sdO, warp * 16, dof);
-    }
+  };
+  auto body = [&](auto ragged, int blk) {   // RG: the ragged last key block: only its 16-key groups that hold keys are worked on
+    constexpr bool RG = decltype(ragged)::value;
+    const int st = blk & 1;
+    const int kb = k0 + blk * ATT_BN;
+    const int npairs = RG ? min(4, (k1 - kb + 15) >> 4) : 4;
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
       dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
     }
-    mma_a_tT<DH>(s, qf, sK + st * TILE);
-    mma_a_tT<DH>(dp, dof, sV + st * TILE);
-    const int kb = k0 + blk * ATT_BN;
+    mma_a_tT<DH, RG>(s, qf, sK + st * TILE, npairs);
+    mma_a_tT<DH, RG>(dp, dof, sV + st * TILE, npairs);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+      if (RG && i >= 2 * npairs) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; continue; }
       const int c = kb + i * 8 + 2 * (lane & 3);
-      const bool v0 = c < k1, v1 = c + 1 < k1;
+      const bool v0 = !RG || c < k1, v1 = !RG || c + 1 < k1;
       const float p0 = v0 ? exp2f((s[i][0] * p.scale - lse[0]) * L2E) : 0.f;
       const float p1 = v1 ? exp2f((s[i][1] * p.scale - lse[0]) * L2E) : 0.f;
       const float p2 = v0 ? exp2f((s[i][2] * p.scale - lse[1]) * L2E) : 0.f;
@@ -375,8 +385,34 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const AttnPara
       s[i][2] = p2 * (dp[i][2] - dl[1]);
       s[i][3] = p3 * (dp[i][3] - dl[1]);
     }
-    mma_p_t<DH>(dq, s, sK + st * TILE);  // dQ += dS . K
-    __syncthreads();
+    mma_p_t<DH, RG>(dq, s, sK + st * TILE, npairs);  // dQ += dS . K
+  };
+  // A warp whose 16 query rows all lie past the tile's end (the last 64-row tile of 196 tokens holds 4 rows) only takes part in
+  // the cooperative loads and the barriers.
+  const bool warp_live = r0 + warp * 16 < r1;
+  const bool ragged_last = ((k1 - k0) % ATT_BN) != 0;
+  const int nfull = ragged_last ? nblk - 1 : nblk;
+  if (!warp_live) {
+    for (int blk = 0; blk < nblk; ++blk) { stage_in(blk); __syncthreads(); }
+  } else {
+    for (int blk = 0; blk < nfull; ++blk) {
+      stage_in(blk);
+      if (blk == 0) {
+        load_a_frags<DH>(sQ, warp * 16, qf);
+        load_a_frags<DH>(sdO, warp * 16, dof);
+      }
+      body(std::false_type{}, blk);
+      __syncthreads();
+    }
+    if (ragged_last) {
+      stage_in(nfull);
+      if (nfull == 0) {
+        load_a_frags<DH>(sQ, warp * 16, qf);
+        load_a_frags<DH>(sdO, warp * 16, dof);
+      }
+      body(std::true_type{}, nfull);
+      __syncthreads();
+    }
   }
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
@@ -463,7 +499,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
   const float L2E = 1.4426950408889634f;
   const int key_a = c0 + warp * 16 + (lane >> 2);  // this thread's two key rows: key_a, key_a + 8
 
-  for (int blk = 0; blk < nblk; ++blk) {
+  auto stage_in = [&](int blk) {   // every thread: prefetch the next query block, wait for this one
     const int st = blk & 1;
     if (blk + 1 < nblk) {
       issue_q(blk + 1, st ^ 1);
@@ -473,21 +509,27 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (blk == 0) {
-      load_a_frags<DH>(sK, warp * 16, kf);
-      load_a_frags<DH>(sV, warp * 16, vf);
-    }
+  };
+  auto body = [&](auto ragged, int blk, int qrows) {   // RG: a query block with fewer than 64 live rows (lse = +inf beyond them)
+    constexpr bool RG = decltype(ragged)::value;
+    const int st = blk & 1;
+    const int npairs = RG ? min(4, (qrows + 15) >> 4) : 4;
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
       dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
     }
-    mma_a_tT<DH>(s, kf, sQ + st * TILE);     // S^T[key, q]
-    mma_a_tT<DH>(dp, vf, sdO + st * TILE);   // dP^T[key, q]
+    mma_a_tT<DH, RG>(s, kf, sQ + st * TILE, npairs);     // S^T[key, q]
+    mma_a_tT<DH, RG>(dp, vf, sdO + st * TILE, npairs);   // dP^T[key, q]
     const bool kv0 = key_a < c1, kv1 = key_a + 8 < c1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+      if (RG && i >= 2 * npairs) {
+        s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+        continue;
+      }
       const int qc = i * 8 + 2 * (lane & 3);
       const float l0 = s_lse[st * 64 + qc], l1 = s_lse[st * 64 + qc + 1];
       const float d0 = s_dl[st * 64 + qc], d1 = s_dl[st * 64 + qc + 1];
@@ -501,9 +543,23 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnPar
       dp[i][2] = p2 * (dp[i][2] - d0);
       dp[i][3] = p3 * (dp[i][3] - d1);
     }
-    mma_p_t<DH>(dv, s, sdO + st * TILE);  // dV += P^T . dO
-    mma_p_t<DH>(dk, dp, sQ + st * TILE);  // dK += dS^T . Q
-    __syncthreads();
+    mma_p_t<DH, RG>(dv, s, sdO + st * TILE, npairs);  // dV += P^T . dO
+    mma_p_t<DH, RG>(dk, dp, sQ + st * TILE, npairs);  // dK += dS^T . Q
+  };
+  const bool warp_live = c0 + warp * 16 < c1;   // as in attn_bwd_dq_kernel (here the warp's rows are keys, the blocks queries)
+  if (!warp_live) {
+    for (int blk = 0; blk < nblk; ++blk) { stage_in(blk); __syncthreads(); }
+  } else {
+    for (int blk = 0; blk < nblk; ++blk) {
+      stage_in(blk);
+      if (blk == 0) {
+        load_a_frags<DH>(sK, warp * 16, kf);
+        load_a_frags<DH>(sV, warp * 16, vf);
+      }
+      const int qrows = blk < nb0 ? qe[0] - (qa[0] + blk * 64) : qe[1] - (qa[1] + (blk - nb0) * 64);   // warp-uniform
+      if (qrows >= 64) body(std::false_type{}, blk, 64); else body(std::true_type{}, blk, qrows);
+      __syncthreads();
+    }
   }
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
