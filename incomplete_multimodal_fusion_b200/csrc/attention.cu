@@ -168,6 +168,7 @@ __device__ __forceinline__ bool map_tile(const AttnParams& p, int tile, int& r0,
 // ------------------------------------------------------------------------------------------------
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams p) {
+  pdl_wait();   // launched through launch_pdl (common.cuh): nothing another kernel owns is touched before this
   __shared__ __align__(128) uint8_t smem[(64 + 4 * 64) * DH * 2];
   int r0, r1, k0, k1;
   if (!map_tile(p, blockIdx.x, r0, r1, k0, k1)) return;
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const AttnParams 
 // ------------------------------------------------------------------------------------------------
 template <int DH>
 __global__ void attn_delta_kernel(const AttnParams p) {
+  pdl_wait();   // launched through launch_pdl (common.cuh): nothing another kernel owns is touched before this
   // one warp per (b, i): lanes sweep the H*DH row in 16-byte chunks; heads are DH/8 chunks wide
   constexpr int CPH = DH / 8;
   const int lane = threadIdx.x & 31;
@@ -315,7 +317,8 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 //   P = exp(scale*S - lse);  dP = dO.V^T;  dS = P*(dP - delta);  dQ = scale * dS.K
 // ------------------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(ATT_THREADS, (DH == 32 ? 4 : 3)) attn_bwd_dq_kernel(const AttnParams p) {   // register caps of 4 / 3 CTAs per SM (128 / 168)
+__global__ void __launch_bounds__(ATT_THREADS, (DH == 32 ? 4 : 3)) attn_bwd_dq_kernel(const AttnParams p) {
+  pdl_wait();   // launched through launch_pdl (common.cuh): nothing another kernel owns is touched before this   // register caps of 4 / 3 CTAs per SM (128 / 168)
   extern __shared__ __align__(128) uint8_t smem[];
   int r0, r1, k0, k1;
   if (!map_tile(p, blockIdx.x, r0, r1, k0, k1)) return;
@@ -435,6 +438,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (DH == 32 ? 4 : 3)) attn_bwd_dq_k
 // ------------------------------------------------------------------------------------------------
 template <int DH>
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const AttnParams p) {
+  pdl_wait();   // launched through launch_pdl (common.cuh): nothing another kernel owns is touched before this
   extern __shared__ __align__(128) uint8_t smem[];
   // key tile: reuse map_tile on the key axis (self-attention: Nq == Nk, same segments)
   int c0, c1;
@@ -626,8 +630,8 @@ extern "C" int mmf_attn_fwd(const MmfAttnArgs* a, mmf_stream_t stream) {
   const int tiles = (a->Nq + ATT_BM - 1) / ATT_BM + (a->seg ? a->nseg : 0);
   dim3 grid(tiles, a->H, a->B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->dh == 64) attn_fwd_kernel<64><<<grid, ATT_THREADS, 0, st>>>(p);
-  else attn_fwd_kernel<32><<<grid, ATT_THREADS, 0, st>>>(p);
+  if (a->dh == 64) launch_pdl(attn_fwd_kernel<64>, dim3(grid), dim3(ATT_THREADS), 0, st, p);
+  else launch_pdl(attn_fwd_kernel<32>, dim3(grid), dim3(ATT_THREADS), 0, st, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();
   return 0;
@@ -647,7 +651,7 @@ extern "C" int mmf_attn_bwd(const MmfAttnArgs* a, mmf_stream_t stream) {
   {
     static const bool tc_on = !(getenv("MMF_ATTN_TC") && atoi(getenv("MMF_ATTN_TC")) == 0);
     if (tc_on && a->dh == 64 && a->Nq == a->Nk && a->n_head_q == a->n_head_k && !(a->ldo & 7) && !(a->lddo & 7)) {
-      attn_delta_kernel<64><<<dgrid, 256, 0, st>>>(p);
+      launch_pdl(attn_delta_kernel<64>, dim3(dgrid), dim3(256), 0, st, p);
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
       const int rc_tc = attn_bwd_tc_launch(a, st);
       if (rc_tc != -1000) return rc_tc;
@@ -662,13 +666,13 @@ extern "C" int mmf_attn_bwd(const MmfAttnArgs* a, mmf_stream_t stream) {
       cudaFuncSetAttribute(attn_bwd_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
       attr.set(attr_dev);
     }
-    attn_delta_kernel<64><<<dgrid, 256, 0, st>>>(p);
-    attn_bwd_dq_kernel<64><<<dim3(qtiles, a->H, a->B), ATT_THREADS, smem_dq, st>>>(p);
-    attn_bwd_dkv_kernel<64><<<dim3(ktiles, a->H, a->B), ATT_THREADS, smem_dkv, st>>>(p);
+    launch_pdl(attn_delta_kernel<64>, dim3(dgrid), dim3(256), 0, st, p);
+    launch_pdl(attn_bwd_dq_kernel<64>, dim3(dim3(qtiles, a->H, a->B)), dim3(ATT_THREADS), smem_dq, st, p);
+    launch_pdl(attn_bwd_dkv_kernel<64>, dim3(dim3(ktiles, a->H, a->B)), dim3(ATT_THREADS), smem_dkv, st, p);
   } else {
-    attn_delta_kernel<32><<<dgrid, 256, 0, st>>>(p);
-    attn_bwd_dq_kernel<32><<<dim3(qtiles, a->H, a->B), ATT_THREADS, smem_dq, st>>>(p);
-    attn_bwd_dkv_kernel<32><<<dim3(ktiles, a->H, a->B), ATT_THREADS, smem_dkv, st>>>(p);
+    launch_pdl(attn_delta_kernel<32>, dim3(dgrid), dim3(256), 0, st, p);
+    launch_pdl(attn_bwd_dq_kernel<32>, dim3(dim3(qtiles, a->H, a->B)), dim3(ATT_THREADS), smem_dq, st, p);
+    launch_pdl(attn_bwd_dkv_kernel<32>, dim3(dim3(ktiles, a->H, a->B)), dim3(ATT_THREADS), smem_dkv, st, p);
   }
   g_launch_count.fetch_add(3, std::memory_order_relaxed);
   MMF_LAUNCH_CHECK();

@@ -529,6 +529,7 @@ template <int CTAS, int QBUF, int KVST, int POLY>
 __global__ void __launch_bounds__(TC_THREADS, CTAS)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
+  pdl_wait();   // launched through launch_pdl (common.cuh): nothing another kernel owns is touched before this
   extern __shared__ uint8_t smem_raw[];
   int r0 = 0, r1 = 0, k0 = 0, k1 = 0, b = 0, h0 = 0, h1 = 0;
   {
@@ -906,7 +907,7 @@ int attn_fwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   do {                                                                                                                 \
     constexpr int smem = QB * TC_TILE_BYTES + 2 * KS * TC_KV_BYTES + 1024 + 512;                                       \
     if ((rc = prep(reinterpret_cast<const void*>(attn_fwd_tc2_kernel<CT, QB, KS, PL>), smem))) return rc;              \
-    attn_fwd_tc2_kernel<CT, QB, KS, PL><<<grid, TC_THREADS, smem, stream>>>(tq, tk, tv, p);                            \
+    launch_pdl(attn_fwd_tc2_kernel<CT, QB, KS, PL>, dim3(grid), dim3(TC_THREADS), smem, stream, tq, tk, tv, p);                            \
   } while (0)
   switch (variant) {
     case 0:
@@ -1210,6 +1211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                        const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                        const AttnBwdTcParams p) {
+  pdl_wait();   // launched through launch_pdl (common.cuh): nothing another kernel owns is touched before this
   // 1024-byte aligned by declaration (the 128B-swizzle atoms need it): no alignment slack in the allocation, which is what
   // lets 2 CTAs x (64 KB of Q / dO + three 16 KB K / V stages) share an SM
   extern __shared__ __align__(1024) uint8_t smem_dq2[];
@@ -1485,6 +1487,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                        const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                        const AttnBwdTcParams p) {
+  pdl_wait();   // launched through launch_pdl (common.cuh): nothing another kernel owns is touched before this
   extern __shared__ uint8_t smem_raw[];
   // key tile (cut per segment) and the query ranges that attend to it
   int c0 = 0, c1 = 0, qa0 = 0, qe0 = 0, qa1 = 0, qe1 = 0, b = 0;
@@ -1886,7 +1889,7 @@ int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   do {                                                                                                                 \
     constexpr int smem = 4 * TC_TILE_BYTES + 2 * KS * BW_BLK_BYTES + 256;                                              \
     if ((rc = prep(attr_done_v[IDX], reinterpret_cast<const void*>(attn_bwd_dq_tc2_kernel<KS, PL>), smem))) return rc;  \
-    attn_bwd_dq_tc2_kernel<KS, PL><<<grid_q, TC_THREADS, smem, stream>>>(q128, do128, k64, v64, p);                    \
+    launch_pdl(attn_bwd_dq_tc2_kernel<KS, PL>, dim3(grid_q), dim3(TC_THREADS), smem, stream, q128, do128, k64, v64, p);                    \
   } while (0)
   switch (vq) {
     case 0:
@@ -1899,7 +1902,7 @@ int attn_bwd_tc_launch(const MmfAttnArgs* a, cudaStream_t stream) {
   }
 #undef MMF_DQ2
   if ((rc = prep(attr_done_v[4], reinterpret_cast<const void*>(attn_bwd_dkv_tc_kernel), DKV_SMEM))) return rc;
-  attn_bwd_dkv_tc_kernel<<<tiles * a->B, TC_THREADS, DKV_SMEM, stream>>>(k128, v128, q64, do64, p);
+  launch_pdl(attn_bwd_dkv_tc_kernel, dim3(tiles * a->B), dim3(TC_THREADS), DKV_SMEM, stream, k128, v128, q64, do64, p);
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;

@@ -27,6 +27,7 @@ static inline int ew_grid(int64_t work_items, int threads) {
 __global__ void cast_pad_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src,
                                 __nv_bfloat16* __restrict__ dst, int64_t rows_pad, int64_t cols_pad, int64_t ld_dst,
                                 float scale) {
+  pdl_wait();   // launched through launch_pdl (common.cuh)
   const int64_t total = rows_pad * cols_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols_pad, c = i % cols_pad;
@@ -37,6 +38,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, int64_t rows, int
 }
 // contiguous fast path: n % 4 == 0, 16B aligned
 __global__ void cast_vec_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4) {
+  pdl_wait();   // launched through launch_pdl (common.cuh)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = src[i];
     dst[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
@@ -72,6 +74,7 @@ __global__ void geglu_bwd_kernel(const uint4* __restrict__ u, const uint4* __res
 
 // dpre = dy * gelu'(pre)   (bf16, n % 8 == 0)
 __global__ void gelu_bwd_kernel(const uint4* __restrict__ pre, const uint4* __restrict__ dy, uint4* __restrict__ dpre, int64_t n8) {
+  pdl_wait();   // launched through launch_pdl (common.cuh)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 a = pre[i], d = dy[i];
     uint4 o;
@@ -105,6 +108,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, int64_t rows, int cols, i
 // four rows in flight per thread; the row-lanes are combined in shared memory before one atomic per column
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int64_t ld,
                                                          float* __restrict__ out, int rows_per_cta) {
+  pdl_wait();   // launched through launch_pdl (common.cuh)
   const int tcol = threadIdx.x & 31, trow = threadIdx.x >> 5;
   const int64_t col = ((int64_t)blockIdx.x * 32 + tcol) * 8;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
@@ -256,6 +260,7 @@ __global__ void onehot_im2col_kernel(const int64_t* __restrict__ cls, const int3
 // ------------------------------------------------------------------------------------------------
 __global__ void unpatchify_kernel(const uint4* __restrict__ tok, uint4* __restrict__ img, int64_t batch, int C, int H,
                                   int W, int P, int inverse) {
+  pdl_wait();   // launched through launch_pdl (common.cuh)
   const int nw = W / P, nh = H / P, P8 = P >> 3;
   const int64_t total = batch * C * H * (W >> 3);
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -298,6 +303,7 @@ __global__ void gather_rows_kernel(const TS* __restrict__ src, int64_t ld_src, i
 
 // y (f32) += x (f32), n % 4 == 0
 __global__ void add_inplace_kernel(float4* __restrict__ y, const float4* __restrict__ x, int64_t n4) {
+  pdl_wait();   // launched through launch_pdl (common.cuh)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 a = y[i];
     const float4 b = x[i];
@@ -308,6 +314,7 @@ __global__ void add_inplace_kernel(float4* __restrict__ y, const float4* __restr
 
 // out (f32) = x (f32) + d (bf16), n % 4 == 0: materialises the residual stream after the last sub-layer
 __global__ void add_bf16_kernel(float4* __restrict__ out, const float4* __restrict__ x, const uint2* __restrict__ d, int64_t n4) {
+  pdl_wait();   // launched through launch_pdl (common.cuh)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 a = x[i];
     const uint2 u = d[i];
@@ -330,9 +337,9 @@ extern "C" int mmf_cast_f32_bf16(const float* src, int64_t rows, int64_t cols, i
   const bool contiguous = rows == rows_pad && cols == cols_pad && ld_src == cols && ld_dst == cols && scale == 1.0f;
   const int64_t n = rows * cols;
   if (contiguous && (n & 3) == 0 && !(reinterpret_cast<uintptr_t>(src) & 15) && !(reinterpret_cast<uintptr_t>(dst) & 7)) {
-    cast_vec_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n / 4);
+    launch_pdl(cast_vec_kernel, dim3(ew_grid(n / 4, 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n / 4);
   } else {
-    cast_pad_kernel<<<ew_grid(rows_pad * cols_pad, 256), 256, 0, st>>>(src, rows, cols, ld_src,
+    launch_pdl(cast_pad_kernel, dim3(ew_grid(rows_pad * cols_pad, 256)), dim3(256), 0, st, src, rows, cols, ld_src,
                                                                      reinterpret_cast<__nv_bfloat16*>(dst), rows_pad, cols_pad, ld_dst, scale);
   }
   MMF_COUNT_LAUNCH();
@@ -355,7 +362,7 @@ extern "C" int mmf_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t
   if (!pre || !dy || !dpre) MMF_BAD_ARG(1);
   if (n & 7) MMF_BAD_ARG(2);
   if (n == 0) return 0;
-  gelu_bwd_kernel<<<ew_grid(n / 8, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(gelu_bwd_kernel, dim3(ew_grid(n / 8, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(pre), reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(dpre), n / 8);
   MMF_COUNT_LAUNCH();
   MMF_LAUNCH_CHECK();
@@ -371,7 +378,7 @@ extern "C" int mmf_colsum(const void* x, int32_t x_f32, int64_t rows, int64_t co
     if (gyv > rows / 32) gyv = (int)(rows / 32 > 0 ? rows / 32 : 1);
     const int rpc = (int)ceil_div64(rows, gyv);
     gyv = (int)ceil_div64(rows, rpc);
-    colsum_vec_kernel<<<dim3(gxv, gyv), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, ld, out, rpc);
+    launch_pdl(colsum_vec_kernel, dim3(dim3(gxv, gyv)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(x), rows, ld, out, rpc);
     MMF_COUNT_LAUNCH();
     MMF_LAUNCH_CHECK();
     return 0;
@@ -470,7 +477,7 @@ extern "C" int mmf_unpatchify_bf16(void* tokens, void* image, int64_t batch, int
   if (P <= 0 || (P & 7) || H % P || W % P) MMF_BAD_ARG(2);
   const int64_t total = batch * C * H * (W / 8);
   if (total == 0) return 0;
-  unpatchify_kernel<<<ew_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(unpatchify_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint4*>(tokens), reinterpret_cast<uint4*>(image), batch, C, H, W, P, inverse);
   MMF_COUNT_LAUNCH();
   MMF_LAUNCH_CHECK();
@@ -503,7 +510,7 @@ extern "C" int mmf_add_inplace_f32(float* y, const float* x, int64_t n, mmf_stre
   if (!y || !x) MMF_BAD_ARG(1);
   if (n & 3) MMF_BAD_ARG(2);
   if (n == 0) return 0;
-  add_inplace_kernel<<<ew_grid(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(add_inplace_kernel, dim3(ew_grid(n / 4, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), n / 4);
   MMF_COUNT_LAUNCH();
   MMF_LAUNCH_CHECK();
@@ -514,7 +521,7 @@ extern "C" int mmf_add_bf16_f32(float* out, const float* x, const void* d, int64
   if (!out || !x || !d) MMF_BAD_ARG(1);
   if (n & 3) MMF_BAD_ARG(2);
   if (n == 0) return 0;
-  add_bf16_kernel<<<ew_grid(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(add_bf16_kernel, dim3(ew_grid(n / 4, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<float4*>(out), reinterpret_cast<const float4*>(x), reinterpret_cast<const uint2*>(d), n / 4);
   MMF_COUNT_LAUNCH();
   MMF_LAUNCH_CHECK();

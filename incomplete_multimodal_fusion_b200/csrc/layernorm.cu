@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NC <= 6 ? 3 : 2)) ln_fwd_kerne
   const int nchunk = p.D >> 2;
   const float invD = 1.0f / (float)p.D;
   __shared__ float4 g1[NC * 32], b1[NC * 32], g2[NC * 32];
+  pdl_wait();   // launched with the programmatic-serialization attribute (launch_pdl): nothing is read before this
   ln_stage_params(g1, b1, g2, p.g1, p.b1, p.g2, nchunk);
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < p.rows; row += (int64_t)gridDim.x * LN_WARPS) {
     const float4* xr = reinterpret_cast<const float4*>(
@@ -462,6 +463,7 @@ __global__ void __launch_bounds__(LnRing<NC>::WARPS * 32, 1) ln_bwd_ring_kernel(
     for (int s = 0; s < 4; ++s) mbar_init(&bar_a[s], 1);
     mbar_fence_init();
   }
+  pdl_wait();   // launched through launch_pdl: the barrier set-up above overlaps the previous kernel's tail
   ln_stage_params(g1, b1, g2, p.g1, p.b1, p.g2, NC * 32);   // ends with __syncthreads()
   const int64_t row_first = (int64_t)blockIdx.x * W + warp, row_step = (int64_t)gridDim.x * W;
   const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(p.dy);
@@ -667,7 +669,7 @@ extern "C" int mmf_layernorm_fwd(const float* x, const float* x2, int64_t x_spli
   p.l2_prefetch = l2e ? atoi(l2e) : (delta ? 0 : 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nc = ceil_div(D, 128);
-#define MMF_LN_FWD_LAUNCH(NCV, F) ln_fwd_kernel<NCV, F><<<ln_grid(ln_fwd_kernel<NCV, F>, 0, rows, 4), LN_WARPS * 32, 0, st>>>(p)
+#define MMF_LN_FWD_LAUNCH(NCV, F) launch_pdl(ln_fwd_kernel<NCV, F>, dim3(ln_grid(ln_fwd_kernel<NCV, F>, 0, rows, 4)), dim3(LN_WARPS * 32), 0, st, p)
   if (nc <= 2) { if (D == 256) MMF_LN_FWD_LAUNCH(2, true); else MMF_LN_FWD_LAUNCH(2, false); }
   else if (nc <= 4) { if (D == 512) MMF_LN_FWD_LAUNCH(4, true); else MMF_LN_FWD_LAUNCH(4, false); }
   else if (nc <= 6) { if (D == 768) MMF_LN_FWD_LAUNCH(6, true); else MMF_LN_FWD_LAUNCH(6, false); }
@@ -718,7 +720,7 @@ extern "C" int mmf_layernorm_bwd(const void* dy, int64_t lddy, int32_t dy_f32, c
     int sms = 148;                                                                                                          \
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, attr_dev);                                                 \
     const int64_t need = ceil_div64(rows, LnRing<NCV>::WARPS);                                                              \
-    ln_bwd_ring_kernel<NCV, HBV><<<(int)(need < sms ? need : sms), LnRing<NCV>::WARPS * 32, LnRing<NCV>::SMEM, st>>>(p);     \
+    launch_pdl(ln_bwd_ring_kernel<NCV, HBV>, dim3((int)(need < sms ? need : sms)), dim3(LnRing<NCV>::WARPS * 32), LnRing<NCV>::SMEM, st, p); \
   } while (0)
     if (b1) {
       if (ncp == 2) MMF_LN_RING_LAUNCH(2, true); else if (ncp == 4) MMF_LN_RING_LAUNCH(4, true);

@@ -174,6 +174,7 @@ __device__ __forceinline__ void axpy16(float a, const Pk16& r, float (&y)[16]) {
 
 template <bool BWD, int S>
 __global__ void __launch_bounds__(SLOTW_WARPS * 32) slot_attn_wide_kernel(const SlotParams p) {
+  pdl_wait();   // launched through launch_pdl (common.cuh): nothing another kernel owns is touched before this
   const int lane = threadIdx.x & 31;
   const int64_t bp = (int64_t)blockIdx.x * SLOTW_WARPS + (threadIdx.x >> 5);   // b * F + pos
   if (bp >= (int64_t)p.B * p.F) return;
@@ -249,10 +250,10 @@ static void launch_slot_wide(const SlotParams& p, cudaStream_t st) {
   const int64_t n = (int64_t)p.B * p.F;
   const unsigned grid = (unsigned)((n + SLOTW_WARPS - 1) / SLOTW_WARPS);
   switch (p.S) {
-    case 2: slot_attn_wide_kernel<BWD, 2><<<grid, SLOTW_WARPS * 32, 0, st>>>(p); break;
-    case 3: slot_attn_wide_kernel<BWD, 3><<<grid, SLOTW_WARPS * 32, 0, st>>>(p); break;
-    case 4: slot_attn_wide_kernel<BWD, 4><<<grid, SLOTW_WARPS * 32, 0, st>>>(p); break;
-    default: slot_attn_wide_kernel<BWD, 5><<<grid, SLOTW_WARPS * 32, 0, st>>>(p); break;
+    case 2: launch_pdl(slot_attn_wide_kernel<BWD, 2>, dim3(grid), dim3(SLOTW_WARPS * 32), 0, st, p); break;
+    case 3: launch_pdl(slot_attn_wide_kernel<BWD, 3>, dim3(grid), dim3(SLOTW_WARPS * 32), 0, st, p); break;
+    case 4: launch_pdl(slot_attn_wide_kernel<BWD, 4>, dim3(grid), dim3(SLOTW_WARPS * 32), 0, st, p); break;
+    default: launch_pdl(slot_attn_wide_kernel<BWD, 5>, dim3(grid), dim3(SLOTW_WARPS * 32), 0, st, p); break;
   }
 }
 
@@ -261,6 +262,7 @@ static void launch_slot_wide(const SlotParams& p, cudaStream_t st) {
 // shared memory.  Positions / slots that are real tokens contribute nothing (written as 0).
 constexpr int MERED_WARPS = 8;
 __global__ void __launch_bounds__(MERED_WARPS * 32) slot_me_reduce_kernel(const SlotParams p) {
+  pdl_wait();   // launched through launch_pdl (common.cuh): nothing another kernel owns is touched before this
   __shared__ float4 part[MERED_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int pos = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -578,7 +580,7 @@ extern "C" int mmf_slot_attn_bwd(const MmfSlotAttnArgs* a, mmf_stream_t stream) 
   if (slot_wide_ok(*a, true)) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     launch_slot_wide<true>(slot_params(*a), st);
-    slot_me_reduce_kernel<<<(unsigned)(a->F * a->H), MERED_WARPS * 32, 0, st>>>(slot_params(*a));
+    launch_pdl(slot_me_reduce_kernel, dim3((unsigned)(a->F * a->H)), dim3(MERED_WARPS * 32), 0, st, slot_params(*a));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
   } else
   slot_attn_kernel<true><<<(unsigned)((int64_t)a->B * a->F), 32 * a->H, 0, reinterpret_cast<cudaStream_t>(stream)>>>(slot_params(*a));
