@@ -287,9 +287,14 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    # NCCL writes its version banner (NCCL_DEBUG >= VERSION, which includes WARN) to STDOUT; rank 0's stdout is ONE JSON line,
-    # so its log goes to stderr unless the caller chose a file
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # NCCL writes its version banner to STDOUT from C code when NCCL_DEBUG is set in the environment (VERSION / WARN / INFO);
+    # rank 0's stdout is ONE JSON line.  The real stdout is kept aside for that line and file descriptor 1 is pointed at
+    # stderr for everything else this process (or a library in it) prints.
+    json_out = sys.stdout
+    if world > 1:
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
     torch.cuda.set_device(local)
     reserve = int(os.environ.get("MMF_RESERVE_SMS", "0"))
     if world > 1:
@@ -516,7 +521,8 @@ def run_ours(args):
                                             f"{args.batch}-sample workload per step, 2 warm-up + 8 timed steps ({sec:.2f} s/step)"}
     if eager_ref is not None:
         result["gpu_eager_reference"] = eager_ref
-    print(json.dumps(result))
+    print(json.dumps(result), file=json_out)
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
